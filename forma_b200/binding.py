@@ -250,13 +250,20 @@ SIGNATURES = {
     "path_segments": (C.c_int, [_vp, C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_u8p), _u64p]),
     "composition_new": (_vp, []),
     "composition_free": (None, [_vp]),
-    "composition_layer": (C.c_int, [_vp, C.c_uint32]),
-    "composition_remove": (C.c_int, [_vp, C.c_uint32]),
-    "layer_insert_path": (C.c_int, [_vp, C.c_uint32, _vp]),
-    "layer_clear": (C.c_int, [_vp, C.c_uint32]),
-    "layer_set_is_enabled": (C.c_int, [_vp, C.c_uint32, C.c_int]),
-    "layer_set_transform": (C.c_int, [_vp, C.c_uint32, _fp]),
-    "layer_set_props": (C.c_int, [_vp, C.c_uint32, C.POINTER(_CProps)]),
+    "composition_create_layer": (_vp, [_vp]),
+    "composition_insert": (_vp, [_vp, C.c_uint32, _vp, C.POINTER(C.c_int)]),
+    "composition_remove": (_vp, [_vp, C.c_uint32]),
+    "composition_get": (_vp, [_vp, C.c_uint32]),
+    "composition_get_mut_or_insert_default": (_vp, [_vp, C.c_uint32, C.POINTER(C.c_int)]),
+    "composition_len": (C.c_uint64, [_vp]),
+    "layer_drop": (None, [_vp, _vp]),
+    "layer_geom_id": (C.c_uint64, [_vp]),
+    "layer_insert": (C.c_int, [_vp, _vp, _vp]),
+    "layer_clear": (C.c_int, [_vp, _vp]),
+    "layer_set_is_enabled": (C.c_int, [_vp, _vp, C.c_int]),
+    "layer_is_enabled": (C.c_int, [_vp]),
+    "layer_set_transform": (C.c_int, [_vp, _vp, _fp]),
+    "layer_set_props": (C.c_int, [_vp, _vp, C.POINTER(_CProps)]),
     "renderer_new": (_vp, [C.c_int]),
     "renderer_free": (None, [_vp]),
     "layer_cache_new": (_vp, [_vp]),
@@ -421,25 +428,29 @@ def _lower_props(props: Props):
 
 
 class Layer:
-    """forma/src/composition/layer.rs:61-353, addressed through its Order."""
+    """forma/src/composition/layer.rs:61-353. The handle is owned by the
+    Composition; `drop()` is Rust's `Drop for Layer`."""
 
-    def __init__(self, comp: "Composition", order: int):
-        self._c, self._order = comp, order
+    def __init__(self, comp: "Composition", handle):
+        self._c, self._h = comp, handle
 
     def insert(self, path: Path) -> "Layer":
         a = self._c._api
-        a.check(a.layer_insert_path(self._c._h, self._order, path._h), "Layer::insert")
+        a.check(a.layer_insert(self._c._h, self._h, path._h), "Layer::insert")
         return self
 
     def clear(self) -> "Layer":
         a = self._c._api
-        a.check(a.layer_clear(self._c._h, self._order), "Layer::clear")
+        a.check(a.layer_clear(self._c._h, self._h), "Layer::clear")
         return self
+
+    def geom_id(self) -> int:
+        return int(self._c._api.layer_geom_id(self._h))
 
     def set_props(self, props: Props) -> "Layer":
         a = self._c._api
         cp, keep = _lower_props(props)
-        a.check(a.layer_set_props(self._c._h, self._order, C.byref(cp)), "Layer::set_props")
+        a.check(a.layer_set_props(self._c._h, self._h, C.byref(cp)), "Layer::set_props")
         del keep
         return self
 
@@ -447,15 +458,18 @@ class Layer:
         """t = [ux, vx, uy, vy, tx, ty] as GeomPresTransform::try_from([f32; 6])."""
         a = self._c._api
         arr = (C.c_float * 6)(*[float(v) for v in t])
-        st = a.layer_set_transform(self._c._h, self._order, arr)
+        st = a.layer_set_transform(self._c._h, self._h, arr)
         if st == 1:
             raise GeomPresTransformError("exceeded scaling factor")
         a.check(st, "Layer::set_transform")
         return self
 
+    def is_enabled(self) -> bool:
+        return bool(self._c._api.layer_is_enabled(self._h))
+
     def set_is_enabled(self, enabled: bool) -> "Layer":
         a = self._c._api
-        a.check(a.layer_set_is_enabled(self._c._h, self._order, 1 if enabled else 0), "Layer::set_is_enabled")
+        a.check(a.layer_set_is_enabled(self._c._h, self._h, 1 if enabled else 0), "Layer::set_is_enabled")
         return self
 
     def enable(self) -> "Layer":
@@ -463,6 +477,10 @@ class Layer:
 
     def disable(self) -> "Layer":
         return self.set_is_enabled(False)
+
+    def drop(self) -> None:
+        self._c._api.layer_drop(self._c._h, self._h)
+        self._h = None
 
 
 class Composition:
@@ -472,12 +490,36 @@ class Composition:
         self._api = api
         self._h = api.composition_new()
 
-    def get_mut_or_insert_default(self, order: int) -> Layer:
-        self._api.check(self._api.composition_layer(self._h, order), "Order::new")
-        return Layer(self, order)
+    def create_layer(self) -> Layer:
+        return Layer(self, self._api.composition_create_layer(self._h))
 
-    def remove(self, order: int) -> bool:
-        return self._api.composition_remove(self._h, order) == 0
+    def insert(self, order: int, layer: Layer) -> Optional[Layer]:
+        st = C.c_int(0)
+        old = self._api.composition_insert(self._h, order, layer._h, C.byref(st))
+        self._api.check(st.value, "Order::new")
+        return Layer(self, old) if old else None
+
+    def remove(self, order: int) -> Optional[Layer]:
+        h = self._api.composition_remove(self._h, order)
+        return Layer(self, h) if h else None
+
+    def get(self, order: int) -> Optional[Layer]:
+        h = self._api.composition_get(self._h, order)
+        return Layer(self, h) if h else None
+
+    get_mut = get
+
+    def get_mut_or_insert_default(self, order: int) -> Layer:
+        st = C.c_int(0)
+        h = self._api.composition_get_mut_or_insert_default(self._h, order, C.byref(st))
+        self._api.check(st.value, "Order::new")
+        return Layer(self, h)
+
+    def __len__(self) -> int:
+        return int(self._api.composition_len(self._h))
+
+    def is_empty(self) -> bool:
+        return len(self) == 0
 
     def __del__(self):
         try:

@@ -1,0 +1,83 @@
+// POD records shared between the host side and the CUDA kernels.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace forma {
+
+// --- pixel-segment bit layout (forma/src/consts.rs:68-93, TW = TH = 16) -----
+//   63..53 tile_y(11, bias 1) | 52..41 tile_x(12, bias 1) | 40..20 layer(21) |
+//   19..16 local_x | 15..12 local_y | 11..6 double_area_multiplier | 5..0 cover
+constexpr int kSortShift = 20;   // ordering ignores the low 20 bits (pixel_segment.rs:161-171)
+constexpr int kTile = 16;
+constexpr uint32_t kLayerLimit = (1u << 21) - 1;
+
+// One quadratic of a flatten program (path.rs:190-204: Primitives SoA, gathered).
+struct QuadRec {
+    float px[3], py[3], pw[3];  // control points, pre-multiplied by their weights
+    float x0, dx_recip, k0, dk, curv_recip;
+    float prev_curv;  // running curvature of the previous quad iff same spline, else 0 (path.rs:508-514)
+};
+
+// One output point of a flatten program (path.rs:138-168 PointCommand, resolved).
+//   kind 0: literal point (a, b)                  (Start / End of a spline)
+//   kind 1: literal point (a, b), ends a contour  (End with new_contour)
+//   kind 2: evaluate quad `quad` at Incr(a) * pi(b)
+struct PointCmd {
+    uint32_t kind;
+    uint32_t quad;
+    float a, b;
+};
+
+struct FlattenProgram {
+    std::vector<QuadRec> quads;
+    std::vector<PointCmd> cmds;
+};
+
+// A batch entry of flatten_eval_kernel: points [first, first+count) of the
+// batch belong to this insert job (Layer::insert, composition/layer.rs:90-111).
+struct FlattenJob {
+    uint32_t first_point;   // index into the batch's PointCmd array
+    uint32_t count;
+    uint32_t quad_base;     // added to PointCmd::quad
+    uint32_t geom_id;       // id written for non-contour-end points (0 = None)
+    uint32_t has_xf;
+    float xf[6];            // GeomPresTransform: ux, uy, vx, vy, tx, ty
+    uint32_t dst;           // destination offset in the segment buffer
+};
+
+// Per-layer record used by line setup (composition/layer.rs:27-31 InnerLayer).
+struct LayerRec {
+    uint32_t order;
+    uint32_t enabled;
+    uint32_t has_xf;
+    float ux, uy, vx, vy, tx, ty;
+};
+
+// Per-layer style record used by the painter (styling.rs:397-442 Props, flattened).
+struct StyleRec {
+    uint32_t fill_rule;     // 0 NonZero, 1 EvenOdd
+    uint32_t func;          // 0 Draw, 1 Clip
+    uint32_t clip_layers;
+    uint32_t is_clipped;
+    uint32_t blend_mode;
+    uint32_t fill_type;     // 0 solid, 1 gradient, 2 texture
+    float color[4];
+    uint32_t gradient_type; // 0 linear, 1 radial
+    float start[2], end[2];
+    uint32_t stop_first, stop_count;  // into the stops array
+    // texture
+    float tex_xf[6];        // ux, uy, vx, vy, tx, ty
+    float tex_max_x, tex_max_y;
+    uint32_t tex_width;
+    uint32_t tex_first;     // into the texel array (4 x u16 per texel)
+    uint32_t unchanged;     // Layer::is_unchanged(cache_id) for the cache in use
+};
+
+struct StopRec {
+    float color[4];
+    float stop;
+};
+
+}  // namespace forma

@@ -1,0 +1,90 @@
+// forma_b200 host side — Composition / Layer bookkeeping and the HBM-resident
+// segment buffer. Mirrors forma/src/composition/{mod,layer,state}.rs and the
+// storage half of forma/src/segment.rs.
+//
+// Unlike the reference, the flattened points never live in host memory:
+// Layer::insert queues a flatten job and the points are evaluated straight into
+// the device segment buffer (x, y, geometry id per point) the next time the
+// composition is rendered.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "cuda_common.cuh"
+#include "host_path.hpp"
+
+namespace forma {
+
+struct HostProps {
+    StyleRec rec{};                 // stop_first / tex_first are assigned at upload time
+    std::vector<StopRec> stops;
+    std::shared_ptr<std::vector<uint16_t>> texels;  // RGBA f16
+    bool equals(const HostProps& o) const;
+};
+
+struct Layer {
+    bool enabled = true;
+    bool has_xf = false;
+    float xf[6] = {1, 0, 0, 1, 0, 0};  // ux, uy, vx, vy, tx, ty
+    int64_t order = -1;               // InnerLayer.order (kept when detached, layer.rs:148-158)
+    uint64_t geom_id = 0;
+    HostProps props;
+    uint32_t unchanged_bits = 0;      // SmallBitSet over layer-cache ids
+    size_t lines_count = 0;
+};
+
+struct PendingInsert {
+    std::shared_ptr<PathData> data;
+    bool has_xf;
+    float xf[6];
+    uint32_t geom_id;
+    uint32_t dst;    // first point in the segment buffer
+    uint32_t count;  // number of points
+};
+
+class Composition {
+   public:
+    std::map<uint32_t, Layer*> layers;              // attached layers by order
+    std::vector<std::unique_ptr<Layer>> pool;       // every live layer
+    std::unordered_map<uint64_t, int64_t> geom_to_order;  // -1 == None
+    uint64_t next_geom_id = 1;
+
+    Layer* create_layer();
+    Layer* insert(uint32_t order, Layer* layer);    // returns the displaced layer
+    Layer* remove(uint32_t order);
+    Layer* get(uint32_t order);
+    Layer* get_or_insert_default(uint32_t order);
+    void drop(Layer* layer);
+
+    void layer_insert(Layer* layer, const Path& path);
+    void layer_clear(Layer* layer);
+    void mark_dirty() { tables_dirty = true; }
+
+    // --- segment buffer (device) ------------------------------------------------
+    int device = -1;                  // bound at first render
+    uint32_t n_points = 0;            // points appended so far (incl. pending)
+    uint64_t some_ids = 0;            // SegmentBuffer::len(): ids that are Some
+    std::vector<PendingInsert> pending;
+    DeviceBuffer<float> d_x, d_y;
+    DeviceBuffer<uint32_t> d_gid;
+    uint32_t n_resident = 0;          // points already evaluated on the device
+
+    // --- per-frame lookup tables (device), rebuilt when dirty ------------------
+    bool tables_dirty = true;
+    DeviceBuffer<int32_t> d_geom_slot;
+    DeviceBuffer<LayerRec> d_layers;
+    DeviceBuffer<StyleRec> d_styles;
+    DeviceBuffer<int32_t> d_order_to_style;
+    DeviceBuffer<StopRec> d_stops;
+    DeviceBuffer<uint16_t> d_texels;
+    uint32_t n_geoms = 0, n_orders = 0;
+    int64_t tables_cache_id = -2;     // cache id the `unchanged` bits were uploaded for
+
+   private:
+    void set_order(Layer* l, int64_t order);
+};
+
+}  // namespace forma

@@ -1,0 +1,78 @@
+// Host-callable launchers of the CUDA kernels (implemented in kernels_*.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace forma {
+
+// Arguments of the fused line-setup + pixel-grid-intersection kernels.
+struct RasterArgs {
+    const float* x;            // segment buffer (segment.rs:530-534)
+    const float* y;
+    const uint32_t* gid;       // geometry id per point, 0 = None
+    uint32_t n_points;
+    const int32_t* geom_slot;  // geom id -> layer slot, -1 = not in the composition
+    uint32_t n_geoms;
+    const LayerRec* layers;
+    float width, height;       // render target in pixels
+    float band_lo, band_hi;    // pixel rows painted by this GPU ([0, height) on one GPU)
+};
+
+// ---- kernels_raster.cu ------------------------------------------------------
+void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_points,
+                         float* x, float* y, uint32_t* gid, cudaStream_t stream);
+uint32_t raster_num_blocks(uint32_t n_points);
+// block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
+void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, cudaStream_t stream);
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream);
+// In-place exclusive scan of n u32 values by one CTA; total[0] = sum.
+void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, cudaStream_t stream);
+
+// ---- kernels_sort.cu --------------------------------------------------------
+// LSD radix sort of u64 keys on bits [kSortShift, 64) (+ optional u32 payload).
+// Sorted data ends up in keys / vals; *_tmp are same-sized scratch buffers.
+// `scratch` needs radix_scratch_bytes(n) bytes. Launch count is returned.
+size_t radix_scratch_bytes(uint32_t n);
+int launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
+                      void* scratch, cudaStream_t stream);
+
+// ---- kernels_paint.cu -------------------------------------------------------
+struct PaintScene {
+    const StyleRec* styles;       // indexed by style slot
+    const int32_t* order_to_style;// layer id (order) -> style slot
+    uint32_t n_orders;
+    const StopRec* stops;
+    const uint16_t* texels;       // RGBA f16 (styling.rs:224-249), 4 per texel
+    float clear[4];
+    uint32_t channels[4];         // already upgraded Alpha -> One when clear.a == 1
+    uint32_t width, height;       // pixels
+    uint32_t stride;              // bytes
+    uint32_t tiles_x, tiles_y;    // ceil(width / 16), ceil(height / 16)
+    uint32_t tx_lo, tx_hi;        // tile columns painted (crop), [lo, hi)
+    uint32_t ty_lo, ty_hi;        // tile rows painted (crop ∩ band), [lo, hi)
+};
+
+uint32_t cell_num_blocks(uint32_t n);
+// block_counts: cell_num_blocks(n) entries -> exclusive offsets; total[0] = #cells.
+void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* total, cudaStream_t st);
+void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
+                       uint64_t* cell_key, uint32_t n_cells, cudaStream_t st);
+void launch_cell_cover(const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key, uint32_t n_cells,
+                       uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st);
+void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
+                       uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st);
+void launch_entry_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
+                       const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
+                       uint64_t* ekey, uint32_t* eid, uint4* gap_carry, cudaStream_t st);
+void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,
+                        uint32_t* tile_end, cudaStream_t st);
+void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,
+                  const uint32_t* cell_start, const uint4* carry_in, const uint4* gap_carry, uint32_t n_cells,
+                  const uint32_t* tile_begin, const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer,
+                  cudaStream_t st);
+
+}  // namespace forma

@@ -1,0 +1,308 @@
+// Stage 1 (point evaluation), stage 1½ (per-frame line setup) and stage 2
+// (pixel-grid intersection) kernels.
+//
+//   flatten_eval_kernel   <- path.rs:487-534 (one thread per output point)
+//   line_count_kernel     <- segment.rs:298-383 (lengths only) — pass 1
+//   scan_block_sums       <- segment.rs:90-98 prefix_sum (device-wide, exclusive)
+//   raster_emit_kernel    <- segment.rs:298-383 + cpu/rasterizer.rs:93-159 — pass 2
+//
+// The reference materialises a 40 B/line SoA between line setup and
+// rasterization and finds each pixel segment's line with a binary search over
+// the prefix sums (utils/prefix_scan.rs). Here both stages are fused: the line
+// parameters live in shared memory for the 256 lines of a CTA and each warp
+// expands its 32 lines into pixel segments with a warp scan that allocates the
+// output slots, so global traffic is 12 B/point in (twice) and 8 B/segment out,
+// emitted in exactly the reference's (line, k) order with coalesced stores.
+#include "cuda_common.cuh"
+#include "kernels.h"
+
+namespace forma {
+
+// ---------------------------------------------------------------------------
+// Stage 1: flatten point evaluation
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float inv_curvature(float k) {  // path.rs:53-56
+    const float c = 0.39f;
+    return k * (1.0f - c + sqrtf(fmaf(k * k, 0.25f, c * c)));
+}
+
+__global__ void flatten_eval_kernel(const PointCmd* __restrict__ cmds, const QuadRec* __restrict__ quads,
+                                    const FlattenJob* __restrict__ jobs, uint32_t n_points,
+                                    float* __restrict__ out_x, float* __restrict__ out_y,
+                                    uint32_t* __restrict__ out_gid) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    PointCmd c = cmds[i];
+    const FlattenJob job = jobs[c.kind >> 2];
+    uint32_t kind = c.kind & 3u;
+    float px, py;
+    if (kind == 2u) {
+        const QuadRec q = quads[job.quad_base + c.quad];
+        // path.rs:515-522
+        float ratio = fmaf(c.a, c.b, -q.prev_curv) * q.curv_recip;
+        float xx = inv_curvature(fmaf(ratio, q.dk, q.k0));
+        float t = d_clamp((xx - q.x0) * q.dx_recip, 0.0f, 1.0f);
+        // eval_quad, path.rs:447-471
+        float w = d_mix(t, d_mix(t, q.pw[0], q.pw[1]), d_mix(t, q.pw[1], q.pw[2]));
+        float w_recip = d_rcp(w);
+        px = d_mix(t, d_mix(t, q.px[0], q.px[1]), d_mix(t, q.px[1], q.px[2])) * w_recip;
+        py = d_mix(t, d_mix(t, q.py[0], q.py[1]), d_mix(t, q.py[1], q.py[2])) * w_recip;
+    } else {
+        px = c.a;
+        py = c.b;
+    }
+    if (job.has_xf) {  // path.rs:689-706, GeomPresTransform::transform
+        float tx = fmaf(job.xf[0], px, fmaf(job.xf[2], py, job.xf[4]));
+        float ty = fmaf(job.xf[1], px, fmaf(job.xf[3], py, job.xf[5]));
+        px = tx;
+        py = ty;
+    }
+    uint32_t local = i - job.first_point;
+    uint32_t dst = job.dst + local;
+    // ids: None at contour ends; the id of the last point of an insert is
+    // replaced by the trailing None (segment.rs:181-198).
+    bool none = kind == 1u || local + 1u == job.count;
+    out_x[dst] = px;
+    out_y[dst] = py;
+    out_gid[dst] = none ? 0u : job.geom_id;
+}
+
+// ---------------------------------------------------------------------------
+// Stage 1½: line setup (shared by the count and the emit pass)
+// ---------------------------------------------------------------------------
+struct LineParams {
+    float x0, y0, dx, dy;  // sub-pixel space (x16)
+    float a, b, c, d;
+    uint32_t order;
+    uint32_t length;       // number of pixel segments; 0 = no line
+};
+
+__device__ __forceinline__ uint32_t integers_between(float u, float v) {  // segment.rs:54-59
+    float mn = fminf(u, v), mx = fmaxf(u, v);
+    return d_sat_u32(ceilf(mx) - floorf(mn) - 1.0f);
+}
+
+// segment.rs:298-383 for the point pair (i, i+1).
+__device__ __forceinline__ LineParams line_setup(const RasterArgs& A, uint32_t i) {
+    LineParams L;
+    L.length = 0;
+    L.order = 0;
+    L.x0 = L.y0 = L.dx = L.dy = L.a = L.b = L.c = L.d = 0.0f;
+    if (i + 1u >= A.n_points) return L;
+    uint32_t gid = A.gid[i];
+    if (gid == 0u) return L;
+    int32_t slot = gid < A.n_geoms ? A.geom_slot[gid] : -1;
+    if (slot < 0) return L;
+    const LayerRec lay = A.layers[slot];
+    if (!lay.enabled) return L;
+    float p0x = A.x[i], p0y = A.y[i], p1x = A.x[i + 1], p1y = A.y[i + 1];
+    if (lay.has_xf) {  // transform_point, segment.rs:30-39
+        float ax = fmaf(lay.ux, p0x, fmaf(lay.vx, p0y, lay.tx));
+        float ay = fmaf(lay.uy, p0x, fmaf(lay.vy, p0y, lay.ty));
+        float bx = fmaf(lay.ux, p1x, fmaf(lay.vx, p1y, lay.tx));
+        float by = fmaf(lay.uy, p1x, fmaf(lay.vy, p1y, lay.ty));
+        p0x = ax; p0y = ay; p1x = bx; p1y = by;
+    }
+    // skip_line, segment.rs:41-52 (+ the tile-band cull used when the frame is
+    // split over several GPUs; band == [0, height) on a single GPU).
+    bool skip = p0y == p1y || (p0y >= A.height && p1y >= A.height) || (p0x >= A.width && p1x >= A.width) ||
+                (p0y <= 0.0f && p1y <= 0.0f) || (p0y >= A.band_hi && p1y >= A.band_hi) ||
+                (p0y <= A.band_lo && p1y <= A.band_lo);
+    if (skip) return L;
+    float dx = p1x - p0x, dy = p1y - p0y;
+    float dx_recip = d_rcp(dx), dy_recip = d_rcp(dy);
+    L.c = dx != 0.0f ? fmaxf((ceilf(p0x) - p0x) * dx_recip, (floorf(p0x) - p0x) * dx_recip) : 0.0f;
+    L.d = dy != 0.0f ? fmaxf((ceilf(p0y) - p0y) * dy_recip, (floorf(p0y) - p0y) * dy_recip) : 0.0f;
+    L.a = fabsf(dx_recip);
+    L.b = fabsf(dy_recip);
+    L.order = lay.order;
+    L.x0 = p0x * 16.0f;
+    L.y0 = p0y * 16.0f;
+    L.dx = dx * 16.0f;
+    L.dy = dy * 16.0f;
+    L.length = integers_between(p0x, p1x) + integers_between(p0y, p1y) + 1u;
+    return L;
+}
+
+constexpr int kRasterThreads = 256;
+
+// Pass 1: per-CTA sum of line lengths.
+__global__ void __launch_bounds__(kRasterThreads) line_count_kernel(RasterArgs A, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[kRasterThreads / 32];
+    uint32_t i = blockIdx.x * kRasterThreads + threadIdx.x;
+    uint32_t len = line_setup(A, i).length;
+    uint32_t incl = warp_inclusive_scan(len);
+    if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kRasterThreads / 32; ++w) s += warp_sums[w];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+// Device-wide exclusive scan of `n` u32 values by ONE CTA (n = number of CTAs
+// of the producing kernel, a few thousand); writes the grand total to
+// total[0]. 1024 threads, each owning a contiguous chunk.
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restrict__ data, uint32_t n,
+                                                              uint32_t* __restrict__ total) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry, round_total;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t per_round = 1024u * 4u;
+    for (uint32_t base = 0; base < n; base += per_round) {
+        uint32_t idx = base + threadIdx.x * 4u;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (idx + k < n) ? data[idx + k] : 0u;
+        uint32_t sum = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = warp_inclusive_scan(sum);
+        if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_tot[threadIdx.x];
+            uint32_t wi = warp_inclusive_scan(w);
+            warp_tot[threadIdx.x] = wi - w;  // exclusive over warps
+            if (threadIdx.x == 31) round_total = wi;
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + (incl - sum);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (idx + k < n) data[idx + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += round_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = carry;
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2: pixel-grid intersection
+// ---------------------------------------------------------------------------
+
+// cpu/rasterizer.rs:32-61 — the i-th term of the ordered union of a*t+c, b*t+d.
+__device__ __forceinline__ float find_param(int32_t ii, double a_over, double b_over, double cd_over, float a,
+                                            float b, float c, float d) {
+    float i = (float)ii;
+    float ja = isfinite(b) ? (float)ceil(fma(b_over, (double)i, -cd_over)) : i;
+    float jb = isfinite(a) ? (float)ceil(fma(a_over, (double)i, cd_over)) : i;
+    float guess_a = fmaf(a, ja, c);
+    float guess_b = fmaf(b, jb, d);
+    return fminf(guess_a, guess_b);  // NaN-ignoring, like f32::min
+}
+
+__device__ __forceinline__ int32_t round_sub(float v) { return (int32_t)floorf(v + 0.5f); }  // rasterizer.rs:78-80
+
+struct SharedLines {
+    float x0[kRasterThreads], y0[kRasterThreads], dx[kRasterThreads], dy[kRasterThreads];
+    float a[kRasterThreads], b[kRasterThreads], c[kRasterThreads], d[kRasterThreads];
+    double a_over[kRasterThreads], b_over[kRasterThreads], cd_over[kRasterThreads];
+    uint32_t order[kRasterThreads];
+    uint32_t excl[kRasterThreads];  // exclusive offset of the line inside its warp
+};
+
+// Pass 2: recompute the CTA's 256 lines, then each warp expands its 32 lines.
+__global__ void __launch_bounds__(kRasterThreads)
+    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out) {
+    __shared__ SharedLines S;
+    __shared__ uint32_t warp_sums[kRasterThreads / 32];
+    const uint32_t t = threadIdx.x;
+    const uint32_t warp = t >> 5, lane = t & 31u;
+    uint32_t i = blockIdx.x * kRasterThreads + t;
+    LineParams L = line_setup(A, i);
+    uint32_t incl = warp_inclusive_scan(L.length);
+    if (lane == 31) warp_sums[warp] = incl;
+    S.excl[t] = incl - L.length;
+    if (L.length) {
+        S.x0[t] = L.x0; S.y0[t] = L.y0; S.dx[t] = L.dx; S.dy[t] = L.dy;
+        S.a[t] = L.a; S.b[t] = L.b; S.c[t] = L.c; S.d[t] = L.d;
+        S.order[t] = L.order;
+        // get_ith_pixel_segment_params, rasterizer.rs:67-70 — per-line f64 constants.
+        double sum_recip = 1.0 / ((double)L.a + (double)L.b);
+        S.a_over[t] = (double)L.a * sum_recip;
+        S.b_over[t] = (double)L.b * sum_recip;
+        S.cd_over[t] = ((double)L.c - (double)L.d) * sum_recip;
+    }
+    __syncthreads();
+    uint32_t warp_base = block_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) warp_base += warp_sums[w];
+    const uint32_t warp_total = warp_sums[warp];
+    const uint32_t* excl = S.excl + warp * 32u;
+
+    for (uint32_t s = lane; s < warp_total; s += 32u) {
+        // Largest j in [0, 32) with excl[j] <= s (zero-length lines share their
+        // successor's offset and are skipped by taking the largest such j).
+        uint32_t j = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            uint32_t cand = j + step;
+            if (excl[cand] <= s) j = cand;
+        }
+        const uint32_t li = warp * 32u + j;
+        const uint32_t k = s - excl[j];
+        const float a = S.a[li], b = S.b[li], c = S.c[li], d = S.d[li];
+        // rasterizer.rs:63-76
+        int32_t ii = (int32_t)k - (c != 0.0f ? 1 : 0) - (d != 0.0f ? 1 : 0);
+        const double ao = S.a_over[li], bo = S.b_over[li], cdo = S.cd_over[li];
+        float t0 = fmaxf(find_param(ii, ao, bo, cdo, a, b, c, d), 0.0f);
+        float t1 = fminf(find_param(ii + 1, ao, bo, cdo, a, b, c, d), 1.0f);
+        // rasterizer.rs:111-156
+        const float ldx = S.dx[li], ldy = S.dy[li], lx0 = S.x0[li], ly0 = S.y0[li];
+        int32_t x0s = round_sub(fmaf(t0, ldx, lx0));
+        int32_t y0s = round_sub(fmaf(t0, ldy, ly0));
+        int32_t x1s = round_sub(fmaf(t1, ldx, lx0));
+        int32_t y1s = round_sub(fmaf(t1, ldy, ly0));
+        int32_t border_x = min(x0s, x1s) >> 4;
+        int32_t border_y = min(y0s, y1s) >> 4;
+        int32_t tile_x = (int32_t)(int16_t)(border_x >> 4);
+        int32_t tile_y = (int32_t)(int16_t)(border_y >> 4);
+        uint32_t local_x = (uint32_t)(border_x & 15);
+        uint32_t local_y = (uint32_t)(border_y & 15);
+        int32_t border = (border_x << 4) + 16;
+        uint32_t dam = (uint32_t)(abs(x1s - x0s) + 2 * (border - max(x0s, x1s))) & 0xFFu;
+        int32_t cover = (int32_t)(int8_t)(y1s - y0s);
+        // PixelSegment::new, pixel_segment.rs:36-71
+        uint64_t ty = (uint64_t)max((int32_t)(int16_t)(tile_y + 1), 0) & 0x7FFull;
+        uint64_t tx = (uint64_t)max((int32_t)(int16_t)(tile_x + 1), 0) & 0xFFFull;
+        uint64_t v = (ty << 53) | (tx << 41) | ((uint64_t)(S.order[li] & 0x1FFFFFu) << 20) | ((uint64_t)local_x << 16) |
+                     ((uint64_t)local_y << 12) | ((uint64_t)(dam & 0x3Fu) << 6) | ((uint64_t)((uint32_t)cover & 0x3Fu));
+        out[(uint64_t)warp_base + s] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Host launchers
+// ---------------------------------------------------------------------------
+void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_points,
+                         float* x, float* y, uint32_t* gid, cudaStream_t stream) {
+    if (!n_points) return;
+    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(cmds, quads, jobs, n_points, x, y, gid);
+}
+
+uint32_t raster_num_blocks(uint32_t n_points) { return n_points ? (n_points + kRasterThreads - 1) / kRasterThreads : 0; }
+
+void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, cudaStream_t stream) {
+    uint32_t nb = raster_num_blocks(args.n_points);
+    if (!nb) {
+        cudaMemsetAsync(total, 0, sizeof(uint32_t), stream);
+        return;
+    }
+    line_count_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_sums);
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
+}
+
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream) {
+    uint32_t nb = raster_num_blocks(args.n_points);
+    if (!nb) return;
+    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out);
+}
+
+void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, cudaStream_t stream) {
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(data, n, total);
+}
+
+}  // namespace forma

@@ -1,0 +1,895 @@
+// forma_b200 — Composition bookkeeping, Renderer::render orchestration and
+// the C ABI of include/forma_b200.h.
+//
+// Renderer::render follows forma/src/cpu/renderer.rs:75-224 stage by stage;
+// every stage is a CUDA kernel sequence on one stream, and there is no CPU
+// fallback: without a usable sm_100 device forma_renderer_new() fails.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+
+#include "../../include/forma_b200.h"
+#include "cuda_common.cuh"
+#include "host_scene.hpp"
+#include "kernels.h"
+
+namespace forma {
+
+// ---------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+// ---------------------------------------------------------------------------
+// Props
+// ---------------------------------------------------------------------------
+static bool same4(const float* a, const float* b, int n) {
+    for (int i = 0; i < n; ++i)
+        if (!(a[i] == b[i])) return false;
+    return true;
+}
+
+// Props: PartialEq (styling.rs derives + Gradient/Image impls).
+bool HostProps::equals(const HostProps& o) const {
+    const StyleRec &a = rec, &b = o.rec;
+    if (a.fill_rule != b.fill_rule || a.func != b.func) return false;
+    if (a.func == 1u) return a.clip_layers == b.clip_layers;
+    if (a.is_clipped != b.is_clipped || a.blend_mode != b.blend_mode || a.fill_type != b.fill_type) return false;
+    if (a.fill_type == 0u) return same4(a.color, b.color, 4);
+    if (a.fill_type == 1u) {
+        if (a.gradient_type != b.gradient_type || !same4(a.start, b.start, 2) || !same4(a.end, b.end, 2) ||
+            stops.size() != o.stops.size())
+            return false;
+        for (size_t i = 0; i < stops.size(); ++i)
+            if (!same4(stops[i].color, o.stops[i].color, 4) || !(stops[i].stop == o.stops[i].stop)) return false;
+        return true;
+    }
+    return texels == o.texels && a.tex_max_x == b.tex_max_x && a.tex_max_y == b.tex_max_y &&
+           same4(a.tex_xf, b.tex_xf, 6);
+}
+
+// ---------------------------------------------------------------------------
+// Composition (composition/mod.rs, composition/layer.rs)
+// ---------------------------------------------------------------------------
+Layer* Composition::create_layer() {  // mod.rs:65-83
+    pool.emplace_back(new Layer());
+    Layer* l = pool.back().get();
+    l->geom_id = next_geom_id++;
+    return l;
+}
+
+void Composition::set_order(Layer* l, int64_t order) {  // layer.rs:148-158
+    if (order >= 0 && l->order != order) {
+        l->order = order;
+        l->unchanged_bits = 0;
+    }
+    geom_to_order[l->geom_id] = order;
+    tables_dirty = true;
+}
+
+Layer* Composition::insert(uint32_t order, Layer* layer) {  // mod.rs:121-138
+    set_order(layer, order);
+    Layer* old = nullptr;
+    auto it = layers.find(order);
+    if (it != layers.end()) {
+        old = it->second;
+        it->second = layer;
+    } else {
+        layers.emplace(order, layer);
+    }
+    if (old == layer) return nullptr;
+    if (old) set_order(old, -1);
+    return old;
+}
+
+Layer* Composition::remove(uint32_t order) {  // mod.rs:141-149
+    auto it = layers.find(order);
+    if (it == layers.end()) return nullptr;
+    Layer* l = it->second;
+    layers.erase(it);
+    set_order(l, -1);
+    return l;
+}
+
+Layer* Composition::get(uint32_t order) {
+    auto it = layers.find(order);
+    return it == layers.end() ? nullptr : it->second;
+}
+
+Layer* Composition::get_or_insert_default(uint32_t order) {  // mod.rs:175-182
+    Layer* l = get(order);
+    if (!l) {
+        l = create_layer();
+        insert(order, l);
+    }
+    return l;
+}
+
+void Composition::drop(Layer* l) {  // Drop for Layer, layer.rs:355-363
+    for (auto it = layers.begin(); it != layers.end(); ++it)
+        if (it->second == l) {
+            layers.erase(it);
+            break;
+        }
+    geom_to_order.erase(l->geom_id);
+    for (auto it = pool.begin(); it != pool.end(); ++it)
+        if (it->get() == l) {
+            pool.erase(it);
+            break;
+        }
+    tables_dirty = true;
+}
+
+// Layer::insert (layer.rs:90-111) + SegmentBuffer::push_path (segment.rs:181-198).
+void Composition::layer_insert(Layer* layer, const Path& path) {
+    const FlattenProgram& prog = path.data->program();
+    uint32_t count = (uint32_t)prog.cmds.size();
+    if (count) {
+        PendingInsert job;
+        job.data = path.data;
+        job.has_xf = path.has_xf;
+        std::memcpy(job.xf, path.xf, sizeof(job.xf));
+        job.geom_id = (uint32_t)layer->geom_id;
+        job.dst = n_points;
+        job.count = count;
+        pending.push_back(std::move(job));
+        // ids that are Some: every point that does not end a contour, except the
+        // last point of the insert (its id is the trailing None).
+        uint64_t some = 0;
+        for (uint32_t i = 0; i + 1 < count; ++i) some += prog.cmds[i].kind != 1u;
+        some_ids += some;
+        layer->lines_count += some;
+        n_points += count;
+    }
+    geom_to_order[layer->geom_id] = layer->order;
+    layer->unchanged_bits = 0;
+    tables_dirty = true;
+}
+
+void Composition::layer_clear(Layer* layer) {  // layer.rs:131-146
+    geom_to_order.erase(layer->geom_id);
+    layer->geom_id = next_geom_id++;
+    geom_to_order[layer->geom_id] = layer->order;
+    layer->lines_count = 0;
+    layer->unchanged_bits = 0;
+    tables_dirty = true;
+}
+
+// ---------------------------------------------------------------------------
+// Renderer
+// ---------------------------------------------------------------------------
+struct LayerCache {
+    uint8_t id = 0;
+};
+
+struct Timer {
+    cudaEvent_t ev[5];
+    bool ok = false;
+};
+
+class Renderer {
+   public:
+    int device = 0;
+    cudaStream_t stream = 0;
+    uint64_t launches = 0;
+    uint32_t caches_in_use = 0;
+    Timer timer;
+
+    // Per-frame device scratch (high-water-mark allocations).
+    DeviceBuffer<uint32_t> block_sums, totals;
+    DeviceBuffer<uint64_t> segs, segs_tmp;
+    DeviceBuffer<uint8_t> sort_scratch;
+    DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, tile_begin, tile_end;
+    DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp;
+    DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
+    DeviceBuffer<uint8_t> eflags, framebuffer;
+    // Upload staging.
+    DeviceBuffer<PointCmd> up_cmds;
+    DeviceBuffer<QuadRec> up_quads;
+    DeviceBuffer<FlattenJob> up_jobs;
+
+    uint32_t last_segments = 0;
+    uint32_t* pinned_totals = nullptr;  // 4 x u32 pinned host words for count read-backs
+
+    ~Renderer() {
+        if (pinned_totals) cudaFreeHost(pinned_totals);
+        if (timer.ok)
+            for (auto& e : timer.ev) cudaEventDestroy(e);
+    }
+
+    int flush_geometry(Composition& comp);
+    int upload_tables(Composition& comp, int64_t cache_id);
+    int read_total(uint32_t slot, uint32_t* out);
+    int rasterize(Composition& comp, uint32_t width, uint32_t height, float band_lo, float band_hi, uint32_t* n_out);
+    int render(Composition& comp, uint8_t* buffer, bool buffer_on_device, uint64_t width, uint64_t stride,
+               uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
+               LayerCache* cache, forma_timings* timings);
+};
+
+int Renderer::read_total(uint32_t slot, uint32_t* out) {
+    FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + slot, totals.ptr + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                   stream));
+    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    *out = pinned_totals[slot];
+    return FORMA_STATUS_OK;
+}
+
+// Evaluates all pending Layer::insert jobs into the device segment buffer with
+// one batched upload + one kernel.
+int Renderer::flush_geometry(Composition& comp) {
+    if (comp.device < 0) comp.device = device;
+    if (comp.device != device) {
+        set_error("composition is resident on device %d, renderer uses device %d", comp.device, device);
+        return FORMA_STATUS_INVALID;
+    }
+    if (comp.pending.empty()) return FORMA_STATUS_OK;
+    FORMA_CUDA_TRY(comp.d_x.reserve(comp.n_points, true, stream));
+    FORMA_CUDA_TRY(comp.d_y.reserve(comp.n_points, true, stream));
+    FORMA_CUDA_TRY(comp.d_gid.reserve(comp.n_points, true, stream));
+
+    std::vector<PointCmd> cmds;
+    std::vector<QuadRec> quads;
+    std::vector<FlattenJob> jobs;
+    size_t total_pts = 0;
+    for (auto& p : comp.pending) total_pts += p.count;
+    cmds.reserve(total_pts);
+    jobs.reserve(comp.pending.size());
+    for (auto& p : comp.pending) {
+        const FlattenProgram& prog = p.data->program();
+        FlattenJob job;
+        job.first_point = (uint32_t)cmds.size();
+        job.count = p.count;
+        job.quad_base = (uint32_t)quads.size();
+        job.geom_id = p.geom_id;
+        job.has_xf = p.has_xf ? 1u : 0u;
+        std::memcpy(job.xf, p.xf, sizeof(job.xf));
+        job.dst = p.dst;
+        uint32_t tag = (uint32_t)jobs.size() << 2;
+        for (const PointCmd& c : prog.cmds) {
+            PointCmd cc = c;
+            cc.kind |= tag;
+            cmds.push_back(cc);
+        }
+        quads.insert(quads.end(), prog.quads.begin(), prog.quads.end());
+        jobs.push_back(job);
+    }
+    if (jobs.size() >= (1u << 30)) {
+        set_error("too many pending inserts in one batch");
+        return FORMA_STATUS_CAPACITY;
+    }
+    FORMA_CUDA_TRY(up_cmds.reserve(cmds.size()));
+    FORMA_CUDA_TRY(up_quads.reserve(quads.size() + 1));
+    FORMA_CUDA_TRY(up_jobs.reserve(jobs.size()));
+    FORMA_CUDA_TRY(cudaMemcpyAsync(up_cmds.ptr, cmds.data(), cmds.size() * sizeof(PointCmd), cudaMemcpyHostToDevice, stream));
+    if (!quads.empty())
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads.ptr, quads.data(), quads.size() * sizeof(QuadRec), cudaMemcpyHostToDevice, stream));
+    FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, jobs.data(), jobs.size() * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
+    launch_flatten_eval(up_cmds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)cmds.size(), comp.d_x.ptr, comp.d_y.ptr,
+                        comp.d_gid.ptr, stream);
+    ++launches;
+    FORMA_CUDA_TRY(cudaGetLastError());
+    // The staging vectors are pageable: make sure the copies are done before they die.
+    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    comp.n_resident = comp.n_points;
+    comp.pending.clear();
+    return FORMA_STATUS_OK;
+}
+
+// geom id -> layer slot, layer records, style table (rebuilt when the
+// composition changed; segment.rs:141-149 does these look-ups per point).
+int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
+    if (!comp.tables_dirty && comp.tables_cache_id == cache_id) return FORMA_STATUS_OK;
+    std::vector<LayerRec> lrecs;
+    std::vector<StyleRec> srecs;
+    std::vector<StopRec> stops;
+    std::vector<uint16_t> texels;
+    std::unordered_map<const void*, uint32_t> tex_offsets;
+    std::unordered_map<uint32_t, uint32_t> order_to_slot;
+    uint32_t max_order = 0;
+    lrecs.reserve(comp.layers.size());
+    srecs.reserve(comp.layers.size());
+    for (auto& kv : comp.layers) {
+        const Layer& l = *kv.second;
+        LayerRec r;
+        r.order = kv.first;
+        r.enabled = l.enabled ? 1u : 0u;
+        r.has_xf = l.has_xf ? 1u : 0u;
+        r.ux = l.xf[0]; r.uy = l.xf[1]; r.vx = l.xf[2]; r.vy = l.xf[3]; r.tx = l.xf[4]; r.ty = l.xf[5];
+        StyleRec s = l.props.rec;
+        s.stop_first = (uint32_t)stops.size();
+        s.stop_count = (uint32_t)l.props.stops.size();
+        stops.insert(stops.end(), l.props.stops.begin(), l.props.stops.end());
+        if (s.fill_type == 2u && l.props.texels) {
+            auto it = tex_offsets.find(l.props.texels.get());
+            if (it == tex_offsets.end()) {
+                uint32_t off = (uint32_t)(texels.size() / 4);
+                texels.insert(texels.end(), l.props.texels->begin(), l.props.texels->end());
+                it = tex_offsets.emplace(l.props.texels.get(), off).first;
+            }
+            s.tex_first = it->second;
+        }
+        s.unchanged = (cache_id >= 0 && ((l.unchanged_bits >> cache_id) & 1u)) ? 1u : 0u;
+        order_to_slot[kv.first] = (uint32_t)lrecs.size();
+        max_order = std::max(max_order, kv.first);
+        lrecs.push_back(r);
+        srecs.push_back(s);
+    }
+    uint32_t n_orders = comp.layers.empty() ? 0u : max_order + 1u;
+    std::vector<int32_t> order_to_style(n_orders, -1);
+    for (auto& kv : order_to_slot) order_to_style[kv.first] = (int32_t)kv.second;
+    uint32_t n_geoms = (uint32_t)comp.next_geom_id;
+    std::vector<int32_t> geom_slot(n_geoms, -1);
+    for (auto& kv : comp.geom_to_order) {
+        if (kv.second < 0 || kv.first >= n_geoms) continue;
+        auto it = order_to_slot.find((uint32_t)kv.second);
+        if (it != order_to_slot.end()) geom_slot[kv.first] = (int32_t)it->second;
+    }
+    auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
+        cudaError_t e = buf.reserve(vec.size() + 1);
+        if (e != cudaSuccess || vec.empty()) return e;
+        return cudaMemcpyAsync(buf.ptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, stream);
+    };
+    FORMA_CUDA_TRY(up(comp.d_layers, lrecs));
+    FORMA_CUDA_TRY(up(comp.d_styles, srecs));
+    FORMA_CUDA_TRY(up(comp.d_stops, stops));
+    FORMA_CUDA_TRY(up(comp.d_texels, texels));
+    FORMA_CUDA_TRY(up(comp.d_order_to_style, order_to_style));
+    FORMA_CUDA_TRY(up(comp.d_geom_slot, geom_slot));
+    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    comp.n_geoms = n_geoms;
+    comp.n_orders = n_orders;
+    comp.tables_dirty = false;
+    comp.tables_cache_id = cache_id;
+    return FORMA_STATUS_OK;
+}
+
+// Stages 1½ + 2: fills `segs` with the unsorted pixel segments.
+int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, float band_lo, float band_hi,
+                        uint32_t* n_out) {
+    RasterArgs ra;
+    ra.x = comp.d_x.ptr;
+    ra.y = comp.d_y.ptr;
+    ra.gid = comp.d_gid.ptr;
+    ra.n_points = comp.n_resident;
+    ra.geom_slot = comp.d_geom_slot.ptr;
+    ra.n_geoms = comp.n_geoms;
+    ra.layers = comp.d_layers.ptr;
+    ra.width = (float)width;
+    ra.height = (float)height;
+    ra.band_lo = band_lo;
+    ra.band_hi = band_hi;
+    uint32_t nb = raster_num_blocks(ra.n_points);
+    FORMA_CUDA_TRY(block_sums.reserve(nb + 1));
+    launch_line_count(ra, block_sums.ptr, totals.ptr + 0, stream);
+    launches += nb ? 2 : 0;
+    uint32_t n = 0;
+    int st = read_total(0, &n);
+    if (st) return st;
+    *n_out = n;
+    last_segments = n;
+    if (n >= (1u << 30)) {
+        set_error("%u pixel segments exceed the 2^30 limit of the sort's look-back counters", n);
+        return FORMA_STATUS_CAPACITY;
+    }
+    FORMA_CUDA_TRY(segs.reserve(n + 1));
+    FORMA_CUDA_TRY(segs_tmp.reserve(n + 1));
+    if (timer.ok) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[1], stream));  // end of line setup (count pass)
+    launch_raster_emit(ra, block_sums.ptr, segs.ptr, stream);
+    launches += nb ? 1 : 0;
+    FORMA_CUDA_TRY(cudaGetLastError());
+    return FORMA_STATUS_OK;
+}
+
+int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, uint64_t width, uint64_t stride,
+                     uint64_t height, const uint32_t channels_in[4], const float clear[4], const forma_rect* crop,
+                     LayerCache* cache, forma_timings* timings) {
+    // LinearLayout::new asserts (layout/mod.rs:188-193) + consts.rs limits.
+    if (!buffer || width == 0 || height == 0 || width * 4 > stride || width > FORMA_MAX_WIDTH || height > FORMA_MAX_HEIGHT) {
+        set_error("invalid render target %llux%llu stride %llu", (unsigned long long)width, (unsigned long long)height,
+                  (unsigned long long)stride);
+        return FORMA_STATUS_INVALID;
+    }
+    if (cache) {
+        set_error("layer caches are not implemented in this build");
+        return FORMA_STATUS_INVALID;
+    }
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    if (!timer.ok) {
+        for (auto& e : timer.ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
+        timer.ok = true;
+    }
+
+    PaintScene S{};
+    for (int k = 0; k < 4; ++k) {
+        uint32_t c = channels_in[k];
+        if (c > 5u) {
+            set_error("invalid channel %u", c);
+            return FORMA_STATUS_INVALID;
+        }
+        if (clear[3] == 1.0f && c == FORMA_CHANNEL_ALPHA) c = FORMA_CHANNEL_ONE;  // renderer.rs:87-92
+        S.channels[k] = c;
+        S.clear[k] = clear[k];
+    }
+    S.width = (uint32_t)width;
+    S.height = (uint32_t)height;
+    S.stride = (uint32_t)stride;
+    S.tiles_x = (S.width + 15u) / 16u;
+    S.tiles_y = (S.height + 15u) / 16u;
+    S.tx_lo = 0; S.tx_hi = S.tiles_x; S.ty_lo = 0; S.ty_hi = S.tiles_y;
+    if (crop) {  // Rect::new, renderer.rs:43-52
+        S.tx_lo = (uint32_t)std::min<uint64_t>(crop->hor_start / 16u, S.tiles_x);
+        S.tx_hi = (uint32_t)std::min<uint64_t>((crop->hor_end + 15u) / 16u, S.tiles_x);
+        S.ty_lo = (uint32_t)std::min<uint64_t>(crop->vert_start / 16u, S.tiles_y);
+        S.ty_hi = (uint32_t)std::min<uint64_t>((crop->vert_end + 15u) / 16u, S.tiles_y);
+        if (S.tx_hi < S.tx_lo) S.tx_hi = S.tx_lo;
+        if (S.ty_hi < S.ty_lo) S.ty_hi = S.ty_lo;
+    }
+
+    int st = flush_geometry(comp);
+    if (st) return st;
+    st = upload_tables(comp, -1);
+    if (st) return st;
+    S.styles = comp.d_styles.ptr;
+    S.order_to_style = comp.d_order_to_style.ptr;
+    S.n_orders = comp.n_orders;
+    S.stops = comp.d_stops.ptr;
+    S.texels = comp.d_texels.ptr;
+
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
+    uint32_t n = 0;
+    st = rasterize(comp, S.width, S.height, 0.0f, (float)S.height, &n);
+    if (st) return st;
+
+    // Stage 3: sort.
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[2], stream));
+    if (n > 1) {
+        FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n)));
+        launches += launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, sort_scratch.ptr, stream);
+        FORMA_CUDA_TRY(cudaGetLastError());
+    }
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[3], stream));
+
+    // Stage 4: cells -> carries -> entries -> paint.
+    size_t n_tiles_total = (size_t)S.tiles_x * S.tiles_y;
+    FORMA_CUDA_TRY(tile_begin.reserve(n_tiles_total));
+    FORMA_CUDA_TRY(tile_end.reserve(n_tiles_total));
+    uint8_t* fb = buffer;
+    if (!buffer_on_device) {
+        FORMA_CUDA_TRY(framebuffer.reserve((size_t)stride * height));
+        fb = framebuffer.ptr;
+    }
+    uint32_t n_cells = 0, n_gaps = 0, n_entries = 0;
+    if (n > 0) {
+        uint32_t nb = cell_num_blocks(n);
+        FORMA_CUDA_TRY(block_sums.reserve(nb + 1));
+        launch_cell_count(segs.ptr, n, block_sums.ptr, totals.ptr + 1, stream);
+        launches += 2;
+        st = read_total(1, &n_cells);
+        if (st) return st;
+        FORMA_CUDA_TRY(cell_start.reserve(n_cells + 1));
+        FORMA_CUDA_TRY(cell_key.reserve(n_cells));
+        FORMA_CUDA_TRY(cell_cover.reserve(n_cells));
+        FORMA_CUDA_TRY(carry_in.reserve(n_cells));
+        FORMA_CUDA_TRY(carry_after.reserve(n_cells));
+        FORMA_CUDA_TRY(key2.reserve(n_cells));
+        FORMA_CUDA_TRY(key2_tmp.reserve(n_cells));
+        FORMA_CUDA_TRY(perm.reserve(n_cells));
+        FORMA_CUDA_TRY(perm_tmp.reserve(n_cells));
+        FORMA_CUDA_TRY(gap_count.reserve(n_cells));
+        FORMA_CUDA_TRY(gap_offset.reserve(n_cells));
+        launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, n_cells, stream);
+        launch_cell_cover(segs.ptr, cell_start.ptr, cell_key.ptr, n_cells, cell_cover.ptr, key2.ptr, perm.ptr, stream);
+        launches += 2;
+        FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_cells)));
+        launches += launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, n_cells, sort_scratch.ptr, stream);
+        launch_carry_scan(S, key2.ptr, perm.ptr, cell_cover.ptr, n_cells, carry_in.ptr, carry_after.ptr, gap_count.ptr,
+                          stream);
+        FORMA_CUDA_TRY(cudaMemcpyAsync(gap_offset.ptr, gap_count.ptr, n_cells * sizeof(uint32_t),
+                                       cudaMemcpyDeviceToDevice, stream));
+        launch_scan_u32(gap_offset.ptr, n_cells, totals.ptr + 2, stream);
+        launches += 2;
+        st = read_total(2, &n_gaps);
+        if (st) return st;
+        n_entries = n_cells + n_gaps;
+        FORMA_CUDA_TRY(ekey.reserve(n_entries));
+        FORMA_CUDA_TRY(ekey_tmp.reserve(n_entries));
+        FORMA_CUDA_TRY(eid.reserve(n_entries));
+        FORMA_CUDA_TRY(eid_tmp.reserve(n_entries));
+        FORMA_CUDA_TRY(gap_carry.reserve(n_gaps + 1));
+        FORMA_CUDA_TRY(eflags.reserve(n_entries));
+        launch_entry_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
+                          ekey.ptr, eid.ptr, gap_carry.ptr, stream);
+        ++launches;
+        FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_entries)));
+        launches += launch_radix_sort(ekey.ptr, ekey_tmp.ptr, eid.ptr, eid_tmp.ptr, n_entries, sort_scratch.ptr, stream);
+    }
+    launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
+    launches += n_entries ? 1 : 0;
+    launch_paint(S, segs.ptr, ekey.ptr, eid.ptr, cell_start.ptr, carry_in.ptr, gap_carry.ptr, n_cells, tile_begin.ptr,
+                 tile_end.ptr, eflags.ptr, fb, stream);
+    ++launches;
+    FORMA_CUDA_TRY(cudaGetLastError());
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
+
+    if (!buffer_on_device) {
+        // Only the cropped tile rectangle is written by the reference
+        // (cpu/painter/mod.rs:524-529,589-593); padding bytes beyond width*4 stay untouched.
+        uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
+        uint64_t y0 = (uint64_t)S.ty_lo * 16u, y1 = std::min<uint64_t>((uint64_t)S.ty_hi * 16u, height);
+        if (x1 > x0 && y1 > y0) {
+            FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
+                                             (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (timings) {
+        float ms01 = 0, ms12 = 0, ms23 = 0, ms34 = 0;
+        cudaEventElapsedTime(&ms01, timer.ev[0], timer.ev[1]);
+        cudaEventElapsedTime(&ms12, timer.ev[1], timer.ev[2]);
+        cudaEventElapsedTime(&ms23, timer.ev[2], timer.ev[3]);
+        cudaEventElapsedTime(&ms34, timer.ev[3], timer.ev[4]);
+        timings->line_setup_ms = ms01;
+        timings->rasterize_ms = ms12;
+        timings->sort_ms = ms23;
+        timings->paint_ms = ms34;
+        timings->n_lines = comp.n_resident ? comp.n_resident - 1 : 0;
+        timings->n_segments = n;
+    }
+    return FORMA_STATUS_OK;
+}
+
+}  // namespace forma
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace forma;
+
+struct forma_path_builder { PathBuilder b; };
+struct forma_path { Path p; std::vector<float> x, y; std::vector<uint8_t> c; };
+struct forma_composition { Composition c; };
+struct forma_layer;  // == forma::Layer
+struct forma_renderer { Renderer r; };
+struct forma_layer_cache { LayerCache c; };
+
+static Layer* L(forma_layer* l) { return reinterpret_cast<Layer*>(l); }
+static forma_layer* H(Layer* l) { return reinterpret_cast<forma_layer*>(l); }
+
+extern "C" {
+
+const char* forma_last_error(void) { return g_error.c_str(); }
+
+forma_path_builder* forma_path_builder_new(void) { return new forma_path_builder(); }
+void forma_path_builder_free(forma_path_builder* pb) { delete pb; }
+void forma_path_builder_move_to(forma_path_builder* pb, float x, float y) { pb->b.move_to({x, y}); }
+void forma_path_builder_line_to(forma_path_builder* pb, float x, float y) { pb->b.line_to({x, y}); }
+void forma_path_builder_quad_to(forma_path_builder* pb, float x1, float y1, float x2, float y2) {
+    pb->b.quad_to({x1, y1}, {x2, y2});
+}
+void forma_path_builder_cubic_to(forma_path_builder* pb, float x1, float y1, float x2, float y2, float x3, float y3) {
+    pb->b.cubic_to({x1, y1}, {x2, y2}, {x3, y3});
+}
+void forma_path_builder_rat_quad_to(forma_path_builder* pb, float x1, float y1, float x2, float y2, float w) {
+    pb->b.rat_quad_to({x1, y1}, {x2, y2}, w);
+}
+void forma_path_builder_rat_cubic_to(forma_path_builder* pb, float x1, float y1, float x2, float y2, float x3,
+                                     float y3, float w1, float w2) {
+    pb->b.rat_cubic_to({x1, y1}, {x2, y2}, {x3, y3}, w1, w2);
+}
+forma_path* forma_path_builder_build(forma_path_builder* pb) {
+    forma_path* p = new forma_path();
+    p->p = pb->b.build();
+    return p;
+}
+forma_path* forma_path_transform(const forma_path* src, const float m[9]) {
+    forma_path* p = new forma_path();
+    p->p = src->p.transformed(m);
+    return p;
+}
+void forma_path_free(forma_path* p) { delete p; }
+
+// Evaluates the path's flatten program on the current device and copies the
+// points back (inspection only; rendering never copies points to the host).
+int forma_path_segments(forma_path* p, const float** x, const float** y, const uint8_t** contour, uint64_t* n) {
+    const FlattenProgram& prog = p->p.data->program();
+    uint32_t count = (uint32_t)prog.cmds.size();
+    p->x.assign(count, 0.0f);
+    p->y.assign(count, 0.0f);
+    p->c.assign(count, 0);
+    *n = count;
+    *x = p->x.data();
+    *y = p->y.data();
+    *contour = p->c.data();
+    if (!count) return FORMA_STATUS_OK;
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        set_error("forma_path_segments: no CUDA device (flatten evaluation has no CPU fallback)");
+        return FORMA_STATUS_NO_DEVICE;
+    }
+    DeviceBuffer<PointCmd> dc;
+    DeviceBuffer<QuadRec> dq;
+    DeviceBuffer<FlattenJob> dj;
+    DeviceBuffer<float> dx, dy;
+    DeviceBuffer<uint32_t> dg;
+    FORMA_CUDA_TRY(dc.reserve(count));
+    FORMA_CUDA_TRY(dq.reserve(prog.quads.size() + 1));
+    FORMA_CUDA_TRY(dj.reserve(1));
+    FORMA_CUDA_TRY(dx.reserve(count));
+    FORMA_CUDA_TRY(dy.reserve(count));
+    FORMA_CUDA_TRY(dg.reserve(count));
+    FlattenJob job{};
+    job.first_point = 0;
+    job.count = count;
+    job.quad_base = 0;
+    job.geom_id = 1;
+    job.has_xf = p->p.has_xf ? 1u : 0u;
+    std::memcpy(job.xf, p->p.xf, sizeof(job.xf));
+    job.dst = 0;
+    FORMA_CUDA_TRY(cudaMemcpy(dc.ptr, prog.cmds.data(), count * sizeof(PointCmd), cudaMemcpyHostToDevice));
+    if (!prog.quads.empty())
+        FORMA_CUDA_TRY(cudaMemcpy(dq.ptr, prog.quads.data(), prog.quads.size() * sizeof(QuadRec), cudaMemcpyHostToDevice));
+    FORMA_CUDA_TRY(cudaMemcpy(dj.ptr, &job, sizeof(job), cudaMemcpyHostToDevice));
+    launch_flatten_eval(dc.ptr, dq.ptr, dj.ptr, count, dx.ptr, dy.ptr, dg.ptr, 0);
+    FORMA_CUDA_TRY(cudaGetLastError());
+    FORMA_CUDA_TRY(cudaMemcpy(p->x.data(), dx.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
+    FORMA_CUDA_TRY(cudaMemcpy(p->y.data(), dy.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < count; ++i) p->c[i] = prog.cmds[i].kind == 1u;
+    return FORMA_STATUS_OK;
+}
+
+forma_composition* forma_composition_new(void) { return new forma_composition(); }
+void forma_composition_free(forma_composition* c) { delete c; }
+forma_layer* forma_composition_create_layer(forma_composition* c) { return H(c->c.create_layer()); }
+forma_layer* forma_composition_insert(forma_composition* c, uint32_t order, forma_layer* layer, int* status) {
+    if (order > kLayerLimit) {
+        if (status) *status = FORMA_ERR_ORDER_LIMIT;
+        return nullptr;
+    }
+    if (status) *status = FORMA_OK;
+    return H(c->c.insert(order, L(layer)));
+}
+forma_layer* forma_composition_remove(forma_composition* c, uint32_t order) { return H(c->c.remove(order)); }
+forma_layer* forma_composition_get(forma_composition* c, uint32_t order) { return H(c->c.get(order)); }
+forma_layer* forma_composition_get_mut_or_insert_default(forma_composition* c, uint32_t order, int* status) {
+    if (order > kLayerLimit) {
+        if (status) *status = FORMA_ERR_ORDER_LIMIT;
+        return nullptr;
+    }
+    if (status) *status = FORMA_OK;
+    return H(c->c.get_or_insert_default(order));
+}
+uint64_t forma_composition_len(forma_composition* c) { return c->c.layers.size(); }
+void forma_layer_drop(forma_composition* c, forma_layer* l) { c->c.drop(L(l)); }
+
+uint64_t forma_layer_geom_id(forma_layer* l) { return L(l)->geom_id; }
+int forma_layer_insert(forma_composition* c, forma_layer* l, forma_path* p) {
+    c->c.layer_insert(L(l), p->p);
+    return FORMA_OK;
+}
+int forma_layer_clear(forma_composition* c, forma_layer* l) {
+    c->c.layer_clear(L(l));
+    return FORMA_OK;
+}
+int forma_layer_set_is_enabled(forma_composition* c, forma_layer* l, int enabled) {
+    L(l)->enabled = enabled != 0;
+    c->c.mark_dirty();
+    return FORMA_OK;
+}
+int forma_layer_is_enabled(forma_layer* l) { return L(l)->enabled ? 1 : 0; }
+
+int forma_layer_set_transform(forma_composition* c, forma_layer* l, const float t[6]) {
+    // AffineTransform::from([f32; 6]): ux = t0, vx = t1, uy = t2, vy = t3, tx = t4, ty = t5
+    float ux = t[0], vx = t[1], uy = t[2], vy = t[3], tx = t[4], ty = t[5];
+    if (!geom_pres_ok(ux, uy, vx, vy)) {
+        set_error("GeomPresTransformError::ExceededScalingFactor");
+        return FORMA_ERR_INVALID_ARGUMENT;
+    }
+    Layer* layer = L(l);
+    bool has = !(ux == 1.0f && uy == 0.0f && vx == 0.0f && vy == 1.0f && tx == 0.0f && ty == 0.0f);
+    float xf[6] = {ux, uy, vx, vy, tx, ty};
+    bool same = has == layer->has_xf && (!has || std::memcmp(xf, layer->xf, sizeof(xf)) == 0 ||
+                                         (xf[0] == layer->xf[0] && xf[1] == layer->xf[1] && xf[2] == layer->xf[2] &&
+                                          xf[3] == layer->xf[3] && xf[4] == layer->xf[4] && xf[5] == layer->xf[5]));
+    if (!same) {  // layer.rs:294-299
+        layer->unchanged_bits = 0;
+        layer->has_xf = has;
+        std::memcpy(layer->xf, xf, sizeof(xf));
+        c->c.mark_dirty();
+    }
+    return FORMA_OK;
+}
+
+// styling.rs:224-249 — forma's own f16 (no denormals, values in [0, 1]).
+static uint16_t f16_from(float v) {
+    if (v == 0.0f) return 0;
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    return (uint16_t)((u - 0x38000000u) >> 13);
+}
+
+int forma_layer_set_props(forma_composition* c, forma_layer* l, const forma_props* p) {
+    HostProps hp;
+    StyleRec& s = hp.rec;
+    s.fill_rule = p->fill_rule;
+    s.func = p->func;
+    s.clip_layers = p->clip_layers;
+    s.is_clipped = p->is_clipped ? 1u : 0u;
+    s.blend_mode = p->blend_mode;
+    s.fill_type = p->fill_type;
+    if (s.fill_rule > 1u || s.func > 1u || s.blend_mode > 15u || s.fill_type > 2u) {
+        set_error("forma_layer_set_props: enum value out of range");
+        return FORMA_ERR_INVALID_ARGUMENT;
+    }
+    s.color[0] = p->color.r; s.color[1] = p->color.g; s.color[2] = p->color.b; s.color[3] = p->color.a;
+    if (s.func == FORMA_FUNC_DRAW && s.fill_type == FORMA_FILL_GRADIENT) {
+        if (p->n_stops < 2 || !p->stops) {  // GradientBuilder::build -> None, styling.rs:107-109
+            set_error("a gradient needs at least 2 stops");
+            return FORMA_ERR_INVALID_ARGUMENT;
+        }
+        s.gradient_type = p->gradient_type;
+        s.start[0] = p->start[0]; s.start[1] = p->start[1];
+        s.end[0] = p->end[0]; s.end[1] = p->end[1];
+        float incr = 1.0f / (float)(p->n_stops - 1);
+        for (uint32_t i = 0; i < p->n_stops; ++i) {
+            StopRec r;
+            r.color[0] = p->stops[i].color.r; r.color[1] = p->stops[i].color.g;
+            r.color[2] = p->stops[i].color.b; r.color[3] = p->stops[i].color.a;
+            float stop = p->stops[i].stop;
+            if (stop == -1.0f) stop = (float)i * incr;  // styling.rs:111-116
+            else if (!(stop >= 0.0f && stop <= 1.0f)) {
+                set_error("gradient stops must be between 0.0 and 1.0");
+                return FORMA_ERR_INVALID_ARGUMENT;
+            }
+            r.stop = stop;
+            hp.stops.push_back(r);
+        }
+    }
+    if (s.func == FORMA_FUNC_DRAW && s.fill_type == FORMA_FILL_TEXTURE) {
+        size_t n = (size_t)p->tex_width * p->tex_height;
+        if (!n || !p->tex_linear_rgba) {
+            set_error("empty texture");
+            return FORMA_ERR_INVALID_ARGUMENT;
+        }
+        // Reuse the texel block when the same image is set again on this layer.
+        auto tex = std::make_shared<std::vector<uint16_t>>(n * 4);
+        for (size_t i = 0; i < n * 4; ++i) (*tex)[i] = f16_from(p->tex_linear_rgba[i]);
+        Layer* layer = L(l);
+        if (layer->props.texels && *layer->props.texels == *tex) tex = layer->props.texels;
+        hp.texels = tex;
+        for (int i = 0; i < 6; ++i) s.tex_xf[i] = p->tex_transform[i];
+        s.tex_width = p->tex_width;
+        s.tex_max_x = (float)p->tex_width - 1.0f;
+        s.tex_max_y = (float)p->tex_height - 1.0f;
+    }
+    Layer* layer = L(l);
+    if (!layer->props.equals(hp)) {  // layer.rs:341-348
+        layer->unchanged_bits = 0;
+        layer->props = std::move(hp);
+        c->c.mark_dirty();
+    }
+    return FORMA_OK;
+}
+
+forma_renderer* forma_renderer_new(int device_ordinal) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); forma_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device_ordinal < 0 || device_ordinal >= count) {
+        set_error("device ordinal %d out of range (0..%d)", device_ordinal, count - 1);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess || prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device_ordinal, prop.major, prop.minor);
+        return nullptr;
+    }
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed", device_ordinal);
+        return nullptr;
+    }
+    forma_renderer* r = new forma_renderer();
+    r->r.device = device_ordinal;
+    if (cudaMallocHost(&r->r.pinned_totals, 4 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(4) != cudaSuccess) {
+        set_error("allocation of renderer state failed");
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+void forma_renderer_free(forma_renderer* r) { delete r; }
+
+void forma_renderer_set_stream(forma_renderer* r, void* cuda_stream) { r->r.stream = (cudaStream_t)cuda_stream; }
+
+forma_layer_cache* forma_layer_cache_new(forma_renderer* r) {
+    for (uint8_t id = 0; id < 32; ++id)
+        if (!((r->r.caches_in_use >> id) & 1u)) {
+            r->r.caches_in_use |= 1u << id;
+            forma_layer_cache* c = new forma_layer_cache();
+            c->c.id = id;
+            return c;
+        }
+    return nullptr;
+}
+void forma_layer_cache_free(forma_renderer* r, forma_layer_cache* c) {
+    if (r) r->r.caches_in_use &= ~(1u << c->c.id);
+    delete c;
+}
+void forma_layer_cache_clear(forma_layer_cache*) {}
+
+int forma_renderer_render(forma_renderer* r, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
+                          uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
+                          forma_layer_cache* cache, forma_timings* timings) {
+    return r->r.render(c->c, buffer, false, width, stride, height, channels, clear, crop, cache ? &cache->c : nullptr,
+                       timings);
+}
+int forma_renderer_render_device(forma_renderer* r, forma_composition* c, uint8_t* device_buffer, uint64_t width,
+                                 uint64_t stride, uint64_t height, const uint32_t channels[4], const float clear[4],
+                                 const forma_rect* crop, forma_layer_cache* cache, forma_timings* timings) {
+    return r->r.render(c->c, device_buffer, true, width, stride, height, channels, clear, crop,
+                       cache ? &cache->c : nullptr, timings);
+}
+uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.launches; }
+
+uint64_t forma_renderer_lines(forma_renderer*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,
+                              float*, float*, uint32_t*) {
+    // Line records are never materialised: line setup is fused into the
+    // pixel-grid intersection kernel. Parity of this stage is observable through
+    // forma_renderer_rasterize_only (same segments, same order).
+    return 0;
+}
+uint64_t forma_renderer_segments(forma_renderer* r, uint64_t cap, uint64_t* out) {
+    uint64_t n = r->r.last_segments;
+    if (out && cap) {
+        cudaMemcpy(out, r->r.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    }
+    return n;
+}
+uint64_t forma_renderer_rasterize_only(forma_renderer* r, forma_composition* c, uint64_t width, uint64_t height,
+                                       uint64_t cap, uint64_t* out) {
+    Renderer& R = r->r;
+    if (cudaSetDevice(R.device) != cudaSuccess) return 0;
+    if (R.flush_geometry(c->c) || R.upload_tables(c->c, -1)) return 0;
+    uint32_t n = 0;
+    float h = (float)height;
+    if (R.rasterize(c->c, (uint32_t)std::min<uint64_t>(width, 0xFFFFFFFFu), (uint32_t)std::min<uint64_t>(height, 0xFFFFFFFFu),
+                    -3.0e38f, 3.0e38f, &n))
+        return 0;
+    (void)h;
+    cudaStreamSynchronize(R.stream);
+    if (out && cap) cudaMemcpy(out, R.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    return n;
+}
+int forma_renderer_sort_u64(forma_renderer* r, uint64_t* keys, uint64_t n) {
+    Renderer& R = r->r;
+    if (n >= (1ull << 30)) {
+        set_error("sort_u64: n too large");
+        return FORMA_ERR_CAPACITY;
+    }
+    if (n < 2) return FORMA_OK;
+    FORMA_CUDA_TRY(cudaSetDevice(R.device));
+    FORMA_CUDA_TRY(R.segs.reserve(n));
+    FORMA_CUDA_TRY(R.segs_tmp.reserve(n));
+    FORMA_CUDA_TRY(R.sort_scratch.reserve(radix_scratch_bytes((uint32_t)n)));
+    FORMA_CUDA_TRY(cudaMemcpyAsync(R.segs.ptr, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, R.stream));
+    R.launches += launch_radix_sort(R.segs.ptr, R.segs_tmp.ptr, nullptr, nullptr, (uint32_t)n, R.sort_scratch.ptr, R.stream);
+    FORMA_CUDA_TRY(cudaGetLastError());
+    FORMA_CUDA_TRY(cudaMemcpyAsync(keys, R.segs.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, R.stream));
+    FORMA_CUDA_TRY(cudaStreamSynchronize(R.stream));
+    return FORMA_OK;
+}
+
+}  // extern "C"

@@ -135,19 +135,32 @@ int forma_path_segments(forma_path*, const float** x, const float** y,
 /* Composition / Layer (forma/src/composition/{mod,layer}.rs)               */
 /* ------------------------------------------------------------------------ */
 typedef struct forma_composition forma_composition;
+/* A Layer handle is owned by its Composition and stays valid until
+ * forma_layer_drop() or forma_composition_free(). */
+typedef struct forma_layer forma_layer;
 
 forma_composition* forma_composition_new(void);                   /* Composition::new mod.rs:60 */
 void forma_composition_free(forma_composition*);
-/* Composition::get_mut_or_insert_default(Order::new(order)?) mod.rs:175 */
-int forma_composition_layer(forma_composition*, uint32_t order);
-int forma_composition_remove(forma_composition*, uint32_t order);   /* mod.rs:141 (+ drop) */
-int forma_layer_insert_path(forma_composition*, uint32_t order, forma_path*);      /* layer.rs:90  */
-int forma_layer_clear(forma_composition*, uint32_t order);                         /* layer.rs:131 */
-int forma_layer_set_is_enabled(forma_composition*, uint32_t order, int enabled);   /* layer.rs:234 */
+forma_layer* forma_composition_create_layer(forma_composition*);  /* mod.rs:65  (detached)      */
+/* Composition::insert(Order::new(order)?, layer) mod.rs:121: returns the
+ * displaced layer (now detached) or NULL; *status receives FORMA_ERR_ORDER_LIMIT. */
+forma_layer* forma_composition_insert(forma_composition*, uint32_t order, forma_layer*, int* status);
+forma_layer* forma_composition_remove(forma_composition*, uint32_t order);          /* mod.rs:141 */
+forma_layer* forma_composition_get(forma_composition*, uint32_t order);             /* mod.rs:160 */
+forma_layer* forma_composition_get_mut_or_insert_default(forma_composition*, uint32_t order,
+                                                         int* status);              /* mod.rs:175 */
+uint64_t forma_composition_len(forma_composition*);                                 /* mod.rs:115 */
+void forma_layer_drop(forma_composition*, forma_layer*);               /* Drop for Layer, layer.rs:355 */
+
+uint64_t forma_layer_geom_id(forma_layer*);                                        /* layer.rs:160 */
+int forma_layer_insert(forma_composition*, forma_layer*, forma_path*);             /* layer.rs:90  */
+int forma_layer_clear(forma_composition*, forma_layer*);                           /* layer.rs:131 */
+int forma_layer_set_is_enabled(forma_composition*, forma_layer*, int enabled);     /* layer.rs:234 */
+int forma_layer_is_enabled(forma_layer*);                                          /* layer.rs:207 */
 /* GeomPresTransform::try_from([ux, vx, uy, vy, tx, ty]) + Layer::set_transform
  * (math/transform.rs:196-221, layer.rs:289); INVALID_ARGUMENT if it scales up. */
-int forma_layer_set_transform(forma_composition*, uint32_t order, const float t[6]);
-int forma_layer_set_props(forma_composition*, uint32_t order, const forma_props*); /* layer.rs:341 */
+int forma_layer_set_transform(forma_composition*, forma_layer*, const float t[6]);
+int forma_layer_set_props(forma_composition*, forma_layer*, const forma_props*);   /* layer.rs:341 */
 
 /* ------------------------------------------------------------------------ */
 /* Renderer (forma/src/cpu/renderer.rs:56-224)                              */
@@ -183,6 +196,10 @@ int forma_renderer_render_device(forma_renderer*, forma_composition*, uint8_t* d
                                  const uint32_t channels[4], const float clear_color[4],
                                  const forma_rect* crop, forma_layer_cache* cache,
                                  forma_timings* timings);
+
+/* Launch on `cuda_stream` (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the default stream. */
+void forma_renderer_set_stream(forma_renderer*, void* cuda_stream);
 
 /* Number of CUDA kernels the renderer launched since it was created. */
 uint64_t forma_renderer_launch_count(const forma_renderer*);

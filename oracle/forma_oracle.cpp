@@ -159,8 +159,8 @@ static void render(Renderer& r, Composition& comp, const RenderTarget& rt, const
         cache->has_clear = true;
         cache->clear_color = clear_color;
         for (auto& kv : comp.layers) {
-            if (kv.second.is_enabled) kv.second.is_unchanged |= (1u << cache->id);
-            else kv.second.is_unchanged &= ~(1u << cache->id);
+            if (kv.second->is_enabled) kv.second->is_unchanged |= (1u << cache->id);
+            else kv.second->is_unchanged &= ~(1u << cache->id);
         }
     }
     r.last.line_setup_ms = t1 - t0;
@@ -261,31 +261,45 @@ int fo_path_segments(void* path, const float** x, const float** y, const uint8_t
 void* fo_composition_new() { return new Composition(); }
 void fo_composition_free(void* c) { delete (Composition*)c; }
 
-int fo_composition_layer(void* c, uint32_t order) {
-    if (order > kLayerLimit) return 2;
-    ((Composition*)c)->get_mut_or_insert_default(order);
+// Layer handles stay valid until fo_layer_drop / fo_composition_free.
+void* fo_composition_create_layer(void* c) { return ((Composition*)c)->create_layer(); }
+void* fo_composition_insert(void* c, uint32_t order, void* layer, int* status) {
+    if (order > kLayerLimit) {
+        if (status) *status = 2;
+        return nullptr;
+    }
+    if (status) *status = 0;
+    return ((Composition*)c)->insert(order, (Layer*)layer);
+}
+void* fo_composition_remove(void* c, uint32_t order) { return ((Composition*)c)->remove(order); }
+void* fo_composition_get(void* c, uint32_t order) { return ((Composition*)c)->get(order); }
+void* fo_composition_get_mut_or_insert_default(void* c, uint32_t order, int* status) {
+    if (order > kLayerLimit) {
+        if (status) *status = 2;
+        return nullptr;
+    }
+    if (status) *status = 0;
+    return ((Composition*)c)->get_mut_or_insert_default(order);
+}
+uint64_t fo_composition_len(void* c) { return ((Composition*)c)->layers.size(); }
+void fo_layer_drop(void* c, void* layer) { ((Composition*)c)->drop_layer((Layer*)layer); }
+uint64_t fo_layer_geom_id(void* layer) { return ((Layer*)layer)->geom_id; }
+int fo_layer_insert(void* c, void* layer, void* path) {
+    ((Composition*)c)->layer_insert((Layer*)layer, *(Path*)path);
     return 0;
 }
-int fo_composition_remove(void* c, uint32_t order) { return ((Composition*)c)->remove(order) ? 0 : 1; }
-int fo_layer_insert_path(void* c, uint32_t order, void* path) {
-    if (order > kLayerLimit) return 2;
-    ((Composition*)c)->layer_insert(order, *(Path*)path);
+int fo_layer_clear(void* c, void* layer) {
+    ((Composition*)c)->layer_clear((Layer*)layer);
     return 0;
 }
-int fo_layer_clear(void* c, uint32_t order) {
-    if (order > kLayerLimit) return 2;
-    ((Composition*)c)->layer_clear(order);
+int fo_layer_set_is_enabled(void* c, void* layer, int enabled) {
+    ((Layer*)layer)->is_enabled = enabled != 0;
     return 0;
 }
-int fo_layer_set_is_enabled(void* c, uint32_t order, int enabled) {
-    if (order > kLayerLimit) return 2;
-    ((Composition*)c)->get_mut_or_insert_default(order).is_enabled = enabled != 0;
-    return 0;
-}
+int fo_layer_is_enabled(void* layer) { return ((Layer*)layer)->is_enabled ? 1 : 0; }
 // t = [ux, vx, uy, vy, tx, ty] as in GeomPresTransform::try_from([f32; 6]) /
 // AffineTransform::from([f32; 6]) (math/transform.rs:92-103).
-int fo_layer_set_transform(void* c, uint32_t order, const float t[6]) {
-    if (order > kLayerLimit) return 2;
+int fo_layer_set_transform(void* c, void* layer, const float t[6]) {
     Affine a;
     a.ux = t[0];
     a.vx = t[1];
@@ -294,7 +308,7 @@ int fo_layer_set_transform(void* c, uint32_t order, const float t[6]) {
     a.tx = t[4];
     a.ty = t[5];
     if (!geom_pres_ok(a)) return 1;
-    Layer& l = ((Composition*)c)->get_mut_or_insert_default(order);
+    Layer& l = *(Layer*)layer;
     bool has = !a.is_identity();
     bool same = has == l.has_transform && (!has || a == l.transform);
     if (!same) {
@@ -320,8 +334,7 @@ static bool props_equal(const Props& a, const Props& b) {
     return a.texture.image.data == b.texture.image.data && a.texture.transform == b.texture.transform;
 }
 
-int fo_layer_set_props(void* c, uint32_t order, const fo_props* p) {
-    if (order > kLayerLimit) return 2;
+int fo_layer_set_props(void* c, void* layer, const fo_props* p) {
     Props props;
     props.fill_rule = (FillRule)p->fill_rule;
     props.func = (FuncType)p->func;
@@ -361,7 +374,7 @@ int fo_layer_set_props(void* c, uint32_t order, const fo_props* p) {
         t.transform.tx = p->tex_transform[4];
         t.transform.ty = p->tex_transform[5];
     }
-    Layer& l = ((Composition*)c)->get_mut_or_insert_default(order);
+    Layer& l = *(Layer*)layer;
     if (!props_equal(l.props, props)) {
         l.is_unchanged = 0;
         l.props = props;

@@ -570,13 +570,13 @@ struct Painter {
 };
 
 struct PropsSource {
-    const std::map<uint32_t, Layer>* layers;
+    const std::map<uint32_t, Layer*>* layers;
     bool has_cache = false;
     uint8_t cache_id = 0;
-    const Props& get(uint32_t id) const { return layers->at(id).props; }
+    const Props& get(uint32_t id) const { return layers->at(id)->props; }
     bool is_unchanged(uint32_t id) const {
         if (!has_cache) return false;
-        return (layers->at(id).is_unchanged >> cache_id) & 1;
+        return (layers->at(id)->is_unchanged >> cache_id) & 1;
     }
 };
 

@@ -79,6 +79,7 @@ struct Layer {
     Props props;
     uint32_t is_unchanged = 0;  // SmallBitSet over cache ids
     size_t lines_count = 0;
+    int64_t order = -1;  // Option<Order>
 };
 
 // segment.rs:530-545 (the x/y/ids part) and the per-frame line arrays.
@@ -100,7 +101,10 @@ inline uint32_t integers_between(float a, float b) {
 }
 
 struct Composition {
-    std::map<uint32_t, Layer> layers;  // keyed by Order::as_u32()
+    // Attached layers keyed by Order::as_u32(); every Layer (attached or not)
+    // is owned by `pool` until dropped (Layer::drop, composition/layer.rs:355-363).
+    std::map<uint32_t, Layer*> layers;
+    std::vector<std::unique_ptr<Layer>> pool;
     std::unordered_map<uint64_t, int64_t> geom_id_to_order;  // -1 == None
     uint64_t next_geom_id = 1;
     // SegmentBuffer view: ids 0 == None.
@@ -109,26 +113,77 @@ struct Composition {
 
     uint64_t new_geom_id() { return next_geom_id++; }
 
-    // composition/mod.rs:175-182
-    Layer& get_mut_or_insert_default(uint32_t order) {
-        auto it = layers.find(order);
-        if (it == layers.end()) {
-            Layer l;
-            l.geom_id = new_geom_id();
-            it = layers.emplace(order, l).first;
-            geom_id_to_order[l.geom_id] = order;
+    // composition/mod.rs:65-83
+    Layer* create_layer() {
+        pool.emplace_back(new Layer());
+        Layer* l = pool.back().get();
+        l->geom_id = new_geom_id();
+        return l;
+    }
+
+    // composition/layer.rs:148-158
+    void set_order(Layer* l, int64_t order) {
+        if (order >= 0 && l->order != order) {
+            l->order = order;
+            l->is_unchanged = 0;
         }
-        return it->second;
+        geom_id_to_order[l->geom_id] = order;
+    }
+
+    // composition/mod.rs:121-138 — returns the displaced layer (now detached) or null.
+    Layer* insert(uint32_t order, Layer* layer) {
+        set_order(layer, order);
+        Layer* old = nullptr;
+        auto it = layers.find(order);
+        if (it != layers.end()) {
+            old = it->second;
+            it->second = layer;
+        } else {
+            layers.emplace(order, layer);
+        }
+        if (old == layer) return nullptr;
+        if (old) set_order(old, -1);
+        return old;
     }
 
     // composition/mod.rs:141-149
-    bool remove(uint32_t order) {
+    Layer* remove(uint32_t order) {
         auto it = layers.find(order);
-        if (it == layers.end()) return false;
-        // The removed Layer is dropped by the C API (Layer::drop removes the id).
-        geom_id_to_order.erase(it->second.geom_id);
+        if (it == layers.end()) return nullptr;
+        Layer* l = it->second;
         layers.erase(it);
-        return true;
+        set_order(l, -1);
+        return l;
+    }
+
+    // Layer::drop
+    void drop_layer(Layer* l) {
+        for (auto it = layers.begin(); it != layers.end(); ++it)
+            if (it->second == l) {
+                layers.erase(it);
+                break;
+            }
+        geom_id_to_order.erase(l->geom_id);
+        for (auto it = pool.begin(); it != pool.end(); ++it)
+            if (it->get() == l) {
+                pool.erase(it);
+                break;
+            }
+    }
+
+    Layer* get(uint32_t order) {
+        auto it = layers.find(order);
+        return it == layers.end() ? nullptr : it->second;
+    }
+
+    // composition/mod.rs:175-182
+    Layer* get_mut_or_insert_default(uint32_t order) {
+        Layer* l = get(order);
+        if (!l) {
+            l = create_layer();
+            insert(order, l);
+        }
+        return l;
     }
 
     size_t segment_len(size_t from = 0) const {
@@ -138,8 +193,8 @@ struct Composition {
     }
 
     // composition/layer.rs:90-111 + segment.rs:181-198 + path.rs:677-723
-    void layer_insert(uint32_t order, Path& path) {
-        Layer& layer = get_mut_or_insert_default(order);
+    void layer_insert(Layer* lp, Path& path) {
+        Layer& layer = *lp;
         size_t old_len = segment_len();
         const Segments& s = path.inner->segments();
         for (size_t i = 0; i < s.x.size(); ++i) {
@@ -152,16 +207,16 @@ struct Composition {
         ids.resize(x.size() > 0 ? x.size() - 1 : 0, layer.geom_id);
         if (!ids.empty() && ids.back() != 0) ids.push_back(0);
         layer.lines_count += segment_len() - old_len;
-        geom_id_to_order[layer.geom_id] = order;
+        geom_id_to_order[layer.geom_id] = layer.order;
         layer.is_unchanged = 0;
     }
 
     // composition/layer.rs:131-146
-    void layer_clear(uint32_t order) {
-        Layer& layer = get_mut_or_insert_default(order);
+    void layer_clear(Layer* lp) {
+        Layer& layer = *lp;
         geom_id_to_order.erase(layer.geom_id);
         layer.geom_id = new_geom_id();
-        geom_id_to_order[layer.geom_id] = order;
+        geom_id_to_order[layer.geom_id] = layer.order;
         layer.lines_count = 0;
         layer.is_unchanged = 0;
     }
@@ -169,7 +224,7 @@ struct Composition {
     // segment.rs:237-273 + composition/mod.rs:219-231
     void compact_geom() {
         size_t actual = 0;
-        for (auto& kv : layers) actual += kv.second.lines_count;
+        for (auto& kv : layers) actual += kv.second->lines_count;
         if (segment_len() < actual * 2) return;
         size_t len = x.size(), del = 0;
         uint64_t prev = 0;
@@ -215,7 +270,7 @@ struct Composition {
             if (oit == geom_id_to_order.end() || oit->second < 0) { empty(); continue; }
             auto lit = layers.find((uint32_t)oit->second);
             if (lit == layers.end()) { empty(); continue; }
-            const Layer& layer = lit->second;
+            const Layer& layer = *lit->second;
             if (!layer.is_enabled) { empty(); continue; }
             uint32_t order = lit->first;
 

@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle_api():
+    from oracle import oracle
+    return oracle.load()
+
+
+@pytest.fixture(scope="session")
+def cuda_api():
+    import forma_b200
+    return forma_b200.load()
+
+
+@pytest.fixture(scope="session")
+def cuda_renderer(cuda_api):
+    return cuda_api.Renderer(0)
+
+
+@pytest.fixture(scope="session")
+def oracle_renderer(oracle_api):
+    return oracle_api.Renderer(0)

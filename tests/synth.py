@@ -1,0 +1,136 @@
+"""Deterministic synthetic scenes shared by the parity tests and bench.py.
+
+One splitmix64 generator drives everything so the CUDA library and the oracle
+see bit-identical inputs: the reference's own demos use
+Rust's StdRng, which cannot be reproduced here and need not be.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from forma_b200.binding import (BlendMode, Color, Fill, FillRule, Func, GradientBuilder, GradientType, Point,
+                                Props, Style)
+
+MASK = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed: int):
+        self.s = seed & MASK
+
+    def next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & MASK
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK
+        return z ^ (z >> 31)
+
+    def uniform(self, lo: float = 0.0, hi: float = 1.0) -> float:
+        """float32-representable uniform in [lo, hi)."""
+        u = (self.next() >> 40) / float(1 << 24)
+        return float(np.float32(lo + (hi - lo) * u))
+
+    def randint(self, n: int) -> int:
+        return self.next() % n
+
+
+def f32(v) -> float:
+    return float(np.float32(v))
+
+
+def circle_path(api, cx, cy, r):
+    """Rational-quad circle (shape of e2e-tests/tests/tests.rs:80-105)."""
+    w = f32(np.sqrt(np.float32(2.0)) / np.float32(2.0))
+    return (api.PathBuilder().move_to(Point(f32(cx + r), cy))
+            .rat_quad_to(Point(f32(cx + r), f32(cy - r)), Point(cx, f32(cy - r)), w)
+            .rat_quad_to(Point(f32(cx - r), f32(cy - r)), Point(f32(cx - r), cy), w)
+            .rat_quad_to(Point(f32(cx - r), f32(cy + r)), Point(cx, f32(cy + r)), w)
+            .rat_quad_to(Point(f32(cx + r), f32(cy + r)), Point(f32(cx + r), cy), w).build())
+
+
+def random_cubics(api, comp, n_layers: int, width: int, height: int, seed: int, extent=(20.0, 200.0),
+                  opaque: bool = True, margin: float = 0.0):
+    """BASELINE config 3 shape: each layer is one closed cubic
+    `move_to(p0) cubic_to(p1, p2, p3)` + implicit close, solid fill."""
+    rng = SplitMix64(seed)
+    for i in range(n_layers):
+        cx = rng.uniform(-margin, width + margin)
+        cy = rng.uniform(-margin, height + margin)
+        e = rng.uniform(*extent)
+        pts = [Point(f32(cx + rng.uniform(-e, e)), f32(cy + rng.uniform(-e, e))) for _ in range(4)]
+        path = api.PathBuilder().move_to(pts[0]).cubic_to(pts[1], pts[2], pts[3]).build()
+        a = 1.0 if opaque else rng.uniform(0.3, 1.0)
+        col = Color(rng.uniform(), rng.uniform(), rng.uniform(), a)
+        comp.get_mut_or_insert_default(i).insert(path).set_props(Props(func=Func.Draw(Style(fill=Fill.Solid(col)))))
+
+
+def random_mixed(api, comp, n_layers: int, width: int, height: int, seed: int):
+    """Mixed content for parity: lines/quads/cubics/rational curves, solid and
+    gradient fills, all 12 separable blend modes, both fill rules, translucent
+    colours, geometry partly off-screen (left/top/right/bottom)."""
+    rng = SplitMix64(seed)
+    separable = [BlendMode.Over, BlendMode.Multiply, BlendMode.Screen, BlendMode.Overlay, BlendMode.Darken,
+                 BlendMode.Lighten, BlendMode.ColorDodge, BlendMode.ColorBurn, BlendMode.HardLight,
+                 BlendMode.SoftLight, BlendMode.Difference, BlendMode.Exclusion]
+    for i in range(n_layers):
+        cx = rng.uniform(-0.1 * width, 1.1 * width)
+        cy = rng.uniform(-0.1 * height, 1.1 * height)
+        e = rng.uniform(4.0, 0.35 * min(width, height))
+        kind = rng.randint(5)
+        pb = api.PathBuilder()
+
+        def pt():
+            return Point(f32(cx + rng.uniform(-e, e)), f32(cy + rng.uniform(-e, e)))
+        if kind == 0:      # polygon
+            pb.move_to(pt())
+            for _ in range(3 + rng.randint(4)):
+                pb.line_to(pt())
+            path = pb.build()
+        elif kind == 1:    # quads
+            pb.move_to(pt())
+            for _ in range(2 + rng.randint(3)):
+                pb.quad_to(pt(), pt())
+            path = pb.build()
+        elif kind == 2:    # cubics, two contours
+            pb.move_to(pt()).cubic_to(pt(), pt(), pt())
+            pb.move_to(pt()).cubic_to(pt(), pt(), pt()).line_to(pt())
+            path = pb.build()
+        elif kind == 3:    # circle
+            path = circle_path(api, cx, cy, f32(e * 0.5))
+        else:              # rational cubic + axis-aligned rectangle (integer coordinates)
+            pb.move_to(pt()).rat_cubic_to(pt(), pt(), pt(), rng.uniform(0.3, 2.0), rng.uniform(0.3, 2.0))
+            x0, y0 = float(int(cx)), float(int(cy))
+            pb.move_to(Point(x0, y0)).line_to(Point(x0, y0 + 7.0)).line_to(Point(x0 + 9.0, y0 + 7.0)) \
+              .line_to(Point(x0 + 9.0, y0))
+            path = pb.build()
+        a = 1.0 if rng.randint(3) == 0 else rng.uniform(0.2, 1.0)
+        col = Color(rng.uniform(), rng.uniform(), rng.uniform(), a)
+        if rng.randint(3) == 0:
+            gb = GradientBuilder(Point(f32(cx - e), f32(cy - e)), Point(f32(cx + e), f32(cy + 0.5 * e)))
+            if rng.randint(2):
+                gb.type(GradientType.Radial)
+            for _ in range(2 + rng.randint(3)):
+                gb.color(Color(rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.4, 1.0)))
+            fill = Fill.Gradient(gb.build())
+        else:
+            fill = Fill.Solid(col)
+        style = Style(fill=fill, blend_mode=separable[rng.randint(len(separable))] if rng.randint(2) else BlendMode.Over)
+        rule = FillRule.EvenOdd if rng.randint(4) == 0 else FillRule.NonZero
+        comp.get_mut_or_insert_default(i).insert(path).set_props(Props(fill_rule=rule, func=Func.Draw(style)))
+
+
+def random_circles(api, comp, n_layers: int, width: int, height: int, seed: int, r=(4.0, 40.0)):
+    """BASELINE config 5 shape: rational-quad circles, 3-stop radial gradients
+    centred on the circle, blend mode = layer index mod 8 over separable modes."""
+    rng = SplitMix64(seed)
+    modes = [BlendMode.Over, BlendMode.Multiply, BlendMode.Screen, BlendMode.Overlay, BlendMode.Darken,
+             BlendMode.Lighten, BlendMode.HardLight, BlendMode.Difference]
+    for i in range(n_layers):
+        cx, cy = rng.uniform(0.0, width), rng.uniform(0.0, height)
+        rad = rng.uniform(*r)
+        gb = GradientBuilder(Point(cx, cy), Point(f32(cx + rad), cy)).type(GradientType.Radial)
+        a = rng.uniform(0.3, 1.0)
+        for _ in range(3):
+            gb.color(Color(rng.uniform(), rng.uniform(), rng.uniform(), a))
+        comp.get_mut_or_insert_default(i).insert(circle_path(api, cx, cy, rad)).set_props(
+            Props(func=Func.Draw(Style(fill=Fill.Gradient(gb.build()), blend_mode=modes[i % 8]))))

@@ -502,6 +502,60 @@ void fo_blend_scalar(uint32_t mode, const float dst[4], const float src[4], floa
 void fo_blend_lane(uint32_t mode, const float dst[3], const float src[3], float out[3]) {
     lane_blend::blend((BlendMode)mode, dst[0], dst[1], dst[2], src[0], src[1], src[2], out);
 }
+// #[cfg(test)] SegmentBuffer::push (segment.rs:200-235): appends one raw line
+// to the segment buffer, as the reference's rasterizer/painter unit tests do.
+void fo_test_push_line(void* cv, void* lv, float x0, float y0, float x1, float y1) {
+    Composition& c = *(Composition*)cv;
+    uint64_t id = ((Layer*)lv)->geom_id;
+    bool new_point = c.x.empty() || !(c.x.back() == x0 && c.y.back() == y0);
+    if (new_point) {
+        c.x.push_back(x0);
+        c.y.push_back(y0);
+    }
+    c.x.push_back(x1);
+    c.y.push_back(y1);
+    if (c.ids.size() >= 2) {
+        uint64_t prev = c.ids[c.ids.size() - 2];
+        if (prev != 0 && prev != id) {
+            c.ids.push_back(id);
+            c.ids.push_back(0);
+        } else {
+            c.ids.pop_back();
+            c.ids.push_back(id);
+            c.ids.push_back(0);
+        }
+    } else {
+        c.ids.push_back(id);
+        c.ids.push_back(0);
+    }
+    c.geom_id_to_order[id] = ((Layer*)lv)->order;
+}
+
+// Direct access to Primitives, as the reference's path.rs unit tests use it.
+void* fo_prim_new() { return new Primitives(); }
+void fo_prim_free(void* p) { delete (Primitives*)p; }
+void fo_prim_contour(void* p) { ((Primitives*)p)->push_contour(); }
+void fo_prim_line(void* p, const float v[6]) {
+    ((Primitives*)p)->push_line({{v[0], v[1]}, v[2]}, {{v[3], v[4]}, v[5]});
+}
+void fo_prim_quad(void* p, const float v[9]) {
+    ((Primitives*)p)->push_quad({{v[0], v[1]}, v[2]}, {{v[3], v[4]}, v[5]}, {{v[6], v[7]}, v[8]});
+}
+void fo_prim_cubic(void* p, const float v[12]) {
+    WPoint q[4] = {{{v[0], v[1]}, v[2]}, {{v[3], v[4]}, v[5]}, {{v[6], v[7]}, v[8]}, {{v[9], v[10]}, v[11]}};
+    ((Primitives*)p)->push_cubic(q);
+}
+uint64_t fo_prim_segments(void* p, uint64_t cap, float* x, float* y, uint8_t* c) {
+    Segments s = ((Primitives*)p)->into_segments();
+    size_t n = std::min<size_t>(cap, s.x.size());
+    for (size_t i = 0; i < n; ++i) {
+        x[i] = s.x[i];
+        y[i] = s.y[i];
+        c[i] = s.start_new_contour[i];
+    }
+    return s.x.size();
+}
+
 void fo_set_recip_mode(int mode) { lane_blend::recip_mode() = mode; }
 float fo_approx_atan2(float y, float x) { return approx_atan2(y, x); }
 float fo_coverage(int32_t doubled_area, uint32_t fill_rule) { return Painter::coverage_of(doubled_area, (FillRule)fill_rule); }

@@ -31,9 +31,6 @@ def load() -> binding.Api:
                 "(or __graft_entry__.build()). forma_b200 has no CPU fallback.")
         lib = _C.CDLL(LIB_PATH)
         _api = binding.Api(lib, "forma_")
-        lib.forma_renderer_set_stream.restype = None
-        lib.forma_renderer_set_stream.argtypes = [_C.c_void_p, _C.c_void_p]
-        _api.renderer_set_stream = lib.forma_renderer_set_stream
     return _api
 
 

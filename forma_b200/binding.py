@@ -244,6 +244,7 @@ SIGNATURES = {
     "path_builder_cubic_to": (None, [_vp, _f, _f, _f, _f, _f, _f]),
     "path_builder_rat_quad_to": (None, [_vp, _f, _f, _f, _f, _f]),
     "path_builder_rat_cubic_to": (None, [_vp, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "path_builder_extend": (None, [_vp, _u8p, C.c_uint64, _fp]),
     "path_builder_build": (_vp, [_vp]),
     "path_transform": (_vp, [_vp, _fp]),
     "path_free": (None, [_vp]),
@@ -272,6 +273,11 @@ SIGNATURES = {
     "renderer_render": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _fp, C.POINTER(_CRect), _vp, C.POINTER(_CTimings)]),
     "renderer_render_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _fp, C.POINTER(_CRect), _vp, C.POINTER(_CTimings)]),
     "renderer_launch_count": (C.c_uint64, [_vp]),
+    "renderer_stage_times": (None, [_vp, C.POINTER(C.c_double)]),
+    "renderer_counters": (None, [_vp, _u64p]),
+    "renderer_set_stream": (None, [_vp, _vp]),
+    "composition_evict": (None, [_vp]),
+    "composition_point_count": (C.c_uint64, [_vp]),
     "renderer_lines": (C.c_uint64, [_vp, C.c_uint64, _u32p, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _u32p]),
     "renderer_segments": (C.c_uint64, [_vp, C.c_uint64, _u64p]),
     "renderer_rasterize_only": (C.c_uint64, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u64p]),
@@ -372,6 +378,13 @@ class PathBuilder:
 
     def rat_cubic_to(self, p1: Point, p2: Point, p3: Point, w1: float, w2: float) -> "PathBuilder":
         self._api.path_builder_rat_cubic_to(self._h, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, w1, w2)
+        return self
+
+    def extend(self, cmds: np.ndarray, xy: np.ndarray) -> "PathBuilder":
+        """Bulk move/line/quad/cubic (codes 0..3) with their points (float32, flat)."""
+        cmds = np.ascontiguousarray(cmds, np.uint8)
+        xy = np.ascontiguousarray(xy, np.float32)
+        self._api.path_builder_extend(self._h, cmds.ctypes.data_as(_u8p), cmds.size, xy.ctypes.data_as(_fp))
         return self
 
     def build(self) -> Path:
@@ -515,6 +528,13 @@ class Composition:
         self._api.check(st.value, "Order::new")
         return Layer(self, h)
 
+    def evict(self) -> None:
+        """Drop device residency (next render re-uploads from pinned host memory)."""
+        self._api.composition_evict(self._h)
+
+    def point_count(self) -> int:
+        return int(self._api.composition_point_count(self._h))
+
     def __len__(self) -> int:
         return int(self._api.composition_len(self._h))
 
@@ -593,6 +613,22 @@ class Renderer:
 
     def launch_count(self) -> int:
         return int(self._api.renderer_launch_count(self._h))
+
+    STAGES = ("upload", "line_setup", "rasterize", "sort", "paint_tables", "paint_kernel", "d2h", "total")
+
+    def stage_times(self) -> dict:
+        """Device-timeline ms of the last render, by stage."""
+        out = (C.c_double * 8)()
+        self._api.renderer_stage_times(self._h, out)
+        return dict(zip(self.STAGES, list(out)))
+
+    def counters(self) -> dict:
+        out = (C.c_uint64 * 6)()
+        self._api.renderer_counters(self._h, out)
+        return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries"), [int(v) for v in out]))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._api.renderer_set_stream(self._h, C.c_void_p(cuda_stream))
 
     # stage-level access ----------------------------------------------------
     def lines(self):

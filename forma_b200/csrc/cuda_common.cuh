@@ -68,6 +68,31 @@ struct DeviceBuffer {
     DeviceBuffer& operator=(const DeviceBuffer&) = delete;
 };
 
+// Growable page-locked host buffer (H2D staging at full PCIe rate).
+template <class T>
+struct PinnedBuffer {
+    T* ptr = nullptr;
+    size_t capacity = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= capacity) return cudaSuccess;
+        size_t cap = capacity ? capacity : 1024;
+        while (cap < n) cap += cap / 2 + 1024;
+        T* np = nullptr;
+        cudaError_t e = cudaMallocHost(&np, cap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = np;
+        capacity = cap;
+        return cudaSuccess;
+    }
+    ~PinnedBuffer() {
+        if (ptr) cudaFreeHost(ptr);
+    }
+    PinnedBuffer() = default;
+    PinnedBuffer(const PinnedBuffer&) = delete;
+    PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 

@@ -65,15 +65,35 @@ class Composition {
 
     // --- segment buffer (device) ------------------------------------------------
     int device = -1;                  // bound at first render
-    uint32_t n_points = 0;            // points appended so far (incl. pending)
+    uint32_t n_points = 0;            // points appended so far (incl. not yet resident)
     uint64_t some_ids = 0;            // SegmentBuffer::len(): ids that are Some
-    std::vector<PendingInsert> pending;
+    std::vector<PendingInsert> jobs;  // every Layer::insert so far, in order
+    size_t jobs_resident = 0;         // jobs [0, jobs_resident) are evaluated in HBM
     DeviceBuffer<float> d_x, d_y;
     DeviceBuffer<uint32_t> d_gid;
     uint32_t n_resident = 0;          // points already evaluated on the device
+    // Pinned staging of the flatten programs of jobs [staged_from, staged_to).
+    PinnedBuffer<PointCmd> h_cmds;
+    PinnedBuffer<QuadRec> h_quads;
+    PinnedBuffer<FlattenJob> h_jobs;
+    size_t staged_from = 0, staged_to = 0, staged_cmds = 0, staged_quads = 0;
+    // Drops device residency: the next render re-uploads everything from pinned
+    // host memory (used to measure the cold, end-to-end path).
+    void evict() {
+        jobs_resident = 0;
+        n_resident = 0;
+        tables_resident = false;
+    }
 
     // --- per-frame lookup tables (device), rebuilt when dirty ------------------
-    bool tables_dirty = true;
+    bool tables_dirty = true;         // host-side pinned copies are stale
+    bool tables_resident = false;     // device copies match the pinned copies
+    PinnedBuffer<LayerRec> h_layers;
+    PinnedBuffer<StyleRec> h_styles;
+    PinnedBuffer<int32_t> h_order_to_style, h_geom_slot;
+    PinnedBuffer<StopRec> h_stops;
+    PinnedBuffer<uint16_t> h_texels;
+    size_t n_layer_recs = 0, n_stops = 0, n_texels = 0;
     DeviceBuffer<int32_t> d_geom_slot;
     DeviceBuffer<LayerRec> d_layers;
     DeviceBuffer<StyleRec> d_styles;

@@ -142,7 +142,7 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
         job.geom_id = (uint32_t)layer->geom_id;
         job.dst = n_points;
         job.count = count;
-        pending.push_back(std::move(job));
+        jobs.push_back(std::move(job));
         // ids that are Some: every point that does not end a contour, except the
         // last point of the insert (its id is the trailing None).
         uint64_t some = 0;
@@ -173,7 +173,7 @@ struct LayerCache {
 };
 
 struct Timer {
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[8];
     bool ok = false;
 };
 
@@ -198,7 +198,9 @@ class Renderer {
     DeviceBuffer<QuadRec> up_quads;
     DeviceBuffer<FlattenJob> up_jobs;
 
-    uint32_t last_segments = 0;
+    uint32_t last_segments = 0, last_cells = 0, last_entries = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied over PCIe since creation
+    double stage_ms[8] = {0};               // see forma_renderer_stage_times
     uint32_t* pinned_totals = nullptr;  // 4 x u32 pinned host words for count read-backs
 
     ~Renderer() {
@@ -224,132 +226,155 @@ int Renderer::read_total(uint32_t slot, uint32_t* out) {
     return FORMA_STATUS_OK;
 }
 
-// Evaluates all pending Layer::insert jobs into the device segment buffer with
-// one batched upload + one kernel.
+// Evaluates the Layer::insert jobs that are not resident yet into the device
+// segment buffer: one batched upload from pinned staging + one kernel.
 int Renderer::flush_geometry(Composition& comp) {
     if (comp.device < 0) comp.device = device;
     if (comp.device != device) {
         set_error("composition is resident on device %d, renderer uses device %d", comp.device, device);
         return FORMA_STATUS_INVALID;
     }
-    if (comp.pending.empty()) return FORMA_STATUS_OK;
+    const size_t from = comp.jobs_resident, to = comp.jobs.size();
+    if (from == to) return FORMA_STATUS_OK;
+    if (to - from >= (1u << 30)) {
+        set_error("too many inserts in one batch");
+        return FORMA_STATUS_CAPACITY;
+    }
     FORMA_CUDA_TRY(comp.d_x.reserve(comp.n_points, true, stream));
     FORMA_CUDA_TRY(comp.d_y.reserve(comp.n_points, true, stream));
     FORMA_CUDA_TRY(comp.d_gid.reserve(comp.n_points, true, stream));
 
-    std::vector<PointCmd> cmds;
-    std::vector<QuadRec> quads;
-    std::vector<FlattenJob> jobs;
-    size_t total_pts = 0;
-    for (auto& p : comp.pending) total_pts += p.count;
-    cmds.reserve(total_pts);
-    jobs.reserve(comp.pending.size());
-    for (auto& p : comp.pending) {
-        const FlattenProgram& prog = p.data->program();
-        FlattenJob job;
-        job.first_point = (uint32_t)cmds.size();
-        job.count = p.count;
-        job.quad_base = (uint32_t)quads.size();
-        job.geom_id = p.geom_id;
-        job.has_xf = p.has_xf ? 1u : 0u;
-        std::memcpy(job.xf, p.xf, sizeof(job.xf));
-        job.dst = p.dst;
-        uint32_t tag = (uint32_t)jobs.size() << 2;
-        for (const PointCmd& c : prog.cmds) {
-            PointCmd cc = c;
-            cc.kind |= tag;
-            cmds.push_back(cc);
+    if (comp.staged_from != from || comp.staged_to != to) {
+        // (Re)build the pinned staging copy of the flatten programs of jobs [from, to).
+        size_t n_cmds = 0, n_quads = 0;
+        for (size_t j = from; j < to; ++j) {
+            const FlattenProgram& prog = comp.jobs[j].data->program();
+            n_cmds += prog.cmds.size();
+            n_quads += prog.quads.size();
         }
-        quads.insert(quads.end(), prog.quads.begin(), prog.quads.end());
-        jobs.push_back(job);
+        FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // staging may still be in flight
+        FORMA_CUDA_TRY(comp.h_cmds.reserve(n_cmds));
+        FORMA_CUDA_TRY(comp.h_quads.reserve(n_quads + 1));
+        FORMA_CUDA_TRY(comp.h_jobs.reserve(to - from));
+        size_t ci = 0, qi = 0;
+        for (size_t j = from; j < to; ++j) {
+            const PendingInsert& p = comp.jobs[j];
+            const FlattenProgram& prog = p.data->program();
+            FlattenJob& job = comp.h_jobs.ptr[j - from];
+            job.first_point = (uint32_t)ci;
+            job.count = p.count;
+            job.quad_base = (uint32_t)qi;
+            job.geom_id = p.geom_id;
+            job.has_xf = p.has_xf ? 1u : 0u;
+            std::memcpy(job.xf, p.xf, sizeof(job.xf));
+            job.dst = p.dst;
+            uint32_t tag = (uint32_t)(j - from) << 2;
+            for (const PointCmd& c : prog.cmds) {
+                PointCmd cc = c;
+                cc.kind |= tag;
+                comp.h_cmds.ptr[ci++] = cc;
+            }
+            if (!prog.quads.empty()) std::memcpy(comp.h_quads.ptr + qi, prog.quads.data(), prog.quads.size() * sizeof(QuadRec));
+            qi += prog.quads.size();
+        }
+        comp.staged_from = from;
+        comp.staged_to = to;
+        comp.staged_cmds = n_cmds;
+        comp.staged_quads = n_quads;
     }
-    if (jobs.size() >= (1u << 30)) {
-        set_error("too many pending inserts in one batch");
-        return FORMA_STATUS_CAPACITY;
-    }
-    FORMA_CUDA_TRY(up_cmds.reserve(cmds.size()));
-    FORMA_CUDA_TRY(up_quads.reserve(quads.size() + 1));
-    FORMA_CUDA_TRY(up_jobs.reserve(jobs.size()));
-    FORMA_CUDA_TRY(cudaMemcpyAsync(up_cmds.ptr, cmds.data(), cmds.size() * sizeof(PointCmd), cudaMemcpyHostToDevice, stream));
-    if (!quads.empty())
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads.ptr, quads.data(), quads.size() * sizeof(QuadRec), cudaMemcpyHostToDevice, stream));
-    FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, jobs.data(), jobs.size() * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
-    launch_flatten_eval(up_cmds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)cmds.size(), comp.d_x.ptr, comp.d_y.ptr,
+    FORMA_CUDA_TRY(up_cmds.reserve(comp.staged_cmds));
+    FORMA_CUDA_TRY(up_quads.reserve(comp.staged_quads + 1));
+    FORMA_CUDA_TRY(up_jobs.reserve(to - from));
+    FORMA_CUDA_TRY(cudaMemcpyAsync(up_cmds.ptr, comp.h_cmds.ptr, comp.staged_cmds * sizeof(PointCmd), cudaMemcpyHostToDevice, stream));
+    if (comp.staged_quads)
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads.ptr, comp.h_quads.ptr, comp.staged_quads * sizeof(QuadRec), cudaMemcpyHostToDevice, stream));
+    FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, comp.h_jobs.ptr, (to - from) * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
+    h2d_bytes += comp.staged_cmds * sizeof(PointCmd) + comp.staged_quads * sizeof(QuadRec) + (to - from) * sizeof(FlattenJob);
+    launch_flatten_eval(up_cmds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)comp.staged_cmds, comp.d_x.ptr, comp.d_y.ptr,
                         comp.d_gid.ptr, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
-    // The staging vectors are pageable: make sure the copies are done before they die.
-    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
     comp.n_resident = comp.n_points;
-    comp.pending.clear();
+    comp.jobs_resident = to;
     return FORMA_STATUS_OK;
 }
 
-// geom id -> layer slot, layer records, style table (rebuilt when the
-// composition changed; segment.rs:141-149 does these look-ups per point).
+// geom id -> layer slot, layer records, style table (segment.rs:141-149 does
+// these look-ups per point). The pinned host copies are rebuilt when the
+// composition changed and re-uploaded when they are not resident.
 int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
-    if (!comp.tables_dirty && comp.tables_cache_id == cache_id) return FORMA_STATUS_OK;
-    std::vector<LayerRec> lrecs;
-    std::vector<StyleRec> srecs;
-    std::vector<StopRec> stops;
-    std::vector<uint16_t> texels;
-    std::unordered_map<const void*, uint32_t> tex_offsets;
-    std::unordered_map<uint32_t, uint32_t> order_to_slot;
-    uint32_t max_order = 0;
-    lrecs.reserve(comp.layers.size());
-    srecs.reserve(comp.layers.size());
-    for (auto& kv : comp.layers) {
-        const Layer& l = *kv.second;
-        LayerRec r;
-        r.order = kv.first;
-        r.enabled = l.enabled ? 1u : 0u;
-        r.has_xf = l.has_xf ? 1u : 0u;
-        r.ux = l.xf[0]; r.uy = l.xf[1]; r.vx = l.xf[2]; r.vy = l.xf[3]; r.tx = l.xf[4]; r.ty = l.xf[5];
-        StyleRec s = l.props.rec;
-        s.stop_first = (uint32_t)stops.size();
-        s.stop_count = (uint32_t)l.props.stops.size();
-        stops.insert(stops.end(), l.props.stops.begin(), l.props.stops.end());
-        if (s.fill_type == 2u && l.props.texels) {
-            auto it = tex_offsets.find(l.props.texels.get());
-            if (it == tex_offsets.end()) {
-                uint32_t off = (uint32_t)(texels.size() / 4);
-                texels.insert(texels.end(), l.props.texels->begin(), l.props.texels->end());
-                it = tex_offsets.emplace(l.props.texels.get(), off).first;
+    if (comp.tables_dirty || comp.tables_cache_id != cache_id) {
+        std::vector<StopRec> stops;
+        std::vector<uint16_t> texels;
+        std::unordered_map<const void*, uint32_t> tex_offsets;
+        uint32_t max_order = 0;
+        for (auto& kv : comp.layers) max_order = std::max(max_order, kv.first);
+        uint32_t n_orders = comp.layers.empty() ? 0u : max_order + 1u;
+        uint32_t n_geoms = (uint32_t)comp.next_geom_id;
+        FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+        FORMA_CUDA_TRY(comp.h_layers.reserve(comp.layers.size() + 1));
+        FORMA_CUDA_TRY(comp.h_styles.reserve(comp.layers.size() + 1));
+        FORMA_CUDA_TRY(comp.h_order_to_style.reserve(n_orders + 1));
+        FORMA_CUDA_TRY(comp.h_geom_slot.reserve(n_geoms + 1));
+        std::fill(comp.h_order_to_style.ptr, comp.h_order_to_style.ptr + n_orders, -1);
+        std::fill(comp.h_geom_slot.ptr, comp.h_geom_slot.ptr + n_geoms, -1);
+        uint32_t slot = 0;
+        for (auto& kv : comp.layers) {
+            const Layer& l = *kv.second;
+            LayerRec& r = comp.h_layers.ptr[slot];
+            r.order = kv.first;
+            r.enabled = l.enabled ? 1u : 0u;
+            r.has_xf = l.has_xf ? 1u : 0u;
+            r.ux = l.xf[0]; r.uy = l.xf[1]; r.vx = l.xf[2]; r.vy = l.xf[3]; r.tx = l.xf[4]; r.ty = l.xf[5];
+            StyleRec s = l.props.rec;
+            s.stop_first = (uint32_t)stops.size();
+            s.stop_count = (uint32_t)l.props.stops.size();
+            stops.insert(stops.end(), l.props.stops.begin(), l.props.stops.end());
+            if (s.fill_type == 2u && l.props.texels) {
+                auto it = tex_offsets.find(l.props.texels.get());
+                if (it == tex_offsets.end()) {
+                    uint32_t off = (uint32_t)(texels.size() / 4);
+                    texels.insert(texels.end(), l.props.texels->begin(), l.props.texels->end());
+                    it = tex_offsets.emplace(l.props.texels.get(), off).first;
+                }
+                s.tex_first = it->second;
             }
-            s.tex_first = it->second;
+            s.unchanged = (cache_id >= 0 && ((l.unchanged_bits >> cache_id) & 1u)) ? 1u : 0u;
+            comp.h_styles.ptr[slot] = s;
+            comp.h_order_to_style.ptr[kv.first] = (int32_t)slot;
+            ++slot;
         }
-        s.unchanged = (cache_id >= 0 && ((l.unchanged_bits >> cache_id) & 1u)) ? 1u : 0u;
-        order_to_slot[kv.first] = (uint32_t)lrecs.size();
-        max_order = std::max(max_order, kv.first);
-        lrecs.push_back(r);
-        srecs.push_back(s);
+        for (auto& kv : comp.geom_to_order) {
+            if (kv.second < 0 || kv.first >= n_geoms || (uint64_t)kv.second >= n_orders) continue;
+            comp.h_geom_slot.ptr[kv.first] = comp.h_order_to_style.ptr[kv.second];
+        }
+        FORMA_CUDA_TRY(comp.h_stops.reserve(stops.size() + 1));
+        FORMA_CUDA_TRY(comp.h_texels.reserve(texels.size() + 1));
+        if (!stops.empty()) std::memcpy(comp.h_stops.ptr, stops.data(), stops.size() * sizeof(StopRec));
+        if (!texels.empty()) std::memcpy(comp.h_texels.ptr, texels.data(), texels.size() * sizeof(uint16_t));
+        comp.n_layer_recs = slot;
+        comp.n_stops = stops.size();
+        comp.n_texels = texels.size();
+        comp.n_geoms = n_geoms;
+        comp.n_orders = n_orders;
+        comp.tables_dirty = false;
+        comp.tables_cache_id = cache_id;
+        comp.tables_resident = false;
     }
-    uint32_t n_orders = comp.layers.empty() ? 0u : max_order + 1u;
-    std::vector<int32_t> order_to_style(n_orders, -1);
-    for (auto& kv : order_to_slot) order_to_style[kv.first] = (int32_t)kv.second;
-    uint32_t n_geoms = (uint32_t)comp.next_geom_id;
-    std::vector<int32_t> geom_slot(n_geoms, -1);
-    for (auto& kv : comp.geom_to_order) {
-        if (kv.second < 0 || kv.first >= n_geoms) continue;
-        auto it = order_to_slot.find((uint32_t)kv.second);
-        if (it != order_to_slot.end()) geom_slot[kv.first] = (int32_t)it->second;
-    }
-    auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
-        cudaError_t e = buf.reserve(vec.size() + 1);
-        if (e != cudaSuccess || vec.empty()) return e;
-        return cudaMemcpyAsync(buf.ptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, stream);
+    if (comp.tables_resident) return FORMA_STATUS_OK;
+    auto up = [&](auto& dbuf, const auto& hbuf, size_t n) -> cudaError_t {
+        cudaError_t e = dbuf.reserve(n + 1);
+        if (e != cudaSuccess || n == 0) return e;
+        h2d_bytes += n * sizeof(*hbuf.ptr);
+        return cudaMemcpyAsync(dbuf.ptr, hbuf.ptr, n * sizeof(*hbuf.ptr), cudaMemcpyHostToDevice, stream);
     };
-    FORMA_CUDA_TRY(up(comp.d_layers, lrecs));
-    FORMA_CUDA_TRY(up(comp.d_styles, srecs));
-    FORMA_CUDA_TRY(up(comp.d_stops, stops));
-    FORMA_CUDA_TRY(up(comp.d_texels, texels));
-    FORMA_CUDA_TRY(up(comp.d_order_to_style, order_to_style));
-    FORMA_CUDA_TRY(up(comp.d_geom_slot, geom_slot));
-    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
-    comp.n_geoms = n_geoms;
-    comp.n_orders = n_orders;
-    comp.tables_dirty = false;
-    comp.tables_cache_id = cache_id;
+    FORMA_CUDA_TRY(up(comp.d_layers, comp.h_layers, comp.n_layer_recs));
+    FORMA_CUDA_TRY(up(comp.d_styles, comp.h_styles, comp.n_layer_recs));
+    FORMA_CUDA_TRY(up(comp.d_stops, comp.h_stops, comp.n_stops));
+    FORMA_CUDA_TRY(up(comp.d_texels, comp.h_texels, comp.n_texels));
+    FORMA_CUDA_TRY(up(comp.d_order_to_style, comp.h_order_to_style, comp.n_orders));
+    FORMA_CUDA_TRY(up(comp.d_geom_slot, comp.h_geom_slot, comp.n_geoms));
+    comp.tables_resident = true;
     return FORMA_STATUS_OK;
 }
 
@@ -435,6 +460,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         if (S.ty_hi < S.ty_lo) S.ty_hi = S.ty_lo;
     }
 
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
     int st = flush_geometry(comp);
     if (st) return st;
     st = upload_tables(comp, -1);
@@ -445,13 +471,16 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     S.stops = comp.d_stops.ptr;
     S.texels = comp.d_texels.ptr;
 
-    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[7], stream));
     uint32_t n = 0;
-    st = rasterize(comp, S.width, S.height, 0.0f, (float)S.height, &n);
+    // Lines entirely above / below the painted tile rows cannot reach a painted
+    // tile; culling them is what lets several GPUs split a frame by tile bands.
+    st = rasterize(comp, S.width, S.height, (float)(S.ty_lo * 16u), (float)std::min<uint64_t>((uint64_t)S.ty_hi * 16u, height), &n);
     if (st) return st;
 
     // Stage 3: sort.
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[2], stream));
+    last_cells = last_entries = 0;
     if (n > 1) {
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n)));
         launches += launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, sort_scratch.ptr, stream);
@@ -501,6 +530,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         st = read_total(2, &n_gaps);
         if (st) return st;
         n_entries = n_cells + n_gaps;
+        last_cells = n_cells;
+        last_entries = n_entries;
         FORMA_CUDA_TRY(ekey.reserve(n_entries));
         FORMA_CUDA_TRY(ekey_tmp.reserve(n_entries));
         FORMA_CUDA_TRY(eid.reserve(n_entries));
@@ -515,11 +546,12 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
     launches += n_entries ? 1 : 0;
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
     launch_paint(S, segs.ptr, ekey.ptr, eid.ptr, cell_start.ptr, carry_in.ptr, gap_carry.ptr, n_cells, tile_begin.ptr,
                  tile_end.ptr, eflags.ptr, fb, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
-    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[5], stream));
 
     if (!buffer_on_device) {
         // Only the cropped tile rectangle is written by the reference
@@ -529,19 +561,31 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         if (x1 > x0 && y1 > y0) {
             FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
                                              (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, stream));
+            d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
         }
     }
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[6], stream));
     FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    {
+        auto el = [&](int a, int b) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, timer.ev[a], timer.ev[b]);
+            return (double)ms;
+        };
+        stage_ms[0] = el(0, 7);  // uploads (geometry programs + flatten eval + tables)
+        stage_ms[1] = el(7, 1);  // line setup: count pass + scan (+ count read-back)
+        stage_ms[2] = el(1, 2);  // pixel-grid intersection (emit)
+        stage_ms[3] = el(2, 3);  // sort (histogram + 6 onesweep passes), no host sync inside
+        stage_ms[4] = el(3, 4);  // painter tables: cells, carries, entries (2 pair sorts, 2 read-backs)
+        stage_ms[5] = el(4, 5);  // paint kernel alone
+        stage_ms[6] = el(5, 6);  // device -> host copy of the framebuffer
+        stage_ms[7] = el(0, 6);  // whole call on the device timeline
+    }
     if (timings) {
-        float ms01 = 0, ms12 = 0, ms23 = 0, ms34 = 0;
-        cudaEventElapsedTime(&ms01, timer.ev[0], timer.ev[1]);
-        cudaEventElapsedTime(&ms12, timer.ev[1], timer.ev[2]);
-        cudaEventElapsedTime(&ms23, timer.ev[2], timer.ev[3]);
-        cudaEventElapsedTime(&ms34, timer.ev[3], timer.ev[4]);
-        timings->line_setup_ms = ms01;
-        timings->rasterize_ms = ms12;
-        timings->sort_ms = ms23;
-        timings->paint_ms = ms34;
+        timings->line_setup_ms = stage_ms[1];
+        timings->rasterize_ms = stage_ms[2];
+        timings->sort_ms = stage_ms[3];
+        timings->paint_ms = stage_ms[4] + stage_ms[5];
         timings->n_lines = comp.n_resident ? comp.n_resident - 1 : 0;
         timings->n_segments = n;
     }
@@ -843,6 +887,31 @@ int forma_renderer_render_device(forma_renderer* r, forma_composition* c, uint8_
                        cache ? &cache->c : nullptr, timings);
 }
 uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.launches; }
+void forma_renderer_stage_times(const forma_renderer* r, double out_ms[8]) {
+    for (int i = 0; i < 8; ++i) out_ms[i] = r->r.stage_ms[i];
+}
+void forma_renderer_counters(const forma_renderer* r, uint64_t out[6]) {
+    out[0] = r->r.launches;
+    out[1] = r->r.h2d_bytes;
+    out[2] = r->r.d2h_bytes;
+    out[3] = r->r.last_segments;
+    out[4] = r->r.last_cells;
+    out[5] = r->r.last_entries;
+}
+void forma_composition_evict(forma_composition* c) { c->c.evict(); }
+uint64_t forma_composition_point_count(forma_composition* c) { return c->c.n_points; }
+void forma_path_builder_extend(forma_path_builder* pb, const uint8_t* cmds, uint64_t n_cmds, const float* xy) {
+    PathBuilder& b = pb->b;
+    const float* p = xy;
+    for (uint64_t i = 0; i < n_cmds; ++i) {
+        switch (cmds[i]) {
+            case 0: b.move_to({p[0], p[1]}); p += 2; break;
+            case 1: b.line_to({p[0], p[1]}); p += 2; break;
+            case 2: b.quad_to({p[0], p[1]}, {p[2], p[3]}); p += 4; break;
+            default: b.cubic_to({p[0], p[1]}, {p[2], p[3]}, {p[4], p[5]}); p += 6; break;
+        }
+    }
+}
 
 uint64_t forma_renderer_lines(forma_renderer*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,
                               float*, float*, uint32_t*) {

@@ -201,6 +201,22 @@ int forma_renderer_render_device(forma_renderer*, forma_composition*, uint8_t* d
  * instead of the default stream. */
 void forma_renderer_set_stream(forma_renderer*, void* cuda_stream);
 
+/* --- extensions (no reference counterpart) --------------------------------- */
+/* Bulk form of move_to/line_to/quad_to/cubic_to: cmds[i] in {0 Move, 1 Line,
+ * 2 Quad, 3 Cubic}, xy = the points they consume (1, 1, 2, 3 points each). */
+void forma_path_builder_extend(forma_path_builder*, const uint8_t* cmds, uint64_t n_cmds, const float* xy);
+/* Drops the composition's device residency: the next render re-uploads every
+ * flatten program and table from pinned host memory (cold end-to-end path). */
+void forma_composition_evict(forma_composition*);
+uint64_t forma_composition_point_count(forma_composition*);
+/* Device-timeline milliseconds of the last render: [0] uploads, [1] line-setup
+ * count pass, [2] pixel-grid intersection, [3] sort, [4] painter tables,
+ * [5] paint kernel, [6] device->host copy, [7] whole call. */
+void forma_renderer_stage_times(const forma_renderer*, double out_ms[8]);
+/* [0] kernel launches, [1] host->device bytes, [2] device->host bytes (all
+ * since creation), [3] pixel segments, [4] cells, [5] entries of the last render. */
+void forma_renderer_counters(const forma_renderer*, uint64_t out[6]);
+
 /* Number of CUDA kernels the renderer launched since it was created. */
 uint64_t forma_renderer_launch_count(const forma_renderer*);
 

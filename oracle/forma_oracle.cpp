@@ -229,6 +229,17 @@ void fo_path_builder_rat_cubic_to(void* pb, float x1, float y1, float x2, float 
                                   float w2) {
     ((PathBuilder*)pb)->rat_cubic_to({x1, y1}, {x2, y2}, {x3, y3}, w1, w2);
 }
+void fo_path_builder_extend(void* pbv, const uint8_t* cmds, uint64_t n_cmds, const float* p) {
+    PathBuilder* pb = (PathBuilder*)pbv;
+    for (uint64_t i = 0; i < n_cmds; ++i) {
+        switch (cmds[i]) {
+            case 0: pb->move_to({p[0], p[1]}); p += 2; break;
+            case 1: pb->line_to({p[0], p[1]}); p += 2; break;
+            case 2: pb->quad_to({p[0], p[1]}, {p[2], p[3]}); p += 4; break;
+            default: pb->cubic_to({p[0], p[1]}, {p[2], p[3]}, {p[4], p[5]}); p += 6; break;
+        }
+    }
+}
 void* fo_path_builder_build(void* pb) { return new Path(((PathBuilder*)pb)->build()); }
 void* fo_path_transform(const void* path, const float m[9]) { return new Path(((const Path*)path)->transformed(m)); }
 void fo_path_free(void* p) { delete (Path*)p; }

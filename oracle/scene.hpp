@@ -195,7 +195,8 @@ struct Composition {
     // composition/layer.rs:90-111 + segment.rs:181-198 + path.rs:677-723
     void layer_insert(Layer* lp, Path& path) {
         Layer& layer = *lp;
-        size_t old_len = segment_len();
+        size_t from_index = ids.size() ? ids.size() - 1 : 0;  // only the tail can change (SegmentBuffer::len caches, segment.rs:163-178)
+        size_t old_len = segment_len(from_index);
         const Segments& s = path.inner->segments();
         for (size_t i = 0; i < s.x.size(); ++i) {
             Point p{s.x[i], s.y[i]};
@@ -206,7 +207,7 @@ struct Composition {
         }
         ids.resize(x.size() > 0 ? x.size() - 1 : 0, layer.geom_id);
         if (!ids.empty() && ids.back() != 0) ids.push_back(0);
-        layer.lines_count += segment_len() - old_len;
+        layer.lines_count += segment_len(from_index) - old_len;
         geom_id_to_order[layer.geom_id] = layer.order;
         layer.is_unchanged = 0;
     }

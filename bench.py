@@ -157,13 +157,13 @@ def run_cuda(args):
     clear = Color(1.0, 1.0, 1.0, 0.0)
 
     # Tile-row bands: rank r paints rows [r0, r1) of 16-pixel tile rows.
-    tiles_y = (h + 15) // 16
-    band = (tiles_y + world - 1) // world
-    r0, r1 = rank * band, min((rank + 1) * band, tiles_y)
-    crop = None if world == 1 else Rect((0, w), (r0 * 16, min(r1 * 16, h)))
+    from forma_b200 import bands
+    bd = bands.band_of(h, world, rank)
+    band, r0, r1 = bd.rows_per_band, bd.tile_row0, bd.tile_row1
+    crop = None if world == 1 else Rect((0, w), (bd.y0, max(bd.y1, bd.y0)))
     stride = w * 4
-    h_pad = band * world * 16
-    fb = torch.zeros((h_pad, stride), dtype=torch.uint8, device=dev)
+    h_pad = bd.padded_height
+    fb = torch.zeros((h_pad + band * 16, stride), dtype=torch.uint8, device=dev)
     band_view = fb[r0 * 16:(r0 + band) * 16]
     gathered = torch.empty((h_pad, stride), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -173,7 +173,7 @@ def run_cuda(args):
     def frame_device():
         renderer.render_device(comp, fb.data_ptr(), w, h, RGBA, clear, crop, None, stride)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), band_view.reshape(-1))
+            bands.gather_frame(band_view, gathered, dist)
 
     def frame_e2e():
         comp.evict()

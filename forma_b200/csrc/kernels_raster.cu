@@ -207,7 +207,8 @@ struct SharedLines {
 
 // Pass 2: recompute the CTA's 256 lines, then each warp expands its 32 lines.
 __global__ void __launch_bounds__(kRasterThreads)
-    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out) {
+    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out,
+                       unsigned long long* __restrict__ key_or) {
     __shared__ SharedLines S;
     __shared__ uint32_t warp_sums[kRasterThreads / 32];
     const uint32_t t = threadIdx.x;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kRasterThreads)
     for (uint32_t w = 0; w < warp; ++w) warp_base += warp_sums[w];
     const uint32_t warp_total = warp_sums[warp];
     const uint32_t* excl = S.excl + warp * 32u;
+    uint64_t or_acc = 0;  // OR of the emitted keys: tells the sort which key bits are in use
 
     for (uint32_t s = lane; s < warp_total; s += 32u) {
         // Largest j in [0, 32) with excl[j] <= s (zero-length lines share their
@@ -271,7 +273,11 @@ __global__ void __launch_bounds__(kRasterThreads)
         uint64_t v = (ty << 53) | (tx << 41) | ((uint64_t)(S.order[li] & 0x1FFFFFu) << 20) | ((uint64_t)local_x << 16) |
                      ((uint64_t)local_y << 12) | ((uint64_t)(dam & 0x3Fu) << 6) | ((uint64_t)((uint32_t)cover & 0x3Fu));
         out[(uint64_t)warp_base + s] = v;
+        or_acc |= v;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) or_acc |= __shfl_xor_sync(kFullMask, or_acc, o);
+    if (lane == 0 && or_acc) atomicOr(key_or, (unsigned long long)or_acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -295,14 +301,89 @@ void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* t
     scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
 }
 
-void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream) {
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out,
+                        unsigned long long* key_or, cudaStream_t stream) {
+    cudaMemsetAsync(key_or, 0, sizeof(unsigned long long), stream);
     uint32_t nb = raster_num_blocks(args.n_points);
     if (!nb) return;
-    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out);
+    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out, key_or);
 }
 
-void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, cudaStream_t stream) {
-    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(data, n, total);
+// Multi-CTA exclusive scan (single pass, decoupled look-back): CTA = 2048
+// values; state[t] = flag (2 bits) | running value (62 bits); state[tiles] is the
+// ticket counter. `state` must hold scan_state_words(n) zeroed u64 words.
+constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+constexpr unsigned long long kScanAggregate = 1ull << 62, kScanInclusive = 2ull << 62, kScanFlags = 3ull << 62;
+
+__global__ void __launch_bounds__(kScanThreads) chained_scan_kernel(uint32_t* __restrict__ data, uint32_t n,
+                                                                  unsigned long long* __restrict__ state, uint32_t tiles,
+                                                                  uint32_t* __restrict__ total) {
+    __shared__ uint32_t warp_tot[kScanThreads / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) s_tile = (uint32_t)atomicAdd(&state[tiles], 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kScanTile + warp * (32u * kScanItems);
+    // Warp-striped: item i of lane l is element base + i*32 + l.
+    uint32_t v[kScanItems], excl[kScanItems];
+    uint32_t running = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        uint32_t idx = base + i * 32u + lane;
+        v[i] = idx < n ? data[idx] : 0u;
+        uint32_t incl = warp_inclusive_scan(v[i]);
+        excl[i] = running + incl - v[i];
+        running += __shfl_sync(kFullMask, incl, 31);
+    }
+    if (lane == 0) warp_tot[warp] = running;
+    __syncthreads();
+    uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        if ((uint32_t)w < warp) warp_off += warp_tot[w];
+        tile_sum += warp_tot[w];
+    }
+    if (t == 0) {
+        volatile unsigned long long* st = state;
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            st[0] = kScanInclusive | tile_sum;
+        } else {
+            st[tile] = kScanAggregate | tile_sum;
+            int32_t p = (int32_t)tile - 1;
+            while (true) {
+                unsigned long long s = st[p];
+                if ((s & kScanFlags) == 0) continue;
+                prefix += s & ~kScanFlags;
+                if ((s & kScanFlags) == kScanInclusive) break;
+                --p;
+            }
+            st[tile] = kScanInclusive | (prefix + tile_sum);
+        }
+        s_prefix = prefix;
+        if (tile + 1 == tiles) total[0] = (uint32_t)(prefix + tile_sum);
+    }
+    __syncthreads();
+    const uint32_t add = (uint32_t)s_prefix + warp_off;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        uint32_t idx = base + i * 32u + lane;
+        if (idx < n) data[idx] = add + excl[i];
+    }
+}
+
+size_t scan_state_words(uint32_t n) { return (size_t)(n + kScanTile - 1) / kScanTile + 2; }
+
+void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long long* state, cudaStream_t stream) {
+    if (n <= 16384u || !state) {
+        scan_block_sums_kernel<<<1, 1024, 0, stream>>>(data, n, total);
+        return;
+    }
+    uint32_t tiles = (n + kScanTile - 1) / kScanTile;
+    cudaMemsetAsync(state, 0, (tiles + 1) * sizeof(unsigned long long), stream);
+    chained_scan_kernel<<<tiles, kScanThreads, 0, stream>>>(data, n, state, tiles, total);
 }
 
 }  // namespace forma

@@ -1,0 +1,303 @@
+// Stage 4: per-tile coverage accumulation and compositing to RGBA8 — replaces
+// forma/src/cpu/painter/{mod.rs, layer_workbench/, styling.rs}.
+//
+// The reference walks each tile row left to right, carrying every layer's
+// winding "cover" (16 x i8, one per pixel row) from tile to tile in a queue
+// (cpu/painter/mod.rs:486-568, layer_workbench/mod.rs:196-342). To paint tiles
+// independently the carries are materialised first:
+//
+//   cells     runs of sorted segments with equal (tile_y, tile_x, layer)
+//   covers    per cell: sum of segment covers by local_y (wrapping i8)
+//   re-sort   cell ids by (tile_y, layer, tile_x)            [pair radix sort]
+//   carries   per (tile_y, layer) group a running sum -> carry-in of every cell
+//             and "carry-only" entries for the tiles a layer spans without
+//             segments (layer_workbench/mod.rs:213-234,328-336)
+//   entries   cells ∪ carry-only entries, sorted by (tile_y, tile_x, layer)
+//   paint     one warp per tile; lane l owns column l/2, rows 8*(l%2)..+8 —
+//             exactly one f32x8 of the reference (cpu/painter/mod.rs:234-244)
+//
+// Integer semantics: areas wrap at i16 and covers at i8 in the reference;
+// sums are formed in i32 / packed bytes and truncated where the reference
+// widens them (truncation commutes with wrapping addition).
+#include "paint_common.cuh"
+
+namespace forma {
+
+// ---------------------------------------------------------------------------
+// Cells
+// ---------------------------------------------------------------------------
+constexpr int kCellThreads = 256;
+
+__device__ __forceinline__ bool is_cell_head(const uint64_t* __restrict__ segs, uint32_t i) {
+    return i == 0 || (segs[i] >> kSortShift) != (segs[i - 1] >> kSortShift);
+}
+
+// A CTA scans kCellItems x 256 consecutive segments (warp-striped so that every
+// load is coalesced and the element order inside a warp is item-major).
+constexpr int kCellItems = 8;
+constexpr int kCellTile = kCellThreads * kCellItems;
+
+__global__ void __launch_bounds__(kCellThreads)
+    cell_count_kernel(const uint64_t* __restrict__ segs, uint32_t n, uint32_t* __restrict__ block_counts) {
+    __shared__ uint32_t warp_cnt[kCellThreads / 32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t base = blockIdx.x * kCellTile + warp * (32u * kCellItems);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kCellItems; ++k) {
+        uint32_t i = base + k * 32u + lane;
+        bool head = i < n && is_cell_head(segs, i);
+        cnt += __popc(__ballot_sync(kFullMask, head));
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kCellThreads / 32; ++w) s += warp_cnt[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kCellThreads)
+    cell_write_kernel(const uint64_t* __restrict__ segs, uint32_t n, const uint32_t* __restrict__ block_offsets,
+                      uint32_t* __restrict__ cell_start, uint64_t* __restrict__ cell_key, uint32_t n_cells) {
+    __shared__ uint32_t warp_cnt[kCellThreads / 32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t base = blockIdx.x * kCellTile + warp * (32u * kCellItems);
+    uint32_t masks[kCellItems];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kCellItems; ++k) {
+        uint32_t i = base + k * 32u + lane;
+        bool head = i < n && is_cell_head(segs, i);
+        masks[k] = __ballot_sync(kFullMask, head);
+        cnt += __popc(masks[k]);
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
+    __syncthreads();
+    uint32_t pos = block_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) pos += warp_cnt[w];
+#pragma unroll
+    for (int k = 0; k < kCellItems; ++k) {
+        if ((masks[k] >> lane) & 1u) {
+            uint32_t i = base + k * 32u + lane;
+            uint32_t p = pos + __popc(masks[k] & ((1u << lane) - 1u));
+            cell_start[p] = i;
+            cell_key[p] = (segs[i] >> kSortShift) << kSortShift;
+        }
+        pos += __popc(masks[k]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[n_cells] = n;
+}
+
+// Per cell: sum of covers by local_y (acc_segment's cover part + cover_carry,
+// cpu/painter/mod.rs:257-271, layer_workbench/mod.rs:218-224), and the
+// (tile_y, layer, tile_x) key for the carry pass.
+
+__global__ void cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
+                                  const uint64_t* __restrict__ cell_key, uint32_t n_cells, uint4* __restrict__ cell_cover,
+                                  uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
+    // One warp per cell: lanes stride over the cell's (contiguous) segments with
+    // coalesced loads, then the packed partial sums are combined with shuffles.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_cells) return;
+    const uint64_t ck = cell_key[c];
+    {
+        int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
+        if (ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi) {
+            if (lane == 0) {
+                perm[c] = c;
+                key2[c] = sentinel_key(S.tiles_y);
+                cell_cover[c] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            return;
+        }
+    }
+    const uint32_t s0 = cell_start[c], s1 = cell_start[c + 1];
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t i = s0 + lane; i < s1; i += 32u) {
+        uint64_t s = segs[i];
+        uint32_t ly = (uint32_t)(s >> 12) & 15u;
+        uint32_t cv = (uint32_t)s & 0x3Fu;
+        cv = (cv ^ 0x20u) - 0x20u;  // sign-extend 6 bits
+        uint32_t v = (cv & 0xFFu) << (8u * (ly & 3u));
+        uint32_t w = ly >> 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = __vadd4(acc[k], w == (uint32_t)k ? v : 0u);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = __vadd4(acc[k], __shfl_xor_sync(kFullMask, acc[k], o));
+    }
+    if (lane == 0) {
+        perm[c] = c;
+        cell_cover[c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        key2[c] = make_key2(ck);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Carries
+// ---------------------------------------------------------------------------
+// One thread per (tile_y, layer) group head walks its group (cells sorted by
+// tile_x), producing each cell's carry-in, the running carry after it and the
+// number of carry-only entries to create before the next cell.
+__global__ void carry_scan_kernel(PaintScene S, const uint64_t* __restrict__ key2, const uint32_t* __restrict__ perm,
+                                  const uint4* __restrict__ cell_cover, uint32_t n_cells, uint4* __restrict__ carry_in,
+                                  uint4* __restrict__ carry_after, uint32_t* __restrict__ gap_count) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cells) return;
+    uint64_t k = key2[j];
+    if (k == sentinel_key(S.tiles_y)) {  // irrelevant cell: no carries, no entries
+        gap_count[j] = 0;
+        return;
+    }
+    if (j > 0 && (key2[j - 1] >> 32) == (k >> 32)) return;  // not a group head
+    const uint32_t layer = key2_layer(k);
+    const uint32_t fill_rule = fill_rule_of(S, layer);
+    const int32_t ty = (int32_t)key_ty(k) - 1;
+    const bool row_painted = ty >= (int32_t)S.ty_lo && ty < (int32_t)S.ty_hi;
+    uint4 run = make_uint4(0u, 0u, 0u, 0u);
+    while (true) {
+        uint32_t c = perm[j];
+        carry_in[c] = run;
+        run = cover_add(run, cell_cover[c]);
+        carry_after[j] = run;
+        int32_t t = (int32_t)key2_tx(k) - 1;
+        bool has_next = j + 1 < n_cells && (key2[j + 1] >> 32) == (k >> 32);
+        int32_t next_t = has_next ? (int32_t)key2_tx(key2[j + 1]) - 1 : (int32_t)S.tx_hi;
+        uint32_t gaps = 0;
+        if (row_painted) {
+            int32_t lo = max(t + 1, (int32_t)S.tx_lo), hi = min(next_t, (int32_t)S.tx_hi);
+            if (!cover_is_empty(run, fill_rule)) {
+                gaps = hi > lo ? (uint32_t)(hi - lo) : 0u;
+            } else if (t < (int32_t)S.tx_lo && next_t > (int32_t)S.tx_lo && S.tx_lo < S.tx_hi) {
+                // covers_left_of_row: a layer with segments left of the first
+                // painted tile is queued for it even when its cover sums to zero
+                // (cpu/painter/mod.rs:501-522).
+                gaps = 1;
+            }
+        }
+        gap_count[j] = gaps;
+        if (!has_next) break;
+        ++j;
+        k = key2[j];
+    }
+}
+
+// Entries: one per cell (payload = cell id) + carry-only entries (payload =
+// n_cells + gap id). Cells that are not painted get the key ~0 (sorted last).
+__global__ void entry_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2, const uint32_t* __restrict__ perm,
+                                  const uint64_t* __restrict__ cell_key, const uint4* __restrict__ carry_after,
+                                  const uint32_t* __restrict__ gap_count, const uint32_t* __restrict__ gap_offset,
+                                  uint32_t n_cells, uint64_t* __restrict__ ekey, uint32_t* __restrict__ eid,
+                                  uint4* __restrict__ gap_carry) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cells) return;
+    uint32_t c = perm[j];
+    uint64_t ck = cell_key[c];
+    int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
+    bool painted = ty >= (int32_t)S.ty_lo && ty < (int32_t)S.ty_hi && tx >= (int32_t)S.tx_lo && tx < (int32_t)S.tx_hi;
+    ekey[c] = painted ? ck : sentinel_key(S.tiles_y);
+    eid[c] = c;
+    uint32_t g = gap_count[j];
+    if (g) {
+        uint32_t off = gap_offset[j];
+        uint4 carry = carry_after[j];
+        int32_t first = max(tx + 1, (int32_t)S.tx_lo);
+        for (uint32_t r = 0; r < g; ++r) {
+            uint64_t key = (ck & ~(0xFFFull << 41)) | ((uint64_t)(uint32_t)(first + (int32_t)r + 1) << 41);
+            ekey[n_cells + off + r] = key;
+            eid[n_cells + off + r] = n_cells + off + r;
+            gap_carry[off + r] = carry;
+        }
+    }
+}
+
+// Per painted tile: [begin, end) of its entries in the sorted entry list.
+__global__ void tile_range_kernel(PaintScene S, const uint64_t* __restrict__ ekey, uint32_t n_entries,
+                                  uint32_t* __restrict__ tile_begin, uint32_t* __restrict__ tile_end) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_entries) return;
+    uint64_t k = ekey[p];
+    if (key_ty(k) > S.tiles_y) return;  // sentinel (unpainted) entries sort last
+    uint64_t tile_bits = k >> 41;
+    uint32_t tid = (key_ty(k) - 1u) * S.tiles_x + (key_tx(k) - 1u);
+    if (p == 0 || (ekey[p - 1] >> 41) != tile_bits) tile_begin[tid] = p;
+    if (p + 1 == n_entries || (ekey[p + 1] >> 41) != tile_bits) tile_end[tid] = p + 1;
+}
+
+// ---------------------------------------------------------------------------
+// Host launchers
+// ---------------------------------------------------------------------------
+uint32_t cell_num_blocks(uint32_t n) { return (n + kCellTile - 1) / kCellTile; }
+
+void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* total, cudaStream_t st) {
+    uint32_t nb = cell_num_blocks(n);
+    cell_count_kernel<<<nb, kCellThreads, 0, st>>>(segs, n, block_counts);
+    launch_scan_u32(block_counts, nb, total, nullptr, st);
+}
+
+void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
+                       uint64_t* cell_key, uint32_t n_cells, cudaStream_t st) {
+    cell_write_kernel<<<cell_num_blocks(n), kCellThreads, 0, st>>>(segs, n, block_offsets, cell_start, cell_key, n_cells);
+}
+
+void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
+                       uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st) {
+    cell_cover_kernel<<<(n_cells + 3) / 4, 128, 0, st>>>(S, segs, cell_start, cell_key, n_cells, cell_cover, key2, perm);
+}
+
+// Largest values the three key fields can take in the pair sorts (sentinel
+// included); the sort plan only spends passes on bits below these bounds.
+static uint64_t field_bounds(const PaintScene& S, int pos_ty, int pos_tx, int pos_layer) {
+    uint64_t max_ty = S.tiles_y + 1u;                        // sentinel row
+    uint64_t max_tx = S.tx_hi;                               // biased tile_x of the last painted column
+    uint64_t max_layer = S.n_orders ? S.n_orders - 1u : 0u;
+    auto ones = [](uint64_t v) {  // all bits up to the highest set bit of v
+        uint64_t m = 0;
+        while (v) {
+            m = (m << 1) | 1u;
+            v >>= 1;
+        }
+        return m;
+    };
+    return (ones(max_ty) << pos_ty) | (ones(max_tx) << pos_tx) | (ones(max_layer) << pos_layer);
+}
+KeyLayout carry_sort_layout(const PaintScene& S) {
+    KeyLayout l = carry_key_layout();
+    l.extra_or = field_bounds(S, 53, 20, 32);
+    return l;
+}
+KeyLayout entry_sort_layout(const PaintScene& S) {
+    KeyLayout l = segment_key_layout();
+    l.extra_or = field_bounds(S, 53, 41, 20);
+    return l;
+}
+
+void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
+                       uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st) {
+    carry_scan_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_cover, n_cells, carry_in, carry_after,
+                                                              gap_count);
+}
+
+void launch_entry_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
+                       const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
+                       uint64_t* ekey, uint32_t* eid, uint4* gap_carry, cudaStream_t st) {
+    entry_fill_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset,
+                                                              n_cells, ekey, eid, gap_carry);
+}
+
+void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,
+                        uint32_t* tile_end, cudaStream_t st) {
+    size_t bytes = (size_t)S.tiles_x * S.tiles_y * sizeof(uint32_t);
+    cudaMemsetAsync(tile_begin, 0, bytes, st);
+    cudaMemsetAsync(tile_end, 0, bytes, st);
+    if (n_entries) tile_range_kernel<<<(n_entries + 255) / 256, 256, 0, st>>>(S, ekey, n_entries, tile_begin, tile_end);
+}
+
+
+}  // namespace forma

@@ -187,6 +187,8 @@ class Renderer {
 
     // Per-frame device scratch (high-water-mark allocations).
     DeviceBuffer<uint32_t> block_sums, totals;
+    DeviceBuffer<unsigned long long> key_or, zero_word;  // OR of the emitted keys; a word that stays 0
+    DeviceBuffer<unsigned long long> scan_state;
     DeviceBuffer<uint64_t> segs, segs_tmp;
     DeviceBuffer<uint8_t> sort_scratch;
     DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, tile_begin, tile_end;
@@ -409,7 +411,7 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     FORMA_CUDA_TRY(segs.reserve(n + 1));
     FORMA_CUDA_TRY(segs_tmp.reserve(n + 1));
     if (timer.ok) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[1], stream));  // end of line setup (count pass)
-    launch_raster_emit(ra, block_sums.ptr, segs.ptr, stream);
+    launch_raster_emit(ra, block_sums.ptr, segs.ptr, key_or.ptr, stream);
     launches += nb ? 1 : 0;
     FORMA_CUDA_TRY(cudaGetLastError());
     return FORMA_STATUS_OK;
@@ -483,7 +485,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     last_cells = last_entries = 0;
     if (n > 1) {
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n)));
-        launches += launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, sort_scratch.ptr, stream);
+        launches += launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, segment_key_layout(), key_or.ptr,
+                                      sort_scratch.ptr, stream);
         FORMA_CUDA_TRY(cudaGetLastError());
     }
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[3], stream));
@@ -517,15 +520,17 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(gap_count.reserve(n_cells));
         FORMA_CUDA_TRY(gap_offset.reserve(n_cells));
         launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, n_cells, stream);
-        launch_cell_cover(segs.ptr, cell_start.ptr, cell_key.ptr, n_cells, cell_cover.ptr, key2.ptr, perm.ptr, stream);
+        launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, n_cells, cell_cover.ptr, key2.ptr, perm.ptr, stream);
         launches += 2;
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_cells)));
-        launches += launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, n_cells, sort_scratch.ptr, stream);
+        launches += launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, n_cells, carry_sort_layout(S),
+                                      zero_word.ptr, sort_scratch.ptr, stream);
         launch_carry_scan(S, key2.ptr, perm.ptr, cell_cover.ptr, n_cells, carry_in.ptr, carry_after.ptr, gap_count.ptr,
                           stream);
         FORMA_CUDA_TRY(cudaMemcpyAsync(gap_offset.ptr, gap_count.ptr, n_cells * sizeof(uint32_t),
                                        cudaMemcpyDeviceToDevice, stream));
-        launch_scan_u32(gap_offset.ptr, n_cells, totals.ptr + 2, stream);
+        FORMA_CUDA_TRY(scan_state.reserve(scan_state_words(n_cells)));
+        launch_scan_u32(gap_offset.ptr, n_cells, totals.ptr + 2, scan_state.ptr, stream);
         launches += 2;
         st = read_total(2, &n_gaps);
         if (st) return st;
@@ -542,13 +547,14 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                           ekey.ptr, eid.ptr, gap_carry.ptr, stream);
         ++launches;
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_entries)));
-        launches += launch_radix_sort(ekey.ptr, ekey_tmp.ptr, eid.ptr, eid_tmp.ptr, n_entries, sort_scratch.ptr, stream);
+        launches += launch_radix_sort(ekey.ptr, ekey_tmp.ptr, eid.ptr, eid_tmp.ptr, n_entries, entry_sort_layout(S),
+                                      zero_word.ptr, sort_scratch.ptr, stream);
     }
     launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
     launches += n_entries ? 1 : 0;
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
     launch_paint(S, segs.ptr, ekey.ptr, eid.ptr, cell_start.ptr, carry_in.ptr, gap_carry.ptr, n_cells, tile_begin.ptr,
-                 tile_end.ptr, eflags.ptr, fb, stream);
+                 tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[5], stream));
@@ -847,7 +853,10 @@ forma_renderer* forma_renderer_new(int device_ordinal) {
     }
     forma_renderer* r = new forma_renderer();
     r->r.device = device_ordinal;
-    if (cudaMallocHost(&r->r.pinned_totals, 4 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(4) != cudaSuccess) {
+    if (cudaMallocHost(&r->r.pinned_totals, 4 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(4) != cudaSuccess ||
+        r->r.key_or.reserve(1) != cudaSuccess || r->r.zero_word.reserve(1) != cudaSuccess ||
+        cudaMemset(r->r.key_or.ptr, 0, r->r.key_or.capacity * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(r->r.zero_word.ptr, 0, r->r.zero_word.capacity * sizeof(unsigned long long)) != cudaSuccess) {
         set_error("allocation of renderer state failed");
         delete r;
         return nullptr;
@@ -954,7 +963,8 @@ int forma_renderer_sort_u64(forma_renderer* r, uint64_t* keys, uint64_t n) {
     FORMA_CUDA_TRY(R.segs_tmp.reserve(n));
     FORMA_CUDA_TRY(R.sort_scratch.reserve(radix_scratch_bytes((uint32_t)n)));
     FORMA_CUDA_TRY(cudaMemcpyAsync(R.segs.ptr, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, R.stream));
-    R.launches += launch_radix_sort(R.segs.ptr, R.segs_tmp.ptr, nullptr, nullptr, (uint32_t)n, R.sort_scratch.ptr, R.stream);
+    R.launches += launch_radix_sort(R.segs.ptr, R.segs_tmp.ptr, nullptr, nullptr, (uint32_t)n, segment_key_layout(), nullptr,
+                                    R.sort_scratch.ptr, R.stream);
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaMemcpyAsync(keys, R.segs.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, R.stream));
     FORMA_CUDA_TRY(cudaStreamSynchronize(R.stream));

@@ -97,8 +97,27 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def tune_cpu_threads(api, render_once):
+    """The CPU port scales poorly past the physical cores / one NUMA node on
+    some hosts: try a few OpenMP thread counts (2 frames each) and keep the best,
+    so the baseline uses "all the host threads it can use" to its advantage."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 24, 32, 48, 64, 96, 128, 192, 256, ncpu, ncpu // 2) if 1 <= c <= ncpu})
+    best, best_dt = cands[-1], float("inf")
+    for c in cands:
+        api.hooks.fo_set_num_threads(c)
+        render_once()
+        t0 = time.perf_counter()
+        render_once()
+        dt = time.perf_counter() - t0
+        if dt < best_dt:
+            best, best_dt = c, dt
+    api.hooks.fo_set_num_threads(best)
+    return best, ncpu
+
+
 def run_reference(args):
-    """CPU arm: the oracle (port of forma's CPU path) on all host threads."""
+    """CPU arm: the oracle (port of forma's CPU path) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -109,6 +128,7 @@ def run_reference(args):
     r = api.Renderer()
     buf = np.zeros(w * h * 4, np.uint8)
     clear = Color(1.0, 1.0, 1.0, 0.0)
+    tune_cpu_threads(api, lambda: r.render(comp, buf, w, h, RGBA, clear))
     for _ in range(args.warmup):
         t = r.render(comp, buf, w, h, RGBA, clear)
     t0 = time.perf_counter()
@@ -301,6 +321,7 @@ def cpu_baseline(args):
     r = api.Renderer()
     buf = np.zeros(w * h * 4, np.uint8)
     clear = Color(1.0, 1.0, 1.0, 0.0)
+    tune_cpu_threads(api, lambda: r.render(comp, buf, w, h, RGBA, clear))
     r.render(comp, buf, w, h, RGBA, clear)
     r.render(comp, buf, w, h, RGBA, clear)
     n, t0, stages = 0, time.perf_counter(), np.zeros(4)

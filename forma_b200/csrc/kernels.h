@@ -27,10 +27,10 @@ void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const Flatt
                          float* x, float* y, uint32_t* gid, cudaStream_t stream);
 uint32_t raster_num_blocks(uint32_t n_points);
 // block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
-void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, cudaStream_t stream);
-// key_or[0] receives the OR of all emitted keys.
-void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out,
-                        unsigned long long* key_or, cudaStream_t stream);
+// max_tile[0..1] = largest biased tile_x / tile_y any emitted segment can carry.
+void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, uint32_t* max_tile,
+                       cudaStream_t stream);
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream);
 // In-place exclusive scan of n u32 values; total[0] = sum. `state` (scan_state_words(n)
 // u64 words) enables the multi-CTA look-back scan for large n; nullptr = one CTA.
 size_t scan_state_words(uint32_t n);
@@ -46,15 +46,32 @@ void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long 
 struct KeyLayout {
     uint32_t pos[3];
     uint32_t maxw[3];
-    uint64_t extra_or;
 };
-inline KeyLayout segment_key_layout() { return KeyLayout{{20, 41, 53}, {21, 12, 11}, 0}; }   // ty | tx | layer
-inline KeyLayout carry_key_layout() { return KeyLayout{{20, 32, 53}, {12, 21, 11}, 0}; }     // ty | layer | tx
+inline KeyLayout segment_key_layout() { return KeyLayout{{20, 41, 53}, {21, 12, 11}}; }   // ty | tx | layer
+inline KeyLayout carry_key_layout() { return KeyLayout{{20, 32, 53}, {12, 21, 11}}; }     // ty | layer | tx
+
+constexpr int kMaxSortPasses = 6;  // ceil(44 / 8)
+// One digit = up to three bit runs of the key, concatenated.
+struct DigitSpec {
+    uint8_t shift[3];
+    uint8_t width[3];
+    uint8_t lsh[3];
+    uint8_t bits;
+};
+struct SortPlan {
+    uint32_t n_passes;
+    uint32_t total_bits;
+    DigitSpec pass[kMaxSortPasses];
+};
+// bound[f] = largest value field f (least significant first) takes in any key.
+SortPlan make_sort_plan(const KeyLayout& layout, const uint64_t bound[3]);
+struct SortResult {
+    int launches;
+    bool in_tmp;  // the sorted data is in keys_tmp / vals_tmp (odd number of passes)
+};
 size_t radix_scratch_bytes(uint32_t n);
-// key_or_device: device word holding the OR of all keys, or nullptr to have the sort compute it.
-int launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
-                      const KeyLayout& layout, const unsigned long long* key_or_device, void* scratch,
-                      cudaStream_t stream);
+SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
+                             const SortPlan& plan, void* scratch, cudaStream_t stream);
 
 // ---- kernels_paint.cu -------------------------------------------------------
 struct PaintScene {
@@ -79,9 +96,9 @@ void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_o
                        uint64_t* cell_key, uint32_t n_cells, cudaStream_t st);
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
                        uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st);
-// Bounds of the keys of the painter's two pair sorts (host-known).
-KeyLayout carry_sort_layout(const PaintScene& S);
-KeyLayout entry_sort_layout(const PaintScene& S);
+// Plans of the painter's two pair sorts (their key bounds are host-known).
+SortPlan carry_sort_plan(const PaintScene& S);
+SortPlan entry_sort_plan(const PaintScene& S);
 void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
                        uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st);
 void launch_entry_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,

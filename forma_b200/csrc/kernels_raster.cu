@@ -127,10 +127,34 @@ __device__ __forceinline__ LineParams line_setup(const RasterArgs& A, uint32_t i
 constexpr int kRasterThreads = 256;
 
 // Pass 1: per-CTA sum of line lengths.
-__global__ void __launch_bounds__(kRasterThreads) line_count_kernel(RasterArgs A, uint32_t* __restrict__ block_sums) {
+// Also tracks the largest (biased) tile coordinates any pixel segment can take,
+// so that the sort only spends passes on key bits that can be set.
+__global__ void __launch_bounds__(kRasterThreads) line_count_kernel(RasterArgs A, uint32_t* __restrict__ block_sums,
+                                                                  uint32_t* __restrict__ max_tile /*[2]: x, y*/) {
     __shared__ uint32_t warp_sums[kRasterThreads / 32];
     uint32_t i = blockIdx.x * kRasterThreads + threadIdx.x;
-    uint32_t len = line_setup(A, i).length;
+    const LineParams L = line_setup(A, i);
+    uint32_t len = L.length;
+    {
+        uint32_t bx = 0, by = 0;
+        if (len) {
+            // Sub-pixel end points -> tile (>> 8) -> bias (+1) -> one tile of slack for rounding.
+            float ex = fmaxf(L.x0, L.x0 + L.dx), ey = fmaxf(L.y0, L.y0 + L.dy);
+            int32_t tx = ((int32_t)floorf(fminf(ex, 3.0e7f) + 0.5f) >> 8) + 2;
+            int32_t ty = ((int32_t)floorf(fminf(ey, 3.0e7f) + 0.5f) >> 8) + 2;
+            bx = (uint32_t)min(max(tx, 0), 4095);
+            by = (uint32_t)min(max(ty, 0), 2047);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bx = max(bx, __shfl_xor_sync(kFullMask, bx, o));
+            by = max(by, __shfl_xor_sync(kFullMask, by, o));
+        }
+        if (lane_id() == 0) {
+            if (bx) atomicMax(&max_tile[0], bx);
+            if (by) atomicMax(&max_tile[1], by);
+        }
+    }
     uint32_t incl = warp_inclusive_scan(len);
     if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
     __syncthreads();
@@ -207,8 +231,7 @@ struct SharedLines {
 
 // Pass 2: recompute the CTA's 256 lines, then each warp expands its 32 lines.
 __global__ void __launch_bounds__(kRasterThreads)
-    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out,
-                       unsigned long long* __restrict__ key_or) {
+    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out) {
     __shared__ SharedLines S;
     __shared__ uint32_t warp_sums[kRasterThreads / 32];
     const uint32_t t = threadIdx.x;
@@ -233,7 +256,6 @@ __global__ void __launch_bounds__(kRasterThreads)
     for (uint32_t w = 0; w < warp; ++w) warp_base += warp_sums[w];
     const uint32_t warp_total = warp_sums[warp];
     const uint32_t* excl = S.excl + warp * 32u;
-    uint64_t or_acc = 0;  // OR of the emitted keys: tells the sort which key bits are in use
 
     for (uint32_t s = lane; s < warp_total; s += 32u) {
         // Largest j in [0, 32) with excl[j] <= s (zero-length lines share their
@@ -273,11 +295,7 @@ __global__ void __launch_bounds__(kRasterThreads)
         uint64_t v = (ty << 53) | (tx << 41) | ((uint64_t)(S.order[li] & 0x1FFFFFu) << 20) | ((uint64_t)local_x << 16) |
                      ((uint64_t)local_y << 12) | ((uint64_t)(dam & 0x3Fu) << 6) | ((uint64_t)((uint32_t)cover & 0x3Fu));
         out[(uint64_t)warp_base + s] = v;
-        or_acc |= v;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) or_acc |= __shfl_xor_sync(kFullMask, or_acc, o);
-    if (lane == 0 && or_acc) atomicOr(key_or, (unsigned long long)or_acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -291,22 +309,22 @@ void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const Flatt
 
 uint32_t raster_num_blocks(uint32_t n_points) { return n_points ? (n_points + kRasterThreads - 1) / kRasterThreads : 0; }
 
-void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, cudaStream_t stream) {
+void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, uint32_t* max_tile,
+                       cudaStream_t stream) {
     uint32_t nb = raster_num_blocks(args.n_points);
+    cudaMemsetAsync(max_tile, 0, 2 * sizeof(uint32_t), stream);
     if (!nb) {
         cudaMemsetAsync(total, 0, sizeof(uint32_t), stream);
         return;
     }
-    line_count_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_sums);
+    line_count_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_sums, max_tile);
     scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
 }
 
-void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out,
-                        unsigned long long* key_or, cudaStream_t stream) {
-    cudaMemsetAsync(key_or, 0, sizeof(unsigned long long), stream);
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream) {
     uint32_t nb = raster_num_blocks(args.n_points);
     if (!nb) return;
-    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out, key_or);
+    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out);
 }
 
 // Multi-CTA exclusive scan (single pass, decoupled look-back): CTA = 2048

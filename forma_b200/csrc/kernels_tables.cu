@@ -97,26 +97,26 @@ __global__ void __launch_bounds__(kCellThreads)
 __global__ void cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
                                   const uint64_t* __restrict__ cell_key, uint32_t n_cells, uint4* __restrict__ cell_cover,
                                   uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
-    // One warp per cell: lanes stride over the cell's (contiguous) segments with
-    // coalesced loads, then the packed partial sums are combined with shuffles.
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_cells) return;
-    const uint64_t ck = cell_key[c];
-    {
+    // Eight lanes per cell (a cell holds ~20-25 segments on average): the lanes
+    // stride over the cell's contiguous segments (64 B per step), then the packed
+    // partial sums are combined with shuffles inside the 8-lane group.
+    const uint32_t sub = threadIdx.x & 7u;
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = c < n_cells;
+    uint64_t ck = 0;
+    bool relevant = false;
+    uint32_t s0 = 0, s1 = 0;
+    if (live) {
+        ck = cell_key[c];
         int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
-        if (ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi) {
-            if (lane == 0) {
-                perm[c] = c;
-                key2[c] = sentinel_key(S.tiles_y);
-                cell_cover[c] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            return;
+        relevant = !(ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi);
+        if (relevant) {
+            s0 = cell_start[c];
+            s1 = cell_start[c + 1];
         }
     }
-    const uint32_t s0 = cell_start[c], s1 = cell_start[c + 1];
     uint32_t acc[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t i = s0 + lane; i < s1; i += 32u) {
+    for (uint32_t i = s0 + sub; i < s1; i += 8u) {
         uint64_t s = segs[i];
         uint32_t ly = (uint32_t)(s >> 12) & 15u;
         uint32_t cv = (uint32_t)s & 0x3Fu;
@@ -128,14 +128,14 @@ __global__ void cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ seg
     }
     __syncwarp();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 4; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[k] = __vadd4(acc[k], __shfl_xor_sync(kFullMask, acc[k], o));
     }
-    if (lane == 0) {
+    if (live && sub == 0) {
         perm[c] = c;
         cell_cover[c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-        key2[c] = make_key2(ck);
+        key2[c] = relevant ? make_key2(ck) : sentinel_key(S.tiles_y);
     }
 }
 
@@ -248,34 +248,19 @@ void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_o
 
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
                        uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st) {
-    cell_cover_kernel<<<(n_cells + 3) / 4, 128, 0, st>>>(S, segs, cell_start, cell_key, n_cells, cell_cover, key2, perm);
+    cell_cover_kernel<<<(n_cells + 31) / 32, 256, 0, st>>>(S, segs, cell_start, cell_key, n_cells, cell_cover, key2, perm);
 }
 
 // Largest values the three key fields can take in the pair sorts (sentinel
 // included); the sort plan only spends passes on bits below these bounds.
-static uint64_t field_bounds(const PaintScene& S, int pos_ty, int pos_tx, int pos_layer) {
-    uint64_t max_ty = S.tiles_y + 1u;                        // sentinel row
-    uint64_t max_tx = S.tx_hi;                               // biased tile_x of the last painted column
-    uint64_t max_layer = S.n_orders ? S.n_orders - 1u : 0u;
-    auto ones = [](uint64_t v) {  // all bits up to the highest set bit of v
-        uint64_t m = 0;
-        while (v) {
-            m = (m << 1) | 1u;
-            v >>= 1;
-        }
-        return m;
-    };
-    return (ones(max_ty) << pos_ty) | (ones(max_tx) << pos_tx) | (ones(max_layer) << pos_layer);
+SortPlan carry_sort_plan(const PaintScene& S) {  // fields, least significant first: tile_x, layer, tile_y
+    const uint64_t bound[3] = {S.tx_hi /* biased tile_x of the last painted column */,
+                               S.n_orders ? S.n_orders - 1u : 0u, S.tiles_y + 1u /* sentinel row */};
+    return make_sort_plan(carry_key_layout(), bound);
 }
-KeyLayout carry_sort_layout(const PaintScene& S) {
-    KeyLayout l = carry_key_layout();
-    l.extra_or = field_bounds(S, 53, 20, 32);
-    return l;
-}
-KeyLayout entry_sort_layout(const PaintScene& S) {
-    KeyLayout l = segment_key_layout();
-    l.extra_or = field_bounds(S, 53, 41, 20);
-    return l;
+SortPlan entry_sort_plan(const PaintScene& S) {  // layer, tile_x, tile_y
+    const uint64_t bound[3] = {S.n_orders ? S.n_orders - 1u : 0u, S.tx_hi, S.tiles_y + 1u};
+    return make_sort_plan(segment_key_layout(), bound);
 }
 
 void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,

@@ -187,8 +187,14 @@ class Renderer {
 
     // Per-frame device scratch (high-water-mark allocations).
     DeviceBuffer<uint32_t> block_sums, totals;
-    DeviceBuffer<unsigned long long> key_or, zero_word;  // OR of the emitted keys; a word that stays 0
     DeviceBuffer<unsigned long long> scan_state;
+    SortPlan segment_plan{};  // digits of the main sort, from the bounds seen by the line-setup pass
+
+    template <class T>
+    static void swap_buffers(DeviceBuffer<T>& a, DeviceBuffer<T>& b) {
+        std::swap(a.ptr, b.ptr);
+        std::swap(a.capacity, b.capacity);
+    }
     DeviceBuffer<uint64_t> segs, segs_tmp;
     DeviceBuffer<uint8_t> sort_scratch;
     DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, tile_begin, tile_end;
@@ -397,11 +403,17 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     ra.band_hi = band_hi;
     uint32_t nb = raster_num_blocks(ra.n_points);
     FORMA_CUDA_TRY(block_sums.reserve(nb + 1));
-    launch_line_count(ra, block_sums.ptr, totals.ptr + 0, stream);
+    launch_line_count(ra, block_sums.ptr, totals.ptr + 0, totals.ptr + 4, stream);
     launches += nb ? 2 : 0;
     uint32_t n = 0;
-    int st = read_total(0, &n);
-    if (st) return st;
+    // One read-back: segment count + the largest tile coordinates (totals[4..5]).
+    FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals, totals.ptr, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    n = pinned_totals[0];
+    {
+        const uint64_t bound[3] = {comp.n_orders ? comp.n_orders - 1u : 0u, pinned_totals[4], pinned_totals[5]};
+        segment_plan = make_sort_plan(segment_key_layout(), bound);  // layer, tile_x, tile_y
+    }
     *n_out = n;
     last_segments = n;
     if (n >= (1u << 30)) {
@@ -411,7 +423,7 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     FORMA_CUDA_TRY(segs.reserve(n + 1));
     FORMA_CUDA_TRY(segs_tmp.reserve(n + 1));
     if (timer.ok) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[1], stream));  // end of line setup (count pass)
-    launch_raster_emit(ra, block_sums.ptr, segs.ptr, key_or.ptr, stream);
+    launch_raster_emit(ra, block_sums.ptr, segs.ptr, stream);
     launches += nb ? 1 : 0;
     FORMA_CUDA_TRY(cudaGetLastError());
     return FORMA_STATUS_OK;
@@ -485,8 +497,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     last_cells = last_entries = 0;
     if (n > 1) {
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n)));
-        launches += launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, segment_key_layout(), key_or.ptr,
-                                      sort_scratch.ptr, stream);
+        SortResult sr = launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, segment_plan, sort_scratch.ptr, stream);
+        launches += sr.launches;
+        if (sr.in_tmp) swap_buffers(segs, segs_tmp);
         FORMA_CUDA_TRY(cudaGetLastError());
     }
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[3], stream));
@@ -523,8 +536,15 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, n_cells, cell_cover.ptr, key2.ptr, perm.ptr, stream);
         launches += 2;
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_cells)));
-        launches += launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, n_cells, carry_sort_layout(S),
-                                      zero_word.ptr, sort_scratch.ptr, stream);
+        {
+            SortResult sr = launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, n_cells, carry_sort_plan(S),
+                                              sort_scratch.ptr, stream);
+            launches += sr.launches;
+            if (sr.in_tmp) {
+                swap_buffers(key2, key2_tmp);
+                swap_buffers(perm, perm_tmp);
+            }
+        }
         launch_carry_scan(S, key2.ptr, perm.ptr, cell_cover.ptr, n_cells, carry_in.ptr, carry_after.ptr, gap_count.ptr,
                           stream);
         FORMA_CUDA_TRY(cudaMemcpyAsync(gap_offset.ptr, gap_count.ptr, n_cells * sizeof(uint32_t),
@@ -547,8 +567,15 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                           ekey.ptr, eid.ptr, gap_carry.ptr, stream);
         ++launches;
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_entries)));
-        launches += launch_radix_sort(ekey.ptr, ekey_tmp.ptr, eid.ptr, eid_tmp.ptr, n_entries, entry_sort_layout(S),
-                                      zero_word.ptr, sort_scratch.ptr, stream);
+        {
+            SortResult sr = launch_radix_sort(ekey.ptr, ekey_tmp.ptr, eid.ptr, eid_tmp.ptr, n_entries, entry_sort_plan(S),
+                                              sort_scratch.ptr, stream);
+            launches += sr.launches;
+            if (sr.in_tmp) {
+                swap_buffers(ekey, ekey_tmp);
+                swap_buffers(eid, eid_tmp);
+            }
+        }
     }
     launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
     launches += n_entries ? 1 : 0;
@@ -853,10 +880,8 @@ forma_renderer* forma_renderer_new(int device_ordinal) {
     }
     forma_renderer* r = new forma_renderer();
     r->r.device = device_ordinal;
-    if (cudaMallocHost(&r->r.pinned_totals, 4 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(4) != cudaSuccess ||
-        r->r.key_or.reserve(1) != cudaSuccess || r->r.zero_word.reserve(1) != cudaSuccess ||
-        cudaMemset(r->r.key_or.ptr, 0, r->r.key_or.capacity * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(r->r.zero_word.ptr, 0, r->r.zero_word.capacity * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMallocHost(&r->r.pinned_totals, 8 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(8) != cudaSuccess ||
+        cudaMemset(r->r.totals.ptr, 0, r->r.totals.capacity * sizeof(uint32_t)) != cudaSuccess) {
         set_error("allocation of renderer state failed");
         delete r;
         return nullptr;
@@ -963,8 +988,14 @@ int forma_renderer_sort_u64(forma_renderer* r, uint64_t* keys, uint64_t n) {
     FORMA_CUDA_TRY(R.segs_tmp.reserve(n));
     FORMA_CUDA_TRY(R.sort_scratch.reserve(radix_scratch_bytes((uint32_t)n)));
     FORMA_CUDA_TRY(cudaMemcpyAsync(R.segs.ptr, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, R.stream));
-    R.launches += launch_radix_sort(R.segs.ptr, R.segs_tmp.ptr, nullptr, nullptr, (uint32_t)n, segment_key_layout(), nullptr,
-                                    R.sort_scratch.ptr, R.stream);
+    // The caller's keys are on the host: take the field bounds from their OR.
+    uint64_t all = 0;
+    for (uint64_t i = 0; i < n; ++i) all |= keys[i];
+    const uint64_t bound[3] = {(all >> 20) & 0x1FFFFFull, (all >> 41) & 0xFFFull, (all >> 53) & 0x7FFull};
+    SortResult sr = launch_radix_sort(R.segs.ptr, R.segs_tmp.ptr, nullptr, nullptr, (uint32_t)n,
+                                      make_sort_plan(segment_key_layout(), bound), R.sort_scratch.ptr, R.stream);
+    R.launches += sr.launches;
+    if (sr.in_tmp) Renderer::swap_buffers(R.segs, R.segs_tmp);
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaMemcpyAsync(keys, R.segs.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, R.stream));
     FORMA_CUDA_TRY(cudaStreamSynchronize(R.stream));

@@ -212,6 +212,12 @@ int fo_num_threads() {
 #endif
 }
 
+void fo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 void* fo_path_builder_new() { return new PathBuilder(); }
 void fo_path_builder_free(void* pb) { delete (PathBuilder*)pb; }
 void fo_path_builder_move_to(void* pb, float x, float y) { ((PathBuilder*)pb)->move_to({x, y}); }

@@ -132,6 +132,7 @@ constexpr int kRasterThreads = 256;
 __global__ void __launch_bounds__(kRasterThreads) line_count_kernel(RasterArgs A, uint32_t* __restrict__ block_sums,
                                                                   uint32_t* __restrict__ max_tile /*[2]: x, y*/) {
     __shared__ uint32_t warp_sums[kRasterThreads / 32];
+    __shared__ uint32_t warp_max[2][kRasterThreads / 32];
     uint32_t i = blockIdx.x * kRasterThreads + threadIdx.x;
     const LineParams L = line_setup(A, i);
     uint32_t len = L.length;
@@ -151,17 +152,24 @@ __global__ void __launch_bounds__(kRasterThreads) line_count_kernel(RasterArgs A
             by = max(by, __shfl_xor_sync(kFullMask, by, o));
         }
         if (lane_id() == 0) {
-            if (bx) atomicMax(&max_tile[0], bx);
-            if (by) atomicMax(&max_tile[1], by);
+            warp_max[0][threadIdx.x >> 5] = bx;
+            warp_max[1][threadIdx.x >> 5] = by;
         }
     }
     uint32_t incl = warp_inclusive_scan(len);
     if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t s = 0;
-        for (int w = 0; w < kRasterThreads / 32; ++w) s += warp_sums[w];
+        uint32_t s = 0, bx = 0, by = 0;
+        for (int w = 0; w < kRasterThreads / 32; ++w) {
+            s += warp_sums[w];
+            bx = max(bx, warp_max[0][w]);
+            by = max(by, warp_max[1][w]);
+        }
         block_sums[blockIdx.x] = s;
+        // Same-address atomics serialise in L2: only raise the maximum when needed.
+        if (bx > *(volatile uint32_t*)&max_tile[0]) atomicMax(&max_tile[0], bx);
+        if (by > *(volatile uint32_t*)&max_tile[1]) atomicMax(&max_tile[1], by);
     }
 }
 

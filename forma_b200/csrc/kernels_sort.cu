@@ -273,8 +273,195 @@ __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Persistent, TMA-staged variant for large key-only sorts (the main pixel
+// segment sort). CTA c owns tiles c, c + G, c + 2G, ... (G = resident CTAs), so
+// every tile's predecessors are being processed in the same or an earlier
+// round. While tile k is ranked and scattered, the keys of tile k + G are
+// already in flight: one thread issues a 32 KB `cp.async.bulk` (1-D TMA) into
+// the other shared-memory stage and the CTA later waits on its mbarrier. The
+// stage that delivered tile k doubles as the digit-order staging buffer of the
+// write-out, so the loads of the next tile, the ranking of this one and the
+// stores of this one overlap inside one CTA instead of relying on other CTAs.
+// ---------------------------------------------------------------------------
+constexpr int kPItems = 16;
+constexpr int kPTile = kSortThreads * kPItems;  // 4096 keys = 32 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+struct PersistentSmem {
+    uint64_t stage[2][kPTile];              // 2 x 32 KB
+    uint32_t warp_hist[kSortWarps][kRadix]; // 8 KB
+    uint32_t digit_start[kRadix];
+    uint32_t global_base[kRadix];
+    uint32_t warp_tot[kSortWarps];
+    uint64_t bar[2];
+};
+
+__global__ void __launch_bounds__(kSortThreads, 2)
+    onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
+                               const uint32_t* __restrict__ global_offsets, uint32_t* __restrict__ lb, uint32_t tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PersistentSmem& S = *reinterpret_cast<PersistentSmem*>(smem_raw);
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t G = gridDim.x;
+    if (t == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t tile, uint32_t st) {  // thread 0 only
+        uint32_t base = tile * (uint32_t)kPTile;
+        uint32_t valid = min((uint32_t)kPTile, n - base);
+        uint32_t bytes = ((valid + 1u) & ~1u) * 8u;  // multiple of 16 B (the buffers have one key of slack)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.bar[st], bytes);
+        tma_load_1d(&S.stage[st][0], keys_in + base, bytes, &S.bar[st]);
+    };
+
+    uint32_t tile = blockIdx.x;
+    if (tile >= tiles) return;
+    if (t == 0) issue(tile, 0);
+    uint32_t st = 0, phase0 = 0, phase1 = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t max_digit = (1u << spec.bits) - 1u;
+
+    for (; tile < tiles; tile += G, st ^= 1u) {
+        if (t == 0 && tile + G < tiles) issue(tile + G, st ^ 1u);
+        for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&S.warp_hist[0][0])[i] = 0;
+        const uint32_t base = tile * (uint32_t)kPTile;
+        const uint32_t valid = min((uint32_t)kPTile, n - base);
+        if (st == 0) {
+            mbar_wait(&S.bar[0], phase0);
+            phase0 ^= 1u;
+        } else {
+            mbar_wait(&S.bar[1], phase1);
+            phase1 ^= 1u;
+        }
+        uint64_t* stage = S.stage[st];
+
+        // Keys from the staged tile, warp-striped like the one-shot kernel.
+        uint64_t key[kPItems];
+        const uint32_t wofs = warp * (32u * kPItems);
+#pragma unroll
+        for (int i = 0; i < kPItems; ++i) key[i] = stage[wofs + i * 32u + lane];
+        __syncthreads();  // everybody has its keys (and the zeroed histograms are visible)
+
+        uint32_t rank[kPItems];
+#pragma unroll
+        for (int i = 0; i < kPItems; ++i) {
+            uint32_t slot = wofs + i * 32u + lane;
+            uint32_t d = slot < valid ? digit_of(key[i], spec) : max_digit;
+            uint32_t peers = __match_any_sync(kFullMask, d);
+            uint32_t leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(kFullMask, old, leader);
+            rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        uint32_t count = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t c = S.warp_hist[w][t];
+            S.warp_hist[w][t] = count;
+            count += c;
+        }
+        uint32_t* my_slot = lb + (size_t)tile * kRadix + t;
+        if (tile != 0) st_relaxed(my_slot, kFlagAggregate | count);
+        uint32_t incl = warp_inclusive_scan(count);
+        if (lane == 31) S.warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t dstart = incl - count;
+        for (uint32_t w = 0; w < warp; ++w) dstart += S.warp_tot[w];
+        S.digit_start[t] = dstart;
+        {
+            uint32_t prefix = 0;
+            int32_t p = (int32_t)tile - 1;
+            bool done = p < 0;
+            while (!done) {
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = (p - j >= 0) ? ld_relaxed(lb + (size_t)(p - j) * kRadix + t) : kFlagInclusive;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (done) break;
+                    uint32_t flag = v[j] & kFlagMask;
+                    if (flag == 0) {
+                        p -= j;
+                        goto retry;
+                    }
+                    prefix += v[j] & kValueMask;
+                    if (flag == kFlagInclusive) done = true;
+                }
+                p -= 4;
+            retry:;
+            }
+            st_relaxed(my_slot, kFlagInclusive | (prefix + count));
+            S.global_base[t] = global_offsets[t] + prefix - dstart;
+        }
+        __syncthreads();
+
+        // Digit-order staging in the buffer that delivered the tile, then coalesced write-out.
+#pragma unroll
+        for (int i = 0; i < kPItems; ++i) {
+            uint32_t d = rank[i] >> 16;
+            stage[S.digit_start[d] + S.warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPItems; ++k) {
+            uint32_t p = t + k * kSortThreads;
+            if (p < valid) {
+                uint64_t kk = stage[p];
+                keys_out[S.global_base[digit_of(kk, spec)] + p] = kk;
+            }
+        }
+        __syncthreads();  // the stage is free again: the next iteration may refill it by TMA
+    }
+}
+
 static uint32_t tiles_for(uint32_t n, int items) { return (n + kSortThreads * items - 1) / (kSortThreads * items); }
 static int items_for(uint32_t n) { return n >= (1u << 21) ? 16 : 4; }
+// FORMA_SORT_PERSISTENT=0 selects the one-shot pass kernel for A/B measurements.
+static bool persistent_sort_enabled() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("FORMA_SORT_PERSISTENT");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    return enabled == 1;
+}
 
 // scratch layout (u32 words): hist[6][256] | tile_counter[8] | lookback[6][tiles][256]
 size_t radix_scratch_bytes(uint32_t n) {
@@ -319,6 +506,30 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     if (vals) {
         if (items == 16) launch_passes<true, 16>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
         else launch_passes<true, 4>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
+    } else if (items == 16 && persistent_sort_enabled()) {
+        // Large key-only sort: persistent CTAs with TMA-staged tiles.
+        static int resident = 0;
+        if (!resident) {
+            cudaFuncSetAttribute(onesweep_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(PersistentSmem));
+            int per_sm = 0, sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onesweep_persistent_kernel, kSortThreads,
+                                                          sizeof(PersistentSmem));
+            resident = per_sm > 0 ? per_sm * sms : 0;
+        }
+        if (resident > 0) {
+            uint32_t grid = min(tiles, (uint32_t)resident);  // all CTAs must be co-resident (look-back)
+            for (uint32_t p = 0; p < plan.n_passes; ++p) {
+                const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
+                uint64_t* kout = (p & 1u) ? keys : keys_tmp;
+                onesweep_persistent_kernel<<<grid, kSortThreads, sizeof(PersistentSmem), stream>>>(
+                    kin, kout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tiles);
+            }
+        } else {
+            launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);
+        }
     } else {
         if (items == 16) launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);
         else launch_passes<false, 4>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);

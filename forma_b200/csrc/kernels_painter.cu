@@ -113,11 +113,43 @@ __device__ __forceinline__ void store_tile_solid(const PaintScene& S, uint8_t* f
 // conflicts when the lanes read back / re-zero their own cells).
 __device__ __forceinline__ uint32_t cell_index(uint32_t lx, uint32_t ly) { return (ly & 7u) * 32u + lx * 2u + (ly >> 3); }
 
+// One pixel of blend_at (cpu/painter/mod.rs:406-447) for any fill / blend
+// mode. Out of line on purpose: inlining it eight times per layer made the
+// kernel 15k instructions long.
+__device__ __noinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ st, const StopRec* __restrict__ stops,
+                                                   const uint16_t* __restrict__ texels, float fx, float fy, int l,
+                                                   float coverage, bool apply_clip, float clip, float4 dst) {
+    float fill[4];
+    if (st->fill_type == 0u) {
+        fill[0] = st->color[0]; fill[1] = st->color[1]; fill[2] = st->color[2]; fill[3] = st->color[3];
+    } else if (st->fill_type == 1u) {
+        gradient_at(*st, stops, fx, fy, l, fill);
+    } else {
+        texture_at(*st, texels, fx, fy, l, fill);
+    }
+    float sa = fill[3] * coverage;
+    if (apply_clip) sa *= clip;
+    float bl[3];
+    vblend::blend(st->blend_mode, dst.x, dst.y, dst.z, fill[0], fill[1], fill[2], bl);
+    float inv_dst_a = 1.0f - dst.w;
+    float inv_dst_a_src_a = inv_dst_a * sa;
+    float inv_src_a = 1.0f - sa;
+    float dst_a_src_a = dst.w * sa;
+    float cr = fmaf(fill[0], inv_dst_a_src_a, bl[0] * dst_a_src_a);
+    float cg = fmaf(fill[1], inv_dst_a_src_a, bl[1] * dst_a_src_a);
+    float cb = fmaf(fill[2], inv_dst_a_src_a, bl[2] * dst_a_src_a);
+    return make_float4(fmaf(dst.x, inv_src_a, cr), fmaf(dst.y, inv_src_a, cg), fmaf(dst.z, inv_src_a, cb),
+                       fmaf(dst.w, inv_src_a, sa));
+}
+
 constexpr int kPaintWarpsPerBlock = 2;
 
-__global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, 8) paint_kernel(PaintScene S, PaintInputs in, uint32_t n_tiles) {
+// kMinBlocks trades registers for resident warps (8 -> 128 regs, 10 -> 96 regs).
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_kernel(PaintScene S, PaintInputs in, uint32_t n_tiles) {
     __shared__ int32_t s_area[kPaintWarpsPerBlock][256];
     __shared__ int32_t s_cover[kPaintWarpsPerBlock][256];
+    __shared__ float s_clip[kPaintWarpsPerBlock][256];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     int32_t* area = s_area[warp];
     int32_t* cover = s_cover[warp];
@@ -261,9 +293,9 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, 8) paint_kernel(Pain
         }
         bool clip_active = false;
         uint32_t clip_last = 0;
-        float clip_mask[8];
-#pragma unroll
-        for (int l = 0; l < 8; ++l) clip_mask[l] = 0.0f;
+        // The clip mask lives in shared memory (lane-private slots l*32 + lane): it
+        // is only touched by tiles that contain clip layers.
+        float* clip_mask = s_clip[warp] + lane;
         const float fx = (float)(x + tx * 16u);
         const float fy = (float)(half * 8u + ty * 16u);
 
@@ -276,22 +308,25 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, 8) paint_kernel(Pain
                 my_flags = in.eflags[p0 + lane];
             }
             // Prefetch the first segment chunk of the first entry of this group.
-            EntryHdr cur = bcast_hdr(mine, 0);
-            uint32_t cur_flags = __shfl_sync(kFullMask, my_flags, 0);
+            uint32_t nflags = __shfl_sync(kFullMask, my_flags, 0);
             uint64_t pre = 0;
-            if (!(cur_flags & kFlagMaskedOut) && cur.seg0 + lane < cur.seg1) pre = in.segs[cur.seg0 + lane];
+            {
+                uint32_t s0 = __shfl_sync(kFullMask, mine.seg0, 0), s1 = __shfl_sync(kFullMask, mine.seg1, 0);
+                if (!(nflags & kFlagMaskedOut) && s0 + lane < s1) pre = in.segs[s0 + lane];
+            }
 
             for (uint32_t k = 0; k < cnt; ++k) {
-                const EntryHdr er = cur;
-                const uint32_t flags = cur_flags;
+                const uint32_t flags = nflags;
                 const uint64_t first_seg = pre;
-                if (k + 1 < cnt) {  // hand round the next header and start fetching its segments
-                    cur = bcast_hdr(mine, (int)k + 1);
-                    cur_flags = __shfl_sync(kFullMask, my_flags, (int)k + 1);
+                if (k + 1 < cnt) {  // start fetching the next entry's segments
+                    nflags = __shfl_sync(kFullMask, my_flags, (int)k + 1);
+                    uint32_t s0 = __shfl_sync(kFullMask, mine.seg0, (int)k + 1);
+                    uint32_t s1 = __shfl_sync(kFullMask, mine.seg1, (int)k + 1);
                     pre = 0;
-                    if (!(cur_flags & kFlagMaskedOut) && cur.seg0 + lane < cur.seg1) pre = in.segs[cur.seg0 + lane];
+                    if (!(nflags & kFlagMaskedOut) && s0 + lane < s1) pre = in.segs[s0 + lane];
                 }
                 if (flags & kFlagMaskedOut) continue;
+                const EntryHdr er = bcast_hdr(mine, (int)k);
                 const uint32_t fill_rule = meta_fill_rule(er.meta);
 
                 // acc_segment: scatter-add the cell's segments (cpu/painter/mod.rs:257-271).
@@ -360,7 +395,7 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, 8) paint_kernel(Pain
                         clip_last = er.layer + er.clip_layers;
                     }
 #pragma unroll
-                    for (int l = 0; l < 8; ++l) clip_mask[l] = cov[l];
+                    for (int l = 0; l < 8; ++l) clip_mask[l * 32] = cov[l];
                     continue;
                 }
                 const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
@@ -369,32 +404,36 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, 8) paint_kernel(Pain
 
                 const uint32_t mode = meta_blend(er.meta);
                 const uint32_t fill_type = meta_fill_type(er.meta);
+                // blend_at, mod.rs:406-447. The mode / fill dispatch is hoisted out of
+                // the pixel loop: a solid `Over` layer (by far the most common) is
+                // straight-line code; everything else goes through one out-of-line
+                // helper per pixel so that the kernel stays small enough for the
+                // instruction cache.
+                if (fill_type == 0u && mode == 0u) {
 #pragma unroll
-                for (int l = 0; l < 8; ++l) {
-                    float fill[4];
-                    if (fill_type == 0u) {
-                        fill[0] = er.color[0]; fill[1] = er.color[1]; fill[2] = er.color[2]; fill[3] = er.color[3];
-                    } else if (fill_type == 1u) {
-                        gradient_at(S.styles[er.slot], S.stops, fx, fy, l, fill);
-                    } else {
-                        texture_at(S.styles[er.slot], S.texels, fx, fy, l, fill);
+                    for (int l = 0; l < 8; ++l) {
+                        float sa = er.color[3] * cov[l];
+                        if (apply_clip) sa *= clip_mask[l * 32];
+                        float inv_dst_a_src_a = (1.0f - da[l]) * sa;
+                        float inv_src_a = 1.0f - sa;
+                        float dst_a_src_a = da[l] * sa;
+                        float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
+                        float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
+                        float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
+                        dr[l] = fmaf(dr[l], inv_src_a, cr);
+                        dg[l] = fmaf(dg[l], inv_src_a, cg);
+                        db[l] = fmaf(db[l], inv_src_a, cb);
+                        da[l] = fmaf(da[l], inv_src_a, sa);
                     }
-                    // blend_at, mod.rs:406-447
-                    float sa = fill[3] * cov[l];
-                    if (apply_clip) sa *= clip_mask[l];
-                    float bl[3];
-                    vblend::blend(mode, dr[l], dg[l], db[l], fill[0], fill[1], fill[2], bl);
-                    float inv_dst_a = 1.0f - da[l];
-                    float inv_dst_a_src_a = inv_dst_a * sa;
-                    float inv_src_a = 1.0f - sa;
-                    float dst_a_src_a = da[l] * sa;
-                    float cr = fmaf(fill[0], inv_dst_a_src_a, bl[0] * dst_a_src_a);
-                    float cg = fmaf(fill[1], inv_dst_a_src_a, bl[1] * dst_a_src_a);
-                    float cb = fmaf(fill[2], inv_dst_a_src_a, bl[2] * dst_a_src_a);
-                    dr[l] = fmaf(dr[l], inv_src_a, cr);
-                    dg[l] = fmaf(dg[l], inv_src_a, cg);
-                    db[l] = fmaf(db[l], inv_src_a, cb);
-                    da[l] = fmaf(da[l], inv_src_a, sa);
+                } else {
+                    const StyleRec* st = &S.styles[er.slot];
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        float4 d = make_float4(dr[l], dg[l], db[l], da[l]);
+                        float m = apply_clip ? clip_mask[l * 32] : 1.0f;
+                        d = blend_pixel_generic(st, S.stops, S.texels, fx, fy, l, cov[l], apply_clip, m, d);
+                        dr[l] = d.x; dg[l] = d.y; db[l] = d.z; da[l] = d.w;
+                    }
                 }
             }
         }
@@ -424,9 +463,13 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* eke
     PaintInputs in{segs, ekey, eid, cell_start, carry_in, gap_carry, n_cells, tile_begin, tile_end, eflags, framebuffer,
                    tile_counter};
     // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy.
-    static int blocks_per_sm = 0;
+    // FORMA_PAINT_REGS=128 selects the 128-register build (default: 96 registers).
+    static int blocks_per_sm = 0, variant = 0;
     if (!blocks_per_sm) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel, kPaintWarpsPerBlock * 32, 0);
+        const char* e = getenv("FORMA_PAINT_REGS");
+        variant = (e && atoi(e) >= 128) ? 8 : 10;
+        if (variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<10>, kPaintWarpsPerBlock * 32, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     int sms = 148, dev = 0;
@@ -434,7 +477,8 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* eke
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint32_t want = (uint32_t)(blocks_per_sm * sms);
     uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
-    paint_kernel<<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    if (variant == 8) paint_kernel<8><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    else paint_kernel<10><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
 }
 
 }  // namespace forma

@@ -47,6 +47,14 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {  // p must be 16-byte aligned
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -322,7 +330,8 @@ struct PersistentSmem {
 
 __global__ void __launch_bounds__(kSortThreads, 2)
     onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
-                               const uint32_t* __restrict__ global_offsets, uint32_t* __restrict__ lb, uint32_t tiles) {
+                               const uint32_t* __restrict__ global_offsets, uint32_t* __restrict__ lb, uint32_t tiles,
+                               uint32_t tiles_pad) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PersistentSmem& S = *reinterpret_cast<PersistentSmem*>(smem_raw);
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
@@ -396,8 +405,11 @@ __global__ void __launch_bounds__(kSortThreads, 2)
             S.warp_hist[w][t] = count;
             count += c;
         }
-        uint32_t* my_slot = lb + (size_t)tile * kRadix + t;
-        if (tile != 0) st_relaxed(my_slot, kFlagAggregate | count);
+        // The look-back table is digit-major here (row t = digit t, one word per
+        // tile, rows padded to a multiple of 4): a thread walks its own row with
+        // 16-byte loads, sixteen predecessors in flight at a time.
+        uint32_t* row = lb + (size_t)t * tiles_pad;
+        if (tile != 0) st_relaxed(row + tile, kFlagAggregate | count);
         uint32_t incl = warp_inclusive_scan(count);
         if (lane == 31) S.warp_tot[warp] = incl;
         __syncthreads();
@@ -406,28 +418,36 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         S.digit_start[t] = dstart;
         {
             uint32_t prefix = 0;
-            int32_t p = (int32_t)tile - 1;
+            int32_t p = (int32_t)tile - 1;  // next predecessor to consume
             bool done = p < 0;
             while (!done) {
-                uint32_t v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    v[j] = (p - j >= 0) ? ld_relaxed(lb + (size_t)(p - j) * kRadix + t) : kFlagInclusive;
+                const int32_t wbase = p & ~3;  // aligned window that contains p
+                uint4 w[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (done) break;
-                    uint32_t flag = v[j] & kFlagMask;
-                    if (flag == 0) {
-                        p -= j;
-                        goto retry;
-                    }
-                    prefix += v[j] & kValueMask;
-                    if (flag == kFlagInclusive) done = true;
+                    int32_t wb = wbase - 4 * j;
+                    w[j] = wb >= 0 ? ld_relaxed_v4(row + wb) : make_uint4(kFlagInclusive, kFlagInclusive, kFlagInclusive, kFlagInclusive);
                 }
-                p -= 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t e4[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+#pragma unroll
+                    for (int e = 3; e >= 0; --e) {
+                        const int32_t idx = wbase - 4 * j + e;
+                        if (done || idx > p) continue;
+                        const uint32_t flag = e4[e] & kFlagMask;
+                        if (flag == 0) {  // not published yet: reload from here
+                            p = idx;
+                            goto retry;
+                        }
+                        prefix += e4[e] & kValueMask;
+                        if (flag == kFlagInclusive) done = true;
+                    }
+                }
+                p = wbase - 16 + 3;
             retry:;
             }
-            st_relaxed(my_slot, kFlagInclusive | (prefix + count));
+            st_relaxed(row + tile, kFlagInclusive | (prefix + count));
             S.global_base[t] = global_offsets[t] + prefix - dstart;
         }
         __syncthreads();
@@ -465,7 +485,7 @@ static bool persistent_sort_enabled() {
 
 // scratch layout (u32 words): hist[6][256] | tile_counter[8] | lookback[6][tiles][256]
 size_t radix_scratch_bytes(uint32_t n) {
-    size_t words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)kMaxSortPasses * tiles_for(n, items_for(n)) * kRadix;
+    size_t words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)kMaxSortPasses * (tiles_for(n, items_for(n)) + 4) * kRadix;
     return words * sizeof(uint32_t) + 256;
 }
 
@@ -497,7 +517,8 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     uint32_t* hist = static_cast<uint32_t*>(scratch);
     uint32_t* counters = hist + kMaxSortPasses * kRadix;
     uint32_t* lookback = counters + 8;
-    size_t total_words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)plan.n_passes * tiles * kRadix;
+    const uint32_t tiles_pad = (tiles + 3u) & ~3u;
+    size_t total_words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)plan.n_passes * tiles_pad * kRadix;
     cudaMemsetAsync(scratch, 0, total_words * sizeof(uint32_t), stream);
     uint32_t hist_blocks = min(tiles_for(n, 16) * 4u, 148u * 8u);
     radix_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, plan, hist);
@@ -525,7 +546,7 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
                 const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
                 uint64_t* kout = (p & 1u) ? keys : keys_tmp;
                 onesweep_persistent_kernel<<<grid, kSortThreads, sizeof(PersistentSmem), stream>>>(
-                    kin, kout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tiles);
+                    kin, kout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles_pad * kRadix, tiles, tiles_pad);
             }
         } else {
             launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);

@@ -405,11 +405,14 @@ __global__ void __launch_bounds__(kSortThreads, 2)
             S.warp_hist[w][t] = count;
             count += c;
         }
-        // The look-back table is digit-major here (row t = digit t, one word per
-        // tile, rows padded to a multiple of 4): a thread walks its own row with
-        // 16-byte loads, sixteen predecessors in flight at a time.
-        uint32_t* row = lb + (size_t)t * tiles_pad;
-        if (tile != 0) st_relaxed(row + tile, kFlagAggregate | count);
+        // The look-back table is blocked in groups of four tiles:
+        // word(tile, digit) = ((tile / 4) * 256 + digit) * 4 + tile % 4, so one 16-byte
+        // load returns a digit's counters of four consecutive tiles while a tile's
+        // publication still goes to one compact 4 KB block. (A fully digit-major
+        // table was tried: every CTA then stores into the same 256 cache lines and
+        // the pass became 4x slower.)
+        auto slot_of = [&](uint32_t tl) { return lb + (((size_t)(tl >> 2) * kRadix + t) << 2) + (tl & 3u); };
+        if (tile != 0) st_relaxed(slot_of(tile), kFlagAggregate | count);
         uint32_t incl = warp_inclusive_scan(count);
         if (lane == 31) S.warp_tot[warp] = incl;
         __syncthreads();
@@ -426,7 +429,8 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     int32_t wb = wbase - 4 * j;
-                    w[j] = wb >= 0 ? ld_relaxed_v4(row + wb) : make_uint4(kFlagInclusive, kFlagInclusive, kFlagInclusive, kFlagInclusive);
+                    w[j] = wb >= 0 ? ld_relaxed_v4(slot_of((uint32_t)wb))
+                                   : make_uint4(kFlagInclusive, kFlagInclusive, kFlagInclusive, kFlagInclusive);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
                 p = wbase - 16 + 3;
             retry:;
             }
-            st_relaxed(row + tile, kFlagInclusive | (prefix + count));
+            st_relaxed(slot_of(tile), kFlagInclusive | (prefix + count));
             S.global_base[t] = global_offsets[t] + prefix - dstart;
         }
         __syncthreads();

@@ -475,3 +475,12 @@ def test_e2e_golden(api, lib, name):
     finally:
         lib.fo_set_recip_mode(0)
     assert np.array_equal(img, GOLD[name + "__cpu"]), name
+
+
+# --- layer cache / damage reuse: composition/mod.rs:520-563,1038-1382 --------------------------
+import cache_scenarios  # noqa: E402
+
+
+@pytest.mark.parametrize("scenario", cache_scenarios.SCENARIOS, ids=lambda f: f.__name__)
+def test_layer_cache_scenarios(api, scenario):
+    scenario(api)  # the reference's asserts live inside the scenario

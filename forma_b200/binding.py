@@ -623,9 +623,10 @@ class Renderer:
         return dict(zip(self.STAGES, list(out)))
 
     def counters(self) -> dict:
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 8)()
         self._api.renderer_counters(self._h, out)
-        return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries"), [int(v) for v in out]))
+        return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries", "written_tiles"),
+                        [int(v) for v in out]))
 
     def set_stream(self, cuda_stream: int) -> None:
         self._api.renderer_set_stream(self._h, C.c_void_p(cuda_stream))

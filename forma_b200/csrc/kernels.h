@@ -87,6 +87,12 @@ struct PaintScene {
     uint32_t tiles_x, tiles_y;    // ceil(width / 16), ceil(height / 16)
     uint32_t tx_lo, tx_hi;        // tile columns painted (crop), [lo, hi)
     uint32_t ty_lo, ty_hi;        // tile rows painted (crop ∩ band), [lo, hi)
+    // Layer cache (damage reuse, cpu/buffer/mod.rs:114-197); all null/0 without a cache.
+    const uint8_t* unchanged;     // per style slot: Layer::is_unchanged(cache_id)
+    uint2* cache_tiles;           // per tile: x = has_count<<31 | has_solid<<30 | layer_count(24), y = solid colour
+    uint32_t* written_list;       // optional: linear ids of the tiles this frame wrote (unordered)
+    uint32_t* written_count;      //           ... and how many
+    uint32_t clear_unchanged;     // previous clear colour == this frame's
 };
 
 uint32_t cell_num_blocks(uint32_t n);
@@ -110,5 +116,7 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* eke
                   const uint32_t* cell_start, const uint4* carry_in, const uint4* gap_carry, uint32_t n_cells,
                   const uint32_t* tile_begin, const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer,
                   uint32_t* tile_counter, cudaStream_t st);
+// Packs the tiles in S.written_list into `packed` (256 u32 per tile, row-major).
+void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st);
 
 }  // namespace forma

@@ -36,7 +36,7 @@ struct PaintInputs {
     uint32_t* tile_counter;
 };
 
-constexpr uint32_t kFlagHasSegs = 1, kFlagFull = 2, kFlagMaskedOut = 4, kFlagSkipClip = 8;
+constexpr uint32_t kFlagHasSegs = 1, kFlagFull = 2, kFlagMaskedOut = 4, kFlagSkipClip = 8, kFlagUnchanged = 16;
 
 // Per-entry header, one entry per lane.
 struct EntryHdr {
@@ -54,6 +54,7 @@ __device__ __forceinline__ uint32_t meta_func(uint32_t m) { return (m >> 1) & 1u
 __device__ __forceinline__ bool meta_is_clipped(uint32_t m) { return (m >> 2) & 1u; }
 __device__ __forceinline__ uint32_t meta_fill_type(uint32_t m) { return (m >> 3) & 3u; }
 __device__ __forceinline__ uint32_t meta_blend(uint32_t m) { return (m >> 5) & 15u; }
+__device__ __forceinline__ bool meta_unchanged(uint32_t m) { return (m >> 9) & 1u; }
 
 __device__ __forceinline__ EntryHdr load_hdr(const PaintScene& S, const PaintInputs& in, uint32_t p) {
     EntryHdr h;
@@ -70,7 +71,7 @@ __device__ __forceinline__ EntryHdr load_hdr(const PaintScene& S, const PaintInp
     h.slot = S.order_to_style[h.layer];
     const StyleRec& st = S.styles[h.slot];
     h.meta = (st.fill_rule & 1u) | ((st.func & 1u) << 1) | ((st.is_clipped ? 1u : 0u) << 2) | ((st.fill_type & 3u) << 3) |
-             ((st.blend_mode & 15u) << 5);
+             ((st.blend_mode & 15u) << 5) | ((S.unchanged && S.unchanged[h.slot]) ? (1u << 9) : 0u);
     h.clip_layers = st.clip_layers;
     h.color[0] = st.color[0];
     h.color[1] = st.color[1];
@@ -175,21 +176,46 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
 
         // ---- optimizer passes (layer_workbench/passes/*.rs) ------------------
         // Pass A: per-entry facts, 32 entries at a time.
-        bool any_clip = false;
+        bool any_clip = false, all_unchanged = true;
         for (uint32_t p0 = b; p0 < e; p0 += 32u) {
             uint32_t p = p0 + lane;
-            bool clipish = false;
+            bool clipish = false, changed = false;
             if (p < e) {
                 EntryHdr h = load_hdr(S, in, p);
                 uint32_t f = 0;
                 if (h.seg1 > h.seg0) f |= kFlagHasSegs;
                 else if (cover_is_full(h.carry, meta_fill_rule(h.meta))) f |= kFlagFull;  // layer_is_full, mod.rs:171-182
+                if (meta_unchanged(h.meta)) f |= kFlagUnchanged;
                 in.eflags[p] = (uint8_t)f;
                 clipish = meta_func(h.meta) == 1u || meta_is_clipped(h.meta);
+                changed = !meta_unchanged(h.meta);
             }
             any_clip |= __any_sync(kFullMask, clipish);
+            all_unchanged = all_unchanged && !__any_sync(kFullMask, changed);
         }
         __syncwarp();
+
+        // tile_unchanged pass (passes/tile_unchanged.rs:24-57) — only with a layer cache.
+        const bool use_cache = S.cache_tiles != nullptr;
+        uint32_t cache_x = 0, cache_solid = 0;
+        bool layers_were_removed = true;  // PassesSharedState::reset
+        if (use_cache) {
+            uint2 c = S.cache_tiles[tid];
+            const uint32_t layers = (e - b) & 0xFFFFFFu;
+            const bool had = (c.x >> 31) != 0u;
+            const uint32_t previous = c.x & 0xFFFFFFu;
+            cache_solid = c.y;
+            cache_x = (1u << 31) | (c.x & (1u << 30)) | layers;  // update_layer_count(Some(layers))
+            bool is_unchanged = false;
+            if (had) {
+                layers_were_removed = layers < previous;
+                is_unchanged = previous == layers && all_unchanged;
+            }
+            if (S.clear_unchanged && is_unchanged) {  // TileWriteOp::None
+                if (lane == 0) S.cache_tiles[tid] = make_uint2(cache_x, cache_solid);
+                continue;
+            }
+        }
 
         // Pass B: skip_trivial_clips (sequential; only tiles that contain clips).
         if (any_clip) {
@@ -232,10 +258,11 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
         uint32_t first_paint = b;  // MaskedVec::skip_until
         bool incomplete = false;   // an "interesting" incomplete cover at or above the opaque layer
         bool have_opaque = false;
+        bool visible_unchanged = !layers_were_removed;  // skip_fully_covered_layers.rs:38-47
         for (uint32_t hi = e; hi > b && !have_opaque;) {
             uint32_t lo = hi - b >= 32u ? hi - 32u : b;
             uint32_t p = lo + lane;
-            bool inc = false, cand = false;
+            bool inc = false, cand = false, changed = false;
             if (p < hi) {
                 uint32_t f = in.eflags[p];
                 if (!(f & kFlagMaskedOut)) {
@@ -243,19 +270,28 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                     bool clipped = st.func == 0u && st.is_clipped && !(f & kFlagSkipClip);
                     if (clipped || !(f & kFlagFull)) inc = true;
                     else if (st.func == 0u && st.fill_type == 0u && st.blend_mode == 0u && st.color[3] == 1.0f) cand = true;
+                    changed = !(f & kFlagUnchanged);
                 }
             }
             uint32_t cand_mask = __ballot_sync(kFullMask, cand);
             uint32_t inc_mask = __ballot_sync(kFullMask, inc);
+            uint32_t changed_mask = __ballot_sync(kFullMask, changed);
             if (cand_mask) {
                 uint32_t top = 31u - (uint32_t)__clz((int)cand_mask);
                 have_opaque = true;
                 first_paint = lo + top;
                 if (top < 31u && (inc_mask >> (top + 1u)) != 0u) incomplete = true;
-            } else if (inc_mask) {
-                incomplete = true;
+                if ((changed_mask >> top) != 0u) visible_unchanged = false;  // layers visited before the break
+            } else {
+                if (inc_mask) incomplete = true;
+                if (changed_mask) visible_unchanged = false;
             }
             hi = lo;
+        }
+        if (use_cache && have_opaque && !incomplete && visible_unchanged) {
+            // Everything visible is unchanged: nothing to draw (skip_fully_covered_layers.rs:86-89).
+            if (lane == 0) S.cache_tiles[tid] = make_uint2(cache_x, cache_solid);
+            continue;
         }
 
         if (!incomplete) {
@@ -280,9 +316,22 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 }
             }
             if (solid) {
-                store_tile_solid(S, in.framebuffer, tx, ty, lane, solid_to_srgb_bytes(dst, S.channels));
+                const uint32_t bytes = solid_to_srgb_bytes(dst, S.channels);
+                // CachedTile::convert_optimizer_op (cpu/painter/mod.rs:686-704): the same
+                // solid colour as last frame is not written again.
+                const bool same = use_cache && ((cache_x >> 30) & 1u) && cache_solid == bytes;
+                if (!same) store_tile_solid(S, in.framebuffer, tx, ty, lane, bytes);
+                if (lane == 0) {
+                    if (use_cache) S.cache_tiles[tid] = make_uint2(cache_x | (1u << 30), bytes);
+                    if (!same && S.written_list) S.written_list[atomicAdd(S.written_count, 1u)] = tid;
+                }
                 continue;
             }
+        }
+        if (lane == 0) {
+            // update_solid_color(None): the tile is painted
+            if (use_cache) S.cache_tiles[tid] = make_uint2(cache_x & ~(1u << 30), cache_solid);
+            if (S.written_list) S.written_list[atomicAdd(S.written_count, 1u)] = tid;
         }
 
         // ---- paint (layer_workbench/mod.rs:301-337, cpu/painter/mod.rs:290-347) ---
@@ -451,6 +500,34 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             }
         }
     }
+}
+
+// Packs the tiles named in `list` (written by paint_kernel) into 1 KB records,
+// row-major 16x16 RGBA8, so that a damaged frame costs a device->host copy
+// proportional to the damage. One warp per tile.
+__global__ void __launch_bounds__(256) gather_tiles_kernel(const uint8_t* __restrict__ fb, uint32_t stride, uint32_t width,
+                                                           uint32_t height, uint32_t tiles_x,
+                                                           const uint32_t* __restrict__ list,
+                                                           const uint32_t* __restrict__ count, uint32_t* __restrict__ out) {
+    const uint32_t n = *count;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5); i < n; i += gridDim.x * 8u) {
+        const uint32_t tid = list[i];
+        const uint32_t x0 = (tid % tiles_x) * 16u, y0 = (tid / tiles_x) * 16u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t p = (uint32_t)k * 32u + lane;  // pixel index in the tile, row-major
+            const uint32_t x = x0 + (p & 15u), y = y0 + (p >> 4);
+            uint32_t v = 0;
+            if (x < width && y < height) v = *reinterpret_cast<const uint32_t*>(fb + (size_t)y * stride + (size_t)x * 4u);
+            out[(size_t)i * 256u + p] = v;
+        }
+    }
+}
+
+void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st) {
+    gather_tiles_kernel<<<148 * 4, 256, 0, st>>>(framebuffer, S.stride, S.width, S.height, S.tiles_x, S.written_list,
+                                                  S.written_count, packed);
 }
 
 void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,

@@ -47,14 +47,6 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {  // p must be 16-byte aligned
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -330,8 +322,7 @@ struct PersistentSmem {
 
 __global__ void __launch_bounds__(kSortThreads, 2)
     onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
-                               const uint32_t* __restrict__ global_offsets, uint32_t* __restrict__ lb, uint32_t tiles,
-                               uint32_t tiles_pad) {
+                               const uint32_t* __restrict__ global_offsets, uint32_t* __restrict__ lb, uint32_t tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PersistentSmem& S = *reinterpret_cast<PersistentSmem*>(smem_raw);
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
@@ -405,14 +396,8 @@ __global__ void __launch_bounds__(kSortThreads, 2)
             S.warp_hist[w][t] = count;
             count += c;
         }
-        // The look-back table is blocked in groups of four tiles:
-        // word(tile, digit) = ((tile / 4) * 256 + digit) * 4 + tile % 4, so one 16-byte
-        // load returns a digit's counters of four consecutive tiles while a tile's
-        // publication still goes to one compact 4 KB block. (A fully digit-major
-        // table was tried: every CTA then stores into the same 256 cache lines and
-        // the pass became 4x slower.)
-        auto slot_of = [&](uint32_t tl) { return lb + (((size_t)(tl >> 2) * kRadix + t) << 2) + (tl & 3u); };
-        if (tile != 0) st_relaxed(slot_of(tile), kFlagAggregate | count);
+        uint32_t* my_slot = lb + (size_t)tile * kRadix + t;
+        if (tile != 0) st_relaxed(my_slot, kFlagAggregate | count);
         uint32_t incl = warp_inclusive_scan(count);
         if (lane == 31) S.warp_tot[warp] = incl;
         __syncthreads();
@@ -421,37 +406,28 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         S.digit_start[t] = dstart;
         {
             uint32_t prefix = 0;
-            int32_t p = (int32_t)tile - 1;  // next predecessor to consume
+            int32_t p = (int32_t)tile - 1;
             bool done = p < 0;
             while (!done) {
-                const int32_t wbase = p & ~3;  // aligned window that contains p
-                uint4 w[4];
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = (p - j >= 0) ? ld_relaxed(lb + (size_t)(p - j) * kRadix + t) : kFlagInclusive;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    int32_t wb = wbase - 4 * j;
-                    w[j] = wb >= 0 ? ld_relaxed_v4(slot_of((uint32_t)wb))
-                                   : make_uint4(kFlagInclusive, kFlagInclusive, kFlagInclusive, kFlagInclusive);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t e4[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
-#pragma unroll
-                    for (int e = 3; e >= 0; --e) {
-                        const int32_t idx = wbase - 4 * j + e;
-                        if (done || idx > p) continue;
-                        const uint32_t flag = e4[e] & kFlagMask;
-                        if (flag == 0) {  // not published yet: reload from here
-                            p = idx;
-                            goto retry;
-                        }
-                        prefix += e4[e] & kValueMask;
-                        if (flag == kFlagInclusive) done = true;
+                    if (done) break;
+                    uint32_t flag = v[j] & kFlagMask;
+                    if (flag == 0) {
+                        p -= j;
+                        goto retry;
                     }
+                    prefix += v[j] & kValueMask;
+                    if (flag == kFlagInclusive) done = true;
                 }
-                p = wbase - 16 + 3;
+                p -= 4;
             retry:;
             }
-            st_relaxed(slot_of(tile), kFlagInclusive | (prefix + count));
+            st_relaxed(my_slot, kFlagInclusive | (prefix + count));
             S.global_base[t] = global_offsets[t] + prefix - dstart;
         }
         __syncthreads();
@@ -489,7 +465,7 @@ static bool persistent_sort_enabled() {
 
 // scratch layout (u32 words): hist[6][256] | tile_counter[8] | lookback[6][tiles][256]
 size_t radix_scratch_bytes(uint32_t n) {
-    size_t words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)kMaxSortPasses * (tiles_for(n, items_for(n)) + 4) * kRadix;
+    size_t words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)kMaxSortPasses * tiles_for(n, items_for(n)) * kRadix;
     return words * sizeof(uint32_t) + 256;
 }
 
@@ -521,8 +497,7 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     uint32_t* hist = static_cast<uint32_t*>(scratch);
     uint32_t* counters = hist + kMaxSortPasses * kRadix;
     uint32_t* lookback = counters + 8;
-    const uint32_t tiles_pad = (tiles + 3u) & ~3u;
-    size_t total_words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)plan.n_passes * tiles_pad * kRadix;
+    size_t total_words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)plan.n_passes * tiles * kRadix;
     cudaMemsetAsync(scratch, 0, total_words * sizeof(uint32_t), stream);
     uint32_t hist_blocks = min(tiles_for(n, 16) * 4u, 148u * 8u);
     radix_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, plan, hist);
@@ -550,7 +525,7 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
                 const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
                 uint64_t* kout = (p & 1u) ? keys : keys_tmp;
                 onesweep_persistent_kernel<<<grid, kSortThreads, sizeof(PersistentSmem), stream>>>(
-                    kin, kout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles_pad * kRadix, tiles, tiles_pad);
+                    kin, kout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tiles);
             }
         } else {
             launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);

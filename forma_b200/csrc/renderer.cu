@@ -168,8 +168,21 @@ void Composition::layer_clear(Layer* layer) {  // layer.rs:131-146
 // ---------------------------------------------------------------------------
 // Renderer
 // ---------------------------------------------------------------------------
+// BufferLayerCache (cpu/buffer/mod.rs:114-197). The per-tile records live on the
+// device (the painter reads and updates them); the host only keeps the size and
+// clear colour of the last frame.
 struct LayerCache {
     uint8_t id = 0;
+    DeviceBuffer<uint2> tiles;  // CachedTile per tile, see PaintScene::cache_tiles
+    bool has_size = false;
+    uint64_t width = 0, height = 0;
+    bool has_clear = false;
+    float clear_color[4] = {0, 0, 0, 0};
+    bool needs_reset = true;  // the tile records must be zeroed before their next use
+    void clear() {            // BufferLayerCache::clear, mod.rs:189-196
+        has_clear = false;
+        needs_reset = true;
+    }
 };
 
 struct Timer {
@@ -201,6 +214,13 @@ class Renderer {
     DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp;
     DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
     DeviceBuffer<uint8_t> eflags, framebuffer;
+    // Layer-cache frames: per-slot `is_unchanged` flags, the list of written
+    // tiles and their packed pixels (only these travel back to a host buffer).
+    DeviceBuffer<uint8_t> d_unchanged;
+    PinnedBuffer<uint8_t> h_unchanged;
+    DeviceBuffer<uint32_t> written_list, packed_tiles;
+    PinnedBuffer<uint32_t> h_written_list, h_packed_tiles;
+    uint32_t last_written_tiles = 0;
     // Upload staging.
     DeviceBuffer<PointCmd> up_cmds;
     DeviceBuffer<QuadRec> up_quads;
@@ -438,10 +458,6 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                   (unsigned long long)stride);
         return FORMA_STATUS_INVALID;
     }
-    if (cache) {
-        set_error("layer caches are not implemented in this build");
-        return FORMA_STATUS_INVALID;
-    }
     FORMA_CUDA_TRY(cudaSetDevice(device));
     if (!timer.ok) {
         for (auto& e : timer.ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
@@ -484,6 +500,42 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     S.n_orders = comp.n_orders;
     S.stops = comp.d_stops.ptr;
     S.texels = comp.d_texels.ptr;
+
+    const bool pack_written = cache && !buffer_on_device;
+    if (cache) {  // renderer.rs:94-110
+        const size_t cache_tiles = (size_t)S.tiles_x * S.tiles_y;
+        if (!cache->has_size || cache->width != width || cache->height != height) {
+            cache->has_size = true;
+            cache->width = width;
+            cache->height = height;
+            cache->clear();
+        }
+        FORMA_CUDA_TRY(cache->tiles.reserve(cache_tiles));
+        if (cache->needs_reset) {
+            FORMA_CUDA_TRY(cudaMemsetAsync(cache->tiles.ptr, 0, cache_tiles * sizeof(uint2), stream));
+            cache->needs_reset = false;
+        }
+        S.cache_tiles = cache->tiles.ptr;
+        S.clear_unchanged = cache->has_clear && cache->clear_color[0] == clear[0] && cache->clear_color[1] == clear[1] &&
+                            cache->clear_color[2] == clear[2] && cache->clear_color[3] == clear[3];
+        // Layer::is_unchanged(cache_id) per style slot (renderer.rs:144-157); the slots
+        // follow the iteration order of upload_tables.
+        FORMA_CUDA_TRY(h_unchanged.reserve(comp.n_layer_recs + 1));
+        FORMA_CUDA_TRY(d_unchanged.reserve(comp.n_layer_recs + 1));
+        size_t slot = 0;
+        for (auto& kv : comp.layers) h_unchanged.ptr[slot++] = (uint8_t)((kv.second->unchanged_bits >> cache->id) & 1u);
+        if (slot) {
+            FORMA_CUDA_TRY(cudaMemcpyAsync(d_unchanged.ptr, h_unchanged.ptr, slot, cudaMemcpyHostToDevice, stream));
+            h2d_bytes += slot;
+        }
+        S.unchanged = d_unchanged.ptr;
+        if (pack_written) {
+            FORMA_CUDA_TRY(written_list.reserve(cache_tiles));
+            FORMA_CUDA_TRY(cudaMemsetAsync(totals.ptr + 6, 0, sizeof(uint32_t), stream));
+            S.written_list = written_list.ptr;
+            S.written_count = totals.ptr + 6;
+        }
+    }
 
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[7], stream));
     uint32_t n = 0;
@@ -586,7 +638,37 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[5], stream));
 
-    if (!buffer_on_device) {
+    last_written_tiles = 0;
+    if (pack_written) {
+        // With a layer cache only the tiles this frame wrote may touch the host
+        // buffer (TileWriteOp::None leaves its bytes alone): pack them on the
+        // device, copy count + ids + pixels, scatter on the host.
+        FORMA_CUDA_TRY(packed_tiles.reserve((size_t)S.tiles_x * S.tiles_y * 256u));
+        launch_gather_tiles(S, fb, packed_tiles.ptr, stream);
+        ++launches;
+        uint32_t n_written = 0;
+        st = read_total(6, &n_written);
+        if (st) return st;
+        last_written_tiles = n_written;
+        if (n_written) {
+            FORMA_CUDA_TRY(h_written_list.reserve(n_written));
+            FORMA_CUDA_TRY(h_packed_tiles.reserve((size_t)n_written * 256u));
+            FORMA_CUDA_TRY(cudaMemcpyAsync(h_written_list.ptr, written_list.ptr, n_written * sizeof(uint32_t),
+                                           cudaMemcpyDeviceToHost, stream));
+            FORMA_CUDA_TRY(cudaMemcpyAsync(h_packed_tiles.ptr, packed_tiles.ptr, (size_t)n_written * 1024u,
+                                           cudaMemcpyDeviceToHost, stream));
+            FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+            d2h_bytes += (uint64_t)n_written * (1024u + 4u);
+            for (uint32_t i = 0; i < n_written; ++i) {  // LinearLayout::write, layout/mod.rs:265-282
+                const uint32_t tile = h_written_list.ptr[i];
+                const uint64_t x0 = (uint64_t)(tile % S.tiles_x) * 16u, y0 = (uint64_t)(tile / S.tiles_x) * 16u;
+                const uint64_t cols = std::min<uint64_t>(16u, width - x0), rows = std::min<uint64_t>(16u, height - y0);
+                const uint32_t* src = h_packed_tiles.ptr + (size_t)i * 256u;
+                for (uint64_t r = 0; r < rows; ++r)
+                    std::memcpy(buffer + (y0 + r) * stride + x0 * 4u, src + r * 16u, cols * 4u);
+            }
+        }
+    } else if (!buffer_on_device) {
         // Only the cropped tile rectangle is written by the reference
         // (cpu/painter/mod.rs:524-529,589-593); padding bytes beyond width*4 stay untouched.
         uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
@@ -621,6 +703,14 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         timings->paint_ms = stage_ms[4] + stage_ms[5];
         timings->n_lines = comp.n_resident ? comp.n_resident - 1 : 0;
         timings->n_segments = n;
+    }
+    if (cache) {  // renderer.rs:217-223
+        cache->has_clear = true;
+        std::memcpy(cache->clear_color, clear, sizeof(cache->clear_color));
+        for (auto& kv : comp.layers) {
+            if (kv.second->enabled) kv.second->unchanged_bits |= 1u << cache->id;
+            else kv.second->unchanged_bits &= ~(1u << cache->id);
+        }
     }
     return FORMA_STATUS_OK;
 }
@@ -906,7 +996,9 @@ void forma_layer_cache_free(forma_renderer* r, forma_layer_cache* c) {
     if (r) r->r.caches_in_use &= ~(1u << c->c.id);
     delete c;
 }
-void forma_layer_cache_clear(forma_layer_cache*) {}
+void forma_layer_cache_clear(forma_layer_cache* c) {
+    if (c) c->c.clear();
+}
 
 int forma_renderer_render(forma_renderer* r, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
                           uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
@@ -924,7 +1016,9 @@ uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.laun
 void forma_renderer_stage_times(const forma_renderer* r, double out_ms[8]) {
     for (int i = 0; i < 8; ++i) out_ms[i] = r->r.stage_ms[i];
 }
-void forma_renderer_counters(const forma_renderer* r, uint64_t out[6]) {
+void forma_renderer_counters(const forma_renderer* r, uint64_t out[8]) {
+    out[6] = r->r.last_written_tiles;
+    out[7] = 0;
     out[0] = r->r.launches;
     out[1] = r->r.h2d_bytes;
     out[2] = r->r.d2h_bytes;

@@ -214,8 +214,9 @@ uint64_t forma_composition_point_count(forma_composition*);
  * [5] paint kernel, [6] device->host copy, [7] whole call. */
 void forma_renderer_stage_times(const forma_renderer*, double out_ms[8]);
 /* [0] kernel launches, [1] host->device bytes, [2] device->host bytes (all
- * since creation), [3] pixel segments, [4] cells, [5] entries of the last render. */
-void forma_renderer_counters(const forma_renderer*, uint64_t out[6]);
+ * since creation), [3] pixel segments, [4] cells, [5] entries of the last render,
+ * [6] tiles the last layer-cache render copied back to a host buffer, [7] 0. */
+void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
 
 /* Number of CUDA kernels the renderer launched since it was created. */
 uint64_t forma_renderer_launch_count(const forma_renderer*);

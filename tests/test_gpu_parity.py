@@ -293,3 +293,70 @@ def test_large_frame_properties(cuda_api, cuda_renderer):
     cuda_renderer.render(comp, buf2, w, h, RGBA, Color(1, 1, 1, 1))
     assert np.array_equal(buf1, buf2), "render is not idempotent"
     assert np.all(buf1.reshape(-1, 4)[:, 3] == 255)
+
+
+# --- layer cache / damage reuse (cpu/buffer/mod.rs:114-197, composition/mod.rs:520-563,1038-1382) ---
+import cache_scenarios  # noqa: E402
+
+
+@pytest.mark.parametrize("scenario", cache_scenarios.SCENARIOS, ids=lambda f: f.__name__)
+def test_layer_cache_scenarios(cuda_api, oracle_api, scenario):
+    got = scenario(cuda_api)  # the reference's own asserts run inside
+    want = scenario(oracle_api)
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), f"{scenario.__name__}: frame {i} differs"
+
+
+def test_layer_cache_animation_matches_oracle(cuda_api, oracle_api):
+    got = cache_scenarios.animated_scene(cuda_api)
+    want = cache_scenarios.animated_scene(oracle_api)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert_same(a.reshape(120, -1), b.reshape(120, -1), f"animated frame {i}")
+
+
+def test_layer_cache_copies_back_only_damage(cuda_api):
+    """The second frame of an unchanged scene writes no tile; moving one small
+    layer damages only the tiles it leaves and enters."""
+    w, h = 512, 256
+    r = cuda_api.Renderer(0)
+    cache = r.create_buffer_layer_cache()
+    comp = cuda_api.Composition()
+    synth.random_mixed(cuda_api, comp, 40, w, h, 9)
+    comp.get_mut_or_insert_default(1000).insert(synth.circle_path(cuda_api, 100.0, 100.0, 10.0)).set_props(
+        Props(func=Func.Draw(Style(fill=Fill.Solid(Color(1, 0, 0, 1))))))
+    buf = np.zeros(w * h * 4, np.uint8)
+    r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1), None, cache)
+    first = r.counters()["written_tiles"]
+    assert first == (w // 16) * (h // 16)
+    r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1), None, cache)
+    assert r.counters()["written_tiles"] == 0
+    comp.get(1000).set_transform([1.0, 0.0, 0.0, 1.0, 64.0, 0.0])
+    full = buf.copy()
+    r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1), None, cache)
+    moved = r.counters()["written_tiles"]
+    assert 0 < moved <= 16
+    fresh = np.zeros_like(buf)
+    r.render(comp, fresh, w, h, RGBA, Color(1, 1, 1, 1))
+    assert np.array_equal(buf, fresh)
+    assert not np.array_equal(buf, full)
+
+
+def test_render_device_matches_host_buffer(cuda_api, cuda_renderer):
+    import torch
+    w, h = 300, 200
+    comp = cuda_api.Composition()
+    synth.random_mixed(cuda_api, comp, 50, w, h, 4)
+    host = np.zeros(w * h * 4, np.uint8)
+    cuda_renderer.render(comp, host, w, h, RGBA, Color(0.5, 0.5, 0.5, 1))
+    dev = torch.zeros(w * h * 4, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    cuda_renderer.render_device(comp, dev.data_ptr(), w, h, RGBA, Color(0.5, 0.5, 0.5, 1))
+    assert np.array_equal(dev.cpu().numpy(), host)
+    # With a layer cache the device buffer keeps the bytes of unwritten tiles.
+    cache = cuda_renderer.create_buffer_layer_cache()
+    cuda_renderer.render_device(comp, dev.data_ptr(), w, h, RGBA, Color(0.5, 0.5, 0.5, 1), None, cache)
+    dev.fill_(7)
+    torch.cuda.synchronize()
+    cuda_renderer.render_device(comp, dev.data_ptr(), w, h, RGBA, Color(0.5, 0.5, 0.5, 1), None, cache)
+    assert bool((dev == 7).all())

@@ -101,6 +101,10 @@ class Composition {
     DeviceBuffer<StopRec> d_stops;
     DeviceBuffer<uint16_t> d_texels;
     uint32_t n_geoms = 0, n_orders = 0;
+    // The inserts' layer orders never decrease along the segment buffer, so the
+    // rasterizer emits the pixel segments already ordered by layer and the
+    // (stable) sort only needs the tile_x / tile_y digits.
+    bool layers_in_order = false;
     int64_t tables_cache_id = -2;     // cache id the `unchanged` bits were uploaded for
 
    private:

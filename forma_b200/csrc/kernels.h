@@ -104,12 +104,16 @@ void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t
                        uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st);
 // Plans of the painter's two pair sorts (their key bounds are host-known).
 SortPlan carry_sort_plan(const PaintScene& S);
-SortPlan entry_sort_plan(const PaintScene& S);
+SortPlan gap_sort_plan(const PaintScene& S);
 void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
                        uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st);
-void launch_entry_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
-                       const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
-                       uint64_t* ekey, uint32_t* eid, uint4* gap_carry, cudaStream_t st);
+// Carry-only entries in (layer, tile_y, tile_x) order; payload = n_cells + gap id.
+void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
+                     const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
+                     uint64_t* gkey, uint32_t* gid, uint4* gap_carry, cudaStream_t st);
+// Merges the cells with the sorted carry-only entries into ekey / eid (n_cells + n_gaps).
+void launch_merge_entries(const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey, const uint32_t* gid,
+                          uint32_t n_gaps, uint64_t* ekey, uint32_t* eid, cudaStream_t st);
 void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,
                         uint32_t* tile_end, cudaStream_t st);
 void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,

@@ -451,22 +451,182 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Reduce-then-scan passes for large key-only sorts (the main pixel-segment
+// sort). The look-back of the single-sweep kernels above serialises the tiles
+// of a pass (measured: ~29 ns per 4096-key tile whatever the bandwidth, 34 % of
+// the HBM peak); here no CTA ever waits for another one:
+//   1. upsweep   — one CTA per tile counts the tile's digits     (reads  8 B/key)
+//   2. tile scan — counts -> exclusive global offsets per (tile, digit)
+//   3. downsweep — one CTA per tile ranks, stages in shared memory in digit
+//                  order and writes coalesced runs        (reads + writes 8 B/key)
+// i.e. 24 B/key per pass instead of 16, but every kernel streams.
+// ---------------------------------------------------------------------------
+constexpr int kDsItems = 16;
+constexpr int kDsTile = kSortThreads * kDsItems;  // 4096 keys = 32 KB
+constexpr uint32_t kMaxChunks = 128;              // tile-scan CTAs (chunks of consecutive tiles)
+
+__global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const uint64_t* __restrict__ keys, uint32_t n, DigitSpec spec,
+                                                                   uint32_t* __restrict__ tile_hist /*[tiles][256]*/,
+                                                                   uint32_t* __restrict__ chunk_totals /*[chunks][256], zeroed*/,
+                                                                   uint32_t tiles_per_chunk) {
+    __shared__ uint32_t s_hist[kRadix];
+    const uint32_t t = threadIdx.x, tile = blockIdx.x;
+    s_hist[t] = 0;
+    const uint32_t base = tile * (uint32_t)kDsTile;
+    uint64_t key[kDsItems];
+#pragma unroll
+    for (int i = 0; i < kDsItems; ++i) {
+        uint32_t idx = base + (uint32_t)i * kSortThreads + t;
+        key[i] = idx < n ? keys[idx] : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kDsItems; ++i) {
+        uint32_t idx = base + (uint32_t)i * kSortThreads + t;
+        if (idx < n) atomicAdd(&s_hist[digit_of(key[i], spec)], 1u);
+    }
+    __syncthreads();
+    const uint32_t c = s_hist[t];
+    tile_hist[(size_t)tile * kRadix + t] = c;
+    if (c) atomicAdd(&chunk_totals[(size_t)(tile / tiles_per_chunk) * kRadix + t], c);
+}
+
+// CTA c turns the digit counts of tiles [c * tiles_per_chunk, ...) into the
+// global offset of each tile's first key of each digit. Thread d owns digit d.
+__global__ void __launch_bounds__(kRadix) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist,
+                                                               const uint32_t* __restrict__ chunk_totals, uint32_t tiles,
+                                                               uint32_t tiles_per_chunk, uint32_t chunks) {
+    __shared__ uint32_t s_warp_tot[kRadix / 32];
+    const uint32_t d = threadIdx.x, c = blockIdx.x;
+    uint32_t before = 0, total = 0;  // keys of digit d in earlier chunks / in all chunks
+    for (uint32_t j0 = 0; j0 < chunks; j0 += 16u) {
+        uint32_t v[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16u; ++k) v[k] = (j0 + k < chunks) ? chunk_totals[(size_t)(j0 + k) * kRadix + d] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 16u; ++k) {
+            total += v[k];
+            if (j0 + k < c) before += v[k];
+        }
+    }
+    uint32_t incl = warp_inclusive_scan(total);
+    if ((d & 31u) == 31u) s_warp_tot[d >> 5] = incl;
+    __syncthreads();
+    uint32_t running = incl - total + before;
+    for (uint32_t w = 0; w < (d >> 5); ++w) running += s_warp_tot[w];
+    const uint32_t t0 = c * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+    for (uint32_t tb = t0; tb < t1; tb += 8u) {
+        uint32_t v[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) v[k] = (tb + k < t1) ? tile_hist[(size_t)(tb + k) * kRadix + d] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            if (tb + k < t1) tile_hist[(size_t)(tb + k) * kRadix + d] = running;
+            running += v[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads, 3)
+    radix_downsweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
+                           const uint32_t* __restrict__ tile_base /*[tiles][256]: global offset per (tile, digit)*/) {
+    __shared__ uint64_t s_keys[kDsTile];
+    __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];
+    __shared__ uint32_t s_digit_start[kRadix];
+    __shared__ uint32_t s_global_base[kRadix];
+    __shared__ uint32_t s_warp_tot[kSortWarps];
+
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t gbase = tile_base[(size_t)tile * kRadix + t];  // consumed after the ranking
+    for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
+    const uint32_t base = tile * (uint32_t)kDsTile;
+    const uint32_t valid = min((uint32_t)kDsTile, n - base);
+
+    uint64_t key[kDsItems];
+    const uint32_t warp_base = base + warp * (32u * kDsItems);
+#pragma unroll
+    for (int i = 0; i < kDsItems; ++i) {
+        uint32_t idx = warp_base + i * 32u + lane;
+        key[i] = idx < n ? keys_in[idx] : ~0ull;
+    }
+    __syncthreads();
+
+    // Stable rank of every key among the keys of its warp with the same digit
+    // (out-of-range slots of the last tile take the largest digit: they rank last).
+    uint32_t rank[kDsItems];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t max_digit = (1u << spec.bits) - 1u;
+#pragma unroll
+    for (int i = 0; i < kDsItems; ++i) {
+        uint32_t idx = warp_base + i * 32u + lane;
+        uint32_t d = idx < n ? digit_of(key[i], spec) : max_digit;
+        uint32_t peers = __match_any_sync(kFullMask, d);
+        uint32_t leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(kFullMask, old, leader);
+        rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+        uint32_t c = s_warp_hist[w][t];
+        s_warp_hist[w][t] = count;
+        count += c;
+    }
+    uint32_t incl = warp_inclusive_scan(count);
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t dstart = incl - count;
+    for (uint32_t w = 0; w < warp; ++w) dstart += s_warp_tot[w];
+    s_digit_start[t] = dstart;
+    s_global_base[t] = gbase - dstart;
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < kDsItems; ++i) {
+        uint32_t d = rank[i] >> 16;
+        s_keys[s_digit_start[d] + s_warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kDsItems; ++k) {
+        uint32_t p = t + k * kSortThreads;
+        if (p < valid) {
+            uint64_t kk = s_keys[p];
+            keys_out[s_global_base[digit_of(kk, spec)] + p] = kk;
+        }
+    }
+}
+
 static uint32_t tiles_for(uint32_t n, int items) { return (n + kSortThreads * items - 1) / (kSortThreads * items); }
 static int items_for(uint32_t n) { return n >= (1u << 21) ? 16 : 4; }
-// FORMA_SORT_PERSISTENT=0 selects the one-shot pass kernel for A/B measurements.
-static bool persistent_sort_enabled() {
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("FORMA_SORT_PERSISTENT");
-        enabled = (e && e[0] == '0') ? 0 : 1;
+// Large key-only sorts: FORMA_SORT_MODE = scan (default: reduce-then-scan passes),
+// persistent (TMA-staged single sweep) or oneshot (single sweep), for A/B measurements.
+enum class BigSortMode { Scan, Persistent, OneShot };
+static BigSortMode big_sort_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("FORMA_SORT_MODE");
+        mode = (e && e[0] == 'p') ? 1 : (e && e[0] == 'o') ? 2 : 0;
     }
-    return enabled == 1;
+    return (BigSortMode)mode;
 }
 
 // scratch layout (u32 words): hist[6][256] | tile_counter[8] | lookback[6][tiles][256]
+// or, for the reduce-then-scan passes: chunk_totals[6][128][256] | tile_hist[tiles][256]
 size_t radix_scratch_bytes(uint32_t n) {
     size_t words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)kMaxSortPasses * tiles_for(n, items_for(n)) * kRadix;
-    return words * sizeof(uint32_t) + 256;
+    size_t scan_words = (size_t)kMaxSortPasses * kMaxChunks * kRadix + (size_t)tiles_for(n, kDsItems) * kRadix;
+    return (words > scan_words ? words : scan_words) * sizeof(uint32_t) + 256;
 }
 
 template <bool kPairs, int kItems>
@@ -494,6 +654,24 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     if (n < 2 || plan.n_passes == 0) return res;
     const int items = items_for(n);
     const uint32_t tiles = tiles_for(n, items);
+    if (!vals && items == 16 && big_sort_mode() == BigSortMode::Scan) {
+        const uint32_t tiles_per_chunk = (tiles + kMaxChunks - 1) / kMaxChunks;
+        const uint32_t chunks = (tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+        uint32_t* chunk_totals = static_cast<uint32_t*>(scratch);
+        uint32_t* tile_hist = chunk_totals + (size_t)kMaxSortPasses * kMaxChunks * kRadix;
+        cudaMemsetAsync(chunk_totals, 0, (size_t)plan.n_passes * kMaxChunks * kRadix * sizeof(uint32_t), stream);
+        for (uint32_t p = 0; p < plan.n_passes; ++p) {
+            const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
+            uint64_t* kout = (p & 1u) ? keys : keys_tmp;
+            uint32_t* totals = chunk_totals + (size_t)p * kMaxChunks * kRadix;
+            radix_upsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, n, plan.pass[p], tile_hist, totals, tiles_per_chunk);
+            radix_tile_scan_kernel<<<chunks, kRadix, 0, stream>>>(tile_hist, totals, tiles, tiles_per_chunk, chunks);
+            radix_downsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, kout, n, plan.pass[p], tile_hist);
+        }
+        res.launches = 3 * (int)plan.n_passes;
+        res.in_tmp = (plan.n_passes & 1u) != 0u;
+        return res;
+    }
     uint32_t* hist = static_cast<uint32_t*>(scratch);
     uint32_t* counters = hist + kMaxSortPasses * kRadix;
     uint32_t* lookback = counters + 8;
@@ -506,7 +684,7 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     if (vals) {
         if (items == 16) launch_passes<true, 16>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
         else launch_passes<true, 4>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
-    } else if (items == 16 && persistent_sort_enabled()) {
+    } else if (items == 16 && big_sort_mode() == BigSortMode::Persistent) {
         // Large key-only sort: persistent CTAs with TMA-staged tiles.
         static int resident = 0;
         if (!resident) {

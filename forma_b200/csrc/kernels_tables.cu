@@ -188,32 +188,57 @@ __global__ void carry_scan_kernel(PaintScene S, const uint64_t* __restrict__ key
     }
 }
 
-// Entries: one per cell (payload = cell id) + carry-only entries (payload =
-// n_cells + gap id). Cells that are not painted get the key ~0 (sorted last).
-__global__ void entry_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2, const uint32_t* __restrict__ perm,
-                                  const uint64_t* __restrict__ cell_key, const uint4* __restrict__ carry_after,
-                                  const uint32_t* __restrict__ gap_count, const uint32_t* __restrict__ gap_offset,
-                                  uint32_t n_cells, uint64_t* __restrict__ ekey, uint32_t* __restrict__ eid,
-                                  uint4* __restrict__ gap_carry) {
+// Carry-only entries (payload = n_cells + gap id), generated in (layer, tile_y,
+// tile_x) order: a stable sort on the tile digits alone then orders them by
+// (tile_y, tile_x, layer).
+__global__ void gap_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2, const uint32_t* __restrict__ perm,
+                                const uint64_t* __restrict__ cell_key, const uint4* __restrict__ carry_after,
+                                const uint32_t* __restrict__ gap_count, const uint32_t* __restrict__ gap_offset,
+                                uint32_t n_cells, uint64_t* __restrict__ gkey, uint32_t* __restrict__ gid,
+                                uint4* __restrict__ gap_carry) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_cells) return;
-    uint32_t c = perm[j];
-    uint64_t ck = cell_key[c];
-    int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
-    bool painted = ty >= (int32_t)S.ty_lo && ty < (int32_t)S.ty_hi && tx >= (int32_t)S.tx_lo && tx < (int32_t)S.tx_hi;
-    ekey[c] = painted ? ck : sentinel_key(S.tiles_y);
-    eid[c] = c;
     uint32_t g = gap_count[j];
-    if (g) {
-        uint32_t off = gap_offset[j];
-        uint4 carry = carry_after[j];
-        int32_t first = max(tx + 1, (int32_t)S.tx_lo);
-        for (uint32_t r = 0; r < g; ++r) {
-            uint64_t key = (ck & ~(0xFFFull << 41)) | ((uint64_t)(uint32_t)(first + (int32_t)r + 1) << 41);
-            ekey[n_cells + off + r] = key;
-            eid[n_cells + off + r] = n_cells + off + r;
-            gap_carry[off + r] = carry;
-        }
+    if (!g) return;
+    uint64_t ck = cell_key[perm[j]];
+    int32_t tx = (int32_t)key_tx(ck) - 1;
+    uint32_t off = gap_offset[j];
+    uint4 carry = carry_after[j];
+    int32_t first = max(tx + 1, (int32_t)S.tx_lo);
+    for (uint32_t r = 0; r < g; ++r) {
+        gkey[off + r] = (ck & ~(0xFFFull << 41)) | ((uint64_t)(uint32_t)(first + (int32_t)r + 1) << 41);
+        gid[off + r] = n_cells + off + r;
+        gap_carry[off + r] = carry;
+    }
+}
+
+// Entries = cells (sorted by construction) merged with the sorted carry-only
+// entries; both lists are strictly increasing and share no key, so an element's
+// position is its own index plus its rank in the other list.
+__device__ __forceinline__ uint32_t lower_bound_key(const uint64_t* __restrict__ a, uint32_t n, uint64_t k) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void merge_entries_kernel(const uint64_t* __restrict__ cell_key, uint32_t n_cells, const uint64_t* __restrict__ gkey,
+                                     const uint32_t* __restrict__ gid, uint32_t n_gaps, uint64_t* __restrict__ ekey,
+                                     uint32_t* __restrict__ eid) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_cells) {
+        uint64_t k = cell_key[i];
+        uint32_t pos = i + lower_bound_key(gkey, n_gaps, k);
+        ekey[pos] = k;
+        eid[pos] = i;
+    } else if (i < n_cells + n_gaps) {
+        uint32_t g = i - n_cells;
+        uint64_t k = gkey[g];
+        uint32_t pos = g + lower_bound_key(cell_key, n_cells, k);
+        ekey[pos] = k;
+        eid[pos] = gid[g];
     }
 }
 
@@ -223,7 +248,9 @@ __global__ void tile_range_kernel(PaintScene S, const uint64_t* __restrict__ eke
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_entries) return;
     uint64_t k = ekey[p];
-    if (key_ty(k) > S.tiles_y) return;  // sentinel (unpainted) entries sort last
+    // Entries outside the render target (biased tile coordinate 0 = tile -1, or
+    // beyond the last tile) belong to no painted tile.
+    if (key_ty(k) == 0u || key_ty(k) > S.tiles_y || key_tx(k) == 0u || key_tx(k) > S.tiles_x) return;
     uint64_t tile_bits = k >> 41;
     uint32_t tid = (key_ty(k) - 1u) * S.tiles_x + (key_tx(k) - 1u);
     if (p == 0 || (ekey[p - 1] >> 41) != tile_bits) tile_begin[tid] = p;
@@ -253,13 +280,16 @@ void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t
 
 // Largest values the three key fields can take in the pair sorts (sentinel
 // included); the sort plan only spends passes on bits below these bounds.
+// The cells arrive sorted by (tile_y, tile_x, layer); a stable sort on the layer
+// bits alone leaves them ordered by (layer, tile_y, tile_x), which is all the
+// carry scan needs: every (tile_y, layer) group contiguous, tile_x ascending.
 SortPlan carry_sort_plan(const PaintScene& S) {  // fields, least significant first: tile_x, layer, tile_y
-    const uint64_t bound[3] = {S.tx_hi /* biased tile_x of the last painted column */,
-                               S.n_orders ? S.n_orders - 1u : 0u, S.tiles_y + 1u /* sentinel row */};
+    const uint64_t bound[3] = {0u, S.n_orders ? S.n_orders - 1u : 0u, 0u};
     return make_sort_plan(carry_key_layout(), bound);
 }
-SortPlan entry_sort_plan(const PaintScene& S) {  // layer, tile_x, tile_y
-    const uint64_t bound[3] = {S.n_orders ? S.n_orders - 1u : 0u, S.tx_hi, S.tiles_y + 1u};
+// Carry-only entries: tile digits only (see gap_fill_kernel).
+SortPlan gap_sort_plan(const PaintScene& S) {  // layer, tile_x, tile_y
+    const uint64_t bound[3] = {0u, S.tx_hi, S.ty_hi};
     return make_sort_plan(segment_key_layout(), bound);
 }
 
@@ -269,11 +299,17 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
                                                               gap_count);
 }
 
-void launch_entry_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
-                       const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
-                       uint64_t* ekey, uint32_t* eid, uint4* gap_carry, cudaStream_t st) {
-    entry_fill_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset,
-                                                              n_cells, ekey, eid, gap_carry);
+void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
+                     const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
+                     uint64_t* gkey, uint32_t* gid, uint4* gap_carry, cudaStream_t st) {
+    gap_fill_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset, n_cells,
+                                                            gkey, gid, gap_carry);
+}
+
+void launch_merge_entries(const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey, const uint32_t* gid,
+                          uint32_t n_gaps, uint64_t* ekey, uint32_t* eid, cudaStream_t st) {
+    uint32_t n = n_cells + n_gaps;
+    if (n) merge_entries_kernel<<<(n + 255) / 256, 256, 0, st>>>(cell_key, n_cells, gkey, gid, n_gaps, ekey, eid);
 }
 
 void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,

@@ -210,8 +210,8 @@ class Renderer {
     }
     DeviceBuffer<uint64_t> segs, segs_tmp;
     DeviceBuffer<uint8_t> sort_scratch;
-    DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, tile_begin, tile_end;
-    DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp;
+    DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, gid_tmp, tile_begin, tile_end;
+    DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp, gkey_tmp;
     DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
     DeviceBuffer<uint8_t> eflags, framebuffer;
     // Layer-cache frames: per-slot `is_unchanged` flags, the list of written
@@ -376,6 +376,21 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
             if (kv.second < 0 || kv.first >= n_geoms || (uint64_t)kv.second >= n_orders) continue;
             comp.h_geom_slot.ptr[kv.first] = comp.h_order_to_style.ptr[kv.second];
         }
+        comp.layers_in_order = true;
+        {
+            int64_t last = -1;
+            for (const PendingInsert& job : comp.jobs) {
+                if (job.geom_id >= n_geoms) continue;
+                int32_t s = comp.h_geom_slot.ptr[job.geom_id];
+                if (s < 0) continue;
+                int64_t order = (int64_t)comp.h_layers.ptr[s].order;
+                if (order < last) {
+                    comp.layers_in_order = false;
+                    break;
+                }
+                last = order;
+            }
+        }
         FORMA_CUDA_TRY(comp.h_stops.reserve(stops.size() + 1));
         FORMA_CUDA_TRY(comp.h_texels.reserve(texels.size() + 1));
         if (!stops.empty()) std::memcpy(comp.h_stops.ptr, stops.data(), stops.size() * sizeof(StopRec));
@@ -431,7 +446,10 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
     n = pinned_totals[0];
     {
-        const uint64_t bound[3] = {comp.n_orders ? comp.n_orders - 1u : 0u, pinned_totals[4], pinned_totals[5]};
+        // Already ordered by layer: no layer digits (see Composition::layers_in_order).
+        static const bool skip_layer_digits = !(getenv("FORMA_SORT_FULL_KEY") && getenv("FORMA_SORT_FULL_KEY")[0] == '1');
+        const uint64_t layer_bound = (comp.layers_in_order && skip_layer_digits) ? 0u : (comp.n_orders ? comp.n_orders - 1u : 0u);
+        const uint64_t bound[3] = {layer_bound, pinned_totals[4], pinned_totals[5]};
         segment_plan = make_sort_plan(segment_key_layout(), bound);  // layer, tile_x, tile_y
     }
     *n_out = n;
@@ -610,24 +628,28 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         last_cells = n_cells;
         last_entries = n_entries;
         FORMA_CUDA_TRY(ekey.reserve(n_entries));
-        FORMA_CUDA_TRY(ekey_tmp.reserve(n_entries));
         FORMA_CUDA_TRY(eid.reserve(n_entries));
-        FORMA_CUDA_TRY(eid_tmp.reserve(n_entries));
+        FORMA_CUDA_TRY(ekey_tmp.reserve(n_gaps + 1));  // carry-only entries: keys / ids + sort scratch
+        FORMA_CUDA_TRY(eid_tmp.reserve(n_gaps + 1));
+        FORMA_CUDA_TRY(gkey_tmp.reserve(n_gaps + 1));
+        FORMA_CUDA_TRY(gid_tmp.reserve(n_gaps + 1));
         FORMA_CUDA_TRY(gap_carry.reserve(n_gaps + 1));
         FORMA_CUDA_TRY(eflags.reserve(n_entries));
-        launch_entry_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
-                          ekey.ptr, eid.ptr, gap_carry.ptr, stream);
-        ++launches;
-        FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_entries)));
-        {
-            SortResult sr = launch_radix_sort(ekey.ptr, ekey_tmp.ptr, eid.ptr, eid_tmp.ptr, n_entries, entry_sort_plan(S),
+        if (n_gaps) {
+            FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_gaps)));
+            launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
+                            ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, stream);
+            ++launches;
+            SortResult sr = launch_radix_sort(ekey_tmp.ptr, gkey_tmp.ptr, eid_tmp.ptr, gid_tmp.ptr, n_gaps, gap_sort_plan(S),
                                               sort_scratch.ptr, stream);
             launches += sr.launches;
             if (sr.in_tmp) {
-                swap_buffers(ekey, ekey_tmp);
-                swap_buffers(eid, eid_tmp);
+                swap_buffers(ekey_tmp, gkey_tmp);
+                swap_buffers(eid_tmp, gid_tmp);
             }
         }
+        launch_merge_entries(cell_key.ptr, n_cells, ekey_tmp.ptr, eid_tmp.ptr, n_gaps, ekey.ptr, eid.ptr, stream);
+        ++launches;
     }
     launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
     launches += n_entries ? 1 : 0;

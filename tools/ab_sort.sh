@@ -1,0 +1,6 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for w in paris4k cubics100k; do
+for cfg in "A=1" "FORMA_SORT_FULL_KEY=1" "FORMA_SORT_FULL_KEY=1 FORMA_SORT_MODE=p"; do
+echo "== $w $cfg"
+env $cfg python bench.py --workload $w --steps 20 --warmup 5 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['e2e']['value'],1), d['stage_ms'], d['gpu_launches'])"
+done; done

@@ -275,6 +275,7 @@ SIGNATURES = {
     "renderer_launch_count": (C.c_uint64, [_vp]),
     "renderer_stage_times": (None, [_vp, C.POINTER(C.c_double)]),
     "renderer_counters": (None, [_vp, _u64p]),
+    "renderer_kernel_times": (None, [_vp, C.POINTER(C.c_double), _u32p]),
     "renderer_set_stream": (None, [_vp, _vp]),
     "composition_evict": (None, [_vp]),
     "composition_point_count": (C.c_uint64, [_vp]),
@@ -621,6 +622,13 @@ class Renderer:
         out = (C.c_double * 8)()
         self._api.renderer_stage_times(self._h, out)
         return dict(zip(self.STAGES, list(out)))
+
+    def kernel_times(self) -> dict:
+        """CUDA-event ms and launch counts of single kernels in the last render."""
+        ms, n = (C.c_double * 4)(), (C.c_uint32 * 4)()
+        self._api.renderer_kernel_times(self._h, ms, n)
+        names = ("radix_downsweep", "radix_upsweep_scan", "paint")
+        return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
 
     def counters(self) -> dict:
         out = (C.c_uint64 * 8)()

@@ -68,10 +68,12 @@ SortPlan make_sort_plan(const KeyLayout& layout, const uint64_t bound[3]);
 struct SortResult {
     int launches;
     bool in_tmp;  // the sorted data is in keys_tmp / vals_tmp (odd number of passes)
+    int timed_passes = 0;  // passes whose kernels were bracketed by pass_events
 };
 size_t radix_scratch_bytes(uint32_t n);
 SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
-                             const SortPlan& plan, void* scratch, cudaStream_t stream);
+                             const SortPlan& plan, void* scratch, cudaStream_t stream,
+                             cudaEvent_t* pass_events = nullptr /* 3 per pass: before upsweep, before / after downsweep */);
 
 // ---- kernels_paint.cu -------------------------------------------------------
 struct PaintScene {

@@ -464,11 +464,16 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 // ---------------------------------------------------------------------------
 constexpr int kDsItems = 16;
 constexpr int kDsTile = kSortThreads * kDsItems;  // 4096 keys = 32 KB
-constexpr uint32_t kMaxChunks = 128;              // tile-scan CTAs (chunks of consecutive tiles)
+// The tile scan works on chunks of consecutive tiles (one CTA each) grouped into
+// super-chunks: a CTA needs 32 + 16 loads per digit to know what precedes it.
+constexpr uint32_t kChunksPerSuper = 16;
+constexpr uint32_t kMaxSupers = 32;
+constexpr uint32_t kMaxChunks = kChunksPerSuper * kMaxSupers;  // 512
+constexpr uint32_t kTotalsRows = kMaxChunks + kMaxSupers;      // per pass: chunk rows, then super-chunk rows
 
 __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const uint64_t* __restrict__ keys, uint32_t n, DigitSpec spec,
                                                                    uint32_t* __restrict__ tile_hist /*[tiles][256]*/,
-                                                                   uint32_t* __restrict__ chunk_totals /*[chunks][256], zeroed*/,
+                                                                   uint32_t* __restrict__ totals /*[kTotalsRows][256], zeroed*/,
                                                                    uint32_t tiles_per_chunk) {
     __shared__ uint32_t s_hist[kRadix];
     const uint32_t t = threadIdx.x, tile = blockIdx.x;
@@ -489,26 +494,35 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const uint6
     __syncthreads();
     const uint32_t c = s_hist[t];
     tile_hist[(size_t)tile * kRadix + t] = c;
-    if (c) atomicAdd(&chunk_totals[(size_t)(tile / tiles_per_chunk) * kRadix + t], c);
+    if (c) {
+        const uint32_t chunk = tile / tiles_per_chunk;
+        atomicAdd(&totals[(size_t)chunk * kRadix + t], c);
+        atomicAdd(&totals[(size_t)(kMaxChunks + chunk / kChunksPerSuper) * kRadix + t], c);
+    }
 }
 
 // CTA c turns the digit counts of tiles [c * tiles_per_chunk, ...) into the
 // global offset of each tile's first key of each digit. Thread d owns digit d.
 __global__ void __launch_bounds__(kRadix) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist,
-                                                               const uint32_t* __restrict__ chunk_totals, uint32_t tiles,
-                                                               uint32_t tiles_per_chunk, uint32_t chunks) {
+                                                               const uint32_t* __restrict__ totals, uint32_t tiles,
+                                                               uint32_t tiles_per_chunk) {
     __shared__ uint32_t s_warp_tot[kRadix / 32];
-    const uint32_t d = threadIdx.x, c = blockIdx.x;
+    const uint32_t d = threadIdx.x, c = blockIdx.x, sc = c / kChunksPerSuper;
     uint32_t before = 0, total = 0;  // keys of digit d in earlier chunks / in all chunks
-    for (uint32_t j0 = 0; j0 < chunks; j0 += 16u) {
-        uint32_t v[16];
+    {
+        uint32_t v[kMaxSupers], w[kChunksPerSuper];
 #pragma unroll
-        for (uint32_t k = 0; k < 16u; ++k) v[k] = (j0 + k < chunks) ? chunk_totals[(size_t)(j0 + k) * kRadix + d] : 0u;
+        for (uint32_t k = 0; k < kMaxSupers; ++k) v[k] = totals[(size_t)(kMaxChunks + k) * kRadix + d];
 #pragma unroll
-        for (uint32_t k = 0; k < 16u; ++k) {
+        for (uint32_t k = 0; k < kChunksPerSuper; ++k) w[k] = totals[(size_t)(sc * kChunksPerSuper + k) * kRadix + d];
+#pragma unroll
+        for (uint32_t k = 0; k < kMaxSupers; ++k) {
             total += v[k];
-            if (j0 + k < c) before += v[k];
+            if (k < sc) before += v[k];
         }
+#pragma unroll
+        for (uint32_t k = 0; k < kChunksPerSuper; ++k)
+            if (sc * kChunksPerSuper + k < c) before += w[k];
     }
     uint32_t incl = warp_inclusive_scan(total);
     if ((d & 31u) == 31u) s_warp_tot[d >> 5] = incl;
@@ -607,6 +621,126 @@ __global__ void __launch_bounds__(kSortThreads, 3)
     }
 }
 
+// Persistent downsweep: CTA c owns tiles c, c + G, ...; the keys of the next
+// kDsStages - 1 tiles of the CTA are always in flight as 32 KB `cp.async.bulk`
+// (1-D TMA) copies into a shared-memory ring, so the HBM reads never wait for
+// the ranking or the stores of the current tile. The stage that delivered a
+// tile is reused as its digit-order staging buffer before the write-out.
+constexpr int kDsStages = 3;
+struct DownsweepSmem {
+    uint64_t stage[kDsStages][kDsTile];     // 3 x 32 KB
+    uint32_t warp_hist[kSortWarps][kRadix]; // 8 KB
+    uint32_t digit_start[kRadix];
+    uint32_t global_base[kRadix];
+    uint32_t warp_tot[kSortWarps];
+    uint64_t bar[kDsStages];
+};
+
+__global__ void __launch_bounds__(kSortThreads, 2)
+    radix_downsweep_tma_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
+                               const uint32_t* __restrict__ tile_base, uint32_t tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DownsweepSmem& S = *reinterpret_cast<DownsweepSmem*>(smem_raw);
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t G = gridDim.x;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kDsStages; ++s) mbar_init(&S.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t tile, uint32_t st) {  // thread 0 only
+        uint32_t base = tile * (uint32_t)kDsTile;
+        uint32_t valid = min((uint32_t)kDsTile, n - base);
+        uint32_t bytes = ((valid + 1u) & ~1u) * 8u;  // multiple of 16 B (the buffers have one key of slack)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.bar[st], bytes);
+        tma_load_1d(&S.stage[st][0], keys_in + base, bytes, &S.bar[st]);
+    };
+
+    uint32_t tile = blockIdx.x;
+    if (tile >= tiles) return;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kDsStages - 1; ++s)
+            if (tile + (uint32_t)s * G < tiles) issue(tile + (uint32_t)s * G, (uint32_t)s);
+    }
+    uint32_t st = 0, phases = 0;  // bit s of `phases` = parity to wait for on stage s
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t max_digit = (1u << spec.bits) - 1u;
+
+    for (; tile < tiles; tile += G) {
+        // The stage freed by the previous iteration receives the tile kDsStages - 1 rounds ahead.
+        if (t == 0 && tile + (uint32_t)(kDsStages - 1) * G < tiles)
+            issue(tile + (uint32_t)(kDsStages - 1) * G, (st + kDsStages - 1u) % kDsStages);
+        const uint32_t gbase = tile_base[(size_t)tile * kRadix + t];
+        for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&S.warp_hist[0][0])[i] = 0;
+        const uint32_t base = tile * (uint32_t)kDsTile;
+        const uint32_t valid = min((uint32_t)kDsTile, n - base);
+        mbar_wait(&S.bar[st], (phases >> st) & 1u);
+        phases ^= 1u << st;
+        uint64_t* stage = S.stage[st];
+
+        uint64_t key[kDsItems];
+        const uint32_t wofs = warp * (32u * kDsItems);
+#pragma unroll
+        for (int i = 0; i < kDsItems; ++i) key[i] = stage[wofs + i * 32u + lane];
+        __syncthreads();  // everybody has its keys (and the zeroed histograms are visible)
+
+        uint32_t rank[kDsItems];
+#pragma unroll
+        for (int i = 0; i < kDsItems; ++i) {
+            uint32_t slot = wofs + i * 32u + lane;
+            uint32_t d = slot < valid ? digit_of(key[i], spec) : max_digit;
+            uint32_t peers = __match_any_sync(kFullMask, d);
+            uint32_t leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(kFullMask, old, leader);
+            rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        uint32_t count = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t c = S.warp_hist[w][t];
+            S.warp_hist[w][t] = count;
+            count += c;
+        }
+        uint32_t incl = warp_inclusive_scan(count);
+        if (lane == 31) S.warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t dstart = incl - count;
+        for (uint32_t w = 0; w < warp; ++w) dstart += S.warp_tot[w];
+        S.digit_start[t] = dstart;
+        S.global_base[t] = gbase - dstart;
+        __syncthreads();
+
+#pragma unroll
+        for (int i = 0; i < kDsItems; ++i) {
+            uint32_t d = rank[i] >> 16;
+            stage[S.digit_start[d] + S.warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kDsItems; ++k) {
+            uint32_t p = t + k * kSortThreads;
+            if (p < valid) {
+                uint64_t kk = stage[p];
+                keys_out[S.global_base[digit_of(kk, spec)] + p] = kk;
+            }
+        }
+        __syncthreads();  // the stage is free again: the next iteration refills it by TMA
+        st = (st + 1u) % kDsStages;
+    }
+}
+
 static uint32_t tiles_for(uint32_t n, int items) { return (n + kSortThreads * items - 1) / (kSortThreads * items); }
 static int items_for(uint32_t n) { return n >= (1u << 21) ? 16 : 4; }
 // Large key-only sorts: FORMA_SORT_MODE = scan (default: reduce-then-scan passes),
@@ -622,10 +756,10 @@ static BigSortMode big_sort_mode() {
 }
 
 // scratch layout (u32 words): hist[6][256] | tile_counter[8] | lookback[6][tiles][256]
-// or, for the reduce-then-scan passes: chunk_totals[6][128][256] | tile_hist[tiles][256]
+// or, for the reduce-then-scan passes: totals[6][kTotalsRows][256] | tile_hist[tiles][256]
 size_t radix_scratch_bytes(uint32_t n) {
     size_t words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)kMaxSortPasses * tiles_for(n, items_for(n)) * kRadix;
-    size_t scan_words = (size_t)kMaxSortPasses * kMaxChunks * kRadix + (size_t)tiles_for(n, kDsItems) * kRadix;
+    size_t scan_words = (size_t)kMaxSortPasses * kTotalsRows * kRadix + (size_t)tiles_for(n, kDsItems) * kRadix;
     return (words > scan_words ? words : scan_words) * sizeof(uint32_t) + 256;
 }
 
@@ -649,7 +783,7 @@ static void launch_passes(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, ui
 }
 
 SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
-                             const SortPlan& plan, void* scratch, cudaStream_t stream) {
+                             const SortPlan& plan, void* scratch, cudaStream_t stream, cudaEvent_t* pass_events) {
     SortResult res{0, false};
     if (n < 2 || plan.n_passes == 0) return res;
     const int items = items_for(n);
@@ -658,16 +792,40 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
         const uint32_t tiles_per_chunk = (tiles + kMaxChunks - 1) / kMaxChunks;
         const uint32_t chunks = (tiles + tiles_per_chunk - 1) / tiles_per_chunk;
         uint32_t* chunk_totals = static_cast<uint32_t*>(scratch);
-        uint32_t* tile_hist = chunk_totals + (size_t)kMaxSortPasses * kMaxChunks * kRadix;
-        cudaMemsetAsync(chunk_totals, 0, (size_t)plan.n_passes * kMaxChunks * kRadix * sizeof(uint32_t), stream);
+        uint32_t* tile_hist = chunk_totals + (size_t)kMaxSortPasses * kTotalsRows * kRadix;
+        cudaMemsetAsync(chunk_totals, 0, (size_t)plan.n_passes * kTotalsRows * kRadix * sizeof(uint32_t), stream);
+        // Persistent TMA-staged downsweep unless FORMA_SORT_DS=simple (one CTA per tile).
+        static int ds_grid = -1;
+        if (ds_grid < 0) {
+            const char* e = getenv("FORMA_SORT_DS");
+            ds_grid = 0;
+            if (!(e && e[0] == 's')) {
+                cudaFuncSetAttribute(radix_downsweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(DownsweepSmem));
+                int per_sm = 0, sms = 148, dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_tma_kernel, kSortThreads,
+                                                              sizeof(DownsweepSmem));
+                ds_grid = per_sm > 0 ? per_sm * sms : 0;
+            }
+        }
         for (uint32_t p = 0; p < plan.n_passes; ++p) {
             const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
             uint64_t* kout = (p & 1u) ? keys : keys_tmp;
-            uint32_t* totals = chunk_totals + (size_t)p * kMaxChunks * kRadix;
+            uint32_t* totals = chunk_totals + (size_t)p * kTotalsRows * kRadix;
+            if (pass_events) cudaEventRecord(pass_events[3 * p], stream);
             radix_upsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, n, plan.pass[p], tile_hist, totals, tiles_per_chunk);
-            radix_tile_scan_kernel<<<chunks, kRadix, 0, stream>>>(tile_hist, totals, tiles, tiles_per_chunk, chunks);
-            radix_downsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, kout, n, plan.pass[p], tile_hist);
+            radix_tile_scan_kernel<<<chunks, kRadix, 0, stream>>>(tile_hist, totals, tiles, tiles_per_chunk);
+            if (pass_events) cudaEventRecord(pass_events[3 * p + 1], stream);
+            if (ds_grid > 0)
+                radix_downsweep_tma_kernel<<<min(tiles, (uint32_t)ds_grid), kSortThreads, sizeof(DownsweepSmem), stream>>>(
+                    kin, kout, n, plan.pass[p], tile_hist, tiles);
+            else
+                radix_downsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, kout, n, plan.pass[p], tile_hist);
+            if (pass_events) cudaEventRecord(pass_events[3 * p + 2], stream);
         }
+        res.timed_passes = pass_events ? (int)plan.n_passes : 0;
         res.launches = 3 * (int)plan.n_passes;
         res.in_tmp = (plan.n_passes & 1u) != 0u;
         return res;

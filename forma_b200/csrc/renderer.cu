@@ -187,6 +187,7 @@ struct LayerCache {
 
 struct Timer {
     cudaEvent_t ev[8];
+    cudaEvent_t sort_ev[3 * kMaxSortPasses];  // main sort, per pass: before upsweep, before / after downsweep
     bool ok = false;
 };
 
@@ -229,12 +230,16 @@ class Renderer {
     uint32_t last_segments = 0, last_cells = 0, last_entries = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied over PCIe since creation
     double stage_ms[8] = {0};               // see forma_renderer_stage_times
+    double kernel_ms[4] = {0};              // see forma_renderer_kernel_times
+    uint32_t kernel_launches[4] = {0};
     uint32_t* pinned_totals = nullptr;  // 4 x u32 pinned host words for count read-backs
 
     ~Renderer() {
         if (pinned_totals) cudaFreeHost(pinned_totals);
-        if (timer.ok)
+        if (timer.ok) {
             for (auto& e : timer.ev) cudaEventDestroy(e);
+            for (auto& e : timer.sort_ev) cudaEventDestroy(e);
+        }
     }
 
     int flush_geometry(Composition& comp);
@@ -479,6 +484,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     FORMA_CUDA_TRY(cudaSetDevice(device));
     if (!timer.ok) {
         for (auto& e : timer.ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
+        for (auto& e : timer.sort_ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
         timer.ok = true;
     }
 
@@ -565,10 +571,13 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     // Stage 3: sort.
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[2], stream));
     last_cells = last_entries = 0;
+    int timed_sort_passes = 0;
     if (n > 1) {
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n)));
-        SortResult sr = launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, segment_plan, sort_scratch.ptr, stream);
+        SortResult sr = launch_radix_sort(segs.ptr, segs_tmp.ptr, nullptr, nullptr, n, segment_plan, sort_scratch.ptr, stream,
+                                          timer.sort_ev);
         launches += sr.launches;
+        timed_sort_passes = sr.timed_passes;
         if (sr.in_tmp) swap_buffers(segs, segs_tmp);
         FORMA_CUDA_TRY(cudaGetLastError());
     }
@@ -717,6 +726,17 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         stage_ms[5] = el(4, 5);  // paint kernel alone
         stage_ms[6] = el(5, 6);  // device -> host copy of the framebuffer
         stage_ms[7] = el(0, 6);  // whole call on the device timeline
+        kernel_ms[0] = kernel_ms[1] = 0;
+        for (int p = 0; p < timed_sort_passes; ++p) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, timer.sort_ev[3 * p], timer.sort_ev[3 * p + 1]);
+            cudaEventElapsedTime(&b, timer.sort_ev[3 * p + 1], timer.sort_ev[3 * p + 2]);
+            kernel_ms[1] += a;  // upsweep + tile scan
+            kernel_ms[0] += b;  // downsweep
+        }
+        kernel_launches[0] = kernel_launches[1] = (uint32_t)timed_sort_passes;
+        kernel_ms[2] = stage_ms[5];
+        kernel_launches[2] = 1;
     }
     if (timings) {
         timings->line_setup_ms = stage_ms[1];
@@ -1037,6 +1057,12 @@ int forma_renderer_render_device(forma_renderer* r, forma_composition* c, uint8_
 uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.launches; }
 void forma_renderer_stage_times(const forma_renderer* r, double out_ms[8]) {
     for (int i = 0; i < 8; ++i) out_ms[i] = r->r.stage_ms[i];
+}
+void forma_renderer_kernel_times(const forma_renderer* r, double out_ms[4], uint32_t out_launches[4]) {
+    for (int i = 0; i < 4; ++i) {
+        out_ms[i] = r->r.kernel_ms[i];
+        out_launches[i] = r->r.kernel_launches[i];
+    }
 }
 void forma_renderer_counters(const forma_renderer* r, uint64_t out[8]) {
     out[6] = r->r.last_written_tiles;

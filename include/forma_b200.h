@@ -213,6 +213,10 @@ uint64_t forma_composition_point_count(forma_composition*);
  * count pass, [2] pixel-grid intersection, [3] sort, [4] painter tables,
  * [5] paint kernel, [6] device->host copy, [7] whole call. */
 void forma_renderer_stage_times(const forma_renderer*, double out_ms[8]);
+/* CUDA-event time of single kernels inside the last render, summed over their
+ * launches: [0] radix downsweep (main sort, one launch per pass), [1] radix
+ * upsweep + tile scan (one pair per pass), [2] paint kernel, [3] unused. */
+void forma_renderer_kernel_times(const forma_renderer*, double out_ms[4], uint32_t out_launches[4]);
 /* [0] kernel launches, [1] host->device bytes, [2] device->host bytes (all
  * since creation), [3] pixel segments, [4] cells, [5] entries of the last render,
  * [6] tiles the last layer-cache render copied back to a host buffer, [7] 0. */

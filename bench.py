@@ -246,7 +246,13 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 1)):
         frame_e2e()
     c2 = renderer.counters()
-    e2e_dev_ms, e2e_wall_ms = timed(frame_e2e, args.steps)
+    e2e_stage_acc = {k: 0.0 for k in renderer.STAGES}
+
+    def frame_e2e_acc():
+        frame_e2e()
+        for k, v in renderer.stage_times().items():
+            e2e_stage_acc[k] += v
+    e2e_dev_ms, e2e_wall_ms = timed(frame_e2e_acc, args.steps)
     c3 = renderer.counters()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
@@ -316,7 +322,8 @@ def run_cuda(args):
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": T_e2e / args.steps,
                 "h2d_bytes_per_step": (c3["h2d_bytes"] - c2["h2d_bytes"]) // args.steps,
                 "d2h_bytes_per_step": ((c3["d2h_bytes"] - c2["d2h_bytes"]) // args.steps) if world == 1 else h * stride,
-                "gpu_launches": c3["launches"] - c2["launches"]},
+                "gpu_launches": c3["launches"] - c2["launches"],
+                "stage_ms": {k: round(v / args.steps, 4) for k, v in e2e_stage_acc.items()}},
         "roofline": roofline,
         "clocks": sampler.summary(),
     }

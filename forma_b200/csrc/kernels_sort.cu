@@ -36,9 +36,11 @@ constexpr uint32_t kFlagMask = 3u << 30;
 constexpr uint32_t kValueMask = ~kFlagMask;
 
 __device__ __forceinline__ uint32_t digit_of(uint64_t key, const DigitSpec& d) {
-    uint32_t v = ((uint32_t)(key >> d.shift[0]) & ((1u << d.width[0]) - 1u)) << d.lsh[0];
-    v |= ((uint32_t)(key >> d.shift[1]) & ((1u << d.width[1]) - 1u)) << d.lsh[1];
-    v |= ((uint32_t)(key >> d.shift[2]) & ((1u << d.width[2]) - 1u)) << d.lsh[2];
+    uint32_t v = (uint32_t)(key >> d.shift[0]) & ((1u << d.width[0]) - 1u);  // lsh[0] == 0
+    if (d.width[1] != 0u) {  // uniform: most digits are a single bit run
+        v |= ((uint32_t)(key >> d.shift[1]) & ((1u << d.width[1]) - 1u)) << d.lsh[1];
+        v |= ((uint32_t)(key >> d.shift[2]) & ((1u << d.width[2]) - 1u)) << d.lsh[2];
+    }
     return v;
 }
 
@@ -741,6 +743,139 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     }
 }
 
+// Same tile (4096 keys) with 512 threads x 8 keys: the ranking chain per warp is
+// half as long and an SM holds 32 warps instead of 16 (2 CTAs, <= 64 registers),
+// which is what the profile of the 256-thread version asked for (short-scoreboard
+// and fixed-latency stalls at 24 % occupancy). Per-warp digit counters are u16
+// (a tile has 4096 keys) so that the shared memory still fits twice per SM.
+constexpr int kWideThreads = 512;
+constexpr int kWideItems = 8;
+constexpr int kWideWarps = kWideThreads / 32;
+static_assert(kWideThreads * kWideItems == kDsTile, "same tile as the upsweep");
+struct DownsweepWideSmem {
+    uint64_t stage[kDsStages][kDsTile];      // 3 x 32 KB
+    uint16_t warp_hist[kWideWarps][kRadix];  // 8 KB
+    uint32_t digit_start[kRadix];
+    uint32_t global_base[kRadix];
+    uint32_t warp_tot[kRadix / 32];
+    uint64_t bar[kDsStages];
+};
+
+__global__ void __launch_bounds__(kWideThreads, 2)
+    radix_downsweep_wide_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
+                                const uint32_t* __restrict__ tile_base, uint32_t tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DownsweepWideSmem& S = *reinterpret_cast<DownsweepWideSmem*>(smem_raw);
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t G = gridDim.x;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kDsStages; ++s) mbar_init(&S.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t tile, uint32_t st) {  // thread 0 only
+        uint32_t base = tile * (uint32_t)kDsTile;
+        uint32_t valid = min((uint32_t)kDsTile, n - base);
+        uint32_t bytes = ((valid + 1u) & ~1u) * 8u;  // multiple of 16 B (the buffers have one key of slack)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.bar[st], bytes);
+        tma_load_1d(&S.stage[st][0], keys_in + base, bytes, &S.bar[st]);
+    };
+
+    uint32_t tile = blockIdx.x;
+    if (tile >= tiles) return;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kDsStages - 1; ++s)
+            if (tile + (uint32_t)s * G < tiles) issue(tile + (uint32_t)s * G, (uint32_t)s);
+    }
+    uint32_t st = 0, phases = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t max_digit = (1u << spec.bits) - 1u;
+
+    for (; tile < tiles; tile += G) {
+        if (t == 0 && tile + (uint32_t)(kDsStages - 1) * G < tiles)
+            issue(tile + (uint32_t)(kDsStages - 1) * G, (st + kDsStages - 1u) % kDsStages);
+        uint32_t gbase = 0;
+        if (t < (uint32_t)kRadix) gbase = tile_base[(size_t)tile * kRadix + t];
+        {
+            uint32_t* z = reinterpret_cast<uint32_t*>(&S.warp_hist[0][0]);
+            for (int i = t; i < kWideWarps * kRadix / 2; i += kWideThreads) z[i] = 0;
+        }
+        const uint32_t base = tile * (uint32_t)kDsTile;
+        const uint32_t valid = min((uint32_t)kDsTile, n - base);
+        mbar_wait(&S.bar[st], (phases >> st) & 1u);
+        phases ^= 1u << st;
+        uint64_t* stage = S.stage[st];
+
+        uint64_t key[kWideItems];
+        const uint32_t wofs = warp * (32u * kWideItems);
+#pragma unroll
+        for (int i = 0; i < kWideItems; ++i) key[i] = stage[wofs + i * 32u + lane];
+        __syncthreads();  // everybody has its keys (and the zeroed histograms are visible)
+
+        uint32_t rank[kWideItems];
+#pragma unroll
+        for (int i = 0; i < kWideItems; ++i) {
+            uint32_t slot = wofs + i * 32u + lane;
+            uint32_t d = slot < valid ? digit_of(key[i], spec) : max_digit;
+            uint32_t peers = __match_any_sync(kFullMask, d);
+            uint32_t leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = S.warp_hist[warp][d];
+                S.warp_hist[warp][d] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(kFullMask, old, leader);
+            rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        if (t < (uint32_t)kRadix) {
+            uint32_t count = 0;
+#pragma unroll
+            for (int w = 0; w < kWideWarps; ++w) {
+                uint32_t c = S.warp_hist[w][t];
+                S.warp_hist[w][t] = (uint16_t)count;
+                count += c;
+            }
+            uint32_t incl = warp_inclusive_scan(count);
+            if (lane == 31) S.warp_tot[warp] = incl;
+            S.digit_start[t] = incl - count;  // completed below with the totals of the lower warps
+            S.global_base[t] = gbase;
+        }
+        __syncthreads();
+        if (t < (uint32_t)kRadix) {
+            uint32_t add = 0;
+            for (uint32_t w = 0; w < warp; ++w) add += S.warp_tot[w];
+            uint32_t dstart = S.digit_start[t] + add;
+            S.digit_start[t] = dstart;
+            S.global_base[t] -= dstart;
+        }
+        __syncthreads();
+
+#pragma unroll
+        for (int i = 0; i < kWideItems; ++i) {
+            uint32_t d = rank[i] >> 16;
+            stage[S.digit_start[d] + S.warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kWideItems; ++k) {
+            uint32_t p = t + k * kWideThreads;
+            if (p < valid) {
+                uint64_t kk = stage[p];
+                keys_out[S.global_base[digit_of(kk, spec)] + p] = kk;
+            }
+        }
+        __syncthreads();  // the stage is free again: the next iteration refills it by TMA
+        st = (st + 1u) % kDsStages;
+    }
+}
+
 static uint32_t tiles_for(uint32_t n, int items) { return (n + kSortThreads * items - 1) / (kSortThreads * items); }
 static int items_for(uint32_t n) { return n >= (1u << 21) ? 16 : 4; }
 // Large key-only sorts: FORMA_SORT_MODE = scan (default: reduce-then-scan passes),
@@ -795,11 +930,21 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
         uint32_t* tile_hist = chunk_totals + (size_t)kMaxSortPasses * kTotalsRows * kRadix;
         cudaMemsetAsync(chunk_totals, 0, (size_t)plan.n_passes * kTotalsRows * kRadix * sizeof(uint32_t), stream);
         // Persistent TMA-staged downsweep unless FORMA_SORT_DS=simple (one CTA per tile).
-        static int ds_grid = -1;
+        static int ds_grid = -1, wide_grid = 0;
         if (ds_grid < 0) {
-            const char* e = getenv("FORMA_SORT_DS");
+            const char* e = getenv("FORMA_SORT_DS");  // simple | tma256 | (default) wide
             ds_grid = 0;
-            if (!(e && e[0] == 's')) {
+            if (!e || (e[0] != 's' && e[0] != 't')) {
+                cudaFuncSetAttribute(radix_downsweep_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(DownsweepWideSmem));
+                int per_sm = 0, sms = 148, dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_wide_kernel, kWideThreads,
+                                                              sizeof(DownsweepWideSmem));
+                wide_grid = per_sm > 0 ? per_sm * sms : 0;
+            }
+            if (!wide_grid && !(e && e[0] == 's')) {
                 cudaFuncSetAttribute(radix_downsweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(DownsweepSmem));
                 int per_sm = 0, sms = 148, dev = 0;
@@ -818,7 +963,10 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
             radix_upsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, n, plan.pass[p], tile_hist, totals, tiles_per_chunk);
             radix_tile_scan_kernel<<<chunks, kRadix, 0, stream>>>(tile_hist, totals, tiles, tiles_per_chunk);
             if (pass_events) cudaEventRecord(pass_events[3 * p + 1], stream);
-            if (ds_grid > 0)
+            if (wide_grid > 0)
+                radix_downsweep_wide_kernel<<<min(tiles, (uint32_t)wide_grid), kWideThreads, sizeof(DownsweepWideSmem), stream>>>(
+                    kin, kout, n, plan.pass[p], tile_hist, tiles);
+            else if (ds_grid > 0)
                 radix_downsweep_tma_kernel<<<min(tiles, (uint32_t)ds_grid), kSortThreads, sizeof(DownsweepSmem), stream>>>(
                     kin, kout, n, plan.pass[p], tile_hist, tiles);
             else

@@ -94,47 +94,73 @@ __global__ void __launch_bounds__(kCellThreads)
 // cpu/painter/mod.rs:257-271, layer_workbench/mod.rs:218-224), and the
 // (tile_y, layer, tile_x) key for the carry pass.
 
-__global__ void cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
-                                  const uint64_t* __restrict__ cell_key, uint32_t n_cells, uint4* __restrict__ cell_cover,
-                                  uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
-    // Eight lanes per cell (a cell holds ~20-25 segments on average): the lanes
-    // stride over the cell's contiguous segments (64 B per step), then the packed
-    // partial sums are combined with shuffles inside the 8-lane group.
-    const uint32_t sub = threadIdx.x & 7u;
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const bool live = c < n_cells;
-    uint64_t ck = 0;
-    bool relevant = false;
-    uint32_t s0 = 0, s1 = 0;
-    if (live) {
-        ck = cell_key[c];
-        int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
-        relevant = !(ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi);
-        if (relevant) {
-            s0 = cell_start[c];
-            s1 = cell_start[c + 1];
+// A CTA owns 256 consecutive cells, i.e. one contiguous range of the sorted
+// segments: its warps stream that range with coalesced loads, find each
+// segment's cell from the run boundaries (ballot of key changes) and add its
+// cover to the cell's row counter in shared memory.
+constexpr int kCoverCells = 256;
+
+__global__ void __launch_bounds__(kCoverCells)
+    cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
+                      const uint64_t* __restrict__ cell_key, uint32_t n_cells, uint4* __restrict__ cell_cover,
+                      uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
+    __shared__ uint32_t s_start[kCoverCells + 1];
+    __shared__ int32_t s_acc[kCoverCells][16];
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const uint32_t c0 = blockIdx.x * kCoverCells;
+    const uint32_t nc = min((uint32_t)kCoverCells, n_cells - c0);
+    if (t <= nc) s_start[t] = cell_start[c0 + t];
+    if (t == 0) s_start[nc] = cell_start[c0 + nc];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s_acc[t][r] = 0;
+    __syncthreads();
+
+    const uint32_t s0 = s_start[0], s1 = s_start[nc];
+    const uint32_t span = (((s1 - s0) + 7u) / 8u + 31u) & ~31u;  // per warp, a multiple of 32
+    const uint32_t w0 = s0 + warp * span, w1 = min(s1, w0 + span);
+    if (w0 < w1) {
+        uint32_t lo = 0, hi = nc;  // largest cell with s_start[cell] <= w0
+        while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_start[mid] <= w0) lo = mid;
+            else hi = mid;
+        }
+        uint32_t base = lo - (s_start[lo] == w0 ? 1u : 0u);  // cell index before the first head (may wrap to ~0)
+        // Key of the segment before the span (a span that starts a cell differs from it by construction).
+        uint64_t carry = w0 > 0u ? (segs[w0 - 1u] >> kSortShift) : ~0ull;
+        const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
+        for (uint32_t i0 = w0; i0 < w1; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            const bool valid = i < w1;
+            const uint64_t s = valid ? segs[i] : 0ull;
+            const uint64_t k = s >> kSortShift;
+            uint64_t kp = __shfl_up_sync(kFullMask, k, 1);
+            if (lane == 0) kp = carry;
+            const uint32_t heads = __ballot_sync(kFullMask, valid && k != kp);
+            if (valid) {
+                const uint32_t cell = base + __popc(heads & le_mask);
+                const uint32_t ly = (uint32_t)(s >> 12) & 15u;
+                const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+                atomicAdd(&s_acc[cell][ly], cv);
+            }
+            base += __popc(heads);
+            carry = __shfl_sync(kFullMask, k, 31);
         }
     }
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t i = s0 + sub; i < s1; i += 8u) {
-        uint64_t s = segs[i];
-        uint32_t ly = (uint32_t)(s >> 12) & 15u;
-        uint32_t cv = (uint32_t)s & 0x3Fu;
-        cv = (cv ^ 0x20u) - 0x20u;  // sign-extend 6 bits
-        uint32_t v = (cv & 0xFFu) << (8u * (ly & 3u));
-        uint32_t w = ly >> 2;
+    __syncthreads();
+
+    if (t < nc) {
+        const uint32_t c = c0 + t;
+        uint32_t w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] = __vadd4(acc[k], w == (uint32_t)k ? v : 0u);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] = __vadd4(acc[k], __shfl_xor_sync(kFullMask, acc[k], o));
-    }
-    if (live && sub == 0) {
+        for (int q = 0; q < 4; ++q)
+            w[q] = ((uint32_t)s_acc[t][4 * q] & 0xFFu) | (((uint32_t)s_acc[t][4 * q + 1] & 0xFFu) << 8) |
+                   (((uint32_t)s_acc[t][4 * q + 2] & 0xFFu) << 16) | (((uint32_t)s_acc[t][4 * q + 3] & 0xFFu) << 24);
+        const uint64_t ck = cell_key[c];
+        const int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
+        const bool relevant = !(ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi);
         perm[c] = c;
-        cell_cover[c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        cell_cover[c] = make_uint4(w[0], w[1], w[2], w[3]);
         key2[c] = relevant ? make_key2(ck) : sentinel_key(S.tiles_y);
     }
 }
@@ -275,7 +301,9 @@ void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_o
 
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
                        uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st) {
-    cell_cover_kernel<<<(n_cells + 31) / 32, 256, 0, st>>>(S, segs, cell_start, cell_key, n_cells, cell_cover, key2, perm);
+    if (n_cells)
+        cell_cover_kernel<<<(n_cells + kCoverCells - 1) / kCoverCells, kCoverCells, 0, st>>>(S, segs, cell_start, cell_key, n_cells,
+                                                                                          cell_cover, key2, perm);
 }
 
 // Largest values the three key fields can take in the pair sorts (sentinel

@@ -18,29 +18,39 @@ struct QuadRec {
     float px[3], py[3], pw[3];  // control points, pre-multiplied by their weights
     float x0, dx_recip, k0, dk, curv_recip;
     float prev_curv;  // running curvature of the previous quad iff same spline, else 0 (path.rs:508-514)
+    float total;      // running curvature of the spline including this quad
 };
 
-// One output point of a flatten program (path.rs:138-168 PointCommand, resolved).
-//   kind 0: literal point (a, b)                  (Start / End of a spline)
-//   kind 1: literal point (a, b), ends a contour  (End with new_contour)
-//   kind 2: evaluate quad `quad` at Incr(a) * pi(b)
-struct PointCmd {
-    uint32_t kind;
-    uint32_t quad;
-    float a, b;
+// One spline of a flatten program: the point commands populate_buffers
+// (path.rs:400-445) emits for it, in closed form. Its output points are
+//   [p0 if it emits a start point] ++ [quads evaluated at step * pi, pi = 1..E] ++ [p2]
+// (path.rs:138-168 PointCommand::Start / Incr / End); the quad of evaluated
+// point pi is the first one whose running curvature reaches pi.
+struct SplineRec {
+    float p0x, p0y, p2x, p2y;
+    float step;            // curvature / subdivisions
+    uint32_t first_quad;   // program-relative
+    uint32_t n_quads;
+    uint32_t first_point;  // program-relative index of the spline's first output point
+    uint32_t info;         // E (= subdivisions - 1, or 0) | emits its start point << 30 | ends a contour << 31
 };
+constexpr uint32_t kSplineEvalMask = (1u << 30) - 1u;
 
 struct FlattenProgram {
     std::vector<QuadRec> quads;
-    std::vector<PointCmd> cmds;
+    std::vector<SplineRec> splines;
+    uint32_t n_points = 0;        // output points
+    uint32_t n_contour_ends = 0;  // points that end a contour, the last point of the program excluded
 };
 
 // A batch entry of flatten_eval_kernel: points [first, first+count) of the
 // batch belong to this insert job (Layer::insert, composition/layer.rs:90-111).
 struct FlattenJob {
-    uint32_t first_point;   // index into the batch's PointCmd array
+    uint32_t first_point;   // first output point of the job in the batch
     uint32_t count;
-    uint32_t quad_base;     // added to PointCmd::quad
+    uint32_t quad_base;     // added to SplineRec::first_quad
+    uint32_t spline_base;   // the job's splines in the batch's SplineRec array
+    uint32_t n_splines;
     uint32_t geom_id;       // id written for non-contour-end points (0 = None)
     uint32_t has_xf;
     float xf[6];            // GeomPresTransform: ux, uy, vx, vy, tx, ty

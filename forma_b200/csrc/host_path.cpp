@@ -123,6 +123,7 @@ class SplineBuilder {
         rec.curv_recip = rcp(cur);
         uint32_t spline_index = (uint32_t)splines_.size() - 1;
         rec.prev_curv = (!quad_spline_.empty() && quad_spline_.back() == spline_index) ? quad_total_.back() : 0.0f;
+        rec.total = total;
         quads_.push_back(rec);
         quad_spline_.push_back(spline_index);
         quad_total_.push_back(total);
@@ -152,21 +153,36 @@ class SplineBuilder {
     // populate_buffers (path.rs:400-445) -> resolved point commands.
     void finish(FlattenProgram& out) {
         out.quads = std::move(quads_);
-        size_t qi = 0;
+        // The quads of a spline are contiguous; the reference walks them with
+        // `if pi > total[qi] { qi += 1 }` per evaluated point (path.rs:424-431), which
+        // — every quad adding more than 1 to the running curvature (path.rs:322-332) —
+        // is "the first quad whose running curvature reaches pi": the kernel
+        // (flatten_eval_kernel) finds it by bisection, no per-point command needed.
+        std::vector<uint32_t> quads_of(splines_.size(), 0u);
+        for (uint32_t si : quad_spline_) quads_of[si] += 1;
+        out.splines.reserve(splines_.size());
+        uint64_t qi = 0, pt = 0;
         for (size_t si = 0; si < splines_.size(); ++si) {
             const Spline& s = splines_[si];
             uint64_t subdivisions = to_count(std::ceil(s.curvature));
             float step = s.curvature / (float)subdivisions;
             bool start = si == 0 || splines_[si - 1].ends_contour ||
                          length({splines_[si - 1].p2.x - s.p0.x, splines_[si - 1].p2.y - s.p0.y}) > kMaxError;
-            if (start) out.cmds.push_back({0u, 0u, s.p0.x, s.p0.y});
-            for (uint64_t pi = 1; pi < subdivisions; ++pi) {
-                if ((float)pi > quad_total_[qi]) qi += 1;
-                out.cmds.push_back({2u, (uint32_t)qi, step, (float)pi});
-            }
-            out.cmds.push_back({s.ends_contour ? 1u : 0u, 0u, s.p2.x, s.p2.y});
-            if (subdivisions > 0) qi += 1;
+            uint64_t evaluated = subdivisions > 0 ? subdivisions - 1 : 0;
+            if (evaluated > kSplineEvalMask) evaluated = kSplineEvalMask;
+            SplineRec r;
+            r.p0x = s.p0.x; r.p0y = s.p0.y; r.p2x = s.p2.x; r.p2y = s.p2.y;
+            r.step = step;
+            r.first_quad = (uint32_t)qi;
+            r.n_quads = quads_of[si];
+            r.first_point = (uint32_t)pt;
+            r.info = (uint32_t)evaluated | (start ? 1u << 30 : 0u) | (s.ends_contour ? 1u << 31 : 0u);
+            out.splines.push_back(r);
+            pt += (start ? 1u : 0u) + evaluated + 1u;
+            qi += quads_of[si];
+            if (s.ends_contour && si + 1 < splines_.size()) out.n_contour_ends += 1;
         }
+        out.n_points = (uint32_t)std::min<uint64_t>(pt, 0xFFFFFFFFull);
     }
 
    private:

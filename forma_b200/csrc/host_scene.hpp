@@ -73,10 +73,10 @@ class Composition {
     DeviceBuffer<uint32_t> d_gid;
     uint32_t n_resident = 0;          // points already evaluated on the device
     // Pinned staging of the flatten programs of jobs [staged_from, staged_to).
-    PinnedBuffer<PointCmd> h_cmds;
+    PinnedBuffer<SplineRec> h_splines;
     PinnedBuffer<QuadRec> h_quads;
     PinnedBuffer<FlattenJob> h_jobs;
-    size_t staged_from = 0, staged_to = 0, staged_cmds = 0, staged_quads = 0;
+    size_t staged_from = 0, staged_to = 0, staged_splines = 0, staged_quads = 0, staged_points = 0;
     // Drops device residency: the next render re-uploads everything from pinned
     // host memory (used to measure the cold, end-to-end path).
     void evict() {

@@ -23,8 +23,8 @@ struct RasterArgs {
 };
 
 // ---- kernels_raster.cu ------------------------------------------------------
-void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_points,
-                         float* x, float* y, uint32_t* gid, cudaStream_t stream);
+void launch_flatten_eval(const SplineRec* splines, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_jobs,
+                         uint32_t n_points, float* x, float* y, uint32_t* gid, cudaStream_t stream);
 uint32_t raster_num_blocks(uint32_t n_points);
 // block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
 // max_tile[0..1] = largest biased tile_x / tile_y any emitted segment can carry.
@@ -113,15 +113,26 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, cudaStream_t st);
-// Merges the cells with the sorted carry-only entries into ekey / eid (n_cells + n_gaps).
-void launch_merge_entries(const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey, const uint32_t* gid,
-                          uint32_t n_gaps, uint64_t* ekey, uint32_t* eid, cudaStream_t st);
+// One painter entry = one (tile, layer) pair with segments and / or a carried cover.
+struct EntryRec {  // 64 B
+    uint32_t layer, seg0, seg1;  // layer order; [seg0, seg1) in the sorted segments (empty for carry-only entries)
+    uint32_t meta;               // packed style bits, see pack_style_meta (paint_common.cuh)
+    uint4 carry;                 // 16 x i8 cover carried in from the tiles on the left
+    float color[4];              // solid fill colour
+    int32_t slot;                // style slot
+    uint32_t clip_layers;
+    uint32_t flags0;             // initial optimizer flags (kFlag*)
+    uint32_t pad;
+};
+// Merges the cells with the sorted carry-only entries: ekey, entry records and
+// initial flags of the n_cells + n_gaps entries, ordered by (tile_y, tile_x, layer).
+void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,
+                          const uint32_t* gid, uint32_t n_gaps, const uint32_t* cell_start, const uint4* carry_in,
+                          const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st);
 void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,
                         uint32_t* tile_end, cudaStream_t st);
-void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,
-                  const uint32_t* cell_start, const uint4* carry_in, const uint4* gap_carry, uint32_t n_cells,
-                  const uint32_t* tile_begin, const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer,
-                  uint32_t* tile_counter, cudaStream_t st);
+void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint32_t* tile_begin,
+                  const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st);
 // Packs the tiles in S.written_list into `packed` (256 u32 per tile, row-major).
 void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st);
 

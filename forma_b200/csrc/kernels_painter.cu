@@ -23,20 +23,13 @@ namespace forma {
 
 struct PaintInputs {
     const uint64_t* segs;
-    const uint64_t* ekey;        // sorted entries
-    const uint32_t* eid;
-    const uint32_t* cell_start;
-    const uint4* carry_in;       // by cell
-    const uint4* gap_carry;      // by gap id
-    uint32_t n_cells;
+    const EntryRec* recs;        // sorted entries (kernels_tables.cu: merge_entries_kernel)
     const uint32_t* tile_begin;
     const uint32_t* tile_end;
-    uint8_t* eflags;             // per sorted entry scratch (optimizer passes)
+    uint8_t* eflags;             // per sorted entry: optimizer flags, initialised with EntryRec::flags0
     uint8_t* framebuffer;
     uint32_t* tile_counter;
 };
-
-constexpr uint32_t kFlagHasSegs = 1, kFlagFull = 2, kFlagMaskedOut = 4, kFlagSkipClip = 8, kFlagUnchanged = 16;
 
 // Per-entry header, one entry per lane.
 struct EntryHdr {
@@ -56,27 +49,21 @@ __device__ __forceinline__ uint32_t meta_fill_type(uint32_t m) { return (m >> 3)
 __device__ __forceinline__ uint32_t meta_blend(uint32_t m) { return (m >> 5) & 15u; }
 __device__ __forceinline__ bool meta_unchanged(uint32_t m) { return (m >> 9) & 1u; }
 
-__device__ __forceinline__ EntryHdr load_hdr(const PaintScene& S, const PaintInputs& in, uint32_t p) {
+__device__ __forceinline__ EntryHdr load_hdr(const PaintInputs& in, uint32_t p) {
+    const uint4* q = reinterpret_cast<const uint4*>(in.recs + p);  // four independent 16-byte loads
+    const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
     EntryHdr h;
-    h.layer = key_layer(in.ekey[p]);
-    uint32_t id = in.eid[p];
-    if (id < in.n_cells) {
-        h.seg0 = in.cell_start[id];
-        h.seg1 = in.cell_start[id + 1];
-        h.carry = in.carry_in[id];
-    } else {
-        h.seg0 = h.seg1 = 0;
-        h.carry = in.gap_carry[id - in.n_cells];
-    }
-    h.slot = S.order_to_style[h.layer];
-    const StyleRec& st = S.styles[h.slot];
-    h.meta = (st.fill_rule & 1u) | ((st.func & 1u) << 1) | ((st.is_clipped ? 1u : 0u) << 2) | ((st.fill_type & 3u) << 3) |
-             ((st.blend_mode & 15u) << 5) | ((S.unchanged && S.unchanged[h.slot]) ? (1u << 9) : 0u);
-    h.clip_layers = st.clip_layers;
-    h.color[0] = st.color[0];
-    h.color[1] = st.color[1];
-    h.color[2] = st.color[2];
-    h.color[3] = st.color[3];
+    h.layer = q0.x;
+    h.seg0 = q0.y;
+    h.seg1 = q0.z;
+    h.meta = q0.w;
+    h.carry = q1;
+    h.color[0] = __uint_as_float(q2.x);
+    h.color[1] = __uint_as_float(q2.y);
+    h.color[2] = __uint_as_float(q2.z);
+    h.color[3] = __uint_as_float(q2.w);
+    h.slot = (int32_t)q3.x;
+    h.clip_layers = q3.y;
     return h;
 }
 
@@ -143,6 +130,9 @@ __device__ __noinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ 
                        fmaf(dst.w, inv_src_a, sa));
 }
 
+// The scalar blend of the solid-tile fold (all 16 modes) stays out of line too.
+__device__ __noinline__ Rgba blend_solid(uint32_t mode, Rgba dst, Rgba src) { return sblend::blend(mode, dst, src); }
+
 constexpr int kPaintWarpsPerBlock = 2;
 
 // kMinBlocks trades registers for resident warps (8 -> 128 regs, 10 -> 96 regs).
@@ -165,35 +155,46 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
     }
     __syncwarp();
 
-    while (true) {
-        uint32_t tile_lin = 0;
-        if (lane == 0) tile_lin = atomicAdd(in.tile_counter, 1u);
-        tile_lin = __shfl_sync(kFullMask, tile_lin, 0);
-        if (tile_lin >= n_tiles) break;
+    // Tile tickets are drawn two tiles ahead and the entry range of the next tile is
+    // loaded while the current one is painted, so a warp never waits for the
+    // counter or for tile_begin / tile_end between tiles.
+    uint32_t cur = 0, next_raw = 0, cur_b = 0, cur_e = 0;
+    if (lane == 0) cur = atomicAdd(in.tile_counter, 1u);
+    cur = __shfl_sync(kFullMask, cur, 0);
+    if (lane == 0) next_raw = atomicAdd(in.tile_counter, 1u);
+    if (cur < n_tiles) {
+        const uint32_t t0 = (S.ty_lo + cur / ntx) * S.tiles_x + S.tx_lo + cur % ntx;
+        cur_b = in.tile_begin[t0];
+        cur_e = in.tile_end[t0];
+    }
+    while (cur < n_tiles) {
+        const uint32_t tile_lin = cur, b = cur_b, e = cur_e;
+        {
+            const uint32_t nxt = __shfl_sync(kFullMask, next_raw, 0);
+            uint32_t nb = 0, ne = 0;
+            if (nxt < n_tiles) {
+                const uint32_t t1 = (S.ty_lo + nxt / ntx) * S.tiles_x + S.tx_lo + nxt % ntx;
+                nb = in.tile_begin[t1];
+                ne = in.tile_end[t1];
+            }
+            if (lane == 0) next_raw = atomicAdd(in.tile_counter, 1u);
+            cur = nxt;
+            cur_b = nb;
+            cur_e = ne;
+        }
         const uint32_t ty = S.ty_lo + tile_lin / ntx, tx = S.tx_lo + tile_lin % ntx;
         const uint32_t tid = ty * S.tiles_x + tx;
-        const uint32_t b = in.tile_begin[tid], e = in.tile_end[tid];
 
         // ---- optimizer passes (layer_workbench/passes/*.rs) ------------------
         // Pass A: per-entry facts, 32 entries at a time.
+        // (has-segments / full / unchanged facts were computed when the entries were built.)
         bool any_clip = false, all_unchanged = true;
         for (uint32_t p0 = b; p0 < e; p0 += 32u) {
             uint32_t p = p0 + lane;
-            bool clipish = false, changed = false;
-            if (p < e) {
-                EntryHdr h = load_hdr(S, in, p);
-                uint32_t f = 0;
-                if (h.seg1 > h.seg0) f |= kFlagHasSegs;
-                else if (cover_is_full(h.carry, meta_fill_rule(h.meta))) f |= kFlagFull;  // layer_is_full, mod.rs:171-182
-                if (meta_unchanged(h.meta)) f |= kFlagUnchanged;
-                in.eflags[p] = (uint8_t)f;
-                clipish = meta_func(h.meta) == 1u || meta_is_clipped(h.meta);
-                changed = !meta_unchanged(h.meta);
-            }
-            any_clip |= __any_sync(kFullMask, clipish);
-            all_unchanged = all_unchanged && !__any_sync(kFullMask, changed);
+            uint32_t f = p < e ? (uint32_t)in.eflags[p] : kFlagUnchanged;
+            any_clip |= __any_sync(kFullMask, (f & kFlagClipish) != 0u);
+            all_unchanged = all_unchanged && !__any_sync(kFullMask, (f & kFlagUnchanged) == 0u);
         }
-        __syncwarp();
 
         // tile_unchanged pass (passes/tile_unchanged.rs:24-57) — only with a layer cache.
         const bool use_cache = S.cache_tiles != nullptr;
@@ -223,18 +224,24 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 bool has_clip = false, clip_full = false, clip_used = false;
                 uint32_t clip_last = 0, clip_i = 0;
                 for (uint32_t p = b; p < e; ++p) {
-                    uint32_t id = key_layer(in.ekey[p]);
-                    const StyleRec& st = S.styles[S.order_to_style[id]];
                     uint32_t f = in.eflags[p];
-                    if (st.func == 1u) {
+                    if (!(f & kFlagClipish)) {  // neither a clip nor a clipped layer
+                        if (has_clip && in.recs[p].layer > clip_last) {
+                            has_clip = false;
+                            if (!clip_used) in.eflags[clip_i] |= (uint8_t)kFlagMaskedOut;
+                        }
+                        continue;
+                    }
+                    const uint32_t id = in.recs[p].layer;
+                    if (!(f & kFlagClippedDraw)) {  // Func::Clip
                         clip_full = (f & kFlagFull) != 0;
-                        clip_last = id + st.clip_layers;
+                        clip_last = id + in.recs[p].clip_layers;
                         clip_i = p;
                         clip_used = false;
                         has_clip = true;
                         if (clip_full) f |= kFlagMaskedOut;
                     }
-                    if (st.func == 0u && st.is_clipped) {
+                    if (f & kFlagClippedDraw) {
                         if (has_clip && id <= clip_last) {
                             if (clip_full) f |= kFlagSkipClip;
                             else clip_used = true;
@@ -266,10 +273,9 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             if (p < hi) {
                 uint32_t f = in.eflags[p];
                 if (!(f & kFlagMaskedOut)) {
-                    const StyleRec& st = S.styles[S.order_to_style[key_layer(in.ekey[p])]];
-                    bool clipped = st.func == 0u && st.is_clipped && !(f & kFlagSkipClip);
+                    bool clipped = (f & kFlagClippedDraw) && !(f & kFlagSkipClip);
                     if (clipped || !(f & kFlagFull)) inc = true;
-                    else if (st.func == 0u && st.fill_type == 0u && st.blend_mode == 0u && st.color[3] == 1.0f) cand = true;
+                    else if (f & kFlagOpaque) cand = true;
                     changed = !(f & kFlagUnchanged);
                 }
             }
@@ -300,16 +306,16 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             Rgba dst = clear;
             uint32_t p = first_paint;
             if (have_opaque) {
-                const StyleRec& st = S.styles[S.order_to_style[key_layer(in.ekey[p])]];
-                dst = Rgba{st.color[0], st.color[1], st.color[2], st.color[3]};
+                const EntryRec& r = in.recs[p];
+                dst = Rgba{r.color[0], r.color[1], r.color[2], r.color[3]};
                 ++p;
             }
             bool solid = true;
             for (; p < e; ++p) {
                 if (in.eflags[p] & kFlagMaskedOut) continue;
-                const StyleRec& st = S.styles[S.order_to_style[key_layer(in.ekey[p])]];
-                if (st.func == 0u && st.fill_type == 0u) {
-                    dst = sblend::blend(st.blend_mode, dst, Rgba{st.color[0], st.color[1], st.color[2], st.color[3]});
+                const EntryRec& r = in.recs[p];
+                if (meta_func(r.meta) == 0u && meta_fill_type(r.meta) == 0u) {
+                    dst = blend_solid(meta_blend(r.meta), dst, Rgba{r.color[0], r.color[1], r.color[2], r.color[3]});
                 } else {
                     solid = false;
                     break;
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             EntryHdr mine{};
             uint32_t my_flags = kFlagMaskedOut;
             if (lane < cnt) {
-                mine = load_hdr(S, in, p0 + lane);
+                mine = load_hdr(in, p0 + lane);
                 my_flags = in.eflags[p0 + lane];
             }
             // Prefetch the first segment chunk of the first entry of this group.
@@ -530,15 +536,12 @@ void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32
                                                   S.written_count, packed);
 }
 
-void launch_paint(const PaintScene& S, const uint64_t* segs, const uint64_t* ekey, const uint32_t* eid,
-                  const uint32_t* cell_start, const uint4* carry_in, const uint4* gap_carry, uint32_t n_cells,
-                  const uint32_t* tile_begin, const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer,
-                  uint32_t* tile_counter, cudaStream_t st) {
+void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint32_t* tile_begin,
+                  const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st) {
     if (S.tx_hi <= S.tx_lo || S.ty_hi <= S.ty_lo) return;
     uint32_t n_tiles = (S.tx_hi - S.tx_lo) * (S.ty_hi - S.ty_lo);
     cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
-    PaintInputs in{segs, ekey, eid, cell_start, carry_in, gap_carry, n_cells, tile_begin, tile_end, eflags, framebuffer,
-                   tile_counter};
+    PaintInputs in{segs, recs, tile_begin, tile_end, eflags, framebuffer, tile_counter};
     // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy.
     // FORMA_PAINT_REGS=96 selects the 96-register build (default: 128 registers,
     // measured 17 % faster on paris@4K: fewer spills beat the extra warps).

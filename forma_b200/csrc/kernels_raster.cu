@@ -26,20 +26,58 @@ __device__ __forceinline__ float inv_curvature(float k) {  // path.rs:53-56
     return k * (1.0f - c + sqrtf(fmaf(k * k, 0.25f, c * c)));
 }
 
-__global__ void flatten_eval_kernel(const PointCmd* __restrict__ cmds, const QuadRec* __restrict__ quads,
-                                    const FlattenJob* __restrict__ jobs, uint32_t n_points,
+// One thread per output point: it finds its insert job, then its spline, by
+// bisection over their first-point offsets (the per-point commands of the
+// reference, path.rs:138-168, are never materialised — 36 B per spline cross
+// PCIe instead of 16 B per point).
+__global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const QuadRec* __restrict__ quads,
+                                    const FlattenJob* __restrict__ jobs, uint32_t n_jobs, uint32_t n_points,
                                     float* __restrict__ out_x, float* __restrict__ out_y,
                                     uint32_t* __restrict__ out_gid) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_points) return;
-    PointCmd c = cmds[i];
-    const FlattenJob job = jobs[c.kind >> 2];
-    uint32_t kind = c.kind & 3u;
+    uint32_t lo = 0, hi = n_jobs - 1u;  // last job with first_point <= i
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1u) >> 1;
+        if (jobs[mid].first_point <= i) lo = mid;
+        else hi = mid - 1u;
+    }
+    const FlattenJob job = jobs[lo];
+    const uint32_t local = i - job.first_point;
+    lo = 0;
+    hi = job.n_splines - 1u;  // last spline with first_point <= local
+    const SplineRec* sp = splines + job.spline_base;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1u) >> 1;
+        if (sp[mid].first_point <= local) lo = mid;
+        else hi = mid - 1u;
+    }
+    const SplineRec s = sp[lo];
+    const uint32_t has_start = (s.info >> 30) & 1u, evaluated = s.info & kSplineEvalMask;
+    const uint32_t j = local - s.first_point;  // point of the spline
+    uint32_t kind;                             // 0 literal, 1 literal + contour end, 2 evaluated
     float px, py;
-    if (kind == 2u) {
-        const QuadRec q = quads[job.quad_base + c.quad];
+    if (has_start && j == 0u) {
+        kind = 0u;
+        px = s.p0x;
+        py = s.p0y;
+    } else if (j - has_start == evaluated) {
+        kind = (s.info >> 31) ? 1u : 0u;
+        px = s.p2x;
+        py = s.p2y;
+    } else {
+        kind = 2u;
+        const float pi = (float)(j - has_start + 1u);
+        const QuadRec* qs = quads + job.quad_base + s.first_quad;
+        uint32_t a = 0, b = s.n_quads - 1u;  // first quad whose running curvature reaches pi (path.rs:424-431)
+        while (a < b) {
+            uint32_t mid = (a + b) >> 1;
+            if (pi > qs[mid].total) a = mid + 1u;
+            else b = mid;
+        }
+        const QuadRec q = qs[a];
         // path.rs:515-522
-        float ratio = fmaf(c.a, c.b, -q.prev_curv) * q.curv_recip;
+        float ratio = fmaf(s.step, pi, -q.prev_curv) * q.curv_recip;
         float xx = inv_curvature(fmaf(ratio, q.dk, q.k0));
         float t = d_clamp((xx - q.x0) * q.dx_recip, 0.0f, 1.0f);
         // eval_quad, path.rs:447-471
@@ -47,9 +85,6 @@ __global__ void flatten_eval_kernel(const PointCmd* __restrict__ cmds, const Qua
         float w_recip = d_rcp(w);
         px = d_mix(t, d_mix(t, q.px[0], q.px[1]), d_mix(t, q.px[1], q.px[2])) * w_recip;
         py = d_mix(t, d_mix(t, q.py[0], q.py[1]), d_mix(t, q.py[1], q.py[2])) * w_recip;
-    } else {
-        px = c.a;
-        py = c.b;
     }
     if (job.has_xf) {  // path.rs:689-706, GeomPresTransform::transform
         float tx = fmaf(job.xf[0], px, fmaf(job.xf[2], py, job.xf[4]));
@@ -57,7 +92,6 @@ __global__ void flatten_eval_kernel(const PointCmd* __restrict__ cmds, const Qua
         px = tx;
         py = ty;
     }
-    uint32_t local = i - job.first_point;
     uint32_t dst = job.dst + local;
     // ids: None at contour ends; the id of the last point of an insert is
     // replaced by the trailing None (segment.rs:181-198).
@@ -309,10 +343,10 @@ __global__ void __launch_bounds__(kRasterThreads)
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
-void launch_flatten_eval(const PointCmd* cmds, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_points,
-                         float* x, float* y, uint32_t* gid, cudaStream_t stream) {
-    if (!n_points) return;
-    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(cmds, quads, jobs, n_points, x, y, gid);
+void launch_flatten_eval(const SplineRec* splines, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_jobs,
+                         uint32_t n_points, float* x, float* y, uint32_t* gid, cudaStream_t stream) {
+    if (!n_points || !n_jobs) return;
+    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, quads, jobs, n_jobs, n_points, x, y, gid);
 }
 
 uint32_t raster_num_blocks(uint32_t n_points) { return n_points ? (n_points + kRasterThreads - 1) / kRasterThreads : 0; }

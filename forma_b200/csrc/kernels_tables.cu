@@ -129,22 +129,31 @@ __global__ void __launch_bounds__(kCoverCells)
         // Key of the segment before the span (a span that starts a cell differs from it by construction).
         uint64_t carry = w0 > 0u ? (segs[w0 - 1u] >> kSortShift) : ~0ull;
         const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
-        for (uint32_t i0 = w0; i0 < w1; i0 += 32u) {
-            const uint32_t i = i0 + lane;
-            const bool valid = i < w1;
-            const uint64_t s = valid ? segs[i] : 0ull;
-            const uint64_t k = s >> kSortShift;
-            uint64_t kp = __shfl_up_sync(kFullMask, k, 1);
-            if (lane == 0) kp = carry;
-            const uint32_t heads = __ballot_sync(kFullMask, valid && k != kp);
-            if (valid) {
-                const uint32_t cell = base + __popc(heads & le_mask);
-                const uint32_t ly = (uint32_t)(s >> 12) & 15u;
-                const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
-                atomicAdd(&s_acc[cell][ly], cv);
+        for (uint32_t i0 = w0; i0 < w1; i0 += 128u) {
+            uint64_t sv[4];  // four coalesced loads in flight per lane
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) {
+                const uint32_t i = i0 + u * 32u + lane;
+                sv[u] = i < w1 ? segs[i] : 0ull;
             }
-            base += __popc(heads);
-            carry = __shfl_sync(kFullMask, k, 31);
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) {
+                const uint32_t i = i0 + u * 32u + lane;
+                const bool valid = i < w1;
+                const uint64_t s = sv[u];
+                const uint64_t k = s >> kSortShift;
+                uint64_t kp = __shfl_up_sync(kFullMask, k, 1);
+                if (lane == 0) kp = carry;
+                const uint32_t heads = __ballot_sync(kFullMask, valid && k != kp);
+                if (valid) {
+                    const uint32_t cell = base + __popc(heads & le_mask);
+                    const uint32_t ly = (uint32_t)(s >> 12) & 15u;
+                    const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+                    atomicAdd(&s_acc[cell][ly], cv);
+                }
+                base += __popc(heads);
+                carry = __shfl_sync(kFullMask, k, 31);
+            }
         }
     }
     __syncthreads();
@@ -250,22 +259,62 @@ __device__ __forceinline__ uint32_t lower_bound_key(const uint64_t* __restrict__
     }
     return lo;
 }
-__global__ void merge_entries_kernel(const uint64_t* __restrict__ cell_key, uint32_t n_cells, const uint64_t* __restrict__ gkey,
-                                     const uint32_t* __restrict__ gid, uint32_t n_gaps, uint64_t* __restrict__ ekey,
-                                     uint32_t* __restrict__ eid) {
+// Besides the sorted key, every entry gets a self-contained 64-byte record (its
+// segment range, carry, style bits and colour) and its initial optimizer flags,
+// so that the painter reaches everything it needs with one round of loads per
+// 32 entries instead of chasing key -> id -> cell -> style pointers per tile.
+__global__ void merge_entries_kernel(PaintScene S, const uint64_t* __restrict__ cell_key, uint32_t n_cells,
+                                     const uint64_t* __restrict__ gkey, const uint32_t* __restrict__ gid, uint32_t n_gaps,
+                                     const uint32_t* __restrict__ cell_start, const uint4* __restrict__ carry_in,
+                                     const uint4* __restrict__ gap_carry, uint64_t* __restrict__ ekey,
+                                     EntryRec* __restrict__ recs, uint8_t* __restrict__ eflags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells + n_gaps) return;
+    uint64_t k;
+    uint32_t pos;
+    EntryRec r;
     if (i < n_cells) {
-        uint64_t k = cell_key[i];
-        uint32_t pos = i + lower_bound_key(gkey, n_gaps, k);
-        ekey[pos] = k;
-        eid[pos] = i;
-    } else if (i < n_cells + n_gaps) {
+        k = cell_key[i];
+        pos = i + lower_bound_key(gkey, n_gaps, k);
+        r.seg0 = cell_start[i];
+        r.seg1 = cell_start[i + 1];
+        r.carry = carry_in[i];
+    } else {
         uint32_t g = i - n_cells;
-        uint64_t k = gkey[g];
-        uint32_t pos = g + lower_bound_key(cell_key, n_cells, k);
-        ekey[pos] = k;
-        eid[pos] = gid[g];
+        k = gkey[g];
+        pos = g + lower_bound_key(cell_key, n_cells, k);
+        r.seg0 = r.seg1 = 0;
+        r.carry = gap_carry[gid[g] - n_cells];
     }
+    r.layer = key_layer(k);
+    r.slot = r.layer < S.n_orders ? S.order_to_style[r.layer] : -1;
+    uint32_t flags = 0;
+    if (r.slot >= 0) {
+        const StyleRec& st = S.styles[r.slot];
+        const bool unchanged = S.unchanged && S.unchanged[r.slot];
+        r.meta = pack_style_meta(st, unchanged);
+        r.clip_layers = st.clip_layers;
+        r.color[0] = st.color[0];
+        r.color[1] = st.color[1];
+        r.color[2] = st.color[2];
+        r.color[3] = st.color[3];
+        if (r.seg1 > r.seg0) flags |= kFlagHasSegs;
+        else if (cover_is_full(r.carry, st.fill_rule & 1u)) flags |= kFlagFull;  // layer_is_full, mod.rs:171-182
+        if (unchanged) flags |= kFlagUnchanged;
+        if (st.func == 1u || st.is_clipped) flags |= kFlagClipish;
+        if (st.func == 0u && st.is_clipped) flags |= kFlagClippedDraw;
+        if (st.func == 0u && st.fill_type == 0u && st.blend_mode == 0u && st.color[3] == 1.0f) flags |= kFlagOpaque;
+    } else {
+        r.meta = 0;
+        r.clip_layers = 0;
+        r.color[0] = r.color[1] = r.color[2] = r.color[3] = 0.0f;
+        flags = kFlagMaskedOut;
+    }
+    r.flags0 = flags;
+    r.pad = 0;
+    ekey[pos] = k;
+    recs[pos] = r;
+    eflags[pos] = (uint8_t)flags;
 }
 
 // Per painted tile: [begin, end) of its entries in the sorted entry list.
@@ -334,10 +383,13 @@ void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* 
                                                             gkey, gid, gap_carry);
 }
 
-void launch_merge_entries(const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey, const uint32_t* gid,
-                          uint32_t n_gaps, uint64_t* ekey, uint32_t* eid, cudaStream_t st) {
+void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,
+                          const uint32_t* gid, uint32_t n_gaps, const uint32_t* cell_start, const uint4* carry_in,
+                          const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st) {
     uint32_t n = n_cells + n_gaps;
-    if (n) merge_entries_kernel<<<(n + 255) / 256, 256, 0, st>>>(cell_key, n_cells, gkey, gid, n_gaps, ekey, eid);
+    if (n)
+        merge_entries_kernel<<<(n + 255) / 256, 256, 0, st>>>(S, cell_key, n_cells, gkey, gid, n_gaps, cell_start, carry_in,
+                                                               gap_carry, ekey, recs, eflags);
 }
 
 void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,

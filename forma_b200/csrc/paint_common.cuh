@@ -36,6 +36,18 @@ __device__ __forceinline__ bool cover_is_full(uint4 c, uint32_t fill_rule) {
     return (c.x & m) == k && (c.y & m) == k && (c.z & m) == k && (c.w & m) == k;
 }
 
+// --- per-entry optimizer flags (layer_workbench passes) -----------------------------
+constexpr uint32_t kFlagHasSegs = 1, kFlagFull = 2, kFlagMaskedOut = 4, kFlagSkipClip = 8, kFlagUnchanged = 16;
+constexpr uint32_t kFlagClipish = 32;      // Func::Clip, or a Draw layer with is_clipped
+constexpr uint32_t kFlagOpaque = 64;       // Draw, solid fill, BlendMode::Over, alpha == 1
+constexpr uint32_t kFlagClippedDraw = 128; // Draw layer with is_clipped
+
+// packed style: fill_rule | func<<1 | is_clipped<<2 | fill_type<<3 | blend_mode<<5 | unchanged<<9
+__device__ __forceinline__ uint32_t pack_style_meta(const StyleRec& st, bool unchanged) {
+    return (st.fill_rule & 1u) | ((st.func & 1u) << 1) | ((st.is_clipped ? 1u : 0u) << 2) | ((st.fill_type & 3u) << 3) |
+           ((st.blend_mode & 15u) << 5) | (unchanged ? (1u << 9) : 0u);
+}
+
 __device__ __forceinline__ uint32_t fill_rule_of(const PaintScene& S, uint32_t layer) {
     int32_t slot = layer < S.n_orders ? S.order_to_style[layer] : -1;
     return slot >= 0 ? S.styles[slot].fill_rule : 0u;

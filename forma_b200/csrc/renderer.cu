@@ -133,7 +133,7 @@ void Composition::drop(Layer* l) {  // Drop for Layer, layer.rs:355-363
 // Layer::insert (layer.rs:90-111) + SegmentBuffer::push_path (segment.rs:181-198).
 void Composition::layer_insert(Layer* layer, const Path& path) {
     const FlattenProgram& prog = path.data->program();
-    uint32_t count = (uint32_t)prog.cmds.size();
+    uint32_t count = prog.n_points;
     if (count) {
         PendingInsert job;
         job.data = path.data;
@@ -145,8 +145,7 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
         jobs.push_back(std::move(job));
         // ids that are Some: every point that does not end a contour, except the
         // last point of the insert (its id is the trailing None).
-        uint64_t some = 0;
-        for (uint32_t i = 0; i + 1 < count; ++i) some += prog.cmds[i].kind != 1u;
+        uint64_t some = (uint64_t)(count - 1u) - prog.n_contour_ends;
         some_ids += some;
         layer->lines_count += some;
         n_points += count;
@@ -215,6 +214,15 @@ class Renderer {
     DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp, gkey_tmp;
     DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
     DeviceBuffer<uint8_t> eflags, framebuffer;
+    DeviceBuffer<EntryRec> recs;
+    // Band-wise copy-back of host frames (see render()).
+    static constexpr uint32_t kCopyBands = 4;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t band_ev[kCopyBands + 1];
+    static bool band_copies_enabled() {  // FORMA_BAND_COPY=0 copies the frame in one piece after the paint kernel
+        static const bool on = !(getenv("FORMA_BAND_COPY") && getenv("FORMA_BAND_COPY")[0] == '0');
+        return on;
+    }
     // Layer-cache frames: per-slot `is_unchanged` flags, the list of written
     // tiles and their packed pixels (only these travel back to a host buffer).
     DeviceBuffer<uint8_t> d_unchanged;
@@ -223,7 +231,7 @@ class Renderer {
     PinnedBuffer<uint32_t> h_written_list, h_packed_tiles;
     uint32_t last_written_tiles = 0;
     // Upload staging.
-    DeviceBuffer<PointCmd> up_cmds;
+    DeviceBuffer<SplineRec> up_splines;
     DeviceBuffer<QuadRec> up_quads;
     DeviceBuffer<FlattenJob> up_jobs;
 
@@ -236,6 +244,10 @@ class Renderer {
 
     ~Renderer() {
         if (pinned_totals) cudaFreeHost(pinned_totals);
+        if (copy_stream) {
+            for (auto& e : band_ev) cudaEventDestroy(e);
+            cudaStreamDestroy(copy_stream);
+        }
         if (timer.ok) {
             for (auto& e : timer.ev) cudaEventDestroy(e);
             for (auto& e : timer.sort_ev) cudaEventDestroy(e);
@@ -279,52 +291,60 @@ int Renderer::flush_geometry(Composition& comp) {
 
     if (comp.staged_from != from || comp.staged_to != to) {
         // (Re)build the pinned staging copy of the flatten programs of jobs [from, to).
-        size_t n_cmds = 0, n_quads = 0;
+        size_t n_splines = 0, n_quads = 0, n_pts = 0;
         for (size_t j = from; j < to; ++j) {
             const FlattenProgram& prog = comp.jobs[j].data->program();
-            n_cmds += prog.cmds.size();
+            n_splines += prog.splines.size();
             n_quads += prog.quads.size();
+            n_pts += prog.n_points;
+        }
+        if (n_pts >= (1ull << 32)) {
+            set_error("too many points in one batch");
+            return FORMA_STATUS_CAPACITY;
         }
         FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // staging may still be in flight
-        FORMA_CUDA_TRY(comp.h_cmds.reserve(n_cmds));
+        FORMA_CUDA_TRY(comp.h_splines.reserve(n_splines + 1));
         FORMA_CUDA_TRY(comp.h_quads.reserve(n_quads + 1));
         FORMA_CUDA_TRY(comp.h_jobs.reserve(to - from));
-        size_t ci = 0, qi = 0;
+        size_t si = 0, qi = 0, pi = 0;
         for (size_t j = from; j < to; ++j) {
             const PendingInsert& p = comp.jobs[j];
             const FlattenProgram& prog = p.data->program();
             FlattenJob& job = comp.h_jobs.ptr[j - from];
-            job.first_point = (uint32_t)ci;
+            job.first_point = (uint32_t)pi;
             job.count = p.count;
             job.quad_base = (uint32_t)qi;
+            job.spline_base = (uint32_t)si;
+            job.n_splines = (uint32_t)prog.splines.size();
             job.geom_id = p.geom_id;
             job.has_xf = p.has_xf ? 1u : 0u;
             std::memcpy(job.xf, p.xf, sizeof(job.xf));
             job.dst = p.dst;
-            uint32_t tag = (uint32_t)(j - from) << 2;
-            for (const PointCmd& c : prog.cmds) {
-                PointCmd cc = c;
-                cc.kind |= tag;
-                comp.h_cmds.ptr[ci++] = cc;
-            }
+            if (!prog.splines.empty())
+                std::memcpy(comp.h_splines.ptr + si, prog.splines.data(), prog.splines.size() * sizeof(SplineRec));
             if (!prog.quads.empty()) std::memcpy(comp.h_quads.ptr + qi, prog.quads.data(), prog.quads.size() * sizeof(QuadRec));
+            si += prog.splines.size();
             qi += prog.quads.size();
+            pi += prog.n_points;
         }
         comp.staged_from = from;
         comp.staged_to = to;
-        comp.staged_cmds = n_cmds;
+        comp.staged_splines = n_splines;
         comp.staged_quads = n_quads;
+        comp.staged_points = n_pts;
     }
-    FORMA_CUDA_TRY(up_cmds.reserve(comp.staged_cmds));
+    FORMA_CUDA_TRY(up_splines.reserve(comp.staged_splines + 1));
     FORMA_CUDA_TRY(up_quads.reserve(comp.staged_quads + 1));
     FORMA_CUDA_TRY(up_jobs.reserve(to - from));
-    FORMA_CUDA_TRY(cudaMemcpyAsync(up_cmds.ptr, comp.h_cmds.ptr, comp.staged_cmds * sizeof(PointCmd), cudaMemcpyHostToDevice, stream));
+    if (comp.staged_splines)
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_splines.ptr, comp.h_splines.ptr, comp.staged_splines * sizeof(SplineRec),
+                                       cudaMemcpyHostToDevice, stream));
     if (comp.staged_quads)
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads.ptr, comp.h_quads.ptr, comp.staged_quads * sizeof(QuadRec), cudaMemcpyHostToDevice, stream));
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, comp.h_jobs.ptr, (to - from) * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
-    h2d_bytes += comp.staged_cmds * sizeof(PointCmd) + comp.staged_quads * sizeof(QuadRec) + (to - from) * sizeof(FlattenJob);
-    launch_flatten_eval(up_cmds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)comp.staged_cmds, comp.d_x.ptr, comp.d_y.ptr,
-                        comp.d_gid.ptr, stream);
+    h2d_bytes += comp.staged_splines * sizeof(SplineRec) + comp.staged_quads * sizeof(QuadRec) + (to - from) * sizeof(FlattenJob);
+    launch_flatten_eval(up_splines.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)(to - from), (uint32_t)comp.staged_points,
+                        comp.d_x.ptr, comp.d_y.ptr, comp.d_gid.ptr, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
     comp.n_resident = comp.n_points;
@@ -657,17 +677,49 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                 swap_buffers(eid_tmp, gid_tmp);
             }
         }
-        launch_merge_entries(cell_key.ptr, n_cells, ekey_tmp.ptr, eid_tmp.ptr, n_gaps, ekey.ptr, eid.ptr, stream);
+        FORMA_CUDA_TRY(recs.reserve(n_entries));
+        launch_merge_entries(S, cell_key.ptr, n_cells, ekey_tmp.ptr, eid_tmp.ptr, n_gaps, cell_start.ptr, carry_in.ptr,
+                             gap_carry.ptr, ekey.ptr, recs.ptr, eflags.ptr, stream);
         ++launches;
     }
     launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
     launches += n_entries ? 1 : 0;
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
-    launch_paint(S, segs.ptr, ekey.ptr, eid.ptr, cell_start.ptr, carry_in.ptr, gap_carry.ptr, n_cells, tile_begin.ptr,
-                 tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
-    ++launches;
+    // Host frame without a layer cache: paint in bands of tile rows and copy each
+    // band back on a second stream while the next one is painted, so most of the
+    // PCIe transfer overlaps the paint kernel.
+    bool copied_in_bands = false;
+    const uint32_t paint_rows = S.ty_hi - S.ty_lo;
+    if (!buffer_on_device && !cache && paint_rows >= 32u && S.tx_hi > S.tx_lo && band_copies_enabled()) {
+        if (!copy_stream) {
+            FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (auto& e : band_ev) FORMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
+        for (uint32_t k = 0; k < kCopyBands; ++k) {
+            PaintScene Sb = S;
+            Sb.ty_lo = S.ty_lo + paint_rows * k / kCopyBands;
+            Sb.ty_hi = S.ty_lo + paint_rows * (k + 1u) / kCopyBands;
+            launch_paint(Sb, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
+            ++launches;
+            FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], stream));
+            FORMA_CUDA_TRY(cudaStreamWaitEvent(copy_stream, band_ev[k], 0));
+            const uint64_t y0 = (uint64_t)Sb.ty_lo * 16u, y1 = std::min<uint64_t>((uint64_t)Sb.ty_hi * 16u, height);
+            if (x1 > x0 && y1 > y0) {
+                FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
+                                                 (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, copy_stream));
+                d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
+            }
+        }
+        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kCopyBands], copy_stream));
+        copied_in_bands = true;
+    } else {
+        launch_paint(S, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
+        ++launches;
+    }
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[5], stream));
+    if (copied_in_bands) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[kCopyBands], 0));
 
     last_written_tiles = 0;
     if (pack_written) {
@@ -699,7 +751,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                     std::memcpy(buffer + (y0 + r) * stride + x0 * 4u, src + r * 16u, cols * 4u);
             }
         }
-    } else if (!buffer_on_device) {
+    } else if (!buffer_on_device && !copied_in_bands) {
         // Only the cropped tile rectangle is written by the reference
         // (cpu/painter/mod.rs:524-529,589-593); padding bytes beyond width*4 stay untouched.
         uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
@@ -811,7 +863,7 @@ void forma_path_free(forma_path* p) { delete p; }
 // points back (inspection only; rendering never copies points to the host).
 int forma_path_segments(forma_path* p, const float** x, const float** y, const uint8_t** contour, uint64_t* n) {
     const FlattenProgram& prog = p->p.data->program();
-    uint32_t count = (uint32_t)prog.cmds.size();
+    uint32_t count = prog.n_points;
     p->x.assign(count, 0.0f);
     p->y.assign(count, 0.0f);
     p->c.assign(count, 0);
@@ -825,12 +877,12 @@ int forma_path_segments(forma_path* p, const float** x, const float** y, const u
         set_error("forma_path_segments: no CUDA device (flatten evaluation has no CPU fallback)");
         return FORMA_STATUS_NO_DEVICE;
     }
-    DeviceBuffer<PointCmd> dc;
+    DeviceBuffer<SplineRec> dc;
     DeviceBuffer<QuadRec> dq;
     DeviceBuffer<FlattenJob> dj;
     DeviceBuffer<float> dx, dy;
     DeviceBuffer<uint32_t> dg;
-    FORMA_CUDA_TRY(dc.reserve(count));
+    FORMA_CUDA_TRY(dc.reserve(prog.splines.size() + 1));
     FORMA_CUDA_TRY(dq.reserve(prog.quads.size() + 1));
     FORMA_CUDA_TRY(dj.reserve(1));
     FORMA_CUDA_TRY(dx.reserve(count));
@@ -840,19 +892,24 @@ int forma_path_segments(forma_path* p, const float** x, const float** y, const u
     job.first_point = 0;
     job.count = count;
     job.quad_base = 0;
+    job.spline_base = 0;
+    job.n_splines = (uint32_t)prog.splines.size();
     job.geom_id = 1;
     job.has_xf = p->p.has_xf ? 1u : 0u;
     std::memcpy(job.xf, p->p.xf, sizeof(job.xf));
     job.dst = 0;
-    FORMA_CUDA_TRY(cudaMemcpy(dc.ptr, prog.cmds.data(), count * sizeof(PointCmd), cudaMemcpyHostToDevice));
+    FORMA_CUDA_TRY(cudaMemcpy(dc.ptr, prog.splines.data(), prog.splines.size() * sizeof(SplineRec), cudaMemcpyHostToDevice));
     if (!prog.quads.empty())
         FORMA_CUDA_TRY(cudaMemcpy(dq.ptr, prog.quads.data(), prog.quads.size() * sizeof(QuadRec), cudaMemcpyHostToDevice));
     FORMA_CUDA_TRY(cudaMemcpy(dj.ptr, &job, sizeof(job), cudaMemcpyHostToDevice));
-    launch_flatten_eval(dc.ptr, dq.ptr, dj.ptr, count, dx.ptr, dy.ptr, dg.ptr, 0);
+    launch_flatten_eval(dc.ptr, dq.ptr, dj.ptr, 1, count, dx.ptr, dy.ptr, dg.ptr, 0);
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaMemcpy(p->x.data(), dx.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
     FORMA_CUDA_TRY(cudaMemcpy(p->y.data(), dy.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
-    for (uint32_t i = 0; i < count; ++i) p->c[i] = prog.cmds[i].kind == 1u;
+    for (const SplineRec& s : prog.splines) {  // the end point of a spline that ends a contour
+        uint32_t end = s.first_point + ((s.info >> 30) & 1u) + (s.info & kSplineEvalMask);
+        if ((s.info >> 31) && end < count) p->c[end] = 1;
+    }
     return FORMA_STATUS_OK;
 }
 

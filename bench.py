@@ -36,7 +36,10 @@ WORKLOADS = {
     # name: (width, height, description)
     "paris4k": (3840, 2160, "paris-30k.svg (50620 layers, solid fills) scaled 2160/1060 at 3840x2160"),
     "cubics100k": (3840, 2160, "100k random closed cubics, opaque solid fills, seed 3, 3840x2160"),
+    "paris4k_grad": (3840, 2160, "paris-30k.svg, every 8th layer filled with a synthetic 3-stop linear gradient over its "
+                                 "bounding box (the file itself has none; SURVEY.md C2 variant, seed 1), 3840x2160"),
     "circles8k": (7680, 4320, "200k rational-quad circles r in [4,40], radial gradients, 8 blend modes, seed 5, 7680x4320"),
+    "circles8k_1m": (7680, 4320, "1M rational-quad circles r in [4,40], radial gradients, 8 blend modes, seed 5, 7680x4320"),
     "smoke": (640, 360, "400 mixed layers, 640x360 (plumbing check)"),
 }
 
@@ -51,8 +54,27 @@ def build_scene(api, name):
         svg.compose(api, comp, paths, scale=2160.0 / 1060.0)
     elif name == "cubics100k":
         synth.random_cubics(api, comp, 100_000, w, h, 3)
+    elif name == "paris4k_grad":
+        from forma_b200.binding import Color, Fill, GradientBuilder, Point
+        paths = svg.PathList.load(os.path.join(ROOT, "tests", "data", "paris30k_paths.npz"))
+        scale = 2160.0 / 1060.0
+        rng = synth.SplitMix64(1)
+
+        def fill_of(i, color):
+            if i % 8 != 7:
+                return Fill.Solid(color)
+            p = paths.pts[int(paths.pt_off[i]):int(paths.pt_off[i + 1])].reshape(-1, 2) * scale
+            lo, hi = p.min(axis=0), p.max(axis=0)
+            gb = GradientBuilder(Point(float(lo[0]), float(lo[1])), Point(float(hi[0]), float(hi[1])))
+            gb.color(color)
+            gb.color(Color(rng.uniform(), rng.uniform(), rng.uniform(), color.a))
+            gb.color(color)
+            return Fill.Gradient(gb.build())
+        svg.compose(api, comp, paths, scale=scale, fill_of=fill_of)
     elif name == "circles8k":
         synth.random_circles(api, comp, 200_000, w, h, 5)
+    elif name == "circles8k_1m":
+        synth.random_circles(api, comp, 1_000_000, w, h, 5)
     else:
         synth.random_mixed(api, comp, 400, w, h, 7)
     return comp, w, h
@@ -311,7 +333,7 @@ def run_cuda(args):
     out = {
         "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": T / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32+f64/u64", "data": "synthetic" if args.workload != "paris4k" else "paris-30k fixture",
+        "vs_baseline": None, "dtype": "f32+f64/u64", "data": "paris-30k fixture" if args.workload.startswith("paris4k") else "synthetic",
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload][2], "pixel_segments": n_seg_total,
                    "points": comp.point_count(), "cells": c1["cells"], "entries": c1["entries"],
                    "l2": "flushed between steps (384 MiB memset, untimed)", "parallelism": f"tile-band x{world}",

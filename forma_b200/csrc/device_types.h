@@ -19,6 +19,16 @@ struct QuadRec {
     float x0, dx_recip, k0, dk, curv_recip;
     float prev_curv;  // running curvature of the previous quad iff same spline, else 0 (path.rs:508-514)
     float total;      // running curvature of the spline including this quad
+    float step;       // curvature / subdivisions of the spline (same for all its quads)
+};
+
+// Point-wise encoding of a flatten program, used instead of SplineRecs when it
+// is smaller (paths made of many short line splines): 8 B + 1 B per output point.
+//   kind 0: literal point (a, b)                  (Start / End of a spline)
+//   kind 1: literal point (a, b), ends a contour  (End with new_contour)
+//   kind 2: a = quad index (u32 bits), b = pi; evaluated at quad.step * pi
+struct PointRec {
+    float a, b;
 };
 
 // One spline of a flatten program: the point commands populate_buffers
@@ -38,7 +48,9 @@ constexpr uint32_t kSplineEvalMask = (1u << 30) - 1u;
 
 struct FlattenProgram {
     std::vector<QuadRec> quads;
-    std::vector<SplineRec> splines;
+    std::vector<SplineRec> splines;  // spline encoding (points / kinds empty) ...
+    std::vector<PointRec> points;    // ... or point encoding (splines empty), whichever is smaller
+    std::vector<uint8_t> kinds;
     uint32_t n_points = 0;        // output points
     uint32_t n_contour_ends = 0;  // points that end a contour, the last point of the program excluded
 };
@@ -49,8 +61,8 @@ struct FlattenJob {
     uint32_t first_point;   // first output point of the job in the batch
     uint32_t count;
     uint32_t quad_base;     // added to SplineRec::first_quad
-    uint32_t spline_base;   // the job's splines in the batch's SplineRec array
-    uint32_t n_splines;
+    uint32_t spline_base;   // the job's splines in the batch's SplineRec array, or its first PointRec
+    uint32_t n_splines;     // 0 = point encoding
     uint32_t geom_id;       // id written for non-contour-end points (0 = None)
     uint32_t has_xf;
     float xf[6];            // GeomPresTransform: ux, uy, vx, vy, tx, ty

@@ -178,11 +178,38 @@ class SplineBuilder {
             r.first_point = (uint32_t)pt;
             r.info = (uint32_t)evaluated | (start ? 1u << 30 : 0u) | (s.ends_contour ? 1u << 31 : 0u);
             out.splines.push_back(r);
+            for (uint32_t q = 0; q < quads_of[si]; ++q) out.quads[qi + q].step = step;
             pt += (start ? 1u : 0u) + evaluated + 1u;
             qi += quads_of[si];
             if (s.ends_contour && si + 1 < splines_.size()) out.n_contour_ends += 1;
         }
         out.n_points = (uint32_t)std::min<uint64_t>(pt, 0xFFFFFFFFull);
+        // Paths made of short line splines are smaller point by point (9 B / point
+        // against 36 B / spline): expand the records on the host in that case.
+        if (sizeof(SplineRec) * out.splines.size() > (sizeof(PointRec) + 1) * (size_t)out.n_points && pt < (1ull << 31)) {
+            out.points.reserve(out.n_points);
+            out.kinds.reserve(out.n_points);
+            for (const SplineRec& r : out.splines) {
+                if ((r.info >> 30) & 1u) {
+                    out.points.push_back({r.p0x, r.p0y});
+                    out.kinds.push_back(0);
+                }
+                const uint32_t evaluated = r.info & kSplineEvalMask;
+                uint32_t q = r.first_quad;
+                for (uint32_t pi = 1; pi <= evaluated; ++pi) {
+                    while (q + 1 < r.first_quad + r.n_quads && (float)pi > out.quads[q].total) ++q;
+                    PointRec p;
+                    std::memcpy(&p.a, &q, sizeof(uint32_t));
+                    p.b = (float)pi;
+                    out.points.push_back(p);
+                    out.kinds.push_back(2);
+                }
+                out.points.push_back({r.p2x, r.p2y});
+                out.kinds.push_back((r.info >> 31) ? 1 : 0);
+            }
+            out.splines.clear();
+            out.splines.shrink_to_fit();
+        }
     }
 
    private:

@@ -74,6 +74,9 @@ class Composition {
     uint32_t n_resident = 0;          // points already evaluated on the device
     // Pinned staging of the flatten programs of jobs [staged_from, staged_to).
     PinnedBuffer<SplineRec> h_splines;
+    PinnedBuffer<PointRec> h_points;
+    PinnedBuffer<uint8_t> h_kinds;
+    size_t staged_recs = 0;
     PinnedBuffer<QuadRec> h_quads;
     PinnedBuffer<FlattenJob> h_jobs;
     size_t staged_from = 0, staged_to = 0, staged_splines = 0, staged_quads = 0, staged_points = 0;

@@ -23,14 +23,16 @@ struct RasterArgs {
 };
 
 // ---- kernels_raster.cu ------------------------------------------------------
-void launch_flatten_eval(const SplineRec* splines, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_jobs,
-                         uint32_t n_points, float* x, float* y, uint32_t* gid, cudaStream_t stream);
+void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const uint8_t* kinds, const QuadRec* quads,
+                         const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, float* x, float* y, uint32_t* gid,
+                         cudaStream_t stream);
 uint32_t raster_num_blocks(uint32_t n_points);
 // block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
 // max_tile[0..1] = largest biased tile_x / tile_y any emitted segment can carry.
 void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* total, uint32_t* max_tile,
                        cudaStream_t stream);
-void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream);
+// Segments at positions >= cap are dropped (speculative launches, see Renderer::rasterize).
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, uint32_t cap, cudaStream_t stream);
 // In-place exclusive scan of n u32 values; total[0] = sum. `state` (scan_state_words(n)
 // u64 words) enables the multi-CTA look-back scan for large n; nullptr = one CTA.
 size_t scan_state_words(uint32_t n);
@@ -100,10 +102,14 @@ struct PaintScene {
 uint32_t cell_num_blocks(uint32_t n);
 // block_counts: cell_num_blocks(n) entries -> exclusive offsets; total[0] = #cells.
 void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* total, cudaStream_t st);
+// Both read the cell count from device memory (n_cells_ptr) and are no-ops when it
+// exceeds `cap`, so that they can be launched before the host has read the count;
+// grid_cells sizes the cover grid (an upper bound of the count, or the count).
 void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
-                       uint64_t* cell_key, uint32_t n_cells, cudaStream_t st);
+                       uint64_t* cell_key, const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st);
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
-                       uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st);
+                       const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
+                       uint32_t* perm, cudaStream_t st);
 // Plans of the painter's two pair sorts (their key bounds are host-known).
 SortPlan carry_sort_plan(const PaintScene& S);
 SortPlan gap_sort_plan(const PaintScene& S);
@@ -112,7 +118,8 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
 // Carry-only entries in (layer, tile_y, tile_x) order; payload = n_cells + gap id.
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
-                     uint64_t* gkey, uint32_t* gid, uint4* gap_carry, cudaStream_t st);
+                     uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
+                     cudaStream_t st);
 // One painter entry = one (tile, layer) pair with segments and / or a carried cover.
 struct EntryRec {  // 64 B
     uint32_t layer, seg0, seg1;  // layer order; [seg0, seg1) in the sorted segments (empty for carry-only entries)

@@ -30,7 +30,8 @@ __device__ __forceinline__ float inv_curvature(float k) {  // path.rs:53-56
 // bisection over their first-point offsets (the per-point commands of the
 // reference, path.rs:138-168, are never materialised — 36 B per spline cross
 // PCIe instead of 16 B per point).
-__global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const QuadRec* __restrict__ quads,
+__global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const PointRec* __restrict__ points,
+                                    const uint8_t* __restrict__ kinds, const QuadRec* __restrict__ quads,
                                     const FlattenJob* __restrict__ jobs, uint32_t n_jobs, uint32_t n_points,
                                     float* __restrict__ out_x, float* __restrict__ out_y,
                                     uint32_t* __restrict__ out_gid) {
@@ -44,40 +45,56 @@ __global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const
     }
     const FlattenJob job = jobs[lo];
     const uint32_t local = i - job.first_point;
-    lo = 0;
-    hi = job.n_splines - 1u;  // last spline with first_point <= local
-    const SplineRec* sp = splines + job.spline_base;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi + 1u) >> 1;
-        if (sp[mid].first_point <= local) lo = mid;
-        else hi = mid - 1u;
-    }
-    const SplineRec s = sp[lo];
-    const uint32_t has_start = (s.info >> 30) & 1u, evaluated = s.info & kSplineEvalMask;
-    const uint32_t j = local - s.first_point;  // point of the spline
-    uint32_t kind;                             // 0 literal, 1 literal + contour end, 2 evaluated
-    float px, py;
-    if (has_start && j == 0u) {
-        kind = 0u;
-        px = s.p0x;
-        py = s.p0y;
-    } else if (j - has_start == evaluated) {
-        kind = (s.info >> 31) ? 1u : 0u;
-        px = s.p2x;
-        py = s.p2y;
-    } else {
-        kind = 2u;
-        const float pi = (float)(j - has_start + 1u);
-        const QuadRec* qs = quads + job.quad_base + s.first_quad;
-        uint32_t a = 0, b = s.n_quads - 1u;  // first quad whose running curvature reaches pi (path.rs:424-431)
-        while (a < b) {
-            uint32_t mid = (a + b) >> 1;
-            if (pi > qs[mid].total) a = mid + 1u;
-            else b = mid;
+    uint32_t kind;  // 0 literal, 1 literal + contour end, 2 evaluated
+    float px = 0.0f, py = 0.0f, pi = 0.0f;
+    const QuadRec* qp = nullptr;
+    if (job.n_splines == 0u) {  // point encoding
+        const PointRec p = points[job.spline_base + local];
+        kind = kinds[job.spline_base + local];
+        if (kind == 2u) {
+            qp = quads + job.quad_base + __float_as_uint(p.a);
+            pi = p.b;
+        } else {
+            px = p.a;
+            py = p.b;
         }
-        const QuadRec q = qs[a];
+    } else {
+        lo = 0;
+        hi = job.n_splines - 1u;  // last spline with first_point <= local
+        const SplineRec* sp = splines + job.spline_base;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi + 1u) >> 1;
+            if (sp[mid].first_point <= local) lo = mid;
+            else hi = mid - 1u;
+        }
+        const SplineRec s = sp[lo];
+        const uint32_t has_start = (s.info >> 30) & 1u, evaluated = s.info & kSplineEvalMask;
+        const uint32_t j = local - s.first_point;  // point of the spline
+        if (has_start && j == 0u) {
+            kind = 0u;
+            px = s.p0x;
+            py = s.p0y;
+        } else if (j - has_start == evaluated) {
+            kind = (s.info >> 31) ? 1u : 0u;
+            px = s.p2x;
+            py = s.p2y;
+        } else {
+            kind = 2u;
+            pi = (float)(j - has_start + 1u);
+            const QuadRec* qs = quads + job.quad_base + s.first_quad;
+            uint32_t a = 0, b = s.n_quads - 1u;  // first quad whose running curvature reaches pi (path.rs:424-431)
+            while (a < b) {
+                uint32_t mid = (a + b) >> 1;
+                if (pi > qs[mid].total) a = mid + 1u;
+                else b = mid;
+            }
+            qp = qs + a;
+        }
+    }
+    if (kind == 2u) {
+        const QuadRec q = *qp;
         // path.rs:515-522
-        float ratio = fmaf(s.step, pi, -q.prev_curv) * q.curv_recip;
+        float ratio = fmaf(q.step, pi, -q.prev_curv) * q.curv_recip;
         float xx = inv_curvature(fmaf(ratio, q.dk, q.k0));
         float t = d_clamp((xx - q.x0) * q.dx_recip, 0.0f, 1.0f);
         // eval_quad, path.rs:447-471
@@ -273,7 +290,7 @@ struct SharedLines {
 
 // Pass 2: recompute the CTA's 256 lines, then each warp expands its 32 lines.
 __global__ void __launch_bounds__(kRasterThreads)
-    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out) {
+    raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out, uint32_t cap) {
     __shared__ SharedLines S;
     __shared__ uint32_t warp_sums[kRasterThreads / 32];
     const uint32_t t = threadIdx.x;
@@ -336,17 +353,20 @@ __global__ void __launch_bounds__(kRasterThreads)
         uint64_t tx = (uint64_t)max((int32_t)(int16_t)(tile_x + 1), 0) & 0xFFFull;
         uint64_t v = (ty << 53) | (tx << 41) | ((uint64_t)(S.order[li] & 0x1FFFFFu) << 20) | ((uint64_t)local_x << 16) |
                      ((uint64_t)local_y << 12) | ((uint64_t)(dam & 0x3Fu) << 6) | ((uint64_t)((uint32_t)cover & 0x3Fu));
-        out[(uint64_t)warp_base + s] = v;
+        // `cap` guards a speculative launch made before the segment count is known on the host.
+        if (warp_base + s < cap) out[(uint64_t)warp_base + s] = v;
     }
 }
 
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
-void launch_flatten_eval(const SplineRec* splines, const QuadRec* quads, const FlattenJob* jobs, uint32_t n_jobs,
-                         uint32_t n_points, float* x, float* y, uint32_t* gid, cudaStream_t stream) {
+void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const uint8_t* kinds, const QuadRec* quads,
+                         const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, float* x, float* y, uint32_t* gid,
+                         cudaStream_t stream) {
     if (!n_points || !n_jobs) return;
-    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, quads, jobs, n_jobs, n_points, x, y, gid);
+    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, points, kinds, quads, jobs, n_jobs, n_points, x, y,
+                                                                    gid);
 }
 
 uint32_t raster_num_blocks(uint32_t n_points) { return n_points ? (n_points + kRasterThreads - 1) / kRasterThreads : 0; }
@@ -363,10 +383,10 @@ void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* t
     scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb, total);
 }
 
-void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, cudaStream_t stream) {
+void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, uint32_t cap, cudaStream_t stream) {
     uint32_t nb = raster_num_blocks(args.n_points);
     if (!nb) return;
-    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out);
+    raster_emit_kernel<<<nb, kRasterThreads, 0, stream>>>(args, block_offsets, out, cap);
 }
 
 // Multi-CTA exclusive scan (single pass, decoupled look-back): CTA = 2048

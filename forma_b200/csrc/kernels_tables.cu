@@ -60,8 +60,13 @@ __global__ void __launch_bounds__(kCellThreads)
 
 __global__ void __launch_bounds__(kCellThreads)
     cell_write_kernel(const uint64_t* __restrict__ segs, uint32_t n, const uint32_t* __restrict__ block_offsets,
-                      uint32_t* __restrict__ cell_start, uint64_t* __restrict__ cell_key, uint32_t n_cells) {
+                      uint32_t* __restrict__ cell_start, uint64_t* __restrict__ cell_key,
+                      const uint32_t* __restrict__ n_cells_ptr, uint32_t cap) {
     __shared__ uint32_t warp_cnt[kCellThreads / 32];
+    // The cell count is read on the device: the kernel may be launched before the
+    // host knows it (Renderer::render); it does nothing if the buffers are too small.
+    const uint32_t n_cells = *n_cells_ptr;
+    if (n_cells > cap) return;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t base = blockIdx.x * kCellTile + warp * (32u * kCellItems);
     uint32_t masks[kCellItems];
@@ -102,12 +107,14 @@ constexpr int kCoverCells = 256;
 
 __global__ void __launch_bounds__(kCoverCells)
     cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
-                      const uint64_t* __restrict__ cell_key, uint32_t n_cells, uint4* __restrict__ cell_cover,
-                      uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
+                      const uint64_t* __restrict__ cell_key, const uint32_t* __restrict__ n_cells_ptr, uint32_t cap,
+                      uint4* __restrict__ cell_cover, uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
     __shared__ uint32_t s_start[kCoverCells + 1];
     __shared__ int32_t s_acc[kCoverCells][16];
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
     const uint32_t c0 = blockIdx.x * kCoverCells;
+    const uint32_t n_cells = *n_cells_ptr;  // see cell_write_kernel
+    if (n_cells > cap || c0 >= n_cells) return;
     const uint32_t nc = min((uint32_t)kCoverCells, n_cells - c0);
     if (t <= nc) s_start[t] = cell_start[c0 + t];
     if (t == 0) s_start[nc] = cell_start[c0 + nc];
@@ -230,9 +237,9 @@ __global__ void gap_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2,
                                 const uint64_t* __restrict__ cell_key, const uint4* __restrict__ carry_after,
                                 const uint32_t* __restrict__ gap_count, const uint32_t* __restrict__ gap_offset,
                                 uint32_t n_cells, uint64_t* __restrict__ gkey, uint32_t* __restrict__ gid,
-                                uint4* __restrict__ gap_carry) {
+                                uint4* __restrict__ gap_carry, const uint32_t* __restrict__ n_gaps_ptr, uint32_t cap) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cells) return;
+    if (j >= n_cells || *n_gaps_ptr > cap) return;  // cap: see cell_write_kernel
     uint32_t g = gap_count[j];
     if (!g) return;
     uint64_t ck = cell_key[perm[j]];
@@ -344,15 +351,16 @@ void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts,
 }
 
 void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
-                       uint64_t* cell_key, uint32_t n_cells, cudaStream_t st) {
-    cell_write_kernel<<<cell_num_blocks(n), kCellThreads, 0, st>>>(segs, n, block_offsets, cell_start, cell_key, n_cells);
+                       uint64_t* cell_key, const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st) {
+    cell_write_kernel<<<cell_num_blocks(n), kCellThreads, 0, st>>>(segs, n, block_offsets, cell_start, cell_key, n_cells_ptr, cap);
 }
 
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
-                       uint32_t n_cells, uint4* cell_cover, uint64_t* key2, uint32_t* perm, cudaStream_t st) {
-    if (n_cells)
-        cell_cover_kernel<<<(n_cells + kCoverCells - 1) / kCoverCells, kCoverCells, 0, st>>>(S, segs, cell_start, cell_key, n_cells,
-                                                                                          cell_cover, key2, perm);
+                       const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
+                       uint32_t* perm, cudaStream_t st) {
+    if (grid_cells)
+        cell_cover_kernel<<<(grid_cells + kCoverCells - 1) / kCoverCells, kCoverCells, 0, st>>>(
+            S, segs, cell_start, cell_key, n_cells_ptr, cap, cell_cover, key2, perm);
 }
 
 // Largest values the three key fields can take in the pair sorts (sentinel
@@ -378,9 +386,10 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
 
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
-                     uint64_t* gkey, uint32_t* gid, uint4* gap_carry, cudaStream_t st) {
+                     uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
+                     cudaStream_t st) {
     gap_fill_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset, n_cells,
-                                                            gkey, gid, gap_carry);
+                                                            gkey, gid, gap_carry, n_gaps_ptr, cap);
 }
 
 void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,

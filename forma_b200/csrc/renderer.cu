@@ -219,6 +219,14 @@ class Renderer {
     static constexpr uint32_t kCopyBands = 4;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t band_ev[kCopyBands + 1];
+    cudaEvent_t count_ev = nullptr;  // completion of a count read-back (waited on instead of the whole stream)
+    cudaError_t ensure_count_event() {
+        return count_ev ? cudaSuccess : cudaEventCreateWithFlags(&count_ev, cudaEventDisableTiming);
+    }
+    static bool speculation_enabled() {  // FORMA_SPECULATE=0: never launch a kernel before its sizes are known on the host
+        static const bool on = !(getenv("FORMA_SPECULATE") && getenv("FORMA_SPECULATE")[0] == '0');
+        return on;
+    }
     static bool band_copies_enabled() {  // FORMA_BAND_COPY=0 copies the frame in one piece after the paint kernel
         static const bool on = !(getenv("FORMA_BAND_COPY") && getenv("FORMA_BAND_COPY")[0] == '0');
         return on;
@@ -232,6 +240,8 @@ class Renderer {
     uint32_t last_written_tiles = 0;
     // Upload staging.
     DeviceBuffer<SplineRec> up_splines;
+    DeviceBuffer<PointRec> up_points;
+    DeviceBuffer<uint8_t> up_kinds;
     DeviceBuffer<QuadRec> up_quads;
     DeviceBuffer<FlattenJob> up_jobs;
 
@@ -291,10 +301,11 @@ int Renderer::flush_geometry(Composition& comp) {
 
     if (comp.staged_from != from || comp.staged_to != to) {
         // (Re)build the pinned staging copy of the flatten programs of jobs [from, to).
-        size_t n_splines = 0, n_quads = 0, n_pts = 0;
+        size_t n_splines = 0, n_quads = 0, n_pts = 0, n_recs = 0;
         for (size_t j = from; j < to; ++j) {
             const FlattenProgram& prog = comp.jobs[j].data->program();
             n_splines += prog.splines.size();
+            n_recs += prog.points.size();
             n_quads += prog.quads.size();
             n_pts += prog.n_points;
         }
@@ -304,9 +315,11 @@ int Renderer::flush_geometry(Composition& comp) {
         }
         FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // staging may still be in flight
         FORMA_CUDA_TRY(comp.h_splines.reserve(n_splines + 1));
+        FORMA_CUDA_TRY(comp.h_points.reserve(n_recs + 1));
+        FORMA_CUDA_TRY(comp.h_kinds.reserve(n_recs + 1));
         FORMA_CUDA_TRY(comp.h_quads.reserve(n_quads + 1));
         FORMA_CUDA_TRY(comp.h_jobs.reserve(to - from));
-        size_t si = 0, qi = 0, pi = 0;
+        size_t si = 0, qi = 0, pi = 0, ri = 0;
         for (size_t j = from; j < to; ++j) {
             const PendingInsert& p = comp.jobs[j];
             const FlattenProgram& prog = p.data->program();
@@ -314,7 +327,7 @@ int Renderer::flush_geometry(Composition& comp) {
             job.first_point = (uint32_t)pi;
             job.count = p.count;
             job.quad_base = (uint32_t)qi;
-            job.spline_base = (uint32_t)si;
+            job.spline_base = (uint32_t)(prog.splines.empty() ? ri : si);
             job.n_splines = (uint32_t)prog.splines.size();
             job.geom_id = p.geom_id;
             job.has_xf = p.has_xf ? 1u : 0u;
@@ -322,6 +335,11 @@ int Renderer::flush_geometry(Composition& comp) {
             job.dst = p.dst;
             if (!prog.splines.empty())
                 std::memcpy(comp.h_splines.ptr + si, prog.splines.data(), prog.splines.size() * sizeof(SplineRec));
+            if (!prog.points.empty()) {
+                std::memcpy(comp.h_points.ptr + ri, prog.points.data(), prog.points.size() * sizeof(PointRec));
+                std::memcpy(comp.h_kinds.ptr + ri, prog.kinds.data(), prog.kinds.size());
+                ri += prog.points.size();
+            }
             if (!prog.quads.empty()) std::memcpy(comp.h_quads.ptr + qi, prog.quads.data(), prog.quads.size() * sizeof(QuadRec));
             si += prog.splines.size();
             qi += prog.quads.size();
@@ -330,21 +348,30 @@ int Renderer::flush_geometry(Composition& comp) {
         comp.staged_from = from;
         comp.staged_to = to;
         comp.staged_splines = n_splines;
+        comp.staged_recs = n_recs;
         comp.staged_quads = n_quads;
         comp.staged_points = n_pts;
     }
     FORMA_CUDA_TRY(up_splines.reserve(comp.staged_splines + 1));
+    FORMA_CUDA_TRY(up_points.reserve(comp.staged_recs + 1));
+    FORMA_CUDA_TRY(up_kinds.reserve(comp.staged_recs + 1));
     FORMA_CUDA_TRY(up_quads.reserve(comp.staged_quads + 1));
     FORMA_CUDA_TRY(up_jobs.reserve(to - from));
     if (comp.staged_splines)
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_splines.ptr, comp.h_splines.ptr, comp.staged_splines * sizeof(SplineRec),
                                        cudaMemcpyHostToDevice, stream));
+    if (comp.staged_recs) {
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_points.ptr, comp.h_points.ptr, comp.staged_recs * sizeof(PointRec), cudaMemcpyHostToDevice,
+                                       stream));
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, comp.h_kinds.ptr, comp.staged_recs, cudaMemcpyHostToDevice, stream));
+    }
     if (comp.staged_quads)
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads.ptr, comp.h_quads.ptr, comp.staged_quads * sizeof(QuadRec), cudaMemcpyHostToDevice, stream));
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, comp.h_jobs.ptr, (to - from) * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
-    h2d_bytes += comp.staged_splines * sizeof(SplineRec) + comp.staged_quads * sizeof(QuadRec) + (to - from) * sizeof(FlattenJob);
-    launch_flatten_eval(up_splines.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)(to - from), (uint32_t)comp.staged_points,
-                        comp.d_x.ptr, comp.d_y.ptr, comp.d_gid.ptr, stream);
+    h2d_bytes += comp.staged_splines * sizeof(SplineRec) + comp.staged_recs * (sizeof(PointRec) + 1) +
+                 comp.staged_quads * sizeof(QuadRec) + (to - from) * sizeof(FlattenJob);
+    launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)(to - from),
+                        (uint32_t)comp.staged_points, comp.d_x.ptr, comp.d_y.ptr, comp.d_gid.ptr, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
     comp.n_resident = comp.n_points;
@@ -468,7 +495,20 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     uint32_t n = 0;
     // One read-back: segment count + the largest tile coordinates (totals[4..5]).
     FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals, totals.ptr, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    // The emit pass does not need the count, only room for its output: launch it
+    // into the buffer of the previous frames before waiting for the read-back, so
+    // that the GPU keeps working while the host wakes up. Segments beyond the
+    // capacity are dropped and the pass is repeated below in that (rare) case.
+    const size_t spec_cap = speculation_enabled() ? std::min<size_t>(segs.capacity, 0xFFFFFFFFu) : 0;
+    const bool speculated = spec_cap > 1 && nb;
+    FORMA_CUDA_TRY(ensure_count_event());
+    FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
+    if (speculated) {
+        if (timer.ok) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[1], stream));  // end of line setup (count pass)
+        launch_raster_emit(ra, block_sums.ptr, segs.ptr, (uint32_t)(spec_cap - 1), stream);
+        ++launches;
+    }
+    FORMA_CUDA_TRY(cudaEventSynchronize(count_ev));  // the read-back only, not the speculative launch
     n = pinned_totals[0];
     {
         // Already ordered by layer: no layer digits (see Composition::layers_in_order).
@@ -485,9 +525,11 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     }
     FORMA_CUDA_TRY(segs.reserve(n + 1));
     FORMA_CUDA_TRY(segs_tmp.reserve(n + 1));
-    if (timer.ok) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[1], stream));  // end of line setup (count pass)
-    launch_raster_emit(ra, block_sums.ptr, segs.ptr, stream);
-    launches += nb ? 1 : 0;
+    if (!speculated || (size_t)n + 1 > spec_cap) {
+        if (!speculated && timer.ok) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[1], stream));  // end of line setup (count pass)
+        launch_raster_emit(ra, block_sums.ptr, segs.ptr, n, stream);
+        launches += nb ? 1 : 0;
+    }
     FORMA_CUDA_TRY(cudaGetLastError());
     return FORMA_STATUS_OK;
 }
@@ -618,8 +660,23 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(block_sums.reserve(nb + 1));
         launch_cell_count(segs.ptr, n, block_sums.ptr, totals.ptr + 1, stream);
         launches += 2;
-        st = read_total(1, &n_cells);
-        if (st) return st;
+        // Read the cell count back; meanwhile the next two kernels already run with
+        // the count taken from device memory, into the buffers of the previous frames
+        // (they do nothing if those are too small, and are then repeated below).
+        FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 1, totals.ptr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
+        size_t cell_cap = 0;
+        if (speculation_enabled() && cell_start.capacity > 1)
+            cell_cap = std::min({cell_start.capacity - 1, cell_key.capacity, cell_cover.capacity, key2.capacity, perm.capacity,
+                                 (size_t)0xFFFFFFFFu});
+        if (cell_cap) {
+            launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, (uint32_t)cell_cap, stream);
+            launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, (uint32_t)cell_cap,
+                              (uint32_t)std::min<size_t>(cell_cap, n), cell_cover.ptr, key2.ptr, perm.ptr, stream);
+            launches += 2;
+        }
+        FORMA_CUDA_TRY(cudaEventSynchronize(count_ev));
+        n_cells = pinned_totals[1];
         FORMA_CUDA_TRY(cell_start.reserve(n_cells + 1));
         FORMA_CUDA_TRY(cell_key.reserve(n_cells));
         FORMA_CUDA_TRY(cell_cover.reserve(n_cells));
@@ -631,9 +688,12 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(perm_tmp.reserve(n_cells));
         FORMA_CUDA_TRY(gap_count.reserve(n_cells));
         FORMA_CUDA_TRY(gap_offset.reserve(n_cells));
-        launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, n_cells, stream);
-        launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, n_cells, cell_cover.ptr, key2.ptr, perm.ptr, stream);
-        launches += 2;
+        if (!cell_cap || n_cells > cell_cap) {
+            launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, n_cells, stream);
+            launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, n_cells, n_cells, cell_cover.ptr, key2.ptr,
+                              perm.ptr, stream);
+            launches += 2;
+        }
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_cells)));
         {
             SortResult sr = launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, n_cells, carry_sort_plan(S),
@@ -651,8 +711,19 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(scan_state.reserve(scan_state_words(n_cells)));
         launch_scan_u32(gap_offset.ptr, n_cells, totals.ptr + 2, scan_state.ptr, stream);
         launches += 2;
-        st = read_total(2, &n_gaps);
-        if (st) return st;
+        // Same scheme for the number of carry-only entries: gap_fill runs ahead of the read-back.
+        FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 2, totals.ptr + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
+        size_t gap_cap = 0;
+        if (speculation_enabled())
+            gap_cap = std::min({ekey_tmp.capacity, eid_tmp.capacity, gap_carry.capacity, (size_t)0xFFFFFFFFu});
+        if (gap_cap) {
+            launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
+                            ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, (uint32_t)gap_cap, stream);
+            ++launches;
+        }
+        FORMA_CUDA_TRY(cudaEventSynchronize(count_ev));
+        n_gaps = pinned_totals[2];
         n_entries = n_cells + n_gaps;
         last_cells = n_cells;
         last_entries = n_entries;
@@ -666,9 +737,11 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(eflags.reserve(n_entries));
         if (n_gaps) {
             FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_gaps)));
-            launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
-                            ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, stream);
-            ++launches;
+            if (!gap_cap || n_gaps > gap_cap) {
+                launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
+                                ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, n_gaps, stream);
+                ++launches;
+            }
             SortResult sr = launch_radix_sort(ekey_tmp.ptr, gkey_tmp.ptr, eid_tmp.ptr, gid_tmp.ptr, n_gaps, gap_sort_plan(S),
                                               sort_scratch.ptr, stream);
             launches += sr.launches;
@@ -898,11 +971,20 @@ int forma_path_segments(forma_path* p, const float** x, const float** y, const u
     job.has_xf = p->p.has_xf ? 1u : 0u;
     std::memcpy(job.xf, p->p.xf, sizeof(job.xf));
     job.dst = 0;
-    FORMA_CUDA_TRY(cudaMemcpy(dc.ptr, prog.splines.data(), prog.splines.size() * sizeof(SplineRec), cudaMemcpyHostToDevice));
+    DeviceBuffer<PointRec> dp;
+    DeviceBuffer<uint8_t> dk;
+    FORMA_CUDA_TRY(dp.reserve(prog.points.size() + 1));
+    FORMA_CUDA_TRY(dk.reserve(prog.kinds.size() + 1));
+    if (!prog.splines.empty())
+        FORMA_CUDA_TRY(cudaMemcpy(dc.ptr, prog.splines.data(), prog.splines.size() * sizeof(SplineRec), cudaMemcpyHostToDevice));
+    if (!prog.points.empty()) {
+        FORMA_CUDA_TRY(cudaMemcpy(dp.ptr, prog.points.data(), prog.points.size() * sizeof(PointRec), cudaMemcpyHostToDevice));
+        FORMA_CUDA_TRY(cudaMemcpy(dk.ptr, prog.kinds.data(), prog.kinds.size(), cudaMemcpyHostToDevice));
+    }
     if (!prog.quads.empty())
         FORMA_CUDA_TRY(cudaMemcpy(dq.ptr, prog.quads.data(), prog.quads.size() * sizeof(QuadRec), cudaMemcpyHostToDevice));
     FORMA_CUDA_TRY(cudaMemcpy(dj.ptr, &job, sizeof(job), cudaMemcpyHostToDevice));
-    launch_flatten_eval(dc.ptr, dq.ptr, dj.ptr, 1, count, dx.ptr, dy.ptr, dg.ptr, 0);
+    launch_flatten_eval(dc.ptr, dp.ptr, dk.ptr, dq.ptr, dj.ptr, 1, count, dx.ptr, dy.ptr, dg.ptr, 0);
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaMemcpy(p->x.data(), dx.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
     FORMA_CUDA_TRY(cudaMemcpy(p->y.data(), dy.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
@@ -910,6 +992,7 @@ int forma_path_segments(forma_path* p, const float** x, const float** y, const u
         uint32_t end = s.first_point + ((s.info >> 30) & 1u) + (s.info & kSplineEvalMask);
         if ((s.info >> 31) && end < count) p->c[end] = 1;
     }
+    for (size_t i = 0; i < prog.kinds.size() && i < count; ++i) p->c[i] = prog.kinds[i] == 1u;
     return FORMA_STATUS_OK;
 }
 

@@ -102,9 +102,9 @@ __device__ __forceinline__ void store_tile_solid(const PaintScene& S, uint8_t* f
 __device__ __forceinline__ uint32_t cell_index(uint32_t lx, uint32_t ly) { return (ly & 7u) * 32u + lx * 2u + (ly >> 3); }
 
 // One pixel of blend_at (cpu/painter/mod.rs:406-447) for any fill / blend
-// mode. Out of line on purpose: inlining it eight times per layer made the
-// kernel 15k instructions long.
-__device__ __noinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ st, const StopRec* __restrict__ stops,
+// mode; only instantiated inside blend_column_generic (inlining it eight times
+// per layer into the kernel made the kernel 15k instructions long).
+__device__ __forceinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ st, const StopRec* __restrict__ stops,
                                                    const uint16_t* __restrict__ texels, float fx, float fy, int l,
                                                    float coverage, bool apply_clip, float clip, float4 dst) {
     float fill[4];
@@ -128,6 +128,24 @@ __device__ __noinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ 
     float cb = fmaf(fill[2], inv_dst_a_src_a, bl[2] * dst_a_src_a);
     return make_float4(fmaf(dst.x, inv_src_a, cr), fmaf(dst.y, inv_src_a, cg), fmaf(dst.z, inv_src_a, cb),
                        fmaf(dst.w, inv_src_a, sa));
+}
+
+// The eight pixels of a lane (one f32x8) in one call: px = r[8] g[8] b[8] a[8] in
+// local memory. One call per layer instead of eight keeps the register
+// save / restore traffic around the call out of the pixel loop.
+__device__ __noinline__ void blend_column_generic(const StyleRec* __restrict__ st, const StopRec* __restrict__ stops,
+                                                  const uint16_t* __restrict__ texels, float fx, float fy,
+                                                  const float* __restrict__ cov, bool apply_clip,
+                                                  const float* __restrict__ clip /* stride 32 */, float* __restrict__ px) {
+#pragma unroll 1
+    for (int l = 0; l < 8; ++l) {
+        float4 d = make_float4(px[l], px[8 + l], px[16 + l], px[24 + l]);
+        d = blend_pixel_generic(st, stops, texels, fx, fy, l, cov[l], apply_clip, apply_clip ? clip[l * 32] : 1.0f, d);
+        px[l] = d.x;
+        px[8 + l] = d.y;
+        px[16 + l] = d.z;
+        px[24 + l] = d.w;
+    }
 }
 
 // The scalar blend of the solid-tile fold (all 16 modes) stays out of line too.
@@ -482,12 +500,16 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                     }
                 } else {
                     const StyleRec* st = &S.styles[er.slot];
+                    float px[32], cv[8];
 #pragma unroll
                     for (int l = 0; l < 8; ++l) {
-                        float4 d = make_float4(dr[l], dg[l], db[l], da[l]);
-                        float m = apply_clip ? clip_mask[l * 32] : 1.0f;
-                        d = blend_pixel_generic(st, S.stops, S.texels, fx, fy, l, cov[l], apply_clip, m, d);
-                        dr[l] = d.x; dg[l] = d.y; db[l] = d.z; da[l] = d.w;
+                        px[l] = dr[l]; px[8 + l] = dg[l]; px[16 + l] = db[l]; px[24 + l] = da[l];
+                        cv[l] = cov[l];
+                    }
+                    blend_column_generic(st, S.stops, S.texels, fx, fy, cv, apply_clip, clip_mask, px);
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        dr[l] = px[l]; dg[l] = px[8 + l]; db[l] = px[16 + l]; da[l] = px[24 + l];
                     }
                 }
             }

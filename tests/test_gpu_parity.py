@@ -173,6 +173,33 @@ def test_random_mixed_scene_bit_exact(cuda_api, oracle_api, cuda_renderer, oracl
     assert_same(a, b, f"random_mixed seed {seed}")
 
 
+@pytest.mark.parametrize("order", ["descending", "shuffled"])
+def test_layers_inserted_out_of_order(cuda_api, oracle_api, cuda_renderer, oracle_renderer, order):
+    """Layer orders that do not follow insertion order: the sort cannot rely on the
+    rasterizer's emission order for the layer digits (Composition::layers_in_order)."""
+    w, h, n = 640, 480, 300
+
+    def build(api, comp):
+        rng = synth.SplitMix64(77)
+        ids = list(range(n))
+        if order == "descending":
+            ids.reverse()
+        else:
+            for i in range(n - 1, 0, -1):
+                j = rng.randint(i + 1)
+                ids[i], ids[j] = ids[j], ids[i]
+        for k in ids:
+            cx, cy, e = rng.uniform(0, w), rng.uniform(0, h), rng.uniform(10, 120)
+            pb = api.PathBuilder()
+            pb.move_to(Point(synth.f32(cx - e), synth.f32(cy - e))).line_to(Point(synth.f32(cx + e), synth.f32(cy - 0.5 * e)))
+            pb.quad_to(Point(synth.f32(cx + e), synth.f32(cy + e)), Point(synth.f32(cx), synth.f32(cy + e)))
+            col = Color(rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.3, 1.0))
+            comp.get_mut_or_insert_default(k * 3).insert(pb.build()).set_props(Props(func=Func.Draw(Style(fill=Fill.Solid(col)))))
+    a, _ = render(cuda_api, cuda_renderer, build, w, h)
+    b, _ = render(oracle_api, oracle_renderer, build, w, h)
+    assert_same(a, b, f"layers inserted in {order} order")
+
+
 def test_opaque_cubics_bit_exact(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
     def build(api, comp):
         synth.random_cubics(api, comp, 3000, 1920, 1080, 3)

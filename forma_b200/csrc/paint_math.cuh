@@ -355,6 +355,69 @@ __device__ inline void gradient_at(const StyleRec& st, const StopRec* __restrict
     for (int k = 0; k < 4; ++k) out[k] = __uint_as_float(bits[k]);
 }
 
+// The same function for gradients of at most four stops whose stops (and the
+// per-gradient terms dx, dy, 1 / dot) were loaded once per layer: the pixel loop
+// then runs out of registers. Identical operations in identical order.
+struct GradientSetup {
+    float dx, dy, dot_recip;
+    StopRec c[4];
+    uint32_t count;
+};
+__device__ __forceinline__ GradientSetup gradient_setup(const StyleRec& st, const StopRec* __restrict__ stops) {
+    GradientSetup g;
+    g.dx = st.end[0] - st.start[0];
+    g.dy = st.end[1] - st.start[1];
+    float dot = g.dx * g.dx + g.dy * g.dy;
+    g.dot_recip = d_rcp(dot);
+    g.count = st.stop_count;
+    const StopRec* sp = stops + st.stop_first;
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) g.c[i] = sp[i < g.count ? i : g.count - 1u];
+    return g;
+}
+__device__ __forceinline__ void gradient_at_small(const StyleRec& st, const GradientSetup& g, float x, float y_base, int lane,
+                                                  float out[4]) {
+    float t;
+    if (st.gradient_type == 0u) {
+        float tx = (x - st.start[0]) * g.dx * g.dot_recip;
+        float ty = y_base - st.start[1];
+        t = fmaf(((float)lane + ty) * g.dy, g.dot_recip, tx);
+    } else {
+        float px = x - st.start[0];
+        float px2 = px * px;
+        float py = (float)lane + (y_base - st.start[1]);
+        t = sqrtf(fmaf(py, py, px2) * g.dot_recip);
+    }
+    uint32_t bits[4] = {0u, 0u, 0u, 0u};
+    bool acc = t <= g.c[0].stop;
+    if (acc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits[k] |= __float_as_uint(g.c[0].color[k]);
+    }
+    float start_stop = 0.0f;
+#pragma unroll
+    for (uint32_t i = 1; i < 4u; ++i) {
+        if (i < g.count) {
+            bool mask = acc != (t < g.c[i].stop);
+            if (mask) {
+                float d = g.c[i].stop - start_stop;
+                float local_t = (t - start_stop) * d_rcp(d);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    bits[k] |= __float_as_uint(fmaf(local_t, g.c[i].color[k], fmaf(-local_t, g.c[i - 1].color[k], g.c[i - 1].color[k])));
+                acc = true;
+            }
+            start_stop = g.c[i].stop;
+        }
+    }
+    if (!acc) {  // g.c[3] is the last stop (padding repeats it)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits[k] |= __float_as_uint(g.c[3].color[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = __uint_as_float(bits[k]);
+}
+
 // Texture::color_at for one lane (cpu/painter/styling.rs:146-193).
 __device__ inline void texture_at(const StyleRec& st, const uint16_t* __restrict__ texels, float x, float y_base,
                                   int lane, float out[4]) {

@@ -212,10 +212,37 @@ def run_cuda(args):
     host_fb = torch.empty((h, stride), dtype=torch.uint8).pin_memory()
     host_np = host_fb.numpy().reshape(-1)
 
+    gather_events = []
+    # Frame assembly over NVLink. "p2p" (default): rank 0 owns the frame, the other
+    # ranks map it (CUDA IPC) and their paint kernels store their bands straight into
+    # rank 0's HBM; a 1-element NCCL all-reduce on the render streams closes the frame.
+    # "gather": every rank paints locally, then one NCCL all-gather of the bands.
+    shared, frame_ptr, flag = None, fb.data_ptr(), None
+    if world > 1 and args.assembly == "p2p":
+        nbytes = h * stride
+        box = [None]
+        if rank == 0:
+            shared = api.SharedFrame(local, nbytes)
+            box = [shared.handle]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            shared = api.SharedFrame(local, nbytes, box[0])
+        frame_ptr = shared.ptr
+        flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        if rank == 0:
+            gathered = torch.as_tensor(shared, device=dev).view(h, stride)
+
     def frame_device():
-        renderer.render_device(comp, fb.data_ptr(), w, h, RGBA, clear, crop, None, stride)
+        renderer.render_device(comp, frame_ptr, w, h, RGBA, clear, crop, None, stride)
         if world > 1:
-            bands.gather_frame(band_view, gathered, dist)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            if shared is not None:
+                dist.all_reduce(flag)
+            else:
+                bands.gather_frame(band_view, gathered, dist)
+            g1.record(stream)
+            gather_events.append((g0, g1))
 
     def frame_e2e():
         comp.evict()
@@ -265,6 +292,8 @@ def run_cuda(args):
             a["launches"] += v["launches"]
     dev_ms, wall_ms = timed(frame_device_acc, args.steps)
     c1 = renderer.counters()
+    gather_ms = sum(a.elapsed_time(b) for a, b in gather_events[-args.steps:]) / args.steps if gather_events else 0.0
+    render_ms = stage_acc["total"] / args.steps
     for _ in range(max(args.warmup, 1)):
         frame_e2e()
     c2 = renderer.counters()
@@ -288,6 +317,8 @@ def run_cuda(args):
 
     # The render call blocks on small device->host count read-backs, so wall time and
     # the device timeline agree; report the slower of the two, max over ranks.
+    gather_ms_max = max_over_ranks(gather_ms)  # includes waiting for the slowest rank's band
+    render_ms_max, render_ms_min = max_over_ranks(render_ms), -max_over_ranks(-render_ms)
     T = max_over_ranks(max(dev_ms, wall_ms))
     T_e2e = max_over_ranks(max(e2e_dev_ms, e2e_wall_ms))
     n_seg = c1["segments"]
@@ -347,6 +378,9 @@ def run_cuda(args):
                 "gpu_launches": c3["launches"] - c2["launches"],
                 "stage_ms": {k: round(v / args.steps, 4) for k, v in e2e_stage_acc.items()}},
         "roofline": roofline,
+        "multi_gpu": {"render_ms_slowest_rank": round(render_ms_max, 4), "render_ms_fastest_rank": round(render_ms_min, 4),
+                      "assembly": args.assembly if world > 1 else None,
+                      "assembly_ms": round(gather_ms_max, 4), "frame_bytes": (h * stride) if world > 1 else 0},
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu:
@@ -387,6 +421,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="paris4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--assembly", default="p2p", choices=["p2p", "gather"],
+                    help="multi-GPU frame assembly: peer stores into rank 0's frame (default) or an NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

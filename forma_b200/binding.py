@@ -277,6 +277,10 @@ SIGNATURES = {
     "renderer_counters": (None, [_vp, _u64p]),
     "renderer_kernel_times": (None, [_vp, C.POINTER(C.c_double), _u32p]),
     "renderer_set_stream": (None, [_vp, _vp]),
+    "shared_frame_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "shared_frame_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "shared_frame_close": (C.c_int, [C.c_int, _vp]),
+    "shared_frame_free": (C.c_int, [C.c_int, _vp]),
     "composition_evict": (None, [_vp]),
     "composition_point_count": (C.c_uint64, [_vp]),
     "renderer_lines": (C.c_uint64, [_vp, C.c_uint64, _u32p, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _u32p]),
@@ -318,6 +322,37 @@ class Api:
 
     def Renderer(self, device: int = 0) -> "Renderer":
         return Renderer(self, device)
+
+    def SharedFrame(self, device: int, nbytes: int, handle: Optional[bytes] = None) -> "SharedFrame":
+        return SharedFrame(self, device, nbytes, handle)
+
+
+class SharedFrame:
+    """A frame in one GPU's HBM that other processes paint into over NVLink
+    (forma_shared_frame_*): the owner passes `handle` (64 bytes) to the other
+    ranks, which construct theirs with it; `ptr` goes to Renderer.render_device.
+    `__cuda_array_interface__` lets torch / cupy view the bytes without a copy."""
+
+    def __init__(self, api: "Api", device: int, nbytes: int, handle: Optional[bytes] = None):
+        self._api, self.device, self.nbytes, self.owner = api, device, nbytes, handle is None
+        p = C.c_void_p()
+        if self.owner:
+            buf = C.create_string_buffer(64)
+            api.check(api.shared_frame_create(device, nbytes, C.byref(p), buf), "shared_frame_create")
+            self.handle = buf.raw
+        else:
+            self.handle = bytes(handle)
+            api.check(api.shared_frame_open(device, self.handle, C.byref(p)), "shared_frame_open")
+        self.ptr = int(p.value)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def close(self):
+        if self.ptr:
+            (self._api.shared_frame_free if self.owner else self._api.shared_frame_close)(self.device, C.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 def _np_f32(ptr, n):

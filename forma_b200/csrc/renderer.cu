@@ -1194,6 +1194,49 @@ int forma_renderer_render_device(forma_renderer* r, forma_composition* c, uint8_
     return r->r.render(c->c, device_buffer, true, width, stride, height, channels, clear, crop,
                        cache ? &cache->c : nullptr, timings);
 }
+// --- shared frames (multi-GPU, see include/forma_b200.h) -----------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(forma_ipc_handle), "CUDA IPC handles are 64 bytes");
+int forma_shared_frame_create(int device, uint64_t bytes, void** device_ptr, forma_ipc_handle* handle) {
+    if (!device_ptr || !handle || !bytes) {
+        set_error("forma_shared_frame_create: bad arguments");
+        return FORMA_STATUS_INVALID;
+    }
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    void* p = nullptr;
+    FORMA_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return FORMA_STATUS_CUDA;
+    }
+    std::memcpy(handle->bytes, &h, sizeof(h));
+    *device_ptr = p;
+    return FORMA_STATUS_OK;
+}
+int forma_shared_frame_open(int device, const forma_ipc_handle* handle, void** device_ptr) {
+    if (!device_ptr || !handle) {
+        set_error("forma_shared_frame_open: bad arguments");
+        return FORMA_STATUS_INVALID;
+    }
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle->bytes, sizeof(h));
+    FORMA_CUDA_TRY(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FORMA_STATUS_OK;
+}
+int forma_shared_frame_close(int device, void* mapped_ptr) {
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    FORMA_CUDA_TRY(cudaIpcCloseMemHandle(mapped_ptr));
+    return FORMA_STATUS_OK;
+}
+int forma_shared_frame_free(int device, void* device_ptr) {
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    FORMA_CUDA_TRY(cudaFree(device_ptr));
+    return FORMA_STATUS_OK;
+}
+
 uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.launches; }
 void forma_renderer_stage_times(const forma_renderer* r, double out_ms[8]) {
     for (int i = 0; i < 8; ++i) out_ms[i] = r->r.stage_ms[i];

@@ -201,6 +201,21 @@ int forma_renderer_render_device(forma_renderer*, forma_composition*, uint8_t* d
  * instead of the default stream. */
 void forma_renderer_set_stream(forma_renderer*, void* cuda_stream);
 
+/* Multi-GPU frame assembly without a copy (one process per GPU, tile-row bands,
+ * SURVEY.md §8e): the process that owns the frame allocates it with
+ * forma_shared_frame_create and passes the 64-byte handle to the others (any
+ * channel, e.g. torch.distributed); they map it with forma_shared_frame_open
+ * (CUDA IPC, peer access over NVLink) and hand the mapped pointer to
+ * forma_renderer_render_device with their band as `crop`: the paint kernel's
+ * stores then land directly in the owner's HBM. The caller synchronises the
+ * ranks (a barrier / 1-element all-reduce on the render streams) before the
+ * owner reads the frame. */
+typedef struct forma_ipc_handle { unsigned char bytes[64]; } forma_ipc_handle;
+int forma_shared_frame_create(int device, uint64_t bytes, void** device_ptr, forma_ipc_handle* handle);
+int forma_shared_frame_open(int device, const forma_ipc_handle* handle, void** device_ptr);
+int forma_shared_frame_close(int device, void* mapped_ptr); /* a pointer from _open   */
+int forma_shared_frame_free(int device, void* device_ptr);  /* a pointer from _create */
+
 /* --- extensions (no reference counterpart) --------------------------------- */
 /* Bulk form of move_to/line_to/quad_to/cubic_to: cmds[i] in {0 Move, 1 Line,
  * 2 Quad, 3 Cubic}, xy = the points they consume (1, 1, 2, 3 points each). */

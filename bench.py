@@ -275,6 +275,15 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 1)):
         frame_device()
     torch.cuda.synchronize()
+    assembled_ok = None
+    if world > 1:  # untimed check: the assembled frame equals rank 0's own single-GPU frame, byte for byte
+        if rank == 0:
+            whole = torch.zeros((h, stride), dtype=torch.uint8, device=dev)
+            renderer.render_device(comp, whole.data_ptr(), w, h, RGBA, clear, None, None, stride)
+            torch.cuda.synchronize()
+            assembled_ok = bool(torch.equal(whole[:, :w * 4], gathered[:h, :w * 4]))
+            del whole
+        dist.barrier()
     c0 = renderer.counters()
     sampler = ClockSampler(local)
     sampler.start()
@@ -380,6 +389,7 @@ def run_cuda(args):
         "roofline": roofline,
         "multi_gpu": {"render_ms_slowest_rank": round(render_ms_max, 4), "render_ms_fastest_rank": round(render_ms_min, 4),
                       "assembly": args.assembly if world > 1 else None,
+                      "assembled_frame_equals_single_gpu_frame": assembled_ok,
                       "assembly_ms": round(gather_ms_max, 4), "frame_bytes": (h * stride) if world > 1 else 0},
         "clocks": sampler.summary(),
     }

@@ -363,8 +363,16 @@ def run_cuda(args):
     name = max(kerns, key=lambda k: kerns[k]["ms_per_step"]) if kerns else None
     dom = kerns.get(name, {"GBps": 0.0, "ms_per_launch": 0.0, "algorithmic_bytes_per_launch": 0.0})
     sort_ms = stages["sort"]
+    # dram__bytes_read + dram__bytes_write of one launch of that kernel, from the committed
+    # `ncu --set full` capture of this command (profiles/ncu_traffic.json), or null.
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(name)
+    except Exception:
+        pass
     roofline = {"kernel": name, "bound": "hbm", "achieved": dom["GBps"], "peak": peak, "peak_source": peak_kind,
-                "unit": "GB/s", "frac": dom["GBps"] / peak, "traffic": None,
+                "unit": "GB/s", "frac": dom["GBps"] / peak, "traffic": traffic,
                 "algorithmic_bytes": dom["algorithmic_bytes_per_launch"], "kernel_ms": dom["ms_per_launch"],
                 "kernels": kerns,
                 # The whole sort against its algorithm-independent bound (16 N).

@@ -136,8 +136,8 @@ __device__ __forceinline__ float4 blend_pixel_generic(const StyleRec* __restrict
     return blend_fill(st->blend_mode, fill, coverage, apply_clip, clip, dst);
 }
 
-// The eight pixels of a lane (one f32x8) in one call: px = the lane's slots in
-// shared memory (channel c, row l at px[c * 256 + l * 32]). One call per layer instead of eight keeps the register
+// The eight pixels of a lane (one f32x8) in one call: px = r[8] g[8] b[8] a[8] in
+// local memory. One call per layer instead of eight keeps the register
 // save / restore traffic around the call out of the pixel loop; the style record
 // (and, for gradients of up to four stops, the stops) are loaded once per call.
 __device__ __noinline__ void blend_column_generic(const StyleRec* __restrict__ st_ptr, const StopRec* __restrict__ stops,
@@ -152,22 +152,22 @@ __device__ __noinline__ void blend_column_generic(const StyleRec* __restrict__ s
             float fill[4];
             gradient_at_small(s, g, fx, fy, l, fill);
             float4 d = blend_fill(s.blend_mode, fill, cov[l], apply_clip, apply_clip ? clip[l * 32] : 1.0f,
-                                  make_float4(px[l * 32], px[256 + l * 32], px[512 + l * 32], px[768 + l * 32]));
-            px[l * 32] = d.x;
-            px[256 + l * 32] = d.y;
-            px[512 + l * 32] = d.z;
-            px[768 + l * 32] = d.w;
+                                  make_float4(px[l], px[8 + l], px[16 + l], px[24 + l]));
+            px[l] = d.x;
+            px[8 + l] = d.y;
+            px[16 + l] = d.z;
+            px[24 + l] = d.w;
         }
         return;
     }
 #pragma unroll 2
     for (int l = 0; l < 8; ++l) {
-        float4 d = make_float4(px[l * 32], px[256 + l * 32], px[512 + l * 32], px[768 + l * 32]);
+        float4 d = make_float4(px[l], px[8 + l], px[16 + l], px[24 + l]);
         d = blend_pixel_generic(&s, stops, texels, fx, fy, l, cov[l], apply_clip, apply_clip ? clip[l * 32] : 1.0f, d);
-        px[l * 32] = d.x;
-        px[256 + l * 32] = d.y;
-        px[512 + l * 32] = d.z;
-        px[768 + l * 32] = d.w;
+        px[l] = d.x;
+        px[8 + l] = d.y;
+        px[16 + l] = d.z;
+        px[24 + l] = d.w;
     }
 }
 
@@ -182,9 +182,6 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
     __shared__ int32_t s_area[kPaintWarpsPerBlock][256];
     __shared__ int32_t s_cover[kPaintWarpsPerBlock][256];
     __shared__ float s_clip[kPaintWarpsPerBlock][256];
-    __shared__ float s_px[kPaintWarpsPerBlock][4][256];  // destination pixels, see below
-    __shared__ uint4 s_hdr[kPaintWarpsPerBlock][32 * 4];  // entry records of the current group of 32 entries
-    uint4* hdr = s_hdr[threadIdx.x >> 5];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     int32_t* area = s_area[warp];
     int32_t* cover = s_cover[warp];
@@ -385,17 +382,10 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
         }
 
         // ---- paint (layer_workbench/mod.rs:301-337, cpu/painter/mod.rs:290-347) ---
-        // The lane's 8 destination pixels live in shared memory (lane-private slots
-        // c*256 + l*32 + lane, conflict-free): 32 fewer live registers per thread buy
-        // more resident warps, which this latency-bound loop needs more than the
-        // extra LDS/STS cost.
-        float* pxs = &s_px[warp][0][0] + lane;
+        float dr[8], dg[8], db[8], da[8];
 #pragma unroll
         for (int l = 0; l < 8; ++l) {
-            pxs[l * 32] = clear.r;
-            pxs[256 + l * 32] = clear.g;
-            pxs[512 + l * 32] = clear.b;
-            pxs[768 + l * 32] = clear.a;
+            dr[l] = clear.r; dg[l] = clear.g; db[l] = clear.b; da[l] = clear.a;
         }
         bool clip_active = false;
         uint32_t clip_last = 0;
@@ -407,48 +397,32 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
 
         for (uint32_t p0 = first_paint; p0 < e; p0 += 32u) {
             const uint32_t cnt = min(32u, e - p0);
-            // The records of up to 32 entries are staged in shared memory by 32 lanes
-            // at once (word 14 = the entry's current optimizer flags) and then read by
-            // the whole warp with broadcast loads, entry by entry.
-            __syncwarp();
+            EntryHdr mine{};
+            uint32_t my_flags = kFlagMaskedOut;
             if (lane < cnt) {
-                const uint4* q = reinterpret_cast<const uint4*>(in.recs + p0 + lane);
-                uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-                q3.z = in.eflags[p0 + lane];
-                hdr[lane * 4u + 0u] = q0;
-                hdr[lane * 4u + 1u] = q1;
-                hdr[lane * 4u + 2u] = q2;
-                hdr[lane * 4u + 3u] = q3;
+                mine = load_hdr(in, p0 + lane);
+                my_flags = in.eflags[p0 + lane];
             }
-            __syncwarp();
             // Prefetch the first segment chunk of the first entry of this group.
-            uint32_t nflags = hdr[3].z;
+            uint32_t nflags = __shfl_sync(kFullMask, my_flags, 0);
             uint64_t pre = 0;
             {
-                const uint4 h0 = hdr[0];
-                if (!(nflags & kFlagMaskedOut) && h0.y + lane < h0.z) pre = in.segs[h0.y + lane];
+                uint32_t s0 = __shfl_sync(kFullMask, mine.seg0, 0), s1 = __shfl_sync(kFullMask, mine.seg1, 0);
+                if (!(nflags & kFlagMaskedOut) && s0 + lane < s1) pre = in.segs[s0 + lane];
             }
 
             for (uint32_t k = 0; k < cnt; ++k) {
                 const uint32_t flags = nflags;
                 const uint64_t first_seg = pre;
                 if (k + 1 < cnt) {  // start fetching the next entry's segments
-                    nflags = hdr[(k + 1u) * 4u + 3u].z;
-                    const uint4 h0 = hdr[(k + 1u) * 4u];
+                    nflags = __shfl_sync(kFullMask, my_flags, (int)k + 1);
+                    uint32_t s0 = __shfl_sync(kFullMask, mine.seg0, (int)k + 1);
+                    uint32_t s1 = __shfl_sync(kFullMask, mine.seg1, (int)k + 1);
                     pre = 0;
-                    if (!(nflags & kFlagMaskedOut) && h0.y + lane < h0.z) pre = in.segs[h0.y + lane];
+                    if (!(nflags & kFlagMaskedOut) && s0 + lane < s1) pre = in.segs[s0 + lane];
                 }
                 if (flags & kFlagMaskedOut) continue;
-                EntryHdr er;
-                {
-                    const uint4 q0 = hdr[k * 4u], q1 = hdr[k * 4u + 1u], q2 = hdr[k * 4u + 2u], q3 = hdr[k * 4u + 3u];
-                    er.layer = q0.x; er.seg0 = q0.y; er.seg1 = q0.z; er.meta = q0.w;
-                    er.carry = q1;
-                    er.color[0] = __uint_as_float(q2.x); er.color[1] = __uint_as_float(q2.y);
-                    er.color[2] = __uint_as_float(q2.z); er.color[3] = __uint_as_float(q2.w);
-                    er.slot = (int32_t)q3.x;
-                    er.clip_layers = q3.y;
-                }
+                const EntryHdr er = bcast_hdr(mine, (int)k);
                 const uint32_t fill_rule = meta_fill_rule(er.meta);
 
                 // acc_segment: scatter-add the cell's segments (cpu/painter/mod.rs:257-271).
@@ -536,24 +510,30 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                     for (int l = 0; l < 8; ++l) {
                         float sa = er.color[3] * cov[l];
                         if (apply_clip) sa *= clip_mask[l * 32];
-                        const float dr = pxs[l * 32], dg = pxs[256 + l * 32], db = pxs[512 + l * 32], da = pxs[768 + l * 32];
-                        float inv_dst_a_src_a = (1.0f - da) * sa;
+                        float inv_dst_a_src_a = (1.0f - da[l]) * sa;
                         float inv_src_a = 1.0f - sa;
-                        float dst_a_src_a = da * sa;
+                        float dst_a_src_a = da[l] * sa;
                         float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
                         float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
                         float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
-                        pxs[l * 32] = fmaf(dr, inv_src_a, cr);
-                        pxs[256 + l * 32] = fmaf(dg, inv_src_a, cg);
-                        pxs[512 + l * 32] = fmaf(db, inv_src_a, cb);
-                        pxs[768 + l * 32] = fmaf(da, inv_src_a, sa);
+                        dr[l] = fmaf(dr[l], inv_src_a, cr);
+                        dg[l] = fmaf(dg[l], inv_src_a, cg);
+                        db[l] = fmaf(db[l], inv_src_a, cb);
+                        da[l] = fmaf(da[l], inv_src_a, sa);
                     }
                 } else {
                     const StyleRec* st = &S.styles[er.slot];
-                    float cv[8];
+                    float px[32], cv[8];
 #pragma unroll
-                    for (int l = 0; l < 8; ++l) cv[l] = cov[l];
-                    blend_column_generic(st, S.stops, S.texels, fx, fy, cv, apply_clip, clip_mask, pxs);
+                    for (int l = 0; l < 8; ++l) {
+                        px[l] = dr[l]; px[8 + l] = dg[l]; px[16 + l] = db[l]; px[24 + l] = da[l];
+                        cv[l] = cov[l];
+                    }
+                    blend_column_generic(st, S.stops, S.texels, fx, fy, cv, apply_clip, clip_mask, px);
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        dr[l] = px[l]; dg[l] = px[8 + l]; db[l] = px[16 + l]; da[l] = px[24 + l];
+                    }
                 }
             }
         }
@@ -565,7 +545,7 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             for (int l = 0; l < 8; ++l) {
                 uint32_t py = ty * 16u + half * 8u + l;
                 if (py < S.height) {
-                    uint32_t rgba = pixel_to_srgb_bytes(pxs[l * 32], pxs[256 + l * 32], pxs[512 + l * 32], pxs[768 + l * 32], S.channels);
+                    uint32_t rgba = pixel_to_srgb_bytes(dr[l], dg[l], db[l], da[l], S.channels);
                     *reinterpret_cast<uint32_t*>(in.framebuffer + (size_t)py * S.stride + (size_t)px * 4u) = rgba;
                 }
             }
@@ -613,10 +593,9 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
     static int blocks_per_sm = 0, variant = 0;
     if (!blocks_per_sm) {
         const char* e = getenv("FORMA_PAINT_REGS");
-        variant = (e && atoi(e) == 96) ? 10 : (e && atoi(e) == 80) ? 12 : 8;
+        variant = (e && atoi(e) == 96) ? 10 : 8;
         if (variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
-        else if (variant == 10) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<10>, kPaintWarpsPerBlock * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<12>, kPaintWarpsPerBlock * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<10>, kPaintWarpsPerBlock * 32, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     int sms = 148, dev = 0;
@@ -625,8 +604,7 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
     uint32_t want = (uint32_t)(blocks_per_sm * sms);
     uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
     if (variant == 8) paint_kernel<8><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
-    else if (variant == 10) paint_kernel<10><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
-    else paint_kernel<12><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    else paint_kernel<10><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
 }
 
 }  // namespace forma

@@ -101,13 +101,16 @@ struct PaintScene {
 
 uint32_t cell_num_blocks(uint32_t n);
 // block_counts: cell_num_blocks(n) entries -> exclusive offsets; total[0] = #cells.
-void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* total, cudaStream_t st);
+// head_masks: (n + 31) / 32 words, one bit per segment that starts a cell (read by launch_cell_write).
+void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* head_masks, uint32_t* total,
+                       cudaStream_t st);
 // Both read the cell count from device memory (n_cells_ptr) and are no-ops when it
 // exceeds `cap`, so that they can be launched before the host has read the count;
 // grid_cells sizes the cover grid (an upper bound of the count, or the count).
-void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
-                       uint64_t* cell_key, const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st);
-void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
+void launch_cell_write(const uint32_t* head_masks, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
+                       const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st);
+// Also writes cell_key (the key of each cell's first segment).
+void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, uint64_t* cell_key,
                        const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
                        uint32_t* perm, cudaStream_t st);
 // Plans of the painter's two pair sorts (their key bounds are host-known).
@@ -119,7 +122,7 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
-                     cudaStream_t st);
+                     uint32_t grid_gaps /* threads to launch: >= the entry count */, cudaStream_t st);
 // One painter entry = one (tile, layer) pair with segments and / or a carried cover.
 struct EntryRec {  // 64 B
     uint32_t layer, seg0, seg1;  // layer order; [seg0, seg1) in the sorted segments (empty for carry-only entries)

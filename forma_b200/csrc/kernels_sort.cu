@@ -877,7 +877,18 @@ __global__ void __launch_bounds__(kWideThreads, 2)
 }
 
 static uint32_t tiles_for(uint32_t n, int items) { return (n + kSortThreads * items - 1) / (kSortThreads * items); }
-static int items_for(uint32_t n) { return n >= (1u << 21) ? 16 : 4; }
+// Keys per thread: 4096-key tiles from 2^19 keys on (fewer tiles = a shorter look-back chain for
+// the single-sweep pair sorts, and the reduce-then-scan path for key-only sorts), 1024-key tiles
+// below that so that small sorts still spread over the SMs. FORMA_SORT_BIG_LOG2 overrides (A/B).
+static int items_for(uint32_t n) {
+    static int log2_big = 0;
+    if (!log2_big) {
+        const char* e = getenv("FORMA_SORT_BIG_LOG2");
+        log2_big = e ? atoi(e) : 19;  // measured: 2^17 costs paris@4K (230 k cells) 4 % of its table stage
+        if (log2_big < 10 || log2_big > 30) log2_big = 19;
+    }
+    return n >= (1u << log2_big) ? 16 : 4;
+}
 // Large key-only sorts: FORMA_SORT_MODE = scan (default: reduce-then-scan passes),
 // persistent (TMA-staged single sweep) or oneshot (single sweep), for A/B measurements.
 enum class BigSortMode { Scan, Persistent, OneShot };

@@ -38,7 +38,8 @@ constexpr int kCellItems = 8;
 constexpr int kCellTile = kCellThreads * kCellItems;
 
 __global__ void __launch_bounds__(kCellThreads)
-    cell_count_kernel(const uint64_t* __restrict__ segs, uint32_t n, uint32_t* __restrict__ block_counts) {
+    cell_count_kernel(const uint64_t* __restrict__ segs, uint32_t n, uint32_t* __restrict__ block_counts,
+                      uint32_t* __restrict__ head_masks /* one bit per segment: starts a cell */) {
     __shared__ uint32_t warp_cnt[kCellThreads / 32];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t base = blockIdx.x * kCellTile + warp * (32u * kCellItems);
@@ -47,7 +48,9 @@ __global__ void __launch_bounds__(kCellThreads)
     for (int k = 0; k < kCellItems; ++k) {
         uint32_t i = base + k * 32u + lane;
         bool head = i < n && is_cell_head(segs, i);
-        cnt += __popc(__ballot_sync(kFullMask, head));
+        uint32_t m = __ballot_sync(kFullMask, head);
+        if (lane == 0 && base + k * 32u < n) head_masks[(base + k * 32u) >> 5] = m;  // cell_write reads these, not the segments
+        cnt += __popc(m);
     }
     if (lane == 0) warp_cnt[warp] = cnt;
     __syncthreads();
@@ -59,9 +62,8 @@ __global__ void __launch_bounds__(kCellThreads)
 }
 
 __global__ void __launch_bounds__(kCellThreads)
-    cell_write_kernel(const uint64_t* __restrict__ segs, uint32_t n, const uint32_t* __restrict__ block_offsets,
-                      uint32_t* __restrict__ cell_start, uint64_t* __restrict__ cell_key,
-                      const uint32_t* __restrict__ n_cells_ptr, uint32_t cap) {
+    cell_write_kernel(const uint32_t* __restrict__ head_masks, uint32_t n, const uint32_t* __restrict__ block_offsets,
+                      uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ n_cells_ptr, uint32_t cap) {
     __shared__ uint32_t warp_cnt[kCellThreads / 32];
     // The cell count is read on the device: the kernel may be launched before the
     // host knows it (Renderer::render); it does nothing if the buffers are too small.
@@ -73,9 +75,7 @@ __global__ void __launch_bounds__(kCellThreads)
     uint32_t cnt = 0;
 #pragma unroll
     for (int k = 0; k < kCellItems; ++k) {
-        uint32_t i = base + k * 32u + lane;
-        bool head = i < n && is_cell_head(segs, i);
-        masks[k] = __ballot_sync(kFullMask, head);
+        masks[k] = base + k * 32u < n ? head_masks[(base + k * 32u) >> 5] : 0u;  // same word for the whole warp
         cnt += __popc(masks[k]);
     }
     if (lane == 0) warp_cnt[warp] = cnt;
@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(kCellThreads)
             uint32_t i = base + k * 32u + lane;
             uint32_t p = pos + __popc(masks[k] & ((1u << lane) - 1u));
             cell_start[p] = i;
-            cell_key[p] = (segs[i] >> kSortShift) << kSortShift;
         }
         pos += __popc(masks[k]);
     }
@@ -107,7 +106,7 @@ constexpr int kCoverCells = 256;
 
 __global__ void __launch_bounds__(kCoverCells)
     cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
-                      const uint64_t* __restrict__ cell_key, const uint32_t* __restrict__ n_cells_ptr, uint32_t cap,
+                      uint64_t* __restrict__ cell_key, const uint32_t* __restrict__ n_cells_ptr, uint32_t cap,
                       uint4* __restrict__ cell_cover, uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
     __shared__ uint32_t s_start[kCoverCells + 1];
     __shared__ int32_t s_acc[kCoverCells][16];
@@ -172,7 +171,8 @@ __global__ void __launch_bounds__(kCoverCells)
         for (int q = 0; q < 4; ++q)
             w[q] = ((uint32_t)s_acc[t][4 * q] & 0xFFu) | (((uint32_t)s_acc[t][4 * q + 1] & 0xFFu) << 8) |
                    (((uint32_t)s_acc[t][4 * q + 2] & 0xFFu) << 16) | (((uint32_t)s_acc[t][4 * q + 3] & 0xFFu) << 24);
-        const uint64_t ck = cell_key[c];
+        const uint64_t ck = (segs[s_start[t]] >> kSortShift) << kSortShift;  // the cell's key = its first segment's
+        cell_key[c] = ck;
         const int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
         const bool relevant = !(ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi);
         perm[c] = c;
@@ -238,20 +238,26 @@ __global__ void gap_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2,
                                 const uint32_t* __restrict__ gap_count, const uint32_t* __restrict__ gap_offset,
                                 uint32_t n_cells, uint64_t* __restrict__ gkey, uint32_t* __restrict__ gid,
                                 uint4* __restrict__ gap_carry, const uint32_t* __restrict__ n_gaps_ptr, uint32_t cap) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cells || *n_gaps_ptr > cap) return;  // cap: see cell_write_kernel
-    uint32_t g = gap_count[j];
-    if (!g) return;
-    uint64_t ck = cell_key[perm[j]];
-    int32_t tx = (int32_t)key_tx(ck) - 1;
-    uint32_t off = gap_offset[j];
-    uint4 carry = carry_after[j];
-    int32_t first = max(tx + 1, (int32_t)S.tx_lo);
-    for (uint32_t r = 0; r < g; ++r) {
-        gkey[off + r] = (ck & ~(0xFFFull << 41)) | ((uint64_t)(uint32_t)(first + (int32_t)r + 1) << 41);
-        gid[off + r] = n_cells + off + r;
-        gap_carry[off + r] = carry;
+    // One thread per carry-only entry q: its source cell is the last one (in carry
+    // order) whose exclusive offset is <= q — cells without entries share their
+    // offset with the next cell and sort before it.
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_gaps = *n_gaps_ptr;
+    if (n_gaps > cap || q >= n_gaps) return;  // cap: see cell_write_kernel
+    uint32_t lo = 0, hi = n_cells;  // first j with gap_offset[j] > q
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (gap_offset[mid] <= q) lo = mid + 1u;
+        else hi = mid;
     }
+    const uint32_t j = lo - 1u;
+    const uint32_t r = q - gap_offset[j];
+    const uint64_t ck = cell_key[perm[j]];
+    const int32_t tx = (int32_t)key_tx(ck) - 1;
+    const int32_t first = max(tx + 1, (int32_t)S.tx_lo);
+    gkey[q] = (ck & ~(0xFFFull << 41)) | ((uint64_t)(uint32_t)(first + (int32_t)r + 1) << 41);
+    gid[q] = n_cells + q;
+    gap_carry[q] = carry_after[j];
 }
 
 // Entries = cells (sorted by construction) merged with the sorted carry-only
@@ -275,21 +281,37 @@ __global__ void merge_entries_kernel(PaintScene S, const uint64_t* __restrict__ 
                                      const uint32_t* __restrict__ cell_start, const uint4* __restrict__ carry_in,
                                      const uint4* __restrict__ gap_carry, uint64_t* __restrict__ ekey,
                                      EntryRec* __restrict__ recs, uint8_t* __restrict__ eflags) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cells + n_gaps) return;
+    // Merge-path style partition: the keys of a CTA's 256 consecutive elements of
+    // one list bracket a short range of the other list, found once per CTA (two
+    // full bisections by threads 0 and 1); every thread then bisects that range only.
+    __shared__ uint32_t s_bound[2];
+    const uint32_t i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x;
+    const uint32_t n_all = n_cells + n_gaps;
+    const bool cell_block = i0 + blockDim.x <= n_cells, gap_block = i0 >= n_cells;  // else: the one mixed CTA
+    if (threadIdx.x < 2u) {
+        const uint32_t last = min(i0 + blockDim.x, n_all) - 1u;
+        uint32_t b = threadIdx.x == 0u ? 0u : (cell_block ? n_gaps : n_cells);
+        if (cell_block) b = lower_bound_key(gkey, n_gaps, cell_key[threadIdx.x == 0u ? i0 : last]);
+        else if (gap_block) b = lower_bound_key(cell_key, n_cells, gkey[(threadIdx.x == 0u ? i0 : last) - n_cells]);
+        s_bound[threadIdx.x] = b;
+    }
+    __syncthreads();
+    if (i >= n_all) return;
     uint64_t k;
     uint32_t pos;
     EntryRec r;
     if (i < n_cells) {
         k = cell_key[i];
-        pos = i + lower_bound_key(gkey, n_gaps, k);
+        const uint32_t lo = cell_block ? s_bound[0] : 0u, hi = cell_block ? s_bound[1] : n_gaps;
+        pos = i + lo + lower_bound_key(gkey + lo, hi - lo, k);
         r.seg0 = cell_start[i];
         r.seg1 = cell_start[i + 1];
         r.carry = carry_in[i];
     } else {
         uint32_t g = i - n_cells;
         k = gkey[g];
-        pos = g + lower_bound_key(cell_key, n_cells, k);
+        const uint32_t lo = gap_block ? s_bound[0] : 0u, hi = gap_block ? s_bound[1] : n_cells;
+        pos = g + lo + lower_bound_key(cell_key + lo, hi - lo, k);
         r.seg0 = r.seg1 = 0;
         r.carry = gap_carry[gid[g] - n_cells];
     }
@@ -344,18 +366,19 @@ __global__ void tile_range_kernel(PaintScene S, const uint64_t* __restrict__ eke
 // ---------------------------------------------------------------------------
 uint32_t cell_num_blocks(uint32_t n) { return (n + kCellTile - 1) / kCellTile; }
 
-void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* total, cudaStream_t st) {
+void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* head_masks, uint32_t* total,
+                       cudaStream_t st) {
     uint32_t nb = cell_num_blocks(n);
-    cell_count_kernel<<<nb, kCellThreads, 0, st>>>(segs, n, block_counts);
+    cell_count_kernel<<<nb, kCellThreads, 0, st>>>(segs, n, block_counts, head_masks);
     launch_scan_u32(block_counts, nb, total, nullptr, st);
 }
 
-void launch_cell_write(const uint64_t* segs, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
-                       uint64_t* cell_key, const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st) {
-    cell_write_kernel<<<cell_num_blocks(n), kCellThreads, 0, st>>>(segs, n, block_offsets, cell_start, cell_key, n_cells_ptr, cap);
+void launch_cell_write(const uint32_t* head_masks, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
+                       const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st) {
+    cell_write_kernel<<<cell_num_blocks(n), kCellThreads, 0, st>>>(head_masks, n, block_offsets, cell_start, n_cells_ptr, cap);
 }
 
-void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, const uint64_t* cell_key,
+void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, uint64_t* cell_key,
                        const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
                        uint32_t* perm, cudaStream_t st) {
     if (grid_cells)
@@ -387,9 +410,10 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
-                     cudaStream_t st) {
-    gap_fill_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset, n_cells,
-                                                            gkey, gid, gap_carry, n_gaps_ptr, cap);
+                     uint32_t grid_gaps, cudaStream_t st) {
+    if (!grid_gaps || !n_cells) return;
+    gap_fill_kernel<<<(grid_gaps + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset, n_cells,
+                                                              gkey, gid, gap_carry, n_gaps_ptr, cap);
 }
 
 void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,

@@ -210,7 +210,7 @@ class Renderer {
     }
     DeviceBuffer<uint64_t> segs, segs_tmp;
     DeviceBuffer<uint8_t> sort_scratch;
-    DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, gid_tmp, tile_begin, tile_end;
+    DeviceBuffer<uint32_t> head_masks, cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, gid_tmp, tile_begin, tile_end;
     DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp, gkey_tmp;
     DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
     DeviceBuffer<uint8_t> eflags, framebuffer;
@@ -245,7 +245,7 @@ class Renderer {
     DeviceBuffer<QuadRec> up_quads;
     DeviceBuffer<FlattenJob> up_jobs;
 
-    uint32_t last_segments = 0, last_cells = 0, last_entries = 0;
+    uint32_t last_segments = 0, last_cells = 0, last_entries = 0, last_gaps = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied over PCIe since creation
     double stage_ms[8] = {0};               // see forma_renderer_stage_times
     double kernel_ms[4] = {0};              // see forma_renderer_kernel_times
@@ -658,7 +658,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     if (n > 0) {
         uint32_t nb = cell_num_blocks(n);
         FORMA_CUDA_TRY(block_sums.reserve(nb + 1));
-        launch_cell_count(segs.ptr, n, block_sums.ptr, totals.ptr + 1, stream);
+        FORMA_CUDA_TRY(head_masks.reserve(n / 32 + 2));
+        launch_cell_count(segs.ptr, n, block_sums.ptr, head_masks.ptr, totals.ptr + 1, stream);
         launches += 2;
         // Read the cell count back; meanwhile the next two kernels already run with
         // the count taken from device memory, into the buffers of the previous frames
@@ -670,7 +671,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             cell_cap = std::min({cell_start.capacity - 1, cell_key.capacity, cell_cover.capacity, key2.capacity, perm.capacity,
                                  (size_t)0xFFFFFFFFu});
         if (cell_cap) {
-            launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, (uint32_t)cell_cap, stream);
+            launch_cell_write(head_masks.ptr, n, block_sums.ptr, cell_start.ptr, totals.ptr + 1, (uint32_t)cell_cap, stream);
             launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, (uint32_t)cell_cap,
                               (uint32_t)std::min<size_t>(cell_cap, n), cell_cover.ptr, key2.ptr, perm.ptr, stream);
             launches += 2;
@@ -689,7 +690,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(gap_count.reserve(n_cells));
         FORMA_CUDA_TRY(gap_offset.reserve(n_cells));
         if (!cell_cap || n_cells > cell_cap) {
-            launch_cell_write(segs.ptr, n, block_sums.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, n_cells, stream);
+            launch_cell_write(head_masks.ptr, n, block_sums.ptr, cell_start.ptr, totals.ptr + 1, n_cells, stream);
             launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, n_cells, n_cells, cell_cover.ptr, key2.ptr,
                               perm.ptr, stream);
             launches += 2;
@@ -716,14 +717,16 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
         size_t gap_cap = 0;
         if (speculation_enabled())
-            gap_cap = std::min({ekey_tmp.capacity, eid_tmp.capacity, gap_carry.capacity, (size_t)0xFFFFFFFFu});
+            gap_cap = std::min({ekey_tmp.capacity, eid_tmp.capacity, gap_carry.capacity,
+                                (size_t)last_gaps * 2u + 4096u /* also the number of threads launched */});
         if (gap_cap) {
             launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
-                            ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, (uint32_t)gap_cap, stream);
+                            ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, (uint32_t)gap_cap, (uint32_t)gap_cap, stream);
             ++launches;
         }
         FORMA_CUDA_TRY(cudaEventSynchronize(count_ev));
         n_gaps = pinned_totals[2];
+        last_gaps = n_gaps;
         n_entries = n_cells + n_gaps;
         last_cells = n_cells;
         last_entries = n_entries;
@@ -739,7 +742,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_gaps)));
             if (!gap_cap || n_gaps > gap_cap) {
                 launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
-                                ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, n_gaps, stream);
+                                ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, n_gaps, n_gaps, stream);
                 ++launches;
             }
             SortResult sr = launch_radix_sort(ekey_tmp.ptr, gkey_tmp.ptr, eid_tmp.ptr, gid_tmp.ptr, n_gaps, gap_sort_plan(S),

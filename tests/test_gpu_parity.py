@@ -369,6 +369,24 @@ def test_layer_cache_copies_back_only_damage(cuda_api):
     assert not np.array_equal(buf, full)
 
 
+def test_shared_frame_owner_side(cuda_api, cuda_renderer):
+    """forma_shared_frame_create / _free and rendering into the shared allocation
+    (the mapping side needs a second process; bench.py --gpus N exercises it)."""
+    import torch
+    w, h = 256, 128
+    comp = cuda_api.Composition()
+    synth.random_mixed(cuda_api, comp, 30, w, h, 12)
+    host = np.zeros(w * h * 4, np.uint8)
+    cuda_renderer.render(comp, host, w, h, RGBA, Color(0.2, 0.3, 0.4, 1))
+    frame = cuda_api.SharedFrame(0, w * h * 4)
+    assert len(frame.handle) == 64 and frame.ptr
+    cuda_renderer.render_device(comp, frame.ptr, w, h, RGBA, Color(0.2, 0.3, 0.4, 1))
+    view = torch.as_tensor(frame, device="cuda:0")
+    assert np.array_equal(view.cpu().numpy(), host)
+    del view
+    frame.close()
+
+
 def test_render_device_matches_host_buffer(cuda_api, cuda_renderer):
     import torch
     w, h = 300, 200

@@ -39,6 +39,8 @@ WORKLOADS = {
     "paris4k_grad": (3840, 2160, "paris-30k.svg, every 8th layer filled with a synthetic 3-stop linear gradient over its "
                                  "bounding box (the file itself has none; SURVEY.md C2 variant, seed 1), 3840x2160"),
     "circles8k": (7680, 4320, "200k rational-quad circles r in [4,40], radial gradients, 8 blend modes, seed 5, 7680x4320"),
+    "spaceship1080p": (1920, 1080, "spaceship-like animation (backdrop + 1 ship + 400 drifting asteroids, seed 43, dt = 1/60 s), "
+                                   "1920x1080, persistent layer cache (per-tile damage reuse), every step = next frame"),
     "circles8k_1m": (7680, 4320, "1M rational-quad circles r in [4,40], radial gradients, 8 blend modes, seed 5, 7680x4320"),
     "smoke": (640, 360, "400 mixed layers, 640x360 (plumbing check)"),
 }
@@ -75,6 +77,8 @@ def build_scene(api, name):
         synth.random_circles(api, comp, 200_000, w, h, 5)
     elif name == "circles8k_1m":
         synth.random_circles(api, comp, 1_000_000, w, h, 5)
+    elif name == "spaceship1080p":
+        comp.animate = synth.spaceship_scene(api, comp, 400, w, h, 43)  # animate(frame) moves the layers
     else:
         synth.random_mixed(api, comp, 400, w, h, 7)
     return comp, w, h
@@ -88,6 +92,25 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
     def run(self):
+        try:  # NVML in-process: a sample every 10 ms, so that even a short timed region is covered
+            import pynvml
+            pynvml.nvmlInit()
+            hd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(hd, pynvml.NVML_CLOCK_SM)
+            bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+            while not self.stop_flag.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(hd, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
+                try:
+                    p = pynvml.nvmlDeviceGetPowerUsage(hd) / 1000.0
+                except Exception:
+                    p = 0.0
+                self.samples.append([str(sm), str(mx), str(p)] + ["Active" if r & b else "Not Active" for b in bits])
+                self.stop_flag.wait(0.01)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -150,13 +173,22 @@ def run_reference(args):
     r = api.Renderer()
     buf = np.zeros(w * h * 4, np.uint8)
     clear = Color(1.0, 1.0, 1.0, 0.0)
-    tune_cpu_threads(api, lambda: r.render(comp, buf, w, h, RGBA, clear))
+    animate = getattr(comp, "animate", None)
+    cache = r.create_buffer_layer_cache() if animate else None
+    frame_no = [0]
+
+    def one_frame():
+        if animate:
+            frame_no[0] += 1
+            animate(frame_no[0])
+        return r.render(comp, buf, w, h, RGBA, clear, None, cache)
+    tune_cpu_threads(api, one_frame)
     for _ in range(args.warmup):
-        t = r.render(comp, buf, w, h, RGBA, clear)
+        t = one_frame()
     t0 = time.perf_counter()
     stages = np.zeros(4)
     for _ in range(args.steps):
-        t = r.render(comp, buf, w, h, RGBA, clear)
+        t = one_frame()
         stages += [t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms]
     dt = time.perf_counter() - t0
     fps = args.steps / dt
@@ -232,8 +264,21 @@ def run_cuda(args):
         if rank == 0:
             gathered = torch.as_tensor(shared, device=dev).view(h, stride)
 
+    # Animated workloads: every frame moves layers and renders with a persistent layer
+    # cache (one per target buffer, like the reference's per-Buffer caches).
+    animate = getattr(comp, "animate", None)
+    cache_dev = renderer.create_buffer_layer_cache() if animate else None
+    cache_host = renderer.create_buffer_layer_cache() if animate else None
+    frame_no = [0]
+
+    def next_frame():
+        if animate:
+            frame_no[0] += 1
+            animate(frame_no[0])
+
     def frame_device():
-        renderer.render_device(comp, frame_ptr, w, h, RGBA, clear, crop, None, stride)
+        next_frame()
+        renderer.render_device(comp, frame_ptr, w, h, RGBA, clear, crop, cache_dev, stride)
         if world > 1:
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(stream)
@@ -247,7 +292,8 @@ def run_cuda(args):
     def frame_e2e():
         comp.evict()
         if world == 1:
-            renderer.render(comp, host_np, w, h, RGBA, clear, None, None, stride)
+            next_frame()
+            renderer.render(comp, host_np, w, h, RGBA, clear, None, cache_host, stride)
         else:
             frame_device()
             if rank == 0:
@@ -417,12 +463,21 @@ def cpu_baseline(args):
     r = api.Renderer()
     buf = np.zeros(w * h * 4, np.uint8)
     clear = Color(1.0, 1.0, 1.0, 0.0)
-    tune_cpu_threads(api, lambda: r.render(comp, buf, w, h, RGBA, clear))
-    r.render(comp, buf, w, h, RGBA, clear)
-    r.render(comp, buf, w, h, RGBA, clear)
+    animate = getattr(comp, "animate", None)
+    cache = r.create_buffer_layer_cache() if animate else None
+    frame_no = [0]
+
+    def one_frame():
+        if animate:
+            frame_no[0] += 1
+            animate(frame_no[0])
+        return r.render(comp, buf, w, h, RGBA, clear, None, cache)
+    tune_cpu_threads(api, one_frame)
+    one_frame()
+    one_frame()
     n, t0, stages = 0, time.perf_counter(), np.zeros(4)
     while n < 40 and time.perf_counter() - t0 < 12.0:
-        t = r.render(comp, buf, w, h, RGBA, clear)
+        t = one_frame()
         stages += [t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms]
         n += 1
     dt = time.perf_counter() - t0

@@ -134,3 +134,47 @@ def random_circles(api, comp, n_layers: int, width: int, height: int, seed: int,
             gb.color(Color(rng.uniform(), rng.uniform(), rng.uniform(), a))
         comp.get_mut_or_insert_default(i).insert(circle_path(api, cx, cy, rad)).set_props(
             Props(func=Func.Draw(Style(fill=Fill.Gradient(gb.build()), blend_mode=modes[i % 8]))))
+
+
+def spaceship_scene(api, comp, n_asteroids: int, width: int, height: int, seed: int):
+    """BASELINE config 4 shape (demo/src/demos/spaceship.rs): an opaque backdrop, one
+    small ship and `n_asteroids` potato-like closed quad paths drifting across the
+    screen with a fixed dt; only the moving layers' transforms change per frame, so
+    a layer cache skips most tiles. Returns `animate(frame)` which moves the layers."""
+    rng = SplitMix64(seed)
+    backdrop = (api.PathBuilder().move_to(Point(0.0, 0.0)).line_to(Point(float(width), 0.0))
+                .line_to(Point(float(width), float(height))).line_to(Point(0.0, float(height))).build())
+    comp.get_mut_or_insert_default(0).insert(backdrop).set_props(
+        Props(func=Func.Draw(Style(fill=Fill.Solid(Color(0.02, 0.02, 0.05, 1.0))))))
+    movers = []
+    for i in range(n_asteroids + 1):
+        ship = i == n_asteroids
+        rad = 14.0 if ship else rng.uniform(8.0, 60.0)
+        k = 3 if ship else 6 + rng.randint(5)
+        pts = []
+        for j in range(k):
+            ang = 2.0 * np.pi * j / k
+            rr = rad * (1.0 if ship else rng.uniform(0.7, 1.3))
+            pts.append((f32(rr * np.cos(ang)), f32(rr * np.sin(ang))))
+        pb = api.PathBuilder().move_to(Point(*pts[0]))
+        for j in range(k):
+            a, b = pts[j], pts[(j + 1) % k]
+            ctrl = Point(f32((a[0] + b[0]) * 0.6), f32((a[1] + b[1]) * 0.6))
+            if ship:
+                pb.line_to(Point(*b))
+            else:
+                pb.quad_to(ctrl, Point(*b))
+        g = rng.uniform(0.3, 0.8)
+        col = Color(1.0, 0.9, 0.2, 1.0) if ship else Color(g, f32(g * 0.9), f32(g * 0.8), 1.0)
+        layer = comp.get_mut_or_insert_default(1 + i)
+        layer.insert(pb.build()).set_props(Props(func=Func.Draw(Style(fill=Fill.Solid(col)))))
+        movers.append((1 + i, rng.uniform(0.0, width), rng.uniform(0.0, height),
+                       rng.uniform(-120.0, 120.0), rng.uniform(-120.0, 120.0)))
+
+    def animate(frame: int, dt: float = 1.0 / 60.0):
+        for order, x0, y0, vx, vy in movers:
+            x = (x0 + vx * dt * frame) % width
+            y = (y0 + vy * dt * frame) % height
+            comp.get(order).set_transform([1.0, 0.0, 0.0, 1.0, f32(x), f32(y)])
+    animate(0)
+    return animate

@@ -34,6 +34,7 @@ struct Layer {
     HostProps props;
     uint32_t unchanged_bits = 0;      // SmallBitSet over layer-cache ids
     size_t lines_count = 0;
+    uint64_t points = 0;              // points this layer's current geometry id owns in the segment buffer
 };
 
 struct PendingInsert {
@@ -61,6 +62,11 @@ class Composition {
 
     void layer_insert(Layer* layer, const Path& path);
     void layer_clear(Layer* layer);
+    // Composition::compact_geom (composition/mod.rs:184-218): drops the inserts of
+    // cleared / dropped layers and re-packs the segment buffer (the survivors are
+    // re-evaluated at the next render). Runs when at least half of the points are dead.
+    void compact_geom();
+    uint64_t garbage_points = 0;      // points whose geometry id no longer maps to a layer
     void mark_dirty() { tables_dirty = true; }
 
     // --- segment buffer (device) ------------------------------------------------

@@ -122,6 +122,7 @@ void Composition::drop(Layer* l) {  // Drop for Layer, layer.rs:355-363
             break;
         }
     geom_to_order.erase(l->geom_id);
+    garbage_points += l->points;
     for (auto it = pool.begin(); it != pool.end(); ++it)
         if (it->get() == l) {
             pool.erase(it);
@@ -148,6 +149,7 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
         uint64_t some = (uint64_t)(count - 1u) - prog.n_contour_ends;
         some_ids += some;
         layer->lines_count += some;
+        layer->points += count;
         n_points += count;
     }
     geom_to_order[layer->geom_id] = layer->order;
@@ -155,7 +157,30 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
     tables_dirty = true;
 }
 
+void Composition::compact_geom() {
+    if (garbage_points < 65536u || garbage_points * 2u < n_points) return;
+    std::vector<PendingInsert> live;
+    live.reserve(jobs.size());
+    uint64_t pts = 0;
+    for (PendingInsert& j : jobs) {
+        if (!geom_to_order.count(j.geom_id)) continue;
+        j.dst = (uint32_t)pts;
+        pts += j.count;
+        live.push_back(std::move(j));
+    }
+    jobs.swap(live);
+    n_points = (uint32_t)pts;
+    garbage_points = 0;
+    jobs_resident = 0;  // everything is evaluated again into the re-packed buffer
+    n_resident = 0;
+    staged_from = staged_to = 0;
+    staged_splines = staged_recs = staged_quads = staged_points = 0;
+    tables_dirty = true;
+}
+
 void Composition::layer_clear(Layer* layer) {  // layer.rs:131-146
+    garbage_points += layer->points;
+    layer->points = 0;
     geom_to_order.erase(layer->geom_id);
     layer->geom_id = next_geom_id++;
     geom_to_order[layer->geom_id] = layer->order;
@@ -289,6 +314,7 @@ int Renderer::flush_geometry(Composition& comp) {
         set_error("composition is resident on device %d, renderer uses device %d", comp.device, device);
         return FORMA_STATUS_INVALID;
     }
+    comp.compact_geom();
     const size_t from = comp.jobs_resident, to = comp.jobs.size();
     if (from == to) return FORMA_STATUS_OK;
     if (to - from >= (1u << 30)) {

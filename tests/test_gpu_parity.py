@@ -369,6 +369,38 @@ def test_layer_cache_copies_back_only_damage(cuda_api):
     assert not np.array_equal(buf, full)
 
 
+def test_cleared_geometry_is_compacted(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
+    """Composition::compact_geom (composition/mod.rs:184-218): clearing and re-inserting
+    a layer every frame must not grow the resident segment buffer without bound, and
+    the frames stay identical to the oracle's."""
+    w, h, frames = 320, 240, 60
+
+    def big_path(api, k):
+        rng = synth.SplitMix64(100 + k)
+        pb = api.PathBuilder().move_to(Point(160.0, 120.0))
+        for i in range(4000):
+            ang = 0.05 * i
+            r = 5.0 + 0.025 * i + rng.uniform(0.0, 1.0)
+            pb.line_to(Point(synth.f32(160.0 + r * np.cos(ang)), synth.f32(120.0 + r * np.sin(ang))))
+        return pb.build()
+
+    outs = []
+    for api, r in ((cuda_api, cuda_renderer), (oracle_api, oracle_renderer)):
+        comp = api.Composition()
+        synth.random_mixed(api, comp, 20, w, h, 3)
+        layer = comp.get_mut_or_insert_default(500)
+        layer.set_props(Props(fill_rule=FillRule.EvenOdd, func=Func.Draw(Style(fill=Fill.Solid(Color(0.1, 0.6, 0.3, 0.8))))))
+        buf = np.zeros(w * h * 4, np.uint8)
+        for k in range(frames):
+            comp.get(500).clear()
+            comp.get(500).insert(big_path(api, k))
+            r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1))
+        outs.append(buf.copy())
+        if api is cuda_api:
+            assert comp.point_count() < 100_000, comp.point_count()  # 60 x 4001 points without compaction
+    assert_same(outs[0].reshape(h, -1), outs[1].reshape(h, -1), "frame after 60 clear / insert cycles")
+
+
 def test_shared_frame_owner_side(cuda_api, cuda_renderer):
     """forma_shared_frame_create / _free and rendering into the shared allocation
     (the mapping side needs a second process; bench.py --gpus N exercises it)."""

@@ -22,6 +22,14 @@ struct QuadRec {
     float step;       // curvature / subdivisions of the spline (same for all its quads)
 };
 
+// What crosses PCIe per quadratic (48 B): the control points and the running
+// curvatures of its spline; quad_expand_kernel rebuilds the full QuadRec on the
+// device (the Levien parameters are recomputed there, quad_math.h).
+struct QuadUp {
+    float px[3], py[3], pw[3];
+    float prev_curv, total, step;
+};
+
 // Point-wise encoding of a flatten program, used instead of SplineRecs when it
 // is smaller (paths made of many short line splines): 8 B + 1 B per output point.
 //   kind 0: literal point (a, b)                  (Start / End of a spline)

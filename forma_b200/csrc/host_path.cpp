@@ -2,6 +2,8 @@
 // See host_path.hpp. Compiled with -ffp-contract=off.
 #include "host_path.hpp"
 
+#include "quad_math.h"
+
 #include <algorithm>
 
 namespace forma {
@@ -42,11 +44,6 @@ struct Angle {
 Angle angle_of(Pt d) {  // math/point.rs:87-89
     if (length(d) >= kEps) return {true, atan2_approx(d.y, d.x)};
     return {false, 0.0f};
-}
-
-float curvature(float x) {  // path.rs:48-51
-    const float c = 0.67f;
-    return x / (1.0f - c + std::sqrt(std::sqrt(fmaf(x * x, 0.25f, c * c * c * c))));
 }
 
 WPt cubic_at(float t, const WPt q[4]) {  // path.rs:75-120
@@ -95,31 +92,18 @@ class SplineBuilder {
         Spline& s = current_spline(in, p0, p0, p2);
         s.p2 = p2;
 
-        Pt h{a.x - b.x, a.y - b.y};
-        float cross = fmaf(p2.x - p0.x, h.y, -(p2.y - p0.y) * h.x);
-        float cross_recip = rcp(cross);
-        float x0 = fmaf(a.x, h.x, a.y * h.y) * cross_recip;
-        float x2 = fmaf(b.x, h.x, b.y * h.y) * cross_recip;
-        float dx_recip = rcp(x2 - x0);
-        float scale = std::fabs(cross / (length(h) * (x2 - x0)));
-        float k0 = curvature(x0);
-        float dk = curvature(x2) - k0;
-        float cur = 0.5f * std::fabs(dk) * std::sqrt(scale * (1.0f / kMaxError));
-        if (!std::isfinite(cur) || cur <= 1.0f) {  // collinear, path.rs:322-332
-            x0 = 0.03662467f;
-            dx_recip = 1.0f;
-            k0 = 0.0f;
-            dk = 1.0f;
-            cur = 2.0f;
-        }
+        // Levien parameters (path.rs:296-332): quad_math.h, shared with the device, which
+        // recomputes them from the control points instead of receiving them over PCIe.
+        const QuadParams qp = quad_params(rec.px, rec.py, rec.pw);
+        const float cur = qp.cur;
         float total = s.curvature + cur;
         s.curvature = total;
         last_angle_ = out;
 
-        rec.x0 = x0;
-        rec.dx_recip = dx_recip;
-        rec.k0 = k0;
-        rec.dk = dk;
+        rec.x0 = qp.x0;
+        rec.dx_recip = qp.dx_recip;
+        rec.k0 = qp.k0;
+        rec.dk = qp.dk;
         rec.curv_recip = rcp(cur);
         uint32_t spline_index = (uint32_t)splines_.size() - 1;
         rec.prev_curv = (!quad_spline_.empty() && quad_spline_.back() == spline_index) ? quad_total_.back() : 0.0f;

@@ -83,7 +83,7 @@ class Composition {
     PinnedBuffer<PointRec> h_points;
     PinnedBuffer<uint8_t> h_kinds;
     size_t staged_recs = 0;
-    PinnedBuffer<QuadRec> h_quads;
+    PinnedBuffer<QuadUp> h_quads;
     PinnedBuffer<FlattenJob> h_jobs;
     size_t staged_from = 0, staged_to = 0, staged_splines = 0, staged_quads = 0, staged_points = 0;
     // Drops device residency: the next render re-uploads everything from pinned
@@ -102,7 +102,7 @@ class Composition {
     PinnedBuffer<int32_t> h_order_to_style, h_geom_slot;
     PinnedBuffer<StopRec> h_stops;
     PinnedBuffer<uint16_t> h_texels;
-    size_t n_layer_recs = 0, n_stops = 0, n_texels = 0;
+    size_t n_layer_recs = 0, n_style_recs = 0, n_stops = 0, n_texels = 0;
     DeviceBuffer<int32_t> d_geom_slot;
     DeviceBuffer<LayerRec> d_layers;
     DeviceBuffer<StyleRec> d_styles;

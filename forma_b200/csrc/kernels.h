@@ -26,6 +26,8 @@ struct RasterArgs {
 void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const uint8_t* kinds, const QuadRec* quads,
                          const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, float* x, float* y, uint32_t* gid,
                          cudaStream_t stream);
+// Rebuilds the device-resident QuadRecs from the uploaded control points (quad_math.h).
+void launch_quad_expand(const QuadUp* in, QuadRec* out, uint32_t n, cudaStream_t stream);
 uint32_t raster_num_blocks(uint32_t n_points);
 // block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
 // max_tile[0..1] = largest biased tile_x / tile_y any emitted segment can carry.
@@ -92,7 +94,7 @@ struct PaintScene {
     uint32_t tx_lo, tx_hi;        // tile columns painted (crop), [lo, hi)
     uint32_t ty_lo, ty_hi;        // tile rows painted (crop ∩ band), [lo, hi)
     // Layer cache (damage reuse, cpu/buffer/mod.rs:114-197); all null/0 without a cache.
-    const uint8_t* unchanged;     // per style slot: Layer::is_unchanged(cache_id)
+    const uint8_t* unchanged;     // per layer order: Layer::is_unchanged(cache_id)
     uint2* cache_tiles;           // per tile: x = has_count<<31 | has_solid<<30 | layer_count(24), y = solid colour
     uint32_t* written_list;       // optional: linear ids of the tiles this frame wrote (unordered)
     uint32_t* written_count;      //           ... and how many

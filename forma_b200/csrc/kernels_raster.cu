@@ -15,6 +15,7 @@
 // emitted in exactly the reference's (line, k) order with coalesced stores.
 #include "cuda_common.cuh"
 #include "kernels.h"
+#include "quad_math.h"
 
 namespace forma {
 
@@ -24,6 +25,35 @@ namespace forma {
 __device__ __forceinline__ float inv_curvature(float k) {  // path.rs:53-56
     const float c = 0.39f;
     return k * (1.0f - c + sqrtf(fmaf(k * k, 0.25f, c * c)));
+}
+
+// QuadUp (48 B, uploaded) -> QuadRec (68 B, device only): the Levien parameters are
+// recomputed with the host's own formulas (quad_math.h).
+__global__ void quad_expand_kernel(const QuadUp* __restrict__ in, QuadRec* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const QuadUp u = in[i];
+    const QuadParams qp = quad_params(u.px, u.py, u.pw);
+    QuadRec r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.px[k] = u.px[k];
+        r.py[k] = u.py[k];
+        r.pw[k] = u.pw[k];
+    }
+    r.x0 = qp.x0;
+    r.dx_recip = qp.dx_recip;
+    r.k0 = qp.k0;
+    r.dk = qp.dk;
+    r.curv_recip = 1.0f / qp.cur;
+    r.prev_curv = u.prev_curv;
+    r.total = u.total;
+    r.step = u.step;
+    out[i] = r;
+}
+
+void launch_quad_expand(const QuadUp* in, QuadRec* out, uint32_t n, cudaStream_t stream) {
+    if (n) quad_expand_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, out, n);
 }
 
 // One thread per output point: it finds its insert job, then its spline, by

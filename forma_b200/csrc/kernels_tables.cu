@@ -320,7 +320,7 @@ __global__ void merge_entries_kernel(PaintScene S, const uint64_t* __restrict__ 
     uint32_t flags = 0;
     if (r.slot >= 0) {
         const StyleRec& st = S.styles[r.slot];
-        const bool unchanged = S.unchanged && S.unchanged[r.slot];
+        const bool unchanged = S.unchanged && S.unchanged[r.layer];
         r.meta = pack_style_meta(st, unchanged);
         r.clip_layers = st.clip_layers;
         r.color[0] = st.color[0];

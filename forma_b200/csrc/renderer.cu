@@ -264,6 +264,7 @@ class Renderer {
     PinnedBuffer<uint32_t> h_written_list, h_packed_tiles;
     uint32_t last_written_tiles = 0;
     // Upload staging.
+    DeviceBuffer<QuadUp> up_quads_raw;  // as uploaded; expanded into up_quads on the device
     DeviceBuffer<SplineRec> up_splines;
     DeviceBuffer<PointRec> up_points;
     DeviceBuffer<uint8_t> up_kinds;
@@ -304,6 +305,19 @@ int Renderer::read_total(uint32_t slot, uint32_t* out) {
     FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
     *out = pinned_totals[slot];
     return FORMA_STATUS_OK;
+}
+
+static QuadUp quad_upload(const QuadRec& q) {
+    QuadUp u;
+    for (int k = 0; k < 3; ++k) {
+        u.px[k] = q.px[k];
+        u.py[k] = q.py[k];
+        u.pw[k] = q.pw[k];
+    }
+    u.prev_curv = q.prev_curv;
+    u.total = q.total;
+    u.step = q.step;
+    return u;
 }
 
 // Evaluates the Layer::insert jobs that are not resident yet into the device
@@ -366,7 +380,7 @@ int Renderer::flush_geometry(Composition& comp) {
                 std::memcpy(comp.h_kinds.ptr + ri, prog.kinds.data(), prog.kinds.size());
                 ri += prog.points.size();
             }
-            if (!prog.quads.empty()) std::memcpy(comp.h_quads.ptr + qi, prog.quads.data(), prog.quads.size() * sizeof(QuadRec));
+            for (size_t q = 0; q < prog.quads.size(); ++q) comp.h_quads.ptr[qi + q] = quad_upload(prog.quads[q]);
             si += prog.splines.size();
             qi += prog.quads.size();
             pi += prog.n_points;
@@ -391,11 +405,16 @@ int Renderer::flush_geometry(Composition& comp) {
                                        stream));
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, comp.h_kinds.ptr, comp.staged_recs, cudaMemcpyHostToDevice, stream));
     }
-    if (comp.staged_quads)
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads.ptr, comp.h_quads.ptr, comp.staged_quads * sizeof(QuadRec), cudaMemcpyHostToDevice, stream));
+    if (comp.staged_quads) {
+        FORMA_CUDA_TRY(up_quads_raw.reserve(comp.staged_quads + 1));
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, comp.h_quads.ptr, comp.staged_quads * sizeof(QuadUp), cudaMemcpyHostToDevice,
+                                       stream));
+        launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)comp.staged_quads, stream);
+        ++launches;
+    }
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, comp.h_jobs.ptr, (to - from) * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
     h2d_bytes += comp.staged_splines * sizeof(SplineRec) + comp.staged_recs * (sizeof(PointRec) + 1) +
-                 comp.staged_quads * sizeof(QuadRec) + (to - from) * sizeof(FlattenJob);
+                 comp.staged_quads * sizeof(QuadUp) + (to - from) * sizeof(FlattenJob);
     launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)(to - from),
                         (uint32_t)comp.staged_points, comp.d_x.ptr, comp.d_y.ptr, comp.d_gid.ptr, stream);
     ++launches;
@@ -424,7 +443,9 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         FORMA_CUDA_TRY(comp.h_geom_slot.reserve(n_geoms + 1));
         std::fill(comp.h_order_to_style.ptr, comp.h_order_to_style.ptr + n_orders, -1);
         std::fill(comp.h_geom_slot.ptr, comp.h_geom_slot.ptr + n_geoms, -1);
-        uint32_t slot = 0;
+        uint32_t slot = 0, n_styles = 0;
+        std::unordered_map<std::string, uint32_t> interned;
+        std::vector<int32_t> order_to_slot(n_orders, -1);
         for (auto& kv : comp.layers) {
             const Layer& l = *kv.second;
             LayerRec& r = comp.h_layers.ptr[slot];
@@ -445,14 +466,25 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
                 }
                 s.tex_first = it->second;
             }
-            s.unchanged = (cache_id >= 0 && ((l.unchanged_bits >> cache_id) & 1u)) ? 1u : 0u;
-            comp.h_styles.ptr[slot] = s;
-            comp.h_order_to_style.ptr[kv.first] = (int32_t)slot;
+            s.unchanged = 0u;
+            // Styles are interned like the reference's props interner (composition/interner.rs):
+            // solid fills that compare equal share one record (paris-30k: 66 records for 50 620
+            // layers); gradients / textures keep one record per layer.
+            uint32_t style_index = n_styles;
+            if (s.fill_type == 0u && s.func == 0u) {
+                std::string key(reinterpret_cast<const char*>(&s), offsetof(StyleRec, gradient_type));
+                auto it = interned.find(key);
+                if (it == interned.end()) interned.emplace(std::move(key), n_styles);
+                else style_index = it->second;
+            }
+            if (style_index == n_styles) comp.h_styles.ptr[n_styles++] = s;
+            comp.h_order_to_style.ptr[kv.first] = (int32_t)style_index;
+            order_to_slot[kv.first] = (int32_t)slot;
             ++slot;
         }
         for (auto& kv : comp.geom_to_order) {
             if (kv.second < 0 || kv.first >= n_geoms || (uint64_t)kv.second >= n_orders) continue;
-            comp.h_geom_slot.ptr[kv.first] = comp.h_order_to_style.ptr[kv.second];
+            comp.h_geom_slot.ptr[kv.first] = order_to_slot[kv.second];
         }
         comp.layers_in_order = true;
         {
@@ -474,6 +506,7 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         if (!stops.empty()) std::memcpy(comp.h_stops.ptr, stops.data(), stops.size() * sizeof(StopRec));
         if (!texels.empty()) std::memcpy(comp.h_texels.ptr, texels.data(), texels.size() * sizeof(uint16_t));
         comp.n_layer_recs = slot;
+        comp.n_style_recs = n_styles;
         comp.n_stops = stops.size();
         comp.n_texels = texels.size();
         comp.n_geoms = n_geoms;
@@ -490,7 +523,7 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         return cudaMemcpyAsync(dbuf.ptr, hbuf.ptr, n * sizeof(*hbuf.ptr), cudaMemcpyHostToDevice, stream);
     };
     FORMA_CUDA_TRY(up(comp.d_layers, comp.h_layers, comp.n_layer_recs));
-    FORMA_CUDA_TRY(up(comp.d_styles, comp.h_styles, comp.n_layer_recs));
+    FORMA_CUDA_TRY(up(comp.d_styles, comp.h_styles, comp.n_style_recs));
     FORMA_CUDA_TRY(up(comp.d_stops, comp.h_stops, comp.n_stops));
     FORMA_CUDA_TRY(up(comp.d_texels, comp.h_texels, comp.n_texels));
     FORMA_CUDA_TRY(up(comp.d_order_to_style, comp.h_order_to_style, comp.n_orders));
@@ -632,10 +665,12 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                             cache->clear_color[2] == clear[2] && cache->clear_color[3] == clear[3];
         // Layer::is_unchanged(cache_id) per style slot (renderer.rs:144-157); the slots
         // follow the iteration order of upload_tables.
-        FORMA_CUDA_TRY(h_unchanged.reserve(comp.n_layer_recs + 1));
-        FORMA_CUDA_TRY(d_unchanged.reserve(comp.n_layer_recs + 1));
-        size_t slot = 0;
-        for (auto& kv : comp.layers) h_unchanged.ptr[slot++] = (uint8_t)((kv.second->unchanged_bits >> cache->id) & 1u);
+        FORMA_CUDA_TRY(h_unchanged.reserve(comp.n_orders + 1));
+        FORMA_CUDA_TRY(d_unchanged.reserve(comp.n_orders + 1));
+        size_t slot = comp.n_orders;  // one byte per layer order
+        std::memset(h_unchanged.ptr, 0, slot);
+        for (auto& kv : comp.layers)
+            if (kv.first < comp.n_orders) h_unchanged.ptr[kv.first] = (uint8_t)((kv.second->unchanged_bits >> cache->id) & 1u);
         if (slot) {
             FORMA_CUDA_TRY(cudaMemcpyAsync(d_unchanged.ptr, h_unchanged.ptr, slot, cudaMemcpyHostToDevice, stream));
             h2d_bytes += slot;
@@ -1010,8 +1045,15 @@ int forma_path_segments(forma_path* p, const float** x, const float** y, const u
         FORMA_CUDA_TRY(cudaMemcpy(dp.ptr, prog.points.data(), prog.points.size() * sizeof(PointRec), cudaMemcpyHostToDevice));
         FORMA_CUDA_TRY(cudaMemcpy(dk.ptr, prog.kinds.data(), prog.kinds.size(), cudaMemcpyHostToDevice));
     }
-    if (!prog.quads.empty())
-        FORMA_CUDA_TRY(cudaMemcpy(dq.ptr, prog.quads.data(), prog.quads.size() * sizeof(QuadRec), cudaMemcpyHostToDevice));
+    if (!prog.quads.empty()) {  // same route as rendering: upload the control points, expand on the device
+        std::vector<QuadUp> ups(prog.quads.size());
+        for (size_t q = 0; q < ups.size(); ++q) ups[q] = quad_upload(prog.quads[q]);
+        DeviceBuffer<QuadUp> du;
+        FORMA_CUDA_TRY(du.reserve(ups.size()));
+        FORMA_CUDA_TRY(cudaMemcpy(du.ptr, ups.data(), ups.size() * sizeof(QuadUp), cudaMemcpyHostToDevice));
+        launch_quad_expand(du.ptr, dq.ptr, (uint32_t)ups.size(), 0);
+        FORMA_CUDA_TRY(cudaDeviceSynchronize());
+    }
     FORMA_CUDA_TRY(cudaMemcpy(dj.ptr, &job, sizeof(job), cudaMemcpyHostToDevice));
     launch_flatten_eval(dc.ptr, dp.ptr, dk.ptr, dq.ptr, dj.ptr, 1, count, dx.ptr, dy.ptr, dg.ptr, 0);
     FORMA_CUDA_TRY(cudaGetLastError());

@@ -884,8 +884,12 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                 const uint64_t x0 = (uint64_t)(tile % S.tiles_x) * 16u, y0 = (uint64_t)(tile / S.tiles_x) * 16u;
                 const uint64_t cols = std::min<uint64_t>(16u, width - x0), rows = std::min<uint64_t>(16u, height - y0);
                 const uint32_t* src = h_packed_tiles.ptr + (size_t)i * 256u;
-                for (uint64_t r = 0; r < rows; ++r)
-                    std::memcpy(buffer + (y0 + r) * stride + x0 * 4u, src + r * 16u, cols * 4u);
+                uint8_t* dst = buffer + y0 * stride + x0 * 4u;
+                if (cols == 16u) {  // whole tile rows: fixed-size copies the compiler turns into vector moves
+                    for (uint64_t r = 0; r < rows; ++r) std::memcpy(dst + r * stride, src + r * 16u, 64);
+                } else {
+                    for (uint64_t r = 0; r < rows; ++r) std::memcpy(dst + r * stride, src + r * 16u, cols * 4u);
+                }
             }
         }
     } else if (!buffer_on_device && !copied_in_bands) {

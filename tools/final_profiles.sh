@@ -11,6 +11,7 @@ python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/${R}_bench_r
 for w in cubics100k circles8k paris4k_grad; do
   python bench.py --workload $w --no-cpu > gpurun_out/${R}_bench_$w.json 2>/dev/null
 done
+python bench.py --workload spaceship1080p --steps 100 --warmup 5 > gpurun_out/${R}_bench_spaceship1080p.json 2>/dev/null
 for w in paris4k cubics100k circles8k; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_$w.csv \
       python bench.py --workload $w --steps 2 --warmup 1 --no-cpu > /dev/null 2>&1

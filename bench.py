@@ -91,26 +91,36 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
-    def run(self):
-        try:  # NVML in-process: a sample every 10 ms, so that even a short timed region is covered
+    def init_nvml(self):
+        """NVML in-process, queried by sample_now() between the timed steps (inside the
+        timed region as a whole, while the GPU runs the untimed L2 flush): polling NVML
+        from a second thread while render() runs can stall CUDA calls for milliseconds."""
+        try:
             import pynvml
             pynvml.nvmlInit()
-            hd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(hd, pynvml.NVML_CLOCK_SM)
-            bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
-                    pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
-            while not self.stop_flag.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(hd, pynvml.NVML_CLOCK_SM)
-                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hd)
-                try:
-                    p = pynvml.nvmlDeviceGetPowerUsage(hd) / 1000.0
-                except Exception:
-                    p = 0.0
-                self.samples.append([str(sm), str(mx), str(p)] + ["Active" if r & b else "Not Active" for b in bits])
-                self.stop_flag.wait(0.01)
+            self.nv = pynvml
+            self.hd = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.hd, pynvml.NVML_CLOCK_SM)
+            self.bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+            return True
+        except Exception:
+            self.nv = None
+            return False
+
+    def sample_now(self):
+        if not getattr(self, "nv", None):
             return
+        try:
+            sm = self.nv.nvmlDeviceGetClockInfo(self.hd, self.nv.NVML_CLOCK_SM)
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.hd)
+            self.samples.append([str(sm), str(self.mx), "0"] + ["Active" if r & b else "Not Active" for b in self.bits])
         except Exception:
             pass
+
+    def run(self):
+        if getattr(self, "nv", None):
+            return  # NVML: sampled synchronously by sample_now()
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -227,6 +237,7 @@ def run_cuda(args):
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream()
 
+    sampler = ClockSampler(local)
     api = forma_b200.load()
     t_build = time.perf_counter()
     comp, w, h = build_scene(api, args.workload)
@@ -309,6 +320,7 @@ def run_cuda(args):
         wall = 0.0
         for a, b in evs:
             flush.zero_()
+            sampler.sample_now()  # SM clock / throttle reasons while the GPU is busy, outside the timed interval
             # Animated workloads: the layer updates of the next frame are host-side API
             # calls (401 ctypes calls ~ 1 ms in this Python stub, microseconds from a
             # compiled host); they run here, outside the timed region, on both arms.
@@ -339,15 +351,19 @@ def run_cuda(args):
             del whole
         dist.barrier()
     c0 = renderer.counters()
-    sampler = ClockSampler(local)
+    sampler.init_nvml()
     sampler.start()
     stage_acc = {k: 0.0 for k in renderer.STAGES}
 
     kern_acc = {}
 
+    step_trace = []
+
     def frame_device_acc():
         frame_device()
-        for k, v in renderer.stage_times().items():
+        st = renderer.stage_times()
+        step_trace.append(round(st["total"], 3))
+        for k, v in st.items():
             stage_acc[k] += v
         for k, v in renderer.kernel_times().items():
             a = kern_acc.setdefault(k, {"ms": 0.0, "launches": 0})
@@ -443,6 +459,7 @@ def run_cuda(args):
                    "scene_build_s": round(t_build, 2)},
         "mpixel_segments_per_s": n_seg_total * fps / 1e6,
         "stage_ms": {k: round(v, 4) for k, v in stages.items()},
+        "step_ms_trace": step_trace,  # device-timeline ms of every timed step (a one-off hiccup shows here)
         "gpu_launches": c1["launches"] - c0["launches"],
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": T_e2e / args.steps,
                 "h2d_bytes_per_step": (c3["h2d_bytes"] - c2["h2d_bytes"]) // args.steps,

@@ -171,6 +171,10 @@ __device__ __noinline__ void blend_column_generic(const StyleRec* __restrict__ s
     }
 }
 
+__device__ __noinline__ uint32_t srgb_bytes_any_order(float r, float g, float b, float a, const uint32_t* ch) {
+    return pixel_to_srgb_bytes(r, g, b, a, ch);
+}
+
 // The scalar blend of the solid-tile fold (all 16 modes) stays out of line too.
 __device__ __noinline__ Rgba blend_solid(uint32_t mode, Rgba dst, Rgba src) { return sblend::blend(mode, dst, src); }
 
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
     int32_t* area = s_area[warp];
     int32_t* cover = s_cover[warp];
     const Rgba clear{S.clear[0], S.clear[1], S.clear[2], S.clear[3]};
+    const bool rgba_order = S.channels[0] == 0u && S.channels[1] == 1u && S.channels[2] == 2u && S.channels[3] == 3u;
     const uint32_t ntx = S.tx_hi - S.tx_lo;
     const uint32_t x = lane >> 1, half = lane & 1u;
     // The cells of this warp start (and are kept) zeroed.
@@ -545,7 +550,10 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             for (int l = 0; l < 8; ++l) {
                 uint32_t py = ty * 16u + half * 8u + l;
                 if (py < S.height) {
-                    uint32_t rgba = pixel_to_srgb_bytes(dr[l], dg[l], db[l], da[l], S.channels);
+                    // RGBA order (kernel-uniform) needs no channel selection; other orders take the
+                    // out-of-line generic conversion.
+                    uint32_t rgba = rgba_order ? pixel_to_srgb_bytes_rgba(dr[l], dg[l], db[l], da[l])
+                                               : srgb_bytes_any_order(dr[l], dg[l], db[l], da[l], S.channels);
                     *reinterpret_cast<uint32_t*>(in.framebuffer + (size_t)py * S.stride + (size_t)px * 4u) = rgba;
                 }
             }

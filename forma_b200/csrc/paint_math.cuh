@@ -66,6 +66,12 @@ __device__ __forceinline__ uint32_t pixel_to_srgb_bytes(float r, float g, float 
            (to_byte(channel_of(s, ch[3])) << 24);
 }
 
+// The same for the RGBA channel order (no channel selection).
+__device__ __forceinline__ uint32_t pixel_to_srgb_bytes_rgba(float r, float g, float b, float a) {
+    return to_byte(linear_to_srgb(r)) | (to_byte(linear_to_srgb(g)) << 8) | (to_byte(linear_to_srgb(b)) << 16) |
+           (to_byte(a) << 24);
+}
+
 // ---------------------------------------------------------------------------
 // Scalar blend: BlendMode::blend (cpu/painter/styling.rs:195-339). Used when a
 // tile folds to one solid colour (skip_fully_covered_layers.rs:103-113).

@@ -9,17 +9,18 @@
 //   be set take part: digits of <= 8 bits over the concatenation of those bits
 //   (paris@4K: 16 + 8 + 8 = 32 bits = 4 passes instead of 6). Exactly the
 //   planned passes are launched; after an odd number the caller swaps buffers.
-// * One upfront histogram kernel reads the keys once and counts the digits of
-//   all planned passes in shared memory.
-// * Every pass is one "onesweep" kernel: a CTA ranks a tile of keys with warp
-//   match/popc (stable), obtains its global digit offsets by decoupled
-//   look-back over the tiles before it (relaxed gpu-scope loads, four
-//   predecessors in flight per thread), stages the tile in shared memory in
-//   digit order and writes it out with coalesced stores: keys are read once and
-//   written once per pass (16 B/key).
-//
-// The same kernels sort (key, u32 payload) pairs for the painter's cell and
-// entry tables (smaller tiles: those sorts are latency-, not bandwidth-bound).
+// * Large key-only sorts (the pixel segments): every pass is reduce-then-scan —
+//   `radix_upsweep_kernel` (per-tile digit counts), `radix_tile_scan_kernel`
+//   (global offset of every (tile, digit) run) and the persistent, TMA-staged
+//   `radix_downsweep_wide_kernel` (stable warp match/popc ranking, digit-order
+//   staging in shared memory, coalesced scatter): 24 B/key per pass, and no CTA
+//   ever waits for another one (see the comment above those kernels).
+// * Small sorts and (key, u32 payload) pairs (the painter's cell / gap tables):
+//   one upfront histogram kernel for all passes, then one single-sweep
+//   ("onesweep") kernel per pass with decoupled look-back (16 B/key per pass;
+//   latency-bound at these sizes). The persistent single-sweep kernel that
+//   preceded the reduce-then-scan passes is kept for A/B runs
+//   (FORMA_SORT_MODE=persistent).
 #include "cuda_common.cuh"
 #include "kernels.h"
 

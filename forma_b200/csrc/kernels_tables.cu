@@ -7,14 +7,17 @@
 // independently the carries are materialised first:
 //
 //   cells     runs of sorted segments with equal (tile_y, tile_x, layer)
-//   covers    per cell: sum of segment covers by local_y (wrapping i8)
-//   re-sort   cell ids by (tile_y, layer, tile_x)            [pair radix sort]
+//             (cell_count writes one head bit per segment, cell_write turns the
+//             bits into cell_start)
+//   covers    per cell: sum of segment covers by local_y (wrapping i8), its key
+//   re-sort   cell ids stably by the layer bits only -> (layer, tile_y, tile_x)
 //   carries   per (tile_y, layer) group a running sum -> carry-in of every cell
 //             and "carry-only" entries for the tiles a layer spans without
-//             segments (layer_workbench/mod.rs:213-234,328-336)
-//   entries   cells ∪ carry-only entries, sorted by (tile_y, tile_x, layer)
-//   paint     one warp per tile; lane l owns column l/2, rows 8*(l%2)..+8 —
-//             exactly one f32x8 of the reference (cpu/painter/mod.rs:234-244)
+//             segments (layer_workbench/mod.rs:213-234,328-336), generated in
+//             that order and stably sorted by the tile digits only
+//   entries   cells merged with the carry-only entries by rank into 64-byte
+//             records ordered by (tile_y, tile_x, layer), + per-tile ranges
+//   paint     kernels_painter.cu: one warp per tile
 //
 // Integer semantics: areas wrap at i16 and covers at i8 in the reference;
 // sums are formed in i32 / packed bytes and truncated where the reference

@@ -200,6 +200,36 @@ def test_layers_inserted_out_of_order(cuda_api, oracle_api, cuda_renderer, oracl
     assert_same(a, b, f"layers inserted in {order} order")
 
 
+def test_layer_orders_up_to_the_limit(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
+    """Orders spread over the whole 21-bit range, inserted high to low: the segment
+    sort needs every layer digit (5 passes with the tile digits)."""
+    w, h = 400, 300
+    top = (1 << 21) - 1
+
+    def build(api, comp):
+        rng = synth.SplitMix64(5)
+        for k in range(60):
+            order = top - k * 34567 if k % 2 == 0 else k * 17
+            cx, cy, r = rng.uniform(0, w), rng.uniform(0, h), rng.uniform(10, 90)
+            col = Color(rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.4, 1.0))
+            comp.get_mut_or_insert_default(order).insert(synth.circle_path(api, synth.f32(cx), synth.f32(cy), synth.f32(r))).set_props(
+                Props(func=Func.Draw(Style(fill=Fill.Solid(col)))))
+    a, _ = render(cuda_api, cuda_renderer, build, w, h)
+    b, _ = render(oracle_api, oracle_renderer, build, w, h)
+    assert_same(a, b, "orders up to LAYER_LIMIT")
+
+
+def test_8k_frame_bit_exact(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
+    """7680x4320: 9-bit tile coordinates (three 6-bit sort passes), band-wise copy-back."""
+    w, h = 7680, 4320
+
+    def build(api, comp):
+        synth.random_circles(api, comp, 300, w, h, 8, r=(20.0, 400.0))
+    a, _ = render(cuda_api, cuda_renderer, build, w, h)
+    b, _ = render(oracle_api, oracle_renderer, build, w, h)
+    assert_same(a, b, "8K frame")
+
+
 def test_opaque_cubics_bit_exact(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
     def build(api, comp):
         synth.random_cubics(api, comp, 3000, 1920, 1080, 3)

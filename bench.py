@@ -268,17 +268,31 @@ def run_cuda(args):
     shared, frame_ptr, flag = None, fb.data_ptr(), None
     if world > 1 and args.assembly == "p2p":
         nbytes = h * stride
-        box = [None]
-        if rank == 0:
-            shared = api.SharedFrame(local, nbytes)
-            box = [shared.handle]
+        box, ok = [None], 1.0
+        try:
+            if rank == 0:
+                shared = api.SharedFrame(local, nbytes)
+                box = [shared.handle]
+        except Exception:
+            ok = 0.0
         dist.broadcast_object_list(box, src=0)
-        if rank != 0:
-            shared = api.SharedFrame(local, nbytes, box[0])
-        frame_ptr = shared.ptr
-        flag = torch.zeros(1, dtype=torch.float32, device=dev)
-        if rank == 0:
-            gathered = torch.as_tensor(shared, device=dev).view(h, stride)
+        try:
+            if rank != 0 and box[0] is not None:
+                shared = api.SharedFrame(local, nbytes, box[0])
+        except Exception:
+            ok = 0.0
+        if shared is None:
+            ok = 0.0
+        flag = torch.tensor([ok], dtype=torch.float32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # CUDA IPC unavailable on some rank -> everybody gathers
+        if float(flag.item()) >= 1.0:
+            frame_ptr = shared.ptr
+            if rank == 0:
+                gathered = torch.as_tensor(shared, device=dev).view(h, stride)
+        else:
+            shared = None
+            args.assembly = "gather"
+        flag = torch.zeros(1, dtype=torch.float32, device=dev)  # the per-frame closing all-reduce works on this
 
     # Animated workloads: every frame moves layers and renders with a persistent layer
     # cache (one per target buffer, like the reference's per-Buffer caches).

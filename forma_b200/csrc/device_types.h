@@ -29,6 +29,12 @@ struct QuadUp {
     float px[3], py[3], pw[3];
     float prev_curv, total, step;
 };
+// The same without weights (36 B), used when no quadratic of the uploaded batch is
+// rational (all weights are exactly 1: SVG-like content).
+struct QuadUpPoly {
+    float px[3], py[3];
+    float prev_curv, total, step;
+};
 
 // Point-wise encoding of a flatten program, used instead of SplineRecs when it
 // is smaller (paths made of many short line splines): 8 B + 1 B per output point.
@@ -59,6 +65,7 @@ struct FlattenProgram {
     std::vector<SplineRec> splines;  // spline encoding (points / kinds empty) ...
     std::vector<PointRec> points;    // ... or point encoding (splines empty), whichever is smaller
     std::vector<uint8_t> kinds;
+    bool rational = false;        // some quadratic has a weight != 1
     uint32_t n_points = 0;        // output points
     uint32_t n_contour_ends = 0;  // points that end a contour, the last point of the program excluded
 };

@@ -137,6 +137,8 @@ class SplineBuilder {
     // populate_buffers (path.rs:400-445) -> resolved point commands.
     void finish(FlattenProgram& out) {
         out.quads = std::move(quads_);
+        for (const QuadRec& q : out.quads)
+            if (q.pw[0] != 1.0f || q.pw[1] != 1.0f || q.pw[2] != 1.0f) out.rational = true;
         // The quads of a spline are contiguous; the reference walks them with
         // `if pi > total[qi] { qi += 1 }` per evaluated point (path.rs:424-431), which
         // — every quad adding more than 1 to the running curvature (path.rs:322-332) —

@@ -83,6 +83,7 @@ class Composition {
     PinnedBuffer<PointRec> h_points;
     PinnedBuffer<uint8_t> h_kinds;
     size_t staged_recs = 0;
+    bool staged_rational = true;      // the staged quadratics are QuadUp (else QuadUpPoly)
     PinnedBuffer<QuadUp> h_quads;
     PinnedBuffer<FlattenJob> h_jobs;
     size_t staged_from = 0, staged_to = 0, staged_splines = 0, staged_quads = 0, staged_points = 0;
@@ -98,6 +99,9 @@ class Composition {
     bool tables_dirty = true;         // host-side pinned copies are stale
     bool tables_resident = false;     // device copies match the pinned copies
     PinnedBuffer<LayerRec> h_layers;
+    PinnedBuffer<uint32_t> h_layer_bits;  // order | enabled << 21: uploaded instead of h_layers when no layer has a transform
+    DeviceBuffer<uint32_t> d_layer_bits;
+    bool layers_have_xf = false;
     PinnedBuffer<StyleRec> h_styles;
     PinnedBuffer<int32_t> h_order_to_style, h_geom_slot;
     PinnedBuffer<StopRec> h_stops;

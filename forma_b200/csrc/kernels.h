@@ -17,7 +17,8 @@ struct RasterArgs {
     uint32_t n_points;
     const int32_t* geom_slot;  // geom id -> layer slot, -1 = not in the composition
     uint32_t n_geoms;
-    const LayerRec* layers;
+    const LayerRec* layers;    // nullptr when no layer has a transform: then ...
+    const uint32_t* layer_bits;// ... order | enabled << 21 per layer slot
     float width, height;       // render target in pixels
     float band_lo, band_hi;    // pixel rows painted by this GPU ([0, height) on one GPU)
 };
@@ -28,6 +29,7 @@ void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const
                          cudaStream_t stream);
 // Rebuilds the device-resident QuadRecs from the uploaded control points (quad_math.h).
 void launch_quad_expand(const QuadUp* in, QuadRec* out, uint32_t n, cudaStream_t stream);
+void launch_quad_expand_poly(const QuadUpPoly* in, QuadRec* out, uint32_t n, cudaStream_t stream);  // all weights 1
 uint32_t raster_num_blocks(uint32_t n_points);
 // block_sums: raster_num_blocks(n) entries, turned into exclusive offsets; total[0] = #segments.
 // max_tile[0..1] = largest biased tile_x / tile_y any emitted segment can carry.

@@ -52,8 +52,35 @@ __global__ void quad_expand_kernel(const QuadUp* __restrict__ in, QuadRec* __res
     out[i] = r;
 }
 
+__global__ void quad_expand_poly_kernel(const QuadUpPoly* __restrict__ in, QuadRec* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const QuadUpPoly u = in[i];
+    const float one[3] = {1.0f, 1.0f, 1.0f};
+    const QuadParams qp = quad_params(u.px, u.py, one);
+    QuadRec r;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.px[k] = u.px[k];
+        r.py[k] = u.py[k];
+        r.pw[k] = 1.0f;
+    }
+    r.x0 = qp.x0;
+    r.dx_recip = qp.dx_recip;
+    r.k0 = qp.k0;
+    r.dk = qp.dk;
+    r.curv_recip = 1.0f / qp.cur;
+    r.prev_curv = u.prev_curv;
+    r.total = u.total;
+    r.step = u.step;
+    out[i] = r;
+}
+
 void launch_quad_expand(const QuadUp* in, QuadRec* out, uint32_t n, cudaStream_t stream) {
     if (n) quad_expand_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, out, n);
+}
+void launch_quad_expand_poly(const QuadUpPoly* in, QuadRec* out, uint32_t n, cudaStream_t stream) {
+    if (n) quad_expand_poly_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, out, n);
 }
 
 // One thread per output point: it finds its insert job, then its spline, by
@@ -174,7 +201,15 @@ __device__ __forceinline__ LineParams line_setup(const RasterArgs& A, uint32_t i
     if (gid == 0u) return L;
     int32_t slot = gid < A.n_geoms ? A.geom_slot[gid] : -1;
     if (slot < 0) return L;
-    const LayerRec lay = A.layers[slot];
+    LayerRec lay;
+    if (A.layers) {
+        lay = A.layers[slot];
+    } else {  // no layer carries a transform: 4 bytes per layer (order | enabled << 21)
+        const uint32_t bits = A.layer_bits[slot];
+        lay.order = bits & 0x1FFFFFu;
+        lay.enabled = (bits >> 21) & 1u;
+        lay.has_xf = 0u;
+    }
     if (!lay.enabled) return L;
     float p0x = A.x[i], p0y = A.y[i], p1x = A.x[i + 1], p1y = A.y[i + 1];
     if (lay.has_xf) {  // transform_point, segment.rs:30-39

@@ -342,8 +342,10 @@ int Renderer::flush_geometry(Composition& comp) {
     if (comp.staged_from != from || comp.staged_to != to) {
         // (Re)build the pinned staging copy of the flatten programs of jobs [from, to).
         size_t n_splines = 0, n_quads = 0, n_pts = 0, n_recs = 0;
+        bool rational = false;  // any weight != 1 in the batch: 48-byte QuadUp, else 36-byte QuadUpPoly
         for (size_t j = from; j < to; ++j) {
             const FlattenProgram& prog = comp.jobs[j].data->program();
+            rational = rational || prog.rational;
             n_splines += prog.splines.size();
             n_recs += prog.points.size();
             n_quads += prog.quads.size();
@@ -380,7 +382,22 @@ int Renderer::flush_geometry(Composition& comp) {
                 std::memcpy(comp.h_kinds.ptr + ri, prog.kinds.data(), prog.kinds.size());
                 ri += prog.points.size();
             }
-            for (size_t q = 0; q < prog.quads.size(); ++q) comp.h_quads.ptr[qi + q] = quad_upload(prog.quads[q]);
+            if (rational) {
+                for (size_t q = 0; q < prog.quads.size(); ++q) comp.h_quads.ptr[qi + q] = quad_upload(prog.quads[q]);
+            } else {  // the pinned buffer is sized for QuadUp; the smaller records share it
+                QuadUpPoly* poly = reinterpret_cast<QuadUpPoly*>(comp.h_quads.ptr);
+                for (size_t q = 0; q < prog.quads.size(); ++q) {
+                    const QuadRec& s = prog.quads[q];
+                    QuadUpPoly& u = poly[qi + q];
+                    for (int k = 0; k < 3; ++k) {
+                        u.px[k] = s.px[k];
+                        u.py[k] = s.py[k];
+                    }
+                    u.prev_curv = s.prev_curv;
+                    u.total = s.total;
+                    u.step = s.step;
+                }
+            }
             si += prog.splines.size();
             qi += prog.quads.size();
             pi += prog.n_points;
@@ -391,7 +408,9 @@ int Renderer::flush_geometry(Composition& comp) {
         comp.staged_recs = n_recs;
         comp.staged_quads = n_quads;
         comp.staged_points = n_pts;
+        comp.staged_rational = rational;
     }
+    const size_t quad_bytes = comp.staged_rational ? sizeof(QuadUp) : sizeof(QuadUpPoly);
     FORMA_CUDA_TRY(up_splines.reserve(comp.staged_splines + 1));
     FORMA_CUDA_TRY(up_points.reserve(comp.staged_recs + 1));
     FORMA_CUDA_TRY(up_kinds.reserve(comp.staged_recs + 1));
@@ -407,14 +426,18 @@ int Renderer::flush_geometry(Composition& comp) {
     }
     if (comp.staged_quads) {
         FORMA_CUDA_TRY(up_quads_raw.reserve(comp.staged_quads + 1));
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, comp.h_quads.ptr, comp.staged_quads * sizeof(QuadUp), cudaMemcpyHostToDevice,
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, comp.h_quads.ptr, comp.staged_quads * quad_bytes, cudaMemcpyHostToDevice,
                                        stream));
-        launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)comp.staged_quads, stream);
+        if (comp.staged_rational)
+            launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)comp.staged_quads, stream);
+        else
+            launch_quad_expand_poly(reinterpret_cast<const QuadUpPoly*>(up_quads_raw.ptr), up_quads.ptr,
+                                    (uint32_t)comp.staged_quads, stream);
         ++launches;
     }
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, comp.h_jobs.ptr, (to - from) * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
     h2d_bytes += comp.staged_splines * sizeof(SplineRec) + comp.staged_recs * (sizeof(PointRec) + 1) +
-                 comp.staged_quads * sizeof(QuadUp) + (to - from) * sizeof(FlattenJob);
+                 comp.staged_quads * quad_bytes + (to - from) * sizeof(FlattenJob);
     launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)(to - from),
                         (uint32_t)comp.staged_points, comp.d_x.ptr, comp.d_y.ptr, comp.d_gid.ptr, stream);
     ++launches;
@@ -444,6 +467,8 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         std::fill(comp.h_order_to_style.ptr, comp.h_order_to_style.ptr + n_orders, -1);
         std::fill(comp.h_geom_slot.ptr, comp.h_geom_slot.ptr + n_geoms, -1);
         uint32_t slot = 0, n_styles = 0;
+        bool any_xf = false;
+        FORMA_CUDA_TRY(comp.h_layer_bits.reserve(comp.layers.size() + 1));
         std::unordered_map<std::string, uint32_t> interned;
         std::vector<int32_t> order_to_slot(n_orders, -1);
         for (auto& kv : comp.layers) {
@@ -453,6 +478,8 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
             r.enabled = l.enabled ? 1u : 0u;
             r.has_xf = l.has_xf ? 1u : 0u;
             r.ux = l.xf[0]; r.uy = l.xf[1]; r.vx = l.xf[2]; r.vy = l.xf[3]; r.tx = l.xf[4]; r.ty = l.xf[5];
+            comp.h_layer_bits.ptr[slot] = (kv.first & 0x1FFFFFu) | (r.enabled << 21);
+            any_xf = any_xf || l.has_xf;
             StyleRec s = l.props.rec;
             s.stop_first = (uint32_t)stops.size();
             s.stop_count = (uint32_t)l.props.stops.size();
@@ -506,6 +533,7 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         if (!stops.empty()) std::memcpy(comp.h_stops.ptr, stops.data(), stops.size() * sizeof(StopRec));
         if (!texels.empty()) std::memcpy(comp.h_texels.ptr, texels.data(), texels.size() * sizeof(uint16_t));
         comp.n_layer_recs = slot;
+        comp.layers_have_xf = any_xf;
         comp.n_style_recs = n_styles;
         comp.n_stops = stops.size();
         comp.n_texels = texels.size();
@@ -522,7 +550,9 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         h2d_bytes += n * sizeof(*hbuf.ptr);
         return cudaMemcpyAsync(dbuf.ptr, hbuf.ptr, n * sizeof(*hbuf.ptr), cudaMemcpyHostToDevice, stream);
     };
-    FORMA_CUDA_TRY(up(comp.d_layers, comp.h_layers, comp.n_layer_recs));
+    // Layers without transforms (the common case) travel as 4 bytes each instead of 36.
+    if (comp.layers_have_xf) FORMA_CUDA_TRY(up(comp.d_layers, comp.h_layers, comp.n_layer_recs));
+    else FORMA_CUDA_TRY(up(comp.d_layer_bits, comp.h_layer_bits, comp.n_layer_recs));
     FORMA_CUDA_TRY(up(comp.d_styles, comp.h_styles, comp.n_style_recs));
     FORMA_CUDA_TRY(up(comp.d_stops, comp.h_stops, comp.n_stops));
     FORMA_CUDA_TRY(up(comp.d_texels, comp.h_texels, comp.n_texels));
@@ -542,7 +572,8 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     ra.n_points = comp.n_resident;
     ra.geom_slot = comp.d_geom_slot.ptr;
     ra.n_geoms = comp.n_geoms;
-    ra.layers = comp.d_layers.ptr;
+    ra.layers = comp.layers_have_xf ? comp.d_layers.ptr : nullptr;
+    ra.layer_bits = comp.d_layer_bits.ptr;
     ra.width = (float)width;
     ra.height = (float)height;
     ra.band_lo = band_lo;

@@ -249,6 +249,7 @@ SIGNATURES = {
     "path_transform": (_vp, [_vp, _fp]),
     "path_free": (None, [_vp]),
     "path_segments": (C.c_int, [_vp, C.POINTER(_fp), C.POINTER(_fp), C.POINTER(_u8p), _u64p]),
+    "path_program_stats": (None, [_vp, _u64p]),
     "composition_new": (_vp, []),
     "composition_free": (None, [_vp]),
     "composition_create_layer": (_vp, [_vp]),
@@ -368,6 +369,12 @@ class Path:
     def transform(self, m: Sequence[float]) -> "Path":
         arr = (C.c_float * 9)(*[float(v) for v in m])
         return Path(self._api, self._api.path_transform(self._h, arr))
+
+    def program_stats(self) -> dict:
+        """Host-side facts of the flatten program (CUDA library only; needs no GPU)."""
+        out = (C.c_uint64 * 6)()
+        self._api.path_program_stats(self._h, out)
+        return dict(zip(("points", "quads", "splines", "point_records", "rational", "contour_ends"), [int(v) for v in out]))
 
     def segments(self):
         """Flattened points: (x, y, start_new_contour) numpy arrays."""

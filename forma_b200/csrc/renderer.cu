@@ -1031,6 +1031,16 @@ forma_path* forma_path_transform(const forma_path* src, const float m[9]) {
 }
 void forma_path_free(forma_path* p) { delete p; }
 
+void forma_path_program_stats(forma_path* p, uint64_t out[6]) {
+    const FlattenProgram& prog = p->p.data->program();
+    out[0] = prog.n_points;
+    out[1] = prog.quads.size();
+    out[2] = prog.splines.size();
+    out[3] = prog.points.size();
+    out[4] = prog.rational ? 1 : 0;
+    out[5] = prog.n_contour_ends;
+}
+
 // Evaluates the path's flatten program on the current device and copies the
 // points back (inspection only; rendering never copies points to the host).
 int forma_path_segments(forma_path* p, const float** x, const float** y, const uint8_t** contour, uint64_t* n) {

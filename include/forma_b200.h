@@ -130,6 +130,11 @@ void forma_path_free(forma_path*);
  * Pointers stay valid until the next call on the same thread. */
 int forma_path_segments(forma_path*, const float** x, const float** y,
                         const uint8_t** start_new_contour, uint64_t* n);
+/* Host-side facts of the path's flatten program (no GPU needed): [0] output
+ * points, [1] quadratics, [2] spline records, [3] point records (one of [2]/[3]
+ * is 0: the smaller encoding is kept), [4] 1 if some quadratic is rational,
+ * [5] contour ends before the last point. */
+void forma_path_program_stats(forma_path*, uint64_t out[6]);
 
 /* ------------------------------------------------------------------------ */
 /* Composition / Layer (forma/src/composition/{mod,layer}.rs)               */

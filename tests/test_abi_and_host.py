@@ -89,6 +89,49 @@ def test_renderer_requires_a_gpu():
         path.segments()
 
 
+def test_flatten_program_matches_the_oracles_point_count(oracle_api):
+    """Host half of the flattener (spline merge, subdivision counts, encoding choice):
+    the program of every path announces exactly as many output points and contour
+    ends as the oracle's flattener produces, and keeps the smaller encoding."""
+    import synth
+    api = forma_b200.load()
+    rng_a, rng_b = synth.SplitMix64(21), synth.SplitMix64(21)
+
+    def random_path(a, rng):
+        pb = a.PathBuilder()
+
+        def pt():
+            return Point(rng.uniform(-200.0, 200.0), rng.uniform(-200.0, 200.0))
+        pb.move_to(pt())
+        for _ in range(1 + rng.randint(12)):
+            k = rng.randint(6)
+            if k <= 1:
+                pb.line_to(pt())
+            elif k == 2:
+                pb.quad_to(pt(), pt())
+            elif k == 3:
+                pb.cubic_to(pt(), pt(), pt())
+            elif k == 4:
+                pb.rat_quad_to(pt(), pt(), rng.uniform(0.3, 2.5))
+            else:
+                pb.move_to(pt())
+        return pb.build()
+
+    seen = set()
+    for i in range(300):
+        p, q = random_path(api, rng_a), random_path(oracle_api, rng_b)
+        s = p.program_stats()
+        x, y, c = q.segments()
+        assert s["points"] == len(x), f"path {i}"
+        assert s["contour_ends"] == int(c[:-1].sum()) if len(c) else s["contour_ends"] == 0, f"path {i}"
+        assert (s["splines"] == 0) != (s["point_records"] == 0) or s["points"] == 0, f"path {i}: both / no encodings"
+        if s["point_records"]:
+            assert s["point_records"] == s["points"]
+        seen.add("points" if s["point_records"] else "splines")
+        seen.add("rational" if s["rational"] else "polynomial")
+    assert seen == {"points", "splines", "rational", "polynomial"}
+
+
 @pytest.mark.parametrize("height,world", [(2160, 1), (2160, 2), (2160, 8), (4320, 8), (1080, 4), (17, 8), (16, 3)])
 def test_bands_partition_the_frame(height, world):
     covered = np.zeros(height, np.int32)

@@ -49,7 +49,7 @@ struct PendingInsert {
 class Composition {
    public:
     std::map<uint32_t, Layer*> layers;              // attached layers by order
-    std::vector<std::unique_ptr<Layer>> pool;       // every live layer
+    std::unordered_map<Layer*, std::unique_ptr<Layer>> pool;  // every live layer (attached or not)
     std::unordered_map<uint64_t, int64_t> geom_to_order;  // -1 == None
     uint64_t next_geom_id = 1;
 

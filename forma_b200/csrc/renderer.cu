@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <string>
 
 #include "../../include/forma_b200.h"
@@ -62,8 +64,9 @@ bool HostProps::equals(const HostProps& o) const {
 // Composition (composition/mod.rs, composition/layer.rs)
 // ---------------------------------------------------------------------------
 Layer* Composition::create_layer() {  // mod.rs:65-83
-    pool.emplace_back(new Layer());
-    Layer* l = pool.back().get();
+    std::unique_ptr<Layer> owned(new Layer());
+    Layer* l = owned.get();
+    pool.emplace(l, std::move(owned));
     l->geom_id = next_geom_id++;
     return l;
 }
@@ -116,18 +119,13 @@ Layer* Composition::get_or_insert_default(uint32_t order) {  // mod.rs:175-182
 }
 
 void Composition::drop(Layer* l) {  // Drop for Layer, layer.rs:355-363
-    for (auto it = layers.begin(); it != layers.end(); ++it)
-        if (it->second == l) {
-            layers.erase(it);
-            break;
-        }
+    if (l->order >= 0) {  // attached layers are found by their order; a detached one keeps a stale order
+        auto it = layers.find((uint32_t)l->order);
+        if (it != layers.end() && it->second == l) layers.erase(it);
+    }
     geom_to_order.erase(l->geom_id);
     garbage_points += l->points;
-    for (auto it = pool.begin(); it != pool.end(); ++it)
-        if (it->get() == l) {
-            pool.erase(it);
-            break;
-        }
+    pool.erase(l);
     tables_dirty = true;
 }
 
@@ -280,6 +278,7 @@ class Renderer {
 
     ~Renderer() {
         if (pinned_totals) cudaFreeHost(pinned_totals);
+        if (count_ev) cudaEventDestroy(count_ev);
         if (copy_stream) {
             for (auto& e : band_ev) cudaEventDestroy(e);
             cudaStreamDestroy(copy_stream);
@@ -998,36 +997,65 @@ struct forma_layer_cache { LayerCache c; };
 static Layer* L(forma_layer* l) { return reinterpret_cast<Layer*>(l); }
 static forma_layer* H(Layer* l) { return reinterpret_cast<forma_layer*>(l); }
 
+// No C++ exception crosses the C ABI: a failed host allocation (std::bad_alloc
+// from the containers behind these calls) is reported through the call's error
+// value and forma_last_error() like any other failure.
+template <class R, class F>
+static R guarded(R on_error, F&& f) noexcept {
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        set_error("host error: %s", e.what());
+    } catch (...) {
+        set_error("host error: unknown exception");
+    }
+    return on_error;
+}
+template <class F>
+static void guarded_void(F&& f) noexcept {
+    guarded(0, [&] { f(); return 0; });
+}
+
 extern "C" {
 
 const char* forma_last_error(void) { return g_error.c_str(); }
 
-forma_path_builder* forma_path_builder_new(void) { return new forma_path_builder(); }
+forma_path_builder* forma_path_builder_new(void) {
+    return guarded((forma_path_builder*)nullptr, [] { return new forma_path_builder(); });
+}
 void forma_path_builder_free(forma_path_builder* pb) { delete pb; }
-void forma_path_builder_move_to(forma_path_builder* pb, float x, float y) { pb->b.move_to({x, y}); }
-void forma_path_builder_line_to(forma_path_builder* pb, float x, float y) { pb->b.line_to({x, y}); }
+void forma_path_builder_move_to(forma_path_builder* pb, float x, float y) {
+    guarded_void([&] { pb->b.move_to({x, y}); });
+}
+void forma_path_builder_line_to(forma_path_builder* pb, float x, float y) {
+    guarded_void([&] { pb->b.line_to({x, y}); });
+}
 void forma_path_builder_quad_to(forma_path_builder* pb, float x1, float y1, float x2, float y2) {
-    pb->b.quad_to({x1, y1}, {x2, y2});
+    guarded_void([&] { pb->b.quad_to({x1, y1}, {x2, y2}); });
 }
 void forma_path_builder_cubic_to(forma_path_builder* pb, float x1, float y1, float x2, float y2, float x3, float y3) {
-    pb->b.cubic_to({x1, y1}, {x2, y2}, {x3, y3});
+    guarded_void([&] { pb->b.cubic_to({x1, y1}, {x2, y2}, {x3, y3}); });
 }
 void forma_path_builder_rat_quad_to(forma_path_builder* pb, float x1, float y1, float x2, float y2, float w) {
-    pb->b.rat_quad_to({x1, y1}, {x2, y2}, w);
+    guarded_void([&] { pb->b.rat_quad_to({x1, y1}, {x2, y2}, w); });
 }
 void forma_path_builder_rat_cubic_to(forma_path_builder* pb, float x1, float y1, float x2, float y2, float x3,
                                      float y3, float w1, float w2) {
-    pb->b.rat_cubic_to({x1, y1}, {x2, y2}, {x3, y3}, w1, w2);
+    guarded_void([&] { pb->b.rat_cubic_to({x1, y1}, {x2, y2}, {x3, y3}, w1, w2); });
 }
 forma_path* forma_path_builder_build(forma_path_builder* pb) {
-    forma_path* p = new forma_path();
-    p->p = pb->b.build();
-    return p;
+    return guarded((forma_path*)nullptr, [&] {
+        std::unique_ptr<forma_path> p(new forma_path());
+        p->p = pb->b.build();
+        return p.release();
+    });
 }
 forma_path* forma_path_transform(const forma_path* src, const float m[9]) {
-    forma_path* p = new forma_path();
-    p->p = src->p.transformed(m);
-    return p;
+    return guarded((forma_path*)nullptr, [&] {
+        std::unique_ptr<forma_path> p(new forma_path());
+        p->p = src->p.transformed(m);
+        return p.release();
+    });
 }
 void forma_path_free(forma_path* p) { delete p; }
 
@@ -1043,7 +1071,7 @@ void forma_path_program_stats(forma_path* p, uint64_t out[6]) {
 
 // Evaluates the path's flatten program on the current device and copies the
 // points back (inspection only; rendering never copies points to the host).
-int forma_path_segments(forma_path* p, const float** x, const float** y, const uint8_t** contour, uint64_t* n) {
+static int path_segments_impl(forma_path* p, const float** x, const float** y, const uint8_t** contour, uint64_t* n) {
     const FlattenProgram& prog = p->p.data->program();
     uint32_t count = prog.n_points;
     p->x.assign(count, 0.0f);
@@ -1111,19 +1139,28 @@ int forma_path_segments(forma_path* p, const float** x, const float** y, const u
     for (size_t i = 0; i < prog.kinds.size() && i < count; ++i) p->c[i] = prog.kinds[i] == 1u;
     return FORMA_STATUS_OK;
 }
+int forma_path_segments(forma_path* p, const float** x, const float** y, const uint8_t** contour, uint64_t* n) {
+    return guarded((int)FORMA_STATUS_CAPACITY, [&] { return path_segments_impl(p, x, y, contour, n); });
+}
 
-forma_composition* forma_composition_new(void) { return new forma_composition(); }
+forma_composition* forma_composition_new(void) {
+    return guarded((forma_composition*)nullptr, [] { return new forma_composition(); });
+}
 void forma_composition_free(forma_composition* c) { delete c; }
-forma_layer* forma_composition_create_layer(forma_composition* c) { return H(c->c.create_layer()); }
+forma_layer* forma_composition_create_layer(forma_composition* c) {
+    return guarded((forma_layer*)nullptr, [&] { return H(c->c.create_layer()); });
+}
 forma_layer* forma_composition_insert(forma_composition* c, uint32_t order, forma_layer* layer, int* status) {
     if (order > kLayerLimit) {
         if (status) *status = FORMA_ERR_ORDER_LIMIT;
         return nullptr;
     }
     if (status) *status = FORMA_OK;
-    return H(c->c.insert(order, L(layer)));
+    return guarded((forma_layer*)nullptr, [&] { return H(c->c.insert(order, L(layer))); });
 }
-forma_layer* forma_composition_remove(forma_composition* c, uint32_t order) { return H(c->c.remove(order)); }
+forma_layer* forma_composition_remove(forma_composition* c, uint32_t order) {
+    return guarded((forma_layer*)nullptr, [&] { return H(c->c.remove(order)); });
+}
 forma_layer* forma_composition_get(forma_composition* c, uint32_t order) { return H(c->c.get(order)); }
 forma_layer* forma_composition_get_mut_or_insert_default(forma_composition* c, uint32_t order, int* status) {
     if (order > kLayerLimit) {
@@ -1131,19 +1168,25 @@ forma_layer* forma_composition_get_mut_or_insert_default(forma_composition* c, u
         return nullptr;
     }
     if (status) *status = FORMA_OK;
-    return H(c->c.get_or_insert_default(order));
+    return guarded((forma_layer*)nullptr, [&] { return H(c->c.get_or_insert_default(order)); });
 }
 uint64_t forma_composition_len(forma_composition* c) { return c->c.layers.size(); }
-void forma_layer_drop(forma_composition* c, forma_layer* l) { c->c.drop(L(l)); }
+void forma_layer_drop(forma_composition* c, forma_layer* l) {
+    guarded_void([&] { c->c.drop(L(l)); });
+}
 
 uint64_t forma_layer_geom_id(forma_layer* l) { return L(l)->geom_id; }
 int forma_layer_insert(forma_composition* c, forma_layer* l, forma_path* p) {
-    c->c.layer_insert(L(l), p->p);
-    return FORMA_OK;
+    return guarded((int)FORMA_ERR_CAPACITY, [&] {
+        c->c.layer_insert(L(l), p->p);
+        return (int)FORMA_OK;
+    });
 }
 int forma_layer_clear(forma_composition* c, forma_layer* l) {
-    c->c.layer_clear(L(l));
-    return FORMA_OK;
+    return guarded((int)FORMA_ERR_CAPACITY, [&] {
+        c->c.layer_clear(L(l));
+        return (int)FORMA_OK;
+    });
 }
 int forma_layer_set_is_enabled(forma_composition* c, forma_layer* l, int enabled) {
     L(l)->enabled = enabled != 0;
@@ -1182,7 +1225,7 @@ static uint16_t f16_from(float v) {
     return (uint16_t)((u - 0x38000000u) >> 13);
 }
 
-int forma_layer_set_props(forma_composition* c, forma_layer* l, const forma_props* p) {
+static int layer_set_props_impl(forma_composition* c, forma_layer* l, const forma_props* p) {
     HostProps hp;
     StyleRec& s = hp.rec;
     s.fill_rule = p->fill_rule;
@@ -1244,8 +1287,11 @@ int forma_layer_set_props(forma_composition* c, forma_layer* l, const forma_prop
     }
     return FORMA_OK;
 }
+int forma_layer_set_props(forma_composition* c, forma_layer* l, const forma_props* p) {
+    return guarded((int)FORMA_ERR_CAPACITY, [&] { return layer_set_props_impl(c, l, p); });
+}
 
-forma_renderer* forma_renderer_new(int device_ordinal) {
+static forma_renderer* renderer_new_impl(int device_ordinal) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -1276,6 +1322,9 @@ forma_renderer* forma_renderer_new(int device_ordinal) {
     }
     return r;
 }
+forma_renderer* forma_renderer_new(int device_ordinal) {
+    return guarded((forma_renderer*)nullptr, [&] { return renderer_new_impl(device_ordinal); });
+}
 void forma_renderer_free(forma_renderer* r) { delete r; }
 
 void forma_renderer_set_stream(forma_renderer* r, void* cuda_stream) { r->r.stream = (cudaStream_t)cuda_stream; }
@@ -1283,11 +1332,16 @@ void forma_renderer_set_stream(forma_renderer* r, void* cuda_stream) { r->r.stre
 forma_layer_cache* forma_layer_cache_new(forma_renderer* r) {
     for (uint8_t id = 0; id < 32; ++id)
         if (!((r->r.caches_in_use >> id) & 1u)) {
+            forma_layer_cache* c = new (std::nothrow) forma_layer_cache();
+            if (!c) {
+                set_error("forma_layer_cache_new: out of host memory");
+                return nullptr;
+            }
             r->r.caches_in_use |= 1u << id;
-            forma_layer_cache* c = new forma_layer_cache();
             c->c.id = id;
             return c;
         }
+    set_error("forma_layer_cache_new: all 32 cache ids of this renderer are in use");
     return nullptr;
 }
 void forma_layer_cache_free(forma_renderer* r, forma_layer_cache* c) {
@@ -1301,14 +1355,18 @@ void forma_layer_cache_clear(forma_layer_cache* c) {
 int forma_renderer_render(forma_renderer* r, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
                           uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
                           forma_layer_cache* cache, forma_timings* timings) {
-    return r->r.render(c->c, buffer, false, width, stride, height, channels, clear, crop, cache ? &cache->c : nullptr,
-                       timings);
+    return guarded((int)FORMA_ERR_CAPACITY, [&] {
+        return r->r.render(c->c, buffer, false, width, stride, height, channels, clear, crop, cache ? &cache->c : nullptr,
+                           timings);
+    });
 }
 int forma_renderer_render_device(forma_renderer* r, forma_composition* c, uint8_t* device_buffer, uint64_t width,
                                  uint64_t stride, uint64_t height, const uint32_t channels[4], const float clear[4],
                                  const forma_rect* crop, forma_layer_cache* cache, forma_timings* timings) {
-    return r->r.render(c->c, device_buffer, true, width, stride, height, channels, clear, crop,
-                       cache ? &cache->c : nullptr, timings);
+    return guarded((int)FORMA_ERR_CAPACITY, [&] {
+        return r->r.render(c->c, device_buffer, true, width, stride, height, channels, clear, crop,
+                           cache ? &cache->c : nullptr, timings);
+    });
 }
 // --- shared frames (multi-GPU, see include/forma_b200.h) -----------------------
 static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(forma_ipc_handle), "CUDA IPC handles are 64 bytes");
@@ -1378,6 +1436,7 @@ uint64_t forma_composition_point_count(forma_composition* c) { return c->c.n_poi
 void forma_path_builder_extend(forma_path_builder* pb, const uint8_t* cmds, uint64_t n_cmds, const float* xy) {
     PathBuilder& b = pb->b;
     const float* p = xy;
+    guarded_void([&] {
     for (uint64_t i = 0; i < n_cmds; ++i) {
         switch (cmds[i]) {
             case 0: b.move_to({p[0], p[1]}); p += 2; break;
@@ -1386,6 +1445,7 @@ void forma_path_builder_extend(forma_path_builder* pb, const uint8_t* cmds, uint
             default: b.cubic_to({p[0], p[1]}, {p[2], p[3]}, {p[4], p[5]}); p += 6; break;
         }
     }
+    });
 }
 
 uint64_t forma_renderer_lines(forma_renderer*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,
@@ -1397,25 +1457,33 @@ uint64_t forma_renderer_lines(forma_renderer*, uint64_t, uint32_t*, float*, floa
 }
 uint64_t forma_renderer_segments(forma_renderer* r, uint64_t cap, uint64_t* out) {
     uint64_t n = r->r.last_segments;
-    if (out && cap) {
-        cudaMemcpy(out, r->r.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (out && cap && n) {
+        cudaError_t e = cudaMemcpy(out, r->r.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("forma_renderer_segments: %s", cudaGetErrorString(e));
+            return 0;
+        }
     }
     return n;
 }
-uint64_t forma_renderer_rasterize_only(forma_renderer* r, forma_composition* c, uint64_t width, uint64_t height,
-                                       uint64_t cap, uint64_t* out) {
+static uint64_t rasterize_only_impl(forma_renderer* r, forma_composition* c, uint64_t width, uint64_t height,
+                                    uint64_t cap, uint64_t* out) {
     Renderer& R = r->r;
     if (cudaSetDevice(R.device) != cudaSuccess) return 0;
     if (R.flush_geometry(c->c) || R.upload_tables(c->c, -1)) return 0;
     uint32_t n = 0;
-    float h = (float)height;
     if (R.rasterize(c->c, (uint32_t)std::min<uint64_t>(width, 0xFFFFFFFFu), (uint32_t)std::min<uint64_t>(height, 0xFFFFFFFFu),
                     -3.0e38f, 3.0e38f, &n))
         return 0;
-    (void)h;
-    cudaStreamSynchronize(R.stream);
-    if (out && cap) cudaMemcpy(out, R.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (cudaStreamSynchronize(R.stream) != cudaSuccess) return 0;
+    if (out && cap && n &&
+        cudaMemcpy(out, R.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return 0;
     return n;
+}
+uint64_t forma_renderer_rasterize_only(forma_renderer* r, forma_composition* c, uint64_t width, uint64_t height,
+                                       uint64_t cap, uint64_t* out) {
+    return guarded((uint64_t)0, [&] { return rasterize_only_impl(r, c, width, height, cap, out); });
 }
 int forma_renderer_sort_u64(forma_renderer* r, uint64_t* keys, uint64_t n) {
     Renderer& R = r->r;

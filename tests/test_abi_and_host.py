@@ -76,6 +76,33 @@ def test_host_bookkeeping_without_device():
     assert GradientBuilder(Point(0, 0), Point(1, 0)).color(Color()).build() is None
 
 
+def test_layer_bookkeeping_scales():
+    """Dropping a layer (Drop for Layer, composition/layer.rs:355-363) is a lookup, not a
+    scan: 60 k layers are created, attached, partly displaced and dropped in well under a
+    second (paris-30k alone has 50 620 layers)."""
+    import time
+    api = forma_b200.load()
+    comp = api.Composition()
+    t0 = time.perf_counter()
+    layers = [comp.create_layer() for _ in range(60_000)]
+    for i, layer in enumerate(layers[:40_000]):
+        assert comp.insert(i, layer) is None
+    displaced = comp.insert(7, layers[50_000])           # 7 is taken: its layer comes back detached
+    assert displaced is not None and len(comp) == 40_000
+    displaced.drop()                                     # detached layer with a stale order: must not remove order 7
+    assert len(comp) == 40_000 and comp.get(7) is not None
+    for layer in layers[40_000:50_000] + layers[50_001:]:
+        layer.drop()                                     # never attached
+    assert len(comp) == 40_000
+    for i, layer in enumerate(layers[:40_000]):
+        if i != 7:
+            layer.drop()
+    assert len(comp) == 1
+    comp.get(7).drop()
+    assert comp.is_empty()
+    assert time.perf_counter() - t0 < 5.0
+
+
 def test_renderer_requires_a_gpu():
     import torch
     if torch.cuda.is_available():

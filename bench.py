@@ -430,8 +430,9 @@ def run_cuda(args):
     fps_e2e = args.steps / (T_e2e / 1e3)
     stages = {k: v / args.steps for k, v in stage_acc.items()}
     peak, peak_kind = measured_peak_gbs()
-    # Dominant kernel group (rank 0): the larger of the sort (histogram + 6 onesweep
-    # passes; algorithmic bytes 16 N) and the paint kernel (8 N + 4 W H).
+    # Dominant kernel (rank 0): the one with the largest time per step among the radix
+    # downsweep, the radix upsweep + scan and the paint kernel, timed per launch with CUDA
+    # events on the launching stream inside Renderer::render.
     band_px = (min(r1 * 16, h) - r0 * 16) * w
     # Per-launch algorithmic bytes: a radix downsweep launch reads and
     # writes every key once (16 N), an upsweep launch reads them once (8 N), the paint

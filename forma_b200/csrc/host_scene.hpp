@@ -30,7 +30,9 @@ struct Layer {
     bool has_xf = false;
     float xf[6] = {1, 0, 0, 1, 0, 0};  // ux, uy, vx, vy, tx, ty
     int64_t order = -1;               // InnerLayer.order (kept when detached, layer.rs:148-158)
-    uint64_t geom_id = 0;
+    uint64_t geom_id = 0;             // GeomId (public, never reused)
+    uint32_t dense_id = 0;            // this geometry's index in the device's id -> layer table (0 = None);
+                                      // renumbered by Composition::compact_geom
     HostProps props;
     uint32_t unchanged_bits = 0;      // SmallBitSet over layer-cache ids
     size_t lines_count = 0;
@@ -41,7 +43,7 @@ struct PendingInsert {
     std::shared_ptr<PathData> data;
     bool has_xf;
     float xf[6];
-    uint32_t geom_id;
+    uint32_t geom_id;  // Layer::dense_id at the time of the insert
     uint32_t dst;    // first point in the segment buffer
     uint32_t count;  // number of points
 };
@@ -50,8 +52,9 @@ class Composition {
    public:
     std::map<uint32_t, Layer*> layers;              // attached layers by order
     std::unordered_map<Layer*, std::unique_ptr<Layer>> pool;  // every live layer (attached or not)
-    std::unordered_map<uint64_t, int64_t> geom_to_order;  // -1 == None
+    std::unordered_map<uint32_t, int64_t> geom_to_order;  // dense id -> order, -1 == None
     uint64_t next_geom_id = 1;
+    uint32_t next_dense_id = 1;
 
     Layer* create_layer();
     Layer* insert(uint32_t order, Layer* layer);    // returns the displaced layer

@@ -68,6 +68,7 @@ Layer* Composition::create_layer() {  // mod.rs:65-83
     Layer* l = owned.get();
     pool.emplace(l, std::move(owned));
     l->geom_id = next_geom_id++;
+    l->dense_id = next_dense_id++;
     return l;
 }
 
@@ -76,7 +77,7 @@ void Composition::set_order(Layer* l, int64_t order) {  // layer.rs:148-158
         l->order = order;
         l->unchanged_bits = 0;
     }
-    geom_to_order[l->geom_id] = order;
+    geom_to_order[l->dense_id] = order;
     tables_dirty = true;
 }
 
@@ -123,7 +124,7 @@ void Composition::drop(Layer* l) {  // Drop for Layer, layer.rs:355-363
         auto it = layers.find((uint32_t)l->order);
         if (it != layers.end() && it->second == l) layers.erase(it);
     }
-    geom_to_order.erase(l->geom_id);
+    geom_to_order.erase(l->dense_id);
     garbage_points += l->points;
     pool.erase(l);
     tables_dirty = true;
@@ -138,7 +139,7 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
         job.data = path.data;
         job.has_xf = path.has_xf;
         std::memcpy(job.xf, path.xf, sizeof(job.xf));
-        job.geom_id = (uint32_t)layer->geom_id;
+        job.geom_id = layer->dense_id;
         job.dst = n_points;
         job.count = count;
         jobs.push_back(std::move(job));
@@ -150,23 +151,47 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
         layer->points += count;
         n_points += count;
     }
-    geom_to_order[layer->geom_id] = layer->order;
+    geom_to_order[layer->dense_id] = layer->order;
     layer->unchanged_bits = 0;
     tables_dirty = true;
 }
 
 void Composition::compact_geom() {
-    if (garbage_points < 65536u || garbage_points * 2u < n_points) return;
+    const bool dead_points = garbage_points >= 65536u && garbage_points * 2u >= n_points;
+    const bool dead_ids = (uint64_t)next_dense_id > 2u * (uint64_t)pool.size() + 65536u;
+    if (!dead_points && !dead_ids) return;
+    // Dense ids are handed out again from 1, in the order the live layers got theirs, so
+    // that the device's id -> layer table stays proportional to the live layers however
+    // often layers are cleared (every Layer::clear takes a new id, layer.rs:131-146).
+    std::vector<Layer*> alive;
+    alive.reserve(pool.size());
+    for (auto& kv : pool) alive.push_back(kv.first);
+    std::sort(alive.begin(), alive.end(), [](const Layer* a, const Layer* b) { return a->dense_id < b->dense_id; });
+    std::unordered_map<uint32_t, uint32_t> renumbered;
+    std::unordered_map<uint32_t, int64_t> orders;
+    renumbered.reserve(alive.size());
+    orders.reserve(alive.size());
+    uint32_t next = 1;
+    for (Layer* l : alive) {
+        auto it = geom_to_order.find(l->dense_id);
+        if (it != geom_to_order.end()) orders.emplace(next, it->second);
+        renumbered.emplace(l->dense_id, next);
+        l->dense_id = next++;
+    }
     std::vector<PendingInsert> live;
     live.reserve(jobs.size());
     uint64_t pts = 0;
     for (PendingInsert& j : jobs) {
-        if (!geom_to_order.count(j.geom_id)) continue;
+        auto it = renumbered.find(j.geom_id);  // inserts of cleared / dropped geometry have no live id
+        if (it == renumbered.end() || !orders.count(it->second)) continue;
+        j.geom_id = it->second;
         j.dst = (uint32_t)pts;
         pts += j.count;
         live.push_back(std::move(j));
     }
     jobs.swap(live);
+    geom_to_order.swap(orders);
+    next_dense_id = next;
     n_points = (uint32_t)pts;
     garbage_points = 0;
     jobs_resident = 0;  // everything is evaluated again into the re-packed buffer
@@ -179,9 +204,10 @@ void Composition::compact_geom() {
 void Composition::layer_clear(Layer* layer) {  // layer.rs:131-146
     garbage_points += layer->points;
     layer->points = 0;
-    geom_to_order.erase(layer->geom_id);
+    geom_to_order.erase(layer->dense_id);
     layer->geom_id = next_geom_id++;
-    geom_to_order[layer->geom_id] = layer->order;
+    layer->dense_id = next_dense_id++;
+    geom_to_order[layer->dense_id] = layer->order;
     layer->lines_count = 0;
     layer->unchanged_bits = 0;
     tables_dirty = true;
@@ -457,7 +483,7 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         uint32_t max_order = 0;
         for (auto& kv : comp.layers) max_order = std::max(max_order, kv.first);
         uint32_t n_orders = comp.layers.empty() ? 0u : max_order + 1u;
-        uint32_t n_geoms = (uint32_t)comp.next_geom_id;
+        uint32_t n_geoms = comp.next_dense_id;
         FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
         FORMA_CUDA_TRY(comp.h_layers.reserve(comp.layers.size() + 1));
         FORMA_CUDA_TRY(comp.h_styles.reserve(comp.layers.size() + 1));
@@ -944,9 +970,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         stage_ms[0] = el(0, 7);  // uploads (geometry programs + flatten eval + tables)
         stage_ms[1] = el(7, 1);  // line setup: count pass + scan (+ count read-back)
         stage_ms[2] = el(1, 2);  // pixel-grid intersection (emit)
-        stage_ms[3] = el(2, 3);  // sort (histogram + 6 onesweep passes), no host sync inside
+        stage_ms[3] = el(2, 3);  // sort (upsweep / tile scan / downsweep per digit), no host sync inside
         stage_ms[4] = el(3, 4);  // painter tables: cells, carries, entries (2 pair sorts, 2 read-backs)
-        stage_ms[5] = el(4, 5);  // paint kernel alone
+        stage_ms[5] = el(4, 5);  // paint kernel alone (host frames: its kCopyBands band launches)
         stage_ms[6] = el(5, 6);  // device -> host copy of the framebuffer
         stage_ms[7] = el(0, 6);  // whole call on the device timeline
         kernel_ms[0] = kernel_ms[1] = 0;
@@ -959,7 +985,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         }
         kernel_launches[0] = kernel_launches[1] = (uint32_t)timed_sort_passes;
         kernel_ms[2] = stage_ms[5];
-        kernel_launches[2] = 1;
+        kernel_launches[2] = copied_in_bands ? kCopyBands : 1u;
     }
     if (timings) {
         timings->line_setup_ms = stage_ms[1];

@@ -431,6 +431,39 @@ def test_cleared_geometry_is_compacted(cuda_api, oracle_api, cuda_renderer, orac
     assert_same(outs[0].reshape(h, -1), outs[1].reshape(h, -1), "frame after 60 clear / insert cycles")
 
 
+def test_cleared_ids_are_renumbered(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
+    """Every Layer::clear takes a new geometry id (layer.rs:131-146). The device's
+    id -> layer table must follow the live layers, not the ids ever handed out: after
+    70 000 clears the tables a frame uploads stay a few hundred bytes, the public
+    geom_id keeps growing, and the frames stay identical to the oracle's."""
+    w, h = 160, 96
+    outs = []
+    for api, r in ((cuda_api, cuda_renderer), (oracle_api, oracle_renderer)):
+        comp = api.Composition()
+        synth.random_mixed(api, comp, 6, w, h, 9)
+        layer = comp.get_mut_or_insert_default(40)
+        layer.set_props(Props(func=Func.Draw(Style(fill=Fill.Solid(Color(0.8, 0.2, 0.1, 0.7))))))
+        tri = api.PathBuilder().move_to(Point(10, 10)).line_to(Point(150, 30)).line_to(Point(60, 90)).build()
+        layer.insert(tri)
+        buf = np.zeros(w * h * 4, np.uint8)
+        r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1))
+        g0 = layer.geom_id()
+        for _ in range(70_000):
+            layer.clear()
+        assert layer.geom_id() == g0 + 70_000
+        layer.insert(tri)
+        r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1))   # renumbers (and re-evaluates) here
+        if api is cuda_api:
+            before = r.counters()["h2d_bytes"]
+            comp.get(40).disable()                           # dirties the tables only
+            r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1))
+            comp.get(40).enable()
+            r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1))
+            assert r.counters()["h2d_bytes"] - before < 8192, r.counters()["h2d_bytes"] - before
+        outs.append(buf.copy())
+    assert_same(outs[0].reshape(h, -1), outs[1].reshape(h, -1), "frame after 70 000 clears")
+
+
 def test_shared_frame_owner_side(cuda_api, cuda_renderer):
     """forma_shared_frame_create / _free and rendering into the shared allocation
     (the mapping side needs a second process; bench.py --gpus N exercises it)."""

@@ -446,6 +446,8 @@ def run_cuda(args):
             kerns[k] = {"ms_per_launch": avg_ms, "launches_per_step": a["launches"] / args.steps,
                         "ms_per_step": a["ms"] / args.steps, "algorithmic_bytes_per_launch": per_launch[k],
                         "GBps": per_launch[k] / (avg_ms * 1e-3) / 1e9}
+    if "paint" in kerns:  # the painter is not bandwidth-shaped; its own unit is pixel·layers/s
+        kerns["paint"]["gpx_layers_per_s"] = c1["entries"] * 256.0 / (kerns["paint"]["ms_per_launch"] * 1e-3) / 1e9
     name = max(kerns, key=lambda k: kerns[k]["ms_per_step"]) if kerns else None
     dom = kerns.get(name, {"GBps": 0.0, "ms_per_launch": 0.0, "algorithmic_bytes_per_launch": 0.0})
     sort_ms = stages["sort"]

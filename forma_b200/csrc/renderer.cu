@@ -6,6 +6,7 @@
 // fallback: without a usable sm_100 device forma_renderer_new() fails.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -265,9 +266,17 @@ class Renderer {
     DeviceBuffer<uint8_t> eflags, framebuffer;
     DeviceBuffer<EntryRec> recs;
     // Band-wise copy-back of host frames (see render()).
-    static constexpr uint32_t kCopyBands = 4;
+    static constexpr uint32_t kMaxCopyBands = 16;
+    static uint32_t copy_bands() {  // FORMA_COPY_BANDS=n (1..16): number of paint / copy-back bands of a host frame
+        static const uint32_t n = [] {
+            const char* e = getenv("FORMA_COPY_BANDS");
+            long v = e ? strtol(e, nullptr, 10) : 4;
+            return (uint32_t)std::min<long>(std::max<long>(v, 1), kMaxCopyBands);
+        }();
+        return n;
+    }
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t band_ev[kCopyBands + 1];
+    cudaEvent_t band_ev[kMaxCopyBands + 1];
     cudaEvent_t count_ev = nullptr;  // completion of a count read-back (waited on instead of the whole stream)
     cudaError_t ensure_count_event() {
         return count_ev ? cudaSuccess : cudaEventCreateWithFlags(&count_ev, cudaEventDisableTiming);
@@ -882,6 +891,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     // band back on a second stream while the next one is painted, so most of the
     // PCIe transfer overlaps the paint kernel.
     bool copied_in_bands = false;
+    uint32_t paint_launches = 1;
     const uint32_t paint_rows = S.ty_hi - S.ty_lo;
     if (!buffer_on_device && !cache && paint_rows >= 32u && S.tx_hi > S.tx_lo && band_copies_enabled()) {
         if (!copy_stream) {
@@ -889,6 +899,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             for (auto& e : band_ev) FORMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         const uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
+        const uint32_t kCopyBands = std::min(copy_bands(), paint_rows / 8u);
         for (uint32_t k = 0; k < kCopyBands; ++k) {
             PaintScene Sb = S;
             Sb.ty_lo = S.ty_lo + paint_rows * k / kCopyBands;
@@ -904,7 +915,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                 d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
             }
         }
-        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kCopyBands], copy_stream));
+        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], copy_stream));
+        paint_launches = kCopyBands;
         copied_in_bands = true;
     } else {
         launch_paint(S, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
@@ -912,7 +924,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[5], stream));
-    if (copied_in_bands) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[kCopyBands], 0));
+    if (copied_in_bands) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[kMaxCopyBands], 0));
 
     last_written_tiles = 0;
     if (pack_written) {
@@ -972,7 +984,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         stage_ms[2] = el(1, 2);  // pixel-grid intersection (emit)
         stage_ms[3] = el(2, 3);  // sort (upsweep / tile scan / downsweep per digit), no host sync inside
         stage_ms[4] = el(3, 4);  // painter tables: cells, carries, entries (2 pair sorts, 2 read-backs)
-        stage_ms[5] = el(4, 5);  // paint kernel alone (host frames: its kCopyBands band launches)
+        stage_ms[5] = el(4, 5);  // paint kernel alone (host frames: its band launches)
         stage_ms[6] = el(5, 6);  // device -> host copy of the framebuffer
         stage_ms[7] = el(0, 6);  // whole call on the device timeline
         kernel_ms[0] = kernel_ms[1] = 0;
@@ -985,7 +997,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         }
         kernel_launches[0] = kernel_launches[1] = (uint32_t)timed_sort_passes;
         kernel_ms[2] = stage_ms[5];
-        kernel_launches[2] = copied_in_bands ? kCopyBands : 1u;
+        kernel_launches[2] = paint_launches;
     }
     if (timings) {
         timings->line_setup_ms = stage_ms[1];

@@ -101,11 +101,6 @@ struct PaintScene {
     uint32_t* written_list;       // optional: linear ids of the tiles this frame wrote (unordered)
     uint32_t* written_count;      //           ... and how many
     uint32_t clear_unchanged;     // previous clear colour == this frame's
-    // Band-wise copy-back of host frames (Renderer::render): when set, every finished tile
-    // adds 1 to band_done[(tile row - ty_lo) / band_rows] after its pixels are visible
-    // system-wide; the copy stream waits on these counters (stream memory operations).
-    uint32_t* band_done;
-    uint32_t band_rows;
 };
 
 uint32_t cell_num_blocks(uint32_t n);

@@ -180,17 +180,6 @@ __device__ __noinline__ Rgba blend_solid(uint32_t mode, Rgba dst, Rgba src) { re
 
 constexpr int kPaintWarpsPerBlock = 2;
 
-// A tile of a host frame is complete: make the warp's framebuffer stores visible to the
-// copy engine, then count the tile for its band (see PaintScene::band_done).
-__device__ __noinline__ void signal_band(uint32_t* counter, uint32_t lane) {
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_system();
-        atomicAdd(counter, 1u);
-    }
-}
-
 // kMinBlocks trades registers for resident warps (8 -> 128 regs, 10 -> 96 regs).
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_kernel(PaintScene S, PaintInputs in, uint32_t n_tiles) {
@@ -224,12 +213,7 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
         cur_b = in.tile_begin[t0];
         cur_e = in.tile_end[t0];
     }
-    uint32_t done_row = 0xFFFFFFFFu;  // row (relative to ty_lo) of the tile this warp painted last
     while (cur < n_tiles) {
-        if (S.band_done) {  // every way out of the previous tile's body comes through here
-            if (done_row != 0xFFFFFFFFu) signal_band(S.band_done + done_row / S.band_rows, lane);
-            done_row = cur / ntx;
-        }
         const uint32_t tile_lin = cur, b = cur_b, e = cur_e;
         {
             const uint32_t nxt = __shfl_sync(kFullMask, next_raw, 0);
@@ -575,7 +559,6 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
             }
         }
     }
-    if (S.band_done && done_row != 0xFFFFFFFFu) signal_band(S.band_done + done_row / S.band_rows, lane);
 }
 
 // Packs the tiles named in `list` (written by paint_kernel) into 1 KB records,

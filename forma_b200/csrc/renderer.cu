@@ -267,28 +267,14 @@ class Renderer {
     DeviceBuffer<EntryRec> recs;
     // Band-wise copy-back of host frames (see render()).
     static constexpr uint32_t kMaxCopyBands = 16;
-    static uint32_t copy_bands(uint32_t dflt) {  // FORMA_COPY_BANDS=n (1..16): number of copy-back bands of a host frame
-        static const long v = getenv("FORMA_COPY_BANDS") ? strtol(getenv("FORMA_COPY_BANDS"), nullptr, 10) : 0;
-        return v > 0 ? (uint32_t)std::min<long>(v, kMaxCopyBands) : dflt;
-    }
-    // cuStreamWaitValue32 (stream memory operation of the driver API), resolved through the
-    // runtime so that the library has no link-time dependency on libcuda. FORMA_BAND_SIGNAL=0
-    // keeps the one-paint-launch-per-band scheme.
-    typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
-    static WaitValue32Fn wait_value32() {
-        static const WaitValue32Fn fn = []() -> WaitValue32Fn {
-            if (getenv("FORMA_BAND_SIGNAL") && getenv("FORMA_BAND_SIGNAL")[0] == '0') return nullptr;
-            void* p = nullptr;
-            cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
-                q != cudaDriverEntryPointSuccess)
-                return nullptr;
-            return (WaitValue32Fn)p;
+    static uint32_t copy_bands() {  // FORMA_COPY_BANDS=n (1..16): number of paint / copy-back bands of a host frame
+        static const uint32_t n = [] {
+            const char* e = getenv("FORMA_COPY_BANDS");
+            long v = e ? strtol(e, nullptr, 10) : 4;
+            return (uint32_t)std::min<long>(std::max<long>(v, 1), kMaxCopyBands);
         }();
-        return fn;
+        return n;
     }
-    bool band_signal_ok = true;            // cleared if the driver refuses the wait operation
-    DeviceBuffer<uint32_t> band_done;      // finished tiles per copy band (PaintScene::band_done)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t band_ev[kMaxCopyBands + 1];
     cudaEvent_t count_ev = nullptr;  // completion of a count read-back (waited on instead of the whole stream)
@@ -901,9 +887,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
     launches += n_entries ? 1 : 0;
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
-    // Host frame without a layer cache: the frame is copied back in bands of tile rows on
-    // a second stream while the rest is still being painted, so most of the PCIe transfer
-    // overlaps the paint kernel.
+    // Host frame without a layer cache: paint in bands of tile rows and copy each
+    // band back on a second stream while the next one is painted, so most of the
+    // PCIe transfer overlaps the paint kernel.
     bool copied_in_bands = false;
     uint32_t paint_launches = 1;
     const uint32_t paint_rows = S.ty_hi - S.ty_lo;
@@ -913,47 +899,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             for (auto& e : band_ev) FORMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         const uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
-        // One paint launch for the whole frame; the kernel counts finished tiles per band
-        // and the copy stream waits for each band's count (a stream memory operation) before
-        // copying that band back: no kernel boundary, hence no tail, between the bands.
-        WaitValue32Fn wait = band_signal_ok ? wait_value32() : nullptr;
-        if (wait) {
-            const uint32_t want = std::min(copy_bands(8u), paint_rows / 4u);
-            const uint32_t band_rows = (paint_rows + want - 1u) / want, nb = (paint_rows + band_rows - 1u) / band_rows;
-            FORMA_CUDA_TRY(band_done.reserve(kMaxCopyBands));
-            FORMA_CUDA_TRY(cudaMemsetAsync(band_done.ptr, 0, nb * sizeof(uint32_t), stream));
-            FORMA_CUDA_TRY(cudaEventRecord(band_ev[0], stream));
-            FORMA_CUDA_TRY(cudaStreamWaitEvent(copy_stream, band_ev[0], 0));  // the counters are zero before any wait reads them
-            for (uint32_t k = 0; k < nb; ++k) {
-                const uint32_t r0 = S.ty_lo + k * band_rows, r1 = std::min(S.ty_hi, r0 + band_rows);
-                const uint32_t tiles = (r1 - r0) * (S.tx_hi - S.tx_lo);
-                const int rc = wait(copy_stream, (unsigned long long)(uintptr_t)(band_done.ptr + k), tiles, 0u /* GEQ */);
-                if (rc != 0) {
-                    if (k == 0) {  // not supported here: nothing is queued behind a wait yet
-                        band_signal_ok = false;
-                        break;
-                    }
-                    set_error("cuStreamWaitValue32 failed (%d)", rc);
-                    return FORMA_STATUS_CUDA;
-                }
-                const uint64_t y0 = (uint64_t)r0 * 16u, y1 = std::min<uint64_t>((uint64_t)r1 * 16u, height);
-                if (x1 > x0 && y1 > y0) {
-                    FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
-                                                     (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, copy_stream));
-                    d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
-                }
-            }
-            if (band_signal_ok) {
-                FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], copy_stream));
-                PaintScene Sb = S;
-                Sb.band_done = band_done.ptr;
-                Sb.band_rows = band_rows;
-                launch_paint(Sb, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
-                ++launches;
-                copied_in_bands = true;
-            }
-        }
-        const uint32_t kCopyBands = copied_in_bands ? 0u : std::min(copy_bands(4u), paint_rows / 8u);
+        const uint32_t kCopyBands = std::min(copy_bands(), paint_rows / 8u);
         for (uint32_t k = 0; k < kCopyBands; ++k) {
             PaintScene Sb = S;
             Sb.ty_lo = S.ty_lo + paint_rows * k / kCopyBands;
@@ -969,11 +915,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                 d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
             }
         }
-        if (!copied_in_bands) {
-            FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], copy_stream));
-            paint_launches = kCopyBands;
-            copied_in_bands = true;
-        }
+        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], copy_stream));
+        paint_launches = kCopyBands;
+        copied_in_bands = true;
     } else {
         launch_paint(S, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
         ++launches;

@@ -231,6 +231,9 @@ def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device. The forma_b200 arm has no CPU fallback; "
+                 "`--impl reference` times the CPU restatement of the reference instead.")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)

@@ -171,6 +171,44 @@ __device__ __noinline__ void blend_column_generic(const StyleRec* __restrict__ s
     }
 }
 
+// Slab mapping (paint_kernel<_, true>): the eight pixels of a lane lie in one row, pixel j
+// at x0 + 2 j; `active` bit j says whether this lane blends pixel j (its f32x8 of the
+// reference has a non-zero coverage, cpu/painter/mod.rs:317-319). (fy, l) is the f32x8 base
+// row and the row inside it, exactly the operands gradient_at / texture_at combine.
+__device__ __noinline__ void blend_row_generic(const StyleRec* __restrict__ st_ptr, const StopRec* __restrict__ stops,
+                                               const uint16_t* __restrict__ texels, uint32_t x0, float fy, int l,
+                                               const float* __restrict__ cov, uint32_t active, bool apply_clip,
+                                               const float* __restrict__ clip /* stride 32 */, float* __restrict__ px) {
+    const StyleRec s = *st_ptr;
+    if (s.fill_type == 1u && s.stop_count <= 4u) {
+        const GradientSetup g = gradient_setup(s, stops);
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            if (!((active >> j) & 1u)) continue;
+            float fill[4];
+            gradient_at_small(s, g, (float)(x0 + 2u * (uint32_t)j), fy, l, fill);
+            float4 d = blend_fill(s.blend_mode, fill, cov[j], apply_clip, apply_clip ? clip[j * 32] : 1.0f,
+                                  make_float4(px[j], px[8 + j], px[16 + j], px[24 + j]));
+            px[j] = d.x;
+            px[8 + j] = d.y;
+            px[16 + j] = d.z;
+            px[24 + j] = d.w;
+        }
+        return;
+    }
+#pragma unroll 2
+    for (int j = 0; j < 8; ++j) {
+        if (!((active >> j) & 1u)) continue;
+        float4 d = make_float4(px[j], px[8 + j], px[16 + j], px[24 + j]);
+        d = blend_pixel_generic(&s, stops, texels, (float)(x0 + 2u * (uint32_t)j), fy, l, cov[j], apply_clip,
+                                apply_clip ? clip[j * 32] : 1.0f, d);
+        px[j] = d.x;
+        px[8 + j] = d.y;
+        px[16 + j] = d.z;
+        px[24 + j] = d.w;
+    }
+}
+
 __device__ __noinline__ uint32_t srgb_bytes_any_order(float r, float g, float b, float a, const uint32_t* ch) {
     return pixel_to_srgb_bytes(r, g, b, a, ch);
 }
@@ -181,7 +219,20 @@ __device__ __noinline__ Rgba blend_solid(uint32_t mode, Rgba dst, Rgba src) { re
 constexpr int kPaintWarpsPerBlock = 2;
 
 // kMinBlocks trades registers for resident warps (8 -> 128 regs, 10 -> 96 regs).
-template <int kMinBlocks>
+//
+// kSlab selects the pixel <-> lane mapping of the per-entry work (everything per tile is the
+// same code):
+//   false  lane = (column x = lane / 2, rows 8 (lane % 2) .. +8): one f32x8 of the reference per
+//          lane; every entry costs the same ~550 warp instructions whatever it covers.
+//   true   lane = (column parity p = lane / 16, row r = lane % 16); the tile is walked in eight
+//          "slabs" of two columns, left to right, carrying the running cover of the lane's row
+//          in a register. Slabs left / right of the entry's segments only see the carry / the
+//          final cover, slabs without any coverage are skipped by the whole warp, and only the
+//          cells of touched slabs are read and re-zeroed: the cost follows the covered area
+//          (profiles/r1_paint_kernel_analysis.md). Per-pixel arithmetic is the same.
+//          EXPERIMENTAL: selected with FORMA_PAINT_KERNEL=slab only; written after the GPU
+//          budget of round 1 was spent, so it has not run on a device yet.
+template <int kMinBlocks, bool kSlab>
 __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_kernel(PaintScene S, PaintInputs in, uint32_t n_tiles) {
     __shared__ int32_t s_area[kPaintWarpsPerBlock][256];
     __shared__ int32_t s_cover[kPaintWarpsPerBlock][256];
@@ -430,120 +481,253 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 const EntryHdr er = bcast_hdr(mine, (int)k);
                 const uint32_t fill_rule = meta_fill_rule(er.meta);
 
-                // acc_segment: scatter-add the cell's segments (cpu/painter/mod.rs:257-271).
-                int32_t a8[8];
-                uint32_t run_lo, run_hi;  // running covers of rows 0-3 / 4-7 of this lane's half, packed i8
-                if (er.seg1 > er.seg0) {
-                    for (uint32_t i = er.seg0 + lane; i < er.seg1; i += 32u) {
-                        uint64_t s = (i < er.seg0 + 32u) ? first_seg : in.segs[i];
-                        uint32_t cell = cell_index((uint32_t)(s >> 16) & 15u, (uint32_t)(s >> 12) & 15u);
-                        int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
-                        int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
-                        atomicAdd(&area[cell], dam * cv);
-                        atomicAdd(&cover[cell], cv);
-                    }
-                    __syncwarp();
-                    uint32_t c_lo = 0, c_hi = 0;
-#pragma unroll
-                    for (int l = 0; l < 8; ++l) {
-                        int idx = l * 32 + (int)lane;  // == cell_index(x, half * 8 + l)
-                        a8[l] = (int32_t)(int16_t)area[idx];
-                        uint32_t cb = (uint32_t)cover[idx] & 0xFFu;
-                        if (l < 4) c_lo |= cb << (8 * l);
-                        else c_hi |= cb << (8 * (l - 4));
-                        area[idx] = 0;
-                        cover[idx] = 0;
-                    }
-                    // Exclusive prefix over columns x' < x (same half): lanes l-2, l-4, ...
-                    uint32_t i_lo = c_lo, i_hi = c_hi;
-#pragma unroll
-                    for (int o = 2; o < 32; o <<= 1) {
-                        uint32_t n_lo = __shfl_up_sync(kFullMask, i_lo, o);
-                        uint32_t n_hi = __shfl_up_sync(kFullMask, i_hi, o);
-                        if (lane >= (uint32_t)o) {
-                            i_lo = __vadd4(i_lo, n_lo);
-                            i_hi = __vadd4(i_hi, n_hi);
+                if constexpr (kSlab) {
+                    // ---- slab walk (see the comment above the kernel) --------------------
+                    const uint32_t row = lane & 15u, par = lane >> 4;
+                    // acc_segment (cpu/painter/mod.rs:257-271) into column-major cells: the cell of
+                    // (column 2 j + par, row) is word 32 j + lane, so a slab is one conflict-free access.
+                    uint32_t x_lo = 16u, x_hi = 0u;  // columns this entry's segments touch
+                    if (er.seg1 > er.seg0) {
+                        for (uint32_t i = er.seg0 + lane; i < er.seg1; i += 32u) {
+                            uint64_t s = (i < er.seg0 + 32u) ? first_seg : in.segs[i];
+                            const uint32_t lx = (uint32_t)(s >> 16) & 15u, ly = (uint32_t)(s >> 12) & 15u;
+                            int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+                            int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
+                            atomicAdd(&area[lx * 16u + ly], dam * cv);
+                            atomicAdd(&cover[lx * 16u + ly], cv);
+                            x_lo = min(x_lo, lx);
+                            x_hi = max(x_hi, lx);
                         }
+                        x_lo = __reduce_min_sync(kFullMask, x_lo);
+                        x_hi = __reduce_max_sync(kFullMask, x_hi);
+                        __syncwarp();
                     }
-                    uint32_t e_lo = __shfl_up_sync(kFullMask, i_lo, 2);
-                    uint32_t e_hi = __shfl_up_sync(kFullMask, i_hi, 2);
-                    if (lane < 2u) e_lo = e_hi = 0u;
-                    run_lo = __vadd4(e_lo, half ? er.carry.z : er.carry.x);
-                    run_hi = __vadd4(e_hi, half ? er.carry.w : er.carry.y);
-                    __syncwarp();
-                } else {
-#pragma unroll
-                    for (int l = 0; l < 8; ++l) a8[l] = 0;
-                    run_lo = half ? er.carry.z : er.carry.x;
-                    run_hi = half ? er.carry.w : er.carry.y;
-                }
+                    const bool has_cells = x_lo <= x_hi;
+                    const uint32_t s_first = x_lo >> 1, s_last = x_hi >> 1;  // slabs with cells (if has_cells)
 
-                if (clip_active && clip_last < er.layer) clip_active = false;  // mod.rs:302-306
-
-                float cov[8];
-                bool all_zero = true;
-#pragma unroll
-                for (int l = 0; l < 8; ++l) {
-                    uint32_t byte = ((l < 4 ? run_lo : run_hi) >> (8 * (l & 3))) & 0xFFu;
-                    int32_t doubled = 32 * (int32_t)(int8_t)byte + a8[l];  // compute_doubled_areas, mod.rs:388-404
-                    cov[l] = coverage_of(doubled, fill_rule);
-                    all_zero = all_zero && (cov[l] == 0.0f);
-                }
-
-                if (meta_func(er.meta) == 1u) {  // clip_at, mod.rs:449-464
-                    if (!clip_active) {
+                    if (clip_active && clip_last < er.layer) clip_active = false;  // mod.rs:302-306
+                    const bool is_clip = meta_func(er.meta) == 1u;
+                    if (is_clip && !clip_active) {  // clip_at, mod.rs:449-464
                         clip_active = true;
                         clip_last = er.layer + er.clip_layers;
                     }
-#pragma unroll
-                    for (int l = 0; l < 8; ++l) clip_mask[l * 32] = cov[l];
-                    continue;
-                }
-                const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
-                if (all_zero) continue;                    // mod.rs:317-319 (whole f32x8 is zero)
-                if (apply_clip && !clip_active) continue;  // mod.rs:321-323
+                    const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
+                    const bool draws = !is_clip && !(apply_clip && !clip_active);  // mod.rs:321-323
 
-                const uint32_t mode = meta_blend(er.meta);
-                const uint32_t fill_type = meta_fill_type(er.meta);
-                // blend_at, mod.rs:406-447. The mode / fill dispatch is hoisted out of
-                // the pixel loop: a solid `Over` layer (by far the most common) is
-                // straight-line code; everything else goes through one out-of-line
-                // helper per pixel so that the kernel stays small enough for the
-                // instruction cache.
-                if (fill_type == 0u && mode == 0u) {
+                    // Running cover of this lane's row over the columns left of the current slab
+                    // (i8, wrapping like the reference's lanes), starting from the carry-in.
+                    const uint32_t cw = row < 4u ? er.carry.x : row < 8u ? er.carry.y : row < 12u ? er.carry.z : er.carry.w;
+                    int32_t run = (int32_t)(int8_t)((cw >> (8u * (row & 3u))) & 0xFFu);
+                    // Slabs without cells see 32 * run only: one coverage before the cells, one after.
+                    float cov_flat = coverage_of(32 * run, fill_rule);
+                    uint32_t nz_flat = __ballot_sync(kFullMask, cov_flat != 0.0f);
+
+                    float cov[8];
+                    uint32_t act = 0u;  // bit j: this lane's f32x8 of slab j has a non-zero coverage
 #pragma unroll
-                    for (int l = 0; l < 8; ++l) {
-                        float sa = er.color[3] * cov[l];
-                        if (apply_clip) sa *= clip_mask[l * 32];
-                        float inv_dst_a_src_a = (1.0f - da[l]) * sa;
-                        float inv_src_a = 1.0f - sa;
-                        float dst_a_src_a = da[l] * sa;
-                        float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
-                        float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
-                        float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
-                        dr[l] = fmaf(dr[l], inv_src_a, cr);
-                        dg[l] = fmaf(dg[l], inv_src_a, cg);
-                        db[l] = fmaf(db[l], inv_src_a, cb);
-                        da[l] = fmaf(da[l], inv_src_a, sa);
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t nz;
+                        if (has_cells && (uint32_t)j >= s_first && (uint32_t)j <= s_last) {
+                            const int idx = j * 32 + (int)lane;
+                            const int32_t a = (int32_t)(int16_t)area[idx];
+                            const int32_t c = (int32_t)(int8_t)cover[idx];
+                            area[idx] = 0;
+                            cover[idx] = 0;
+                            const int32_t c_other = __shfl_xor_sync(kFullMask, c, 16);
+                            // column 2 j sees the covers left of the slab, column 2 j + 1 also column 2 j's
+                            const int32_t here = (int32_t)(int8_t)(run + (par ? c_other : 0));
+                            cov[j] = coverage_of(32 * here + a, fill_rule);  // compute_doubled_areas, mod.rs:388-404
+                            run = (int32_t)(int8_t)(run + c + c_other);
+                            nz = __ballot_sync(kFullMask, cov[j] != 0.0f);
+                            if ((uint32_t)j == s_last) {  // right of the cells only the final cover counts
+                                cov_flat = coverage_of(32 * run, fill_rule);
+                                nz_flat = __ballot_sync(kFullMask, cov_flat != 0.0f);
+                            }
+                        } else {
+                            cov[j] = cov_flat;
+                            nz = nz_flat;
+                        }
+                        if (is_clip) clip_mask[j * 32] = cov[j];
+                        if ((nz >> (lane & 24u)) & 0xFFu) act |= 1u << j;
+                    }
+                    if (has_cells) __syncwarp();
+                    if (!draws) continue;
+                    const uint32_t slabs = __reduce_or_sync(kFullMask, act);  // slabs somebody covers (warp-uniform)
+                    if (!slabs) continue;
+
+                    const uint32_t mode = meta_blend(er.meta);
+                    const uint32_t fill_type = meta_fill_type(er.meta);
+                    if (fill_type == 0u && mode == 0u) {  // blend_at, mod.rs:406-447, solid `Over`
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (!((slabs >> j) & 1u)) continue;  // nobody covers slab j: skipped by the whole warp
+                            if (!((act >> j) & 1u)) continue;    // this lane's f32x8 is all zero (mod.rs:317-319)
+                            float sa = er.color[3] * cov[j];
+                            if (apply_clip) sa *= clip_mask[j * 32];
+                            float inv_dst_a_src_a = (1.0f - da[j]) * sa;
+                            float inv_src_a = 1.0f - sa;
+                            float dst_a_src_a = da[j] * sa;
+                            float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
+                            float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
+                            float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
+                            dr[j] = fmaf(dr[j], inv_src_a, cr);
+                            dg[j] = fmaf(dg[j], inv_src_a, cg);
+                            db[j] = fmaf(db[j], inv_src_a, cb);
+                            da[j] = fmaf(da[j], inv_src_a, sa);
+                        }
+                    } else if (act) {
+                        const StyleRec* st = &S.styles[er.slot];
+                        float px[32];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            px[j] = dr[j]; px[8 + j] = dg[j]; px[16 + j] = db[j]; px[24 + j] = da[j];
+                        }
+                        blend_row_generic(st, S.stops, S.texels, tx * 16u + par, (float)((row >> 3) * 8u + ty * 16u), (int)(row & 7u), cov,
+                                          act, apply_clip, clip_mask, px);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            dr[j] = px[j]; dg[j] = px[8 + j]; db[j] = px[16 + j]; da[j] = px[24 + j];
+                        }
                     }
                 } else {
-                    const StyleRec* st = &S.styles[er.slot];
-                    float px[32], cv[8];
+                    // acc_segment: scatter-add the cell's segments (cpu/painter/mod.rs:257-271).
+                    int32_t a8[8];
+                    uint32_t run_lo, run_hi;  // running covers of rows 0-3 / 4-7 of this lane's half, packed i8
+                    if (er.seg1 > er.seg0) {
+                        for (uint32_t i = er.seg0 + lane; i < er.seg1; i += 32u) {
+                            uint64_t s = (i < er.seg0 + 32u) ? first_seg : in.segs[i];
+                            uint32_t cell = cell_index((uint32_t)(s >> 16) & 15u, (uint32_t)(s >> 12) & 15u);
+                            int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+                            int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
+                            atomicAdd(&area[cell], dam * cv);
+                            atomicAdd(&cover[cell], cv);
+                        }
+                        __syncwarp();
+                        uint32_t c_lo = 0, c_hi = 0;
 #pragma unroll
-                    for (int l = 0; l < 8; ++l) {
-                        px[l] = dr[l]; px[8 + l] = dg[l]; px[16 + l] = db[l]; px[24 + l] = da[l];
-                        cv[l] = cov[l];
+                        for (int l = 0; l < 8; ++l) {
+                            int idx = l * 32 + (int)lane;  // == cell_index(x, half * 8 + l)
+                            a8[l] = (int32_t)(int16_t)area[idx];
+                            uint32_t cb = (uint32_t)cover[idx] & 0xFFu;
+                            if (l < 4) c_lo |= cb << (8 * l);
+                            else c_hi |= cb << (8 * (l - 4));
+                            area[idx] = 0;
+                            cover[idx] = 0;
+                        }
+                        // Exclusive prefix over columns x' < x (same half): lanes l-2, l-4, ...
+                        uint32_t i_lo = c_lo, i_hi = c_hi;
+#pragma unroll
+                        for (int o = 2; o < 32; o <<= 1) {
+                            uint32_t n_lo = __shfl_up_sync(kFullMask, i_lo, o);
+                            uint32_t n_hi = __shfl_up_sync(kFullMask, i_hi, o);
+                            if (lane >= (uint32_t)o) {
+                                i_lo = __vadd4(i_lo, n_lo);
+                                i_hi = __vadd4(i_hi, n_hi);
+                            }
+                        }
+                        uint32_t e_lo = __shfl_up_sync(kFullMask, i_lo, 2);
+                        uint32_t e_hi = __shfl_up_sync(kFullMask, i_hi, 2);
+                        if (lane < 2u) e_lo = e_hi = 0u;
+                        run_lo = __vadd4(e_lo, half ? er.carry.z : er.carry.x);
+                        run_hi = __vadd4(e_hi, half ? er.carry.w : er.carry.y);
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) a8[l] = 0;
+                        run_lo = half ? er.carry.z : er.carry.x;
+                        run_hi = half ? er.carry.w : er.carry.y;
                     }
-                    blend_column_generic(st, S.stops, S.texels, fx, fy, cv, apply_clip, clip_mask, px);
+
+                    if (clip_active && clip_last < er.layer) clip_active = false;  // mod.rs:302-306
+
+                    float cov[8];
+                    bool all_zero = true;
 #pragma unroll
                     for (int l = 0; l < 8; ++l) {
-                        dr[l] = px[l]; dg[l] = px[8 + l]; db[l] = px[16 + l]; da[l] = px[24 + l];
+                        uint32_t byte = ((l < 4 ? run_lo : run_hi) >> (8 * (l & 3))) & 0xFFu;
+                        int32_t doubled = 32 * (int32_t)(int8_t)byte + a8[l];  // compute_doubled_areas, mod.rs:388-404
+                        cov[l] = coverage_of(doubled, fill_rule);
+                        all_zero = all_zero && (cov[l] == 0.0f);
+                    }
+
+                    if (meta_func(er.meta) == 1u) {  // clip_at, mod.rs:449-464
+                        if (!clip_active) {
+                            clip_active = true;
+                            clip_last = er.layer + er.clip_layers;
+                        }
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) clip_mask[l * 32] = cov[l];
+                        continue;
+                    }
+                    const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
+                    if (all_zero) continue;                    // mod.rs:317-319 (whole f32x8 is zero)
+                    if (apply_clip && !clip_active) continue;  // mod.rs:321-323
+
+                    const uint32_t mode = meta_blend(er.meta);
+                    const uint32_t fill_type = meta_fill_type(er.meta);
+                    // blend_at, mod.rs:406-447. The mode / fill dispatch is hoisted out of
+                    // the pixel loop: a solid `Over` layer (by far the most common) is
+                    // straight-line code; everything else goes through one out-of-line
+                    // helper per pixel so that the kernel stays small enough for the
+                    // instruction cache.
+                    if (fill_type == 0u && mode == 0u) {
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            float sa = er.color[3] * cov[l];
+                            if (apply_clip) sa *= clip_mask[l * 32];
+                            float inv_dst_a_src_a = (1.0f - da[l]) * sa;
+                            float inv_src_a = 1.0f - sa;
+                            float dst_a_src_a = da[l] * sa;
+                            float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
+                            float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
+                            float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
+                            dr[l] = fmaf(dr[l], inv_src_a, cr);
+                            dg[l] = fmaf(dg[l], inv_src_a, cg);
+                            db[l] = fmaf(db[l], inv_src_a, cb);
+                            da[l] = fmaf(da[l], inv_src_a, sa);
+                        }
+                    } else {
+                        const StyleRec* st = &S.styles[er.slot];
+                        float px[32], cv[8];
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            px[l] = dr[l]; px[8 + l] = dg[l]; px[16 + l] = db[l]; px[24 + l] = da[l];
+                            cv[l] = cov[l];
+                        }
+                        blend_column_generic(st, S.stops, S.texels, fx, fy, cv, apply_clip, clip_mask, px);
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) {
+                            dr[l] = px[l]; dg[l] = px[8 + l]; db[l] = px[16 + l]; da[l] = px[24 + l];
+                        }
                     }
                 }
             }
         }
 
         // compute_srgb + LinearLayout::write (mod.rs:466-483, layout/mod.rs:265-282).
+        if constexpr (kSlab) {
+            // Pixel j of a lane is (2 j + par, row): transpose through the (now idle) clip-mask
+            // words so that a store instruction writes two whole 64-byte tile rows.
+            uint32_t* stage = reinterpret_cast<uint32_t*>(s_clip[warp]);
+            const uint32_t row = lane & 15u, par = lane >> 4;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                stage[row * 16u + 2u * (uint32_t)j + par] =
+                    rgba_order ? pixel_to_srgb_bytes_rgba(dr[j], dg[j], db[j], da[j])
+                               : srgb_bytes_any_order(dr[j], dg[j], db[j], da[j], S.channels);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t w = (uint32_t)k * 32u + lane;
+                const uint32_t py = ty * 16u + (w >> 4), qx = tx * 16u + (w & 15u);
+                if (qx < S.width && py < S.height)
+                    *reinterpret_cast<uint32_t*>(in.framebuffer + (size_t)py * S.stride + (size_t)qx * 4u) = stage[w];
+            }
+            __syncwarp();
+            continue;
+        }
         const uint32_t px = tx * 16u + x;
         if (px < S.width) {
 #pragma unroll
@@ -598,12 +782,15 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
     // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy.
     // FORMA_PAINT_REGS=96 selects the 96-register build (default: 128 registers,
     // measured 17 % faster on paris@4K: fewer spills beat the extra warps).
+    // FORMA_PAINT_KERNEL=slab selects the experimental slab mapping (see paint_kernel).
     static int blocks_per_sm = 0, variant = 0;
     if (!blocks_per_sm) {
         const char* e = getenv("FORMA_PAINT_REGS");
-        variant = (e && atoi(e) == 96) ? 10 : 8;
-        if (variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<10>, kPaintWarpsPerBlock * 32, 0);
+        const char* k = getenv("FORMA_PAINT_KERNEL");
+        variant = (k && !strcmp(k, "slab")) ? 1 : (e && atoi(e) == 96) ? 10 : 8;
+        if (variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8, false>, kPaintWarpsPerBlock * 32, 0);
+        else if (variant == 10) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<10, false>, kPaintWarpsPerBlock * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8, true>, kPaintWarpsPerBlock * 32, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     int sms = 148, dev = 0;
@@ -611,8 +798,9 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint32_t want = (uint32_t)(blocks_per_sm * sms);
     uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
-    if (variant == 8) paint_kernel<8><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
-    else paint_kernel<10><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    if (variant == 8) paint_kernel<8, false><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    else if (variant == 10) paint_kernel<10, false><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    else paint_kernel<8, true><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
 }
 
 }  // namespace forma

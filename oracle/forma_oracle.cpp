@@ -29,7 +29,11 @@ void sort_segments(std::vector<uint64_t>& segs) {
         std::sort(segs.begin(), segs.end(), [](uint64_t a, uint64_t b) { return (a >> kSortShift) < (b >> kSortShift); });
         return;
     }
-    std::vector<uint64_t> tmp(n);
+    // The ping-pong buffer is kept between frames, like the reference keeps its segment
+    // vector (cpu/renderer.rs:57): a fresh 8 n-byte allocation per frame costs more in page
+    // faults than a radix pass.
+    static thread_local std::vector<uint64_t> tmp;
+    if (tmp.size() < n) tmp.resize(n);
     uint64_t* src = segs.data();
     uint64_t* dst = tmp.data();
     const int kRadixBits = 11, kBuckets = 1 << kRadixBits;

@@ -257,7 +257,15 @@ struct Composition {
         size_t n = ids.empty() ? 0 : ids.size() - 1;
         if (x.size() < 2) n = 0;
         out.resize(n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel
+        {
+        // id -> order -> layer (segment.rs:141-149: two FxHashMap look-ups per point). `layers` is an
+        // ordered map here, so the result is remembered while consecutive points share their id;
+        // otherwise this loop would pay a tree walk per point that the reference does not.
+        uint64_t memo_id = 0;
+        const Layer* memo_layer = nullptr;
+        uint32_t memo_order = 0;
+#pragma omp for schedule(static)
         for (size_t i = 0; i < n; ++i) {
             auto empty = [&] {
                 out.orders[i] = 0;
@@ -267,13 +275,22 @@ struct Composition {
             };
             uint64_t id = ids[i];
             if (id == 0) { empty(); continue; }
-            auto oit = geom_id_to_order.find(id);
-            if (oit == geom_id_to_order.end() || oit->second < 0) { empty(); continue; }
-            auto lit = layers.find((uint32_t)oit->second);
-            if (lit == layers.end()) { empty(); continue; }
-            const Layer& layer = *lit->second;
+            if (id != memo_id) {
+                memo_id = id;
+                memo_layer = nullptr;
+                auto oit = geom_id_to_order.find(id);
+                if (oit != geom_id_to_order.end() && oit->second >= 0) {
+                    auto lit = layers.find((uint32_t)oit->second);
+                    if (lit != layers.end()) {
+                        memo_layer = lit->second;
+                        memo_order = lit->first;
+                    }
+                }
+            }
+            if (!memo_layer) { empty(); continue; }
+            const Layer& layer = *memo_layer;
             if (!layer.is_enabled) { empty(); continue; }
-            uint32_t order = lit->first;
+            uint32_t order = memo_order;
 
             Point p0{x[i], y[i]}, p1{x[i + 1], y[i + 1]};
             if (layer.has_transform) {
@@ -299,6 +316,7 @@ struct Composition {
             out.c[i] = tox;
             out.d[i] = toy;
             out.lengths[i] = integers_between(p0.x, p1.x) + integers_between(p0.y, p1.y) + 1;
+        }
         }
         uint32_t sum = 0;
         for (size_t i = 0; i < n; ++i) {

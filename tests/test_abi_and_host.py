@@ -100,7 +100,7 @@ def test_layer_bookkeeping_scales():
     assert len(comp) == 1
     comp.get(7).drop()
     assert comp.is_empty()
-    assert time.perf_counter() - t0 < 5.0
+    assert time.perf_counter() - t0 < 10.0  # ~0.2 s here; a scan per drop is quadratic (tens of seconds at this size)
 
 
 def test_renderer_requires_a_gpu():

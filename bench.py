@@ -231,6 +231,9 @@ def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        sys.exit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE is {world}; launch one rank per GPU with "
+                 f"`python -m torch.distributed.run --nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...`")
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device. The forma_b200 arm has no CPU fallback; "
                  "`--impl reference` times the CPU restatement of the reference instead.")

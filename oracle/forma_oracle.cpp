@@ -132,7 +132,7 @@ static void render(Renderer& r, Composition& comp, const RenderTarget& rt, const
     double t3 = now_ms();
 
     PropsSource props;
-    props.layers = &comp.layers;
+    props.index(comp.layers);
     props.has_cache = cache != nullptr;
     props.cache_id = cache ? cache->id : 0;
 

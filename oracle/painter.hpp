@@ -486,13 +486,46 @@ struct Painter {
                 for (int half = 0; half < 2; ++half) {
                     float cov[8];
                     bool all_zero = true;
-                    for (int l = 0; l < 8; ++l) {
-                        cov[l] = coverage_of(da[half * 8 + l], props.fill_rule);
-                        if (!(cov[l] == 0.0f)) all_zero = false;
+                    if (props.fill_rule == kNonZero) {
+                        for (int l = 0; l < 8; ++l) cov[l] = coverage_of(da[half * 8 + l], kNonZero);
+                    } else {
+                        for (int l = 0; l < 8; ++l) cov[l] = coverage_of(da[half * 8 + l], kEvenOdd);
                     }
+                    for (int l = 0; l < 8; ++l)
+                        if (!(cov[l] == 0.0f)) all_zero = false;
                     if (props.func == kDraw) {
                         if (all_zero) continue;
                         if (apply_clip && !clip_active) continue;
+                        if (props.fill_type == kSolid && props.blend_mode == kOver) {
+                            // The f32x8 of the reference (cpu/painter/mod.rs:406-447) for the common
+                            // style, written so that the compiler turns it into 8-lane AVX2 code like
+                            // the reference's SIMD shim: same operations as blend_at with blend = src.
+                            const int base = px * kTile + half * 8;
+                            const float sr = props.color.r, sg = props.color.g, sb = props.color.b, fa = props.color.a;
+                            const bool clip = apply_clip && clip_active;
+                            float* __restrict__ pr = red + base;
+                            float* __restrict__ pg = green + base;
+                            float* __restrict__ pb = blue + base;
+                            float* __restrict__ pa = alpha + base;
+                            const float* __restrict__ pm = clip_mask + base;
+#pragma GCC ivdep
+                            for (int l = 0; l < 8; ++l) {
+                                float sa = fa * cov[l];
+                                if (clip) sa *= pm[l];
+                                const float da_ = pa[l];
+                                const float inv_dst_a_src_a = (1.0f - da_) * sa;
+                                const float inv_src_a = 1.0f - sa;
+                                const float dst_a_src_a = da_ * sa;
+                                const float cr = std::fmaf(sr, inv_dst_a_src_a, sr * dst_a_src_a);
+                                const float cg = std::fmaf(sg, inv_dst_a_src_a, sg * dst_a_src_a);
+                                const float cb = std::fmaf(sb, inv_dst_a_src_a, sb * dst_a_src_a);
+                                pr[l] = std::fmaf(pr[l], inv_src_a, cr);
+                                pg[l] = std::fmaf(pg[l], inv_src_a, cg);
+                                pb[l] = std::fmaf(pb[l], inv_src_a, cb);
+                                pa[l] = std::fmaf(da_, inv_src_a, sa);
+                            }
+                            continue;
+                        }
                         float fx = (float)(px + tile_x * kTile);
                         float fy = (float)(half * 8 + tile_y * kTile);
                         for (int l = 0; l < 8; ++l) {
@@ -550,33 +583,50 @@ struct Painter {
 
     // cpu/painter/mod.rs:466-483
     void compute_srgb(const Channel ch[4]) {
-        for (int i = 0; i < kTile * kTile; ++i) {
-            float r = linear_to_srgb(red[i]), g = linear_to_srgb(green[i]), b = linear_to_srgb(blue[i]);
-            float a = alpha[i];
-            for (int k = 0; k < 4; ++k) {
-                float v;
-                switch (ch[k]) {
-                    case kRed: v = r; break;
-                    case kGreen: v = g; break;
-                    case kBlue: v = b; break;
-                    case kAlpha: v = a; break;
-                    case kZero: v = 0.0f; break;
-                    default: v = 1.0f; break;
-                }
-                srgb[i * 4 + k] = to_byte(v);
+        // Plane by plane (vectorisable like the reference's f32x8 code), then interleaved in
+        // the requested channel order.
+        alignas(32) uint8_t plane[6][kTile * kTile];
+        for (int i = 0; i < kTile * kTile; ++i) plane[0][i] = to_byte(linear_to_srgb(red[i]));
+        for (int i = 0; i < kTile * kTile; ++i) plane[1][i] = to_byte(linear_to_srgb(green[i]));
+        for (int i = 0; i < kTile * kTile; ++i) plane[2][i] = to_byte(linear_to_srgb(blue[i]));
+        for (int i = 0; i < kTile * kTile; ++i) plane[3][i] = to_byte(alpha[i]);
+        std::memset(plane[4], to_byte(0.0f), sizeof(plane[4]));
+        std::memset(plane[5], to_byte(1.0f), sizeof(plane[5]));
+        const uint8_t* src[4];
+        for (int k = 0; k < 4; ++k) {
+            switch (ch[k]) {
+                case kRed: src[k] = plane[0]; break;
+                case kGreen: src[k] = plane[1]; break;
+                case kBlue: src[k] = plane[2]; break;
+                case kAlpha: src[k] = plane[3]; break;
+                case kZero: src[k] = plane[4]; break;
+                default: src[k] = plane[5]; break;
             }
+        }
+        for (int i = 0; i < kTile * kTile; ++i) {
+            srgb[i * 4 + 0] = src[0][i];
+            srgb[i * 4 + 1] = src[1][i];
+            srgb[i * 4 + 2] = src[2][i];
+            srgb[i * 4 + 3] = src[3][i];
         }
     }
 };
 
+// LayerProps (cpu/painter/mod.rs:164-167). The reference answers `get` with a hash look-up
+// (FxHashMap); here the layers are spread once per frame into an array indexed by order, so
+// that the per-(tile, layer) look-ups of the painter cost no more than they do there.
 struct PropsSource {
-    const std::map<uint32_t, Layer*>* layers;
+    std::vector<const Layer*> by_order;
     bool has_cache = false;
     uint8_t cache_id = 0;
-    const Props& get(uint32_t id) const { return layers->at(id)->props; }
+    void index(const std::map<uint32_t, Layer*>& layers) {
+        by_order.assign(layers.empty() ? 0 : (size_t)layers.rbegin()->first + 1, nullptr);
+        for (auto& kv : layers) by_order[kv.first] = kv.second;
+    }
+    const Props& get(uint32_t id) const { return by_order.at(id)->props; }
     bool is_unchanged(uint32_t id) const {
         if (!has_cache) return false;
-        return (layers->at(id)->is_unchanged >> cache_id) & 1;
+        return (by_order.at(id)->is_unchanged >> cache_id) & 1;
     }
 };
 
@@ -594,17 +644,30 @@ struct TileContext {
 
 // layer_workbench/mod.rs:147-343 + passes/*.rs
 struct Workbench {
+    // The reference keeps `segment_ranges`, `queue_indices` and `skip_clipping` in per-tile
+    // FxHashMaps keyed by layer id. Both the segments of a tile and the carry queue are ordered
+    // by layer id, so here the same look-ups are binary searches over those two sorted arrays
+    // and a flag next to each id — same answers, no per-tile node allocations.
     struct Id {
         uint32_t id;
         bool mask;
+        bool skip_clipping;
+    };
+    struct SegRange {
+        uint32_t id;
+        size_t first, last;  // inclusive
     };
     std::vector<Id> ids;
     size_t skipped = 0;
-    std::map<uint32_t, std::pair<size_t, size_t>> segment_ranges;  // inclusive
-    std::map<uint32_t, size_t> queue_indices;
-    std::vector<CoverCarry> queue, next_queue;
-    std::map<uint32_t, bool> skip_clipping;
+    std::vector<SegRange> segment_ranges;        // ascending ids
+    std::vector<CoverCarry> queue, next_queue;   // ascending layer ids
     bool layers_were_removed = true;
+
+    const SegRange* segments_of(uint32_t id) const {
+        auto it = std::lower_bound(segment_ranges.begin(), segment_ranges.end(), id,
+                                   [](const SegRange& r, uint32_t v) { return r.id < v; });
+        return it != segment_ranges.end() && it->id == id ? &*it : nullptr;
+    }
 
     void init(std::vector<CoverCarry>&& carries) { queue = std::move(carries); }
 
@@ -612,18 +675,17 @@ struct Workbench {
         ids.clear();
         skipped = 0;
         segment_ranges.clear();
-        queue_indices.clear();
         std::swap(queue, next_queue);
         next_queue.clear();
-        skip_clipping.clear();
         layers_were_removed = true;
     }
 
     const Cover* cover(uint32_t id) const {
-        auto it = queue_indices.find(id);
-        return it == queue_indices.end() ? nullptr : &queue[it->second].cover;
+        auto it = std::lower_bound(queue.begin(), queue.end(), id,
+                                   [](const CoverCarry& c, uint32_t v) { return c.layer_id < v; });
+        return it != queue.end() && it->layer_id == id ? &it->cover : nullptr;
     }
-    bool has_segments(uint32_t id) const { return segment_ranges.count(id) != 0; }
+    bool has_segments(uint32_t id) const { return segments_of(id) != nullptr; }
     bool layer_is_full(uint32_t id, FillRule fr) const {
         if (has_segments(id)) return false;
         const Cover* c = cover(id);
@@ -633,9 +695,8 @@ struct Workbench {
     // layer_workbench/mod.rs:213-234
     bool cover_carry(const TileContext& ctx, uint32_t id, CoverCarry* out) const {
         Cover acc;
-        auto it = segment_ranges.find(id);
-        if (it != segment_ranges.end()) {
-            for (size_t i = it->second.first; i <= it->second.second; ++i) {
+        if (const SegRange* r = segments_of(id)) {
+            for (size_t i = r->first; i <= r->last; ++i) {
                 int y = seg_local_y(ctx.segs[i]);
                 acc.c[y] = (int8_t)(acc.c[y] + seg_cover(ctx.segs[i]));
             }
@@ -656,16 +717,22 @@ struct Workbench {
             uint32_t id = seg_layer(ctx.segs[start]);
             size_t end = start;
             while (end + 1 < ctx.n_segs && seg_layer(ctx.segs[end + 1]) == id) ++end;
-            segment_ranges[id] = {start, end};
+            segment_ranges.push_back({id, start, end});
             start = end + 1;
         }
-        for (size_t i = 0; i < queue.size(); ++i) queue_indices[queue[i].layer_id] = i;
-        std::vector<uint32_t> all;
-        for (auto& kv : segment_ranges) all.push_back(kv.first);
-        for (auto& kv : queue_indices) all.push_back(kv.first);
-        std::sort(all.begin(), all.end());
-        all.erase(std::unique(all.begin(), all.end()), all.end());
-        for (uint32_t id : all) ids.push_back({id, true});
+        // Union of the two ascending id lists (layers with segments, carried layers).
+        size_t a = 0, b = 0;
+        while (a < segment_ranges.size() || b < queue.size()) {
+            uint32_t id;
+            if (b == queue.size() || (a < segment_ranges.size() && segment_ranges[a].id <= queue[b].layer_id)) {
+                id = segment_ranges[a].id;
+                if (b < queue.size() && queue[b].layer_id == id) ++b;
+                ++a;
+            } else {
+                id = queue[b++].layer_id;
+            }
+            ids.push_back({id, true, false});
+        }
     }
 
     enum class Flow { Continue, BreakNone, BreakSolid };
@@ -716,7 +783,7 @@ struct Workbench {
             }
             if (props.func == kDraw && props.is_clipped) {
                 if (has_clip && id <= clip.last_layer_id) {
-                    if (clip.is_full) skip_clipping[id] = true;
+                    if (clip.is_full) ids[i].skip_clipping = true;
                     else clip.is_used = true;
                 } else {
                     ids[i].mask = false;
@@ -740,7 +807,7 @@ struct Workbench {
             uint32_t id = ids[k].id;
             const Props& props = ctx.props->get(id);
             if (!ctx.props->is_unchanged(id)) visible_unchanged = false;
-            bool is_clipped = props.func == kDraw && props.is_clipped && !skip_clipping.count(id);
+            bool is_clipped = props.func == kDraw && props.is_clipped && !ids[k].skip_clipping;
             if (is_clipped || !layer_is_full(id, props.fill_rule)) {
                 if (first == kNoneYet) first = kIncomplete;
             } else if (props.func == kDraw && props.fill_type == kSolid && props.blend_mode == kOver) {
@@ -833,13 +900,12 @@ struct Workbench {
             bool mask = k >= skipped && ids[k].mask;
             if (mask) {
                 painter.clear_cells();
-                auto it = segment_ranges.find(id);
-                if (it != segment_ranges.end())
-                    for (size_t i = it->second.first; i <= it->second.second; ++i) painter.acc_segment(ctx.segs[i]);
+                if (const SegRange* r = segments_of(id))
+                    for (size_t i = r->first; i <= r->last; ++i) painter.acc_segment(ctx.segs[i]);
                 if (const Cover* c = cover(id)) painter.acc_cover(*c);
                 const Props& props = ctx.props->get(id);
                 bool apply_clip = false;
-                if (props.func == kDraw) apply_clip = props.is_clipped && !skip_clipping.count(id);
+                if (props.func == kDraw) apply_clip = props.is_clipped && !ids[k].skip_clipping;
                 Cover out = painter.paint_layer(ctx.tile_x, ctx.tile_y, id, props, apply_clip);
                 if (!out.is_empty(props.fill_rule)) next_queue.push_back({out, id});
             } else {
@@ -887,8 +953,6 @@ inline void paint_tile_row(Painter& painter, Workbench& wb, size_t tile_y, const
     wb.ids.clear();
     wb.skipped = 0;
     wb.segment_ranges.clear();
-    wb.queue_indices.clear();
-    wb.skip_clipping.clear();
     wb.layers_were_removed = true;
 
     size_t width_in_tiles = (rt.width + kTile - 1) / kTile;

@@ -288,6 +288,9 @@ SIGNATURES = {
     "renderer_segments": (C.c_uint64, [_vp, C.c_uint64, _u64p]),
     "renderer_rasterize_only": (C.c_uint64, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u64p]),
     "renderer_sort_u64": (C.c_int, [_vp, _u64p, C.c_uint64]),
+    "debug_selftest": (C.c_int, [C.c_int, _u64p]),
+    "set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
 }
 
 
@@ -304,7 +307,7 @@ class Api:
                     continue
                 raise
             fn.restype, fn.argtypes = res, args
-            setattr(self, name, fn)
+            setattr(self, name + "_fn" if name in ("set_option", "get_option") else name, fn)
 
     def check(self, status: int, what: str) -> None:
         if status == 0:
@@ -313,6 +316,15 @@ class Api:
         if status == 2:
             raise OrderError(f"{what}: exceeded layer limit ({LAYER_LIMIT})")
         raise FormaError(f"{what}: status {status} {msg}")
+
+    def set_option(self, name: str, value: int) -> None:
+        """Schedule switch of the library (see include/forma_b200.h: forma_set_option)."""
+        self.check(self.__dict__["set_option_fn"](name.encode(), int(value)), f"set_option({name})")
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int(0)
+        self.check(self.__dict__["get_option_fn"](name.encode(), C.byref(v)), f"get_option({name})")
+        return int(v.value)
 
     # Constructors bound to this library -----------------------------------
     def PathBuilder(self) -> "PathBuilder":

@@ -33,6 +33,26 @@ constexpr int FORMA_STATUS_CAPACITY = 5;
 
 void set_error(const char* fmt, ...);
 
+// Function attributes (dynamic shared memory opt-in, carve-out) and occupancy-derived grids
+// are per device: the launchers cache them in tables indexed by the current device, so that
+// one process can drive renderers on several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device_index() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+inline int device_sm_count() {
+    static int sms[kMaxDevices] = {0};
+    const int d = current_device_index();
+    if (!sms[d]) {
+        int v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+        sms[d] = v > 0 ? v : 148;
+    }
+    return sms[d];
+}
+
 // Growable device buffer (never shrinks). 180 GB of HBM3e makes "keep the high
 // water mark" the right policy for per-frame scratch.
 template <class T>

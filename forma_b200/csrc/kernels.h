@@ -9,6 +9,20 @@
 
 namespace forma {
 
+// Schedule switches (none of them changes results). Initialised from the environment
+// (FORMA_<NAME>) on first use and settable at run time through forma_set_option(), which is
+// how the parity tests cover every value (tests/test_gpu_options.py).
+struct Options {
+    int speculate = 1;       // launch kernels ahead of their count read-backs (0: strictly after)
+    int band_copy = 1;       // host frames: paint / copy back in bands of tile rows
+    int copy_bands = 4;      //   ... how many (1..16)
+    int sort_full_key = 0;   // 1: sort the layer digits even when the inserts are in layer order
+    int sort_big_log2 = 19;  // key count from which the 4096-key tiles / reduce-then-scan passes are used
+    int test_gap_cap = 0;    // test hook: cap of the speculative carry-only-entry launch (0 = none)
+    int paint_lpt = 1;       // heavy tiles first (longest-processing-time order) in the paint kernel
+};
+Options& options();
+
 // Arguments of the fused line-setup + pixel-grid-intersection kernels.
 struct RasterArgs {
     const float* x;            // segment buffer (segment.rs:530-534)
@@ -37,6 +51,10 @@ void launch_line_count(const RasterArgs& args, uint32_t* block_sums, uint32_t* t
                        cudaStream_t stream);
 // Segments at positions >= cap are dropped (speculative launches, see Renderer::rasterize).
 void launch_raster_emit(const RasterArgs& args, const uint32_t* block_offsets, uint64_t* out, uint32_t cap, cudaStream_t stream);
+// Line records of the n = n_points - 1 point pairs (inspection only): orders, then
+// f = {x0, y0, dx, dy, a, b, c, d}, then the per-line segment counts.
+void launch_line_records(const RasterArgs& args, uint32_t n, uint32_t* orders, float* const f[8], uint32_t* lengths,
+                         cudaStream_t stream);
 // In-place exclusive scan of n u32 values; total[0] = sum. `state` (scan_state_words(n)
 // u64 words) enables the multi-CTA look-back scan for large n; nullptr = one CTA.
 size_t scan_state_words(uint32_t n);
@@ -143,10 +161,16 @@ struct EntryRec {  // 64 B
 void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,
                           const uint32_t* gid, uint32_t n_gaps, const uint32_t* cell_start, const uint4* carry_in,
                           const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st);
-void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,
-                        uint32_t* tile_end, cudaStream_t st);
-void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint32_t* tile_begin,
-                  const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st);
+// Per-tile entry ranges (zero for tiles without entries) and, when `heavy` is not null, the
+// lists of tiles with many entries: kHeavyListClasses arrays of tiles_x * tiles_y ids each,
+// their lengths in heavy_count[kHeavyListClasses] (both written here).
+constexpr int kHeavyListClasses = 4;
+void launch_tile_index(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint2* tile_range, uint32_t* heavy,
+                       uint32_t* heavy_count, cudaStream_t st);
+void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint2* tile_range, const uint32_t* heavy,
+                  const uint32_t* heavy_count, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st);
+// Packed fp32 (f32x2) arithmetic of the painter against scalar IEEE operations; mismatches are added to out[0].
+void launch_f32x2_selftest(const float* a, const float* b, const float* c, uint32_t n, uint32_t* out, cudaStream_t st);
 // Packs the tiles in S.written_list into `packed` (256 u32 per tile, row-major).
 void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st);
 

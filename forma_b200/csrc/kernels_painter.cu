@@ -5,17 +5,33 @@
 // (cpu/painter/mod.rs:290-483) and LinearLayout::write
 // (cpu/buffer/layout/mod.rs:265-282).
 //
-// Lane l owns pixel column x = l / 2 and rows 8*(l % 2) .. +8 of the tile:
-// exactly one f32x8 of the reference (cpu/painter/mod.rs:234-244), so the
-// reference's only cross-lane rule ("skip the f32x8 when all 8 coverages are
-// zero", mod.rs:317-319) is a per-thread test here.
+// Lane l owns eight horizontally consecutive pixels: row r = l / 2, columns 8 (l % 2) .. +8.
+//   * the winding cover of a pixel is the carry-in of its row plus the covers of the
+//     segments left of it in the same row: a running sum inside the lane and one shuffle
+//     for the right half (the reference sweeps its columns left to right,
+//     cpu/painter/mod.rs:388-404);
+//   * the lane's eight cells are two 16-byte words of shared memory and its eight output
+//     pixels one 32-byte run of the frame buffer;
+//   * an entry without segments has one coverage value per lane.
+// The reference's f32x8 is eight rows of one column; its "skip when all eight coverages
+// are zero" (mod.rs:317-319) is reproduced from eight ballots where it can matter (any
+// fill / blend other than a solid `Over`, for which blending with zero coverage is the
+// identity on finite values).
 //
-// Warps are persistent: each takes the next tile from an atomic counter, so
-// heavy tiles (dozens of translucent layers) do not hold back a whole CTA.
-// The per-layer metadata of a tile (segment range, carry-in, packed style) is
-// fetched by 32 lanes at once and handed round with shuffles, so the layer loop
-// itself contains no dependent global loads besides the segment words, whose
-// first chunk is prefetched one layer ahead.
+// Per (tile, layer) entry the segments are scatter-added into packed cells — area in the
+// high and cover in the low 16 bits of one word, one shared-memory atomic per segment —
+// one entry ahead of the blend: while entry k is blended from one cell buffer, entry k + 1
+// is accumulated into the other and the segments of entry k + 2 are in flight.
+//
+// Blend arithmetic runs on pixel pairs with Blackwell's packed fp32 instructions
+// (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): each half is the IEEE operation the
+// reference performs; additions and subtractions are written as fma(x, +-1, y), which is
+// the same single rounding, so that no product is ever contracted into a sum.
+//
+// Warps are persistent and take tiles by ticket. Tiles with many entries come first
+// (tile_index_kernel sorts them into four classes by entry count): a tile is painted by
+// one warp from its first to its last layer, so the heaviest tile bounds the kernel's
+// tail unless it starts early (longest-processing-time order).
 #include "paint_common.cuh"
 #include "paint_math.cuh"
 
@@ -24,22 +40,13 @@ namespace forma {
 struct PaintInputs {
     const uint64_t* segs;
     const EntryRec* recs;        // sorted entries (kernels_tables.cu: merge_entries_kernel)
-    const uint32_t* tile_begin;
-    const uint32_t* tile_end;
+    const uint2* tile_range;     // per tile: [begin, end) of its entries
+    const uint32_t* heavy;       // kHeavyClasses lists of heavy tiles (linear ids), n_tiles_total each
+    const uint32_t* heavy_count; // their lengths
+    uint32_t n_tiles_total;
     uint8_t* eflags;             // per sorted entry: optimizer flags, initialised with EntryRec::flags0
     uint8_t* framebuffer;
     uint32_t* tile_counter;
-};
-
-// Per-entry header, one entry per lane.
-struct EntryHdr {
-    uint32_t layer, seg0, seg1;
-    uint4 carry;
-    int32_t slot;
-    // packed style: fill_rule | func<<1 | is_clipped<<2 | fill_type<<3 | blend_mode<<5
-    uint32_t meta;
-    uint32_t clip_layers;
-    float color[4];
 };
 
 __device__ __forceinline__ uint32_t meta_fill_rule(uint32_t m) { return m & 1u; }
@@ -47,67 +54,103 @@ __device__ __forceinline__ uint32_t meta_func(uint32_t m) { return (m >> 1) & 1u
 __device__ __forceinline__ bool meta_is_clipped(uint32_t m) { return (m >> 2) & 1u; }
 __device__ __forceinline__ uint32_t meta_fill_type(uint32_t m) { return (m >> 3) & 3u; }
 __device__ __forceinline__ uint32_t meta_blend(uint32_t m) { return (m >> 5) & 15u; }
-__device__ __forceinline__ bool meta_unchanged(uint32_t m) { return (m >> 9) & 1u; }
 
-__device__ __forceinline__ EntryHdr load_hdr(const PaintInputs& in, uint32_t p) {
-    const uint4* q = reinterpret_cast<const uint4*>(in.recs + p);  // four independent 16-byte loads
-    const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-    EntryHdr h;
-    h.layer = q0.x;
-    h.seg0 = q0.y;
-    h.seg1 = q0.z;
-    h.meta = q0.w;
-    h.carry = q1;
-    h.color[0] = __uint_as_float(q2.x);
-    h.color[1] = __uint_as_float(q2.y);
-    h.color[2] = __uint_as_float(q2.z);
-    h.color[3] = __uint_as_float(q2.w);
-    h.slot = (int32_t)q3.x;
-    h.clip_layers = q3.y;
-    return h;
+// ---------------------------------------------------------------------------
+// Packed fp32 pairs
+// ---------------------------------------------------------------------------
+struct f2 {
+    float x, y;
+};
+__device__ __forceinline__ unsigned long long f2_bits(f2 v) {
+    return (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32);
 }
-
-__device__ __forceinline__ EntryHdr bcast_hdr(const EntryHdr& h, int src) {
-    EntryHdr o;
-    o.layer = __shfl_sync(kFullMask, h.layer, src);
-    o.seg0 = __shfl_sync(kFullMask, h.seg0, src);
-    o.seg1 = __shfl_sync(kFullMask, h.seg1, src);
-    o.carry.x = __shfl_sync(kFullMask, h.carry.x, src);
-    o.carry.y = __shfl_sync(kFullMask, h.carry.y, src);
-    o.carry.z = __shfl_sync(kFullMask, h.carry.z, src);
-    o.carry.w = __shfl_sync(kFullMask, h.carry.w, src);
-    o.slot = __shfl_sync(kFullMask, h.slot, src);
-    o.meta = __shfl_sync(kFullMask, h.meta, src);
-    o.clip_layers = __shfl_sync(kFullMask, h.clip_layers, src);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o.color[k] = __shfl_sync(kFullMask, h.color[k], src);
-    return o;
+__device__ __forceinline__ f2 f2_from(unsigned long long b) {
+    return f2{__uint_as_float((uint32_t)b), __uint_as_float((uint32_t)(b >> 32))};
 }
+__device__ __forceinline__ f2 f2_splat(float v) { return f2{v, v}; }
+#ifndef FORMA_SCALAR_PAIRS
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(r);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(r);
+}
+#else
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return f2{a.x * b.x, a.y * b.y}; }
+#endif
+// a + b and a - b as one fused operation each (exact product, one rounding: the IEEE sum).
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return fma2(a, f2_splat(1.0f), b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return fma2(b, f2_splat(-1.0f), a); }
+__device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.x, -a.y}; }
+__device__ __forceinline__ f2 min2(f2 a, f2 b) { return f2{fminf(a.x, b.x), fminf(a.y, b.y)}; }
+__device__ __forceinline__ f2 max2(f2 a, f2 b) { return f2{fmaxf(a.x, b.x), fmaxf(a.y, b.y)}; }
 
-__device__ __forceinline__ void store_tile_solid(const PaintScene& S, uint8_t* fb, uint32_t tx, uint32_t ty, uint32_t lane,
-                                                 uint32_t rgba) {
-    uint32_t px = tx * 16u + (lane >> 1);
-    uint32_t py0 = ty * 16u + (lane & 1u) * 8u;
-    if (px >= S.width) return;
-#pragma unroll
-    for (int l = 0; l < 8; ++l) {
-        uint32_t py = py0 + l;
-        if (py < S.height) *reinterpret_cast<uint32_t*>(fb + (size_t)py * S.stride + (size_t)px * 4u) = rgba;
+// The 12 separable blend modes of the vector macro blend_function! (styling.rs:438-592) on a
+// pixel pair, same operation order as vblend::blend (paint_math.cuh). `mode` is uniform.
+__device__ __forceinline__ f2 hard2(f2 d, f2 s, f2 sel) {
+    // sel <= 0.5 ? d * s * 2 : 2 * (d + s - fma(d, s, 0.5))
+    const f2 lo = mul2(mul2(d, s), f2_splat(2.0f));
+    const f2 hi = mul2(f2_splat(2.0f), sub2(add2(d, s), fma2(d, s, f2_splat(0.5f))));
+    return f2{sel.x <= 0.5f ? lo.x : hi.x, sel.y <= 0.5f ? lo.y : hi.y};
+}
+__device__ __forceinline__ float soft1(float d, float s) {
+    float dd = d <= 0.25f ? fmaf(fmaf(16.0f, d, -12.0f), d, 4.0f) * d : sqrtf(d);
+    float k = fmaf(2.0f, s, -1.0f);
+    return s <= 0.5f ? fmaf(d * (1.0f - d), k, d) : fmaf(dd - d, k, d);
+}
+__device__ __forceinline__ f2 blend_sep2(uint32_t mode, f2 d, f2 s) {
+    switch (mode) {
+        case 0: return s;
+        case 1: return mul2(d, s);
+        case 2: return add2(fma2(d, neg2(s), d), s);
+        case 3: return hard2(d, s, d);
+        case 4: return min2(d, s);
+        case 5: return max2(d, s);
+        case 6: return f2{s.x == 1.0f ? 1.0f : fminf(1.0f, d.x / (1.0f - s.x)), s.y == 1.0f ? 1.0f : fminf(1.0f, d.y / (1.0f - s.y))};
+        case 7:
+            return f2{s.x == 0.0f ? 0.0f : 1.0f - fminf(1.0f, (1.0f - d.x) / s.x),
+                      s.y == 0.0f ? 0.0f : 1.0f - fminf(1.0f, (1.0f - d.y) / s.y)};
+        case 8: return hard2(d, s, s);
+        case 9: return f2{soft1(d.x, s.x), soft1(d.y, s.y)};
+        case 10: {
+            const f2 t = sub2(d, s);
+            return f2{fabsf(t.x), fabsf(t.y)};
+        }
+        default: return add2(fma2(mul2(f2_splat(-2.0f), d), s, d), s);  // 11 Exclusion
     }
 }
 
-// Shared-memory cell of pixel (local_x, local_y): the 8 cells of lane l are at
-// l + 32*k, so a warp's row-k access touches 32 consecutive words (no bank
-// conflicts when the lanes read back / re-zero their own cells).
-__device__ __forceinline__ uint32_t cell_index(uint32_t lx, uint32_t ly) { return (ly & 7u) * 32u + lx * 2u + (ly >> 3); }
+// blend_at's composition (cpu/painter/mod.rs:434-446) for a pixel pair and one channel:
+//   current = fma(src, inv_dst_a * src_a, blended * (dst_a * src_a)); dst = fma(dst, 1 - src_a, current)
+__device__ __forceinline__ f2 compose2(f2 dst, f2 src, f2 blended, f2 inv_dst_a_src_a, f2 dst_a_src_a, f2 inv_src_a) {
+    const f2 cur = fma2(src, inv_dst_a_src_a, mul2(blended, dst_a_src_a));
+    return fma2(dst, inv_src_a, cur);
+}
 
-// blend_at for one pixel once its fill colour is known (cpu/painter/mod.rs:420-447).
-__device__ __forceinline__ float4 blend_fill(uint32_t mode, const float fill[4], float coverage, bool apply_clip, float clip,
-                                             float4 dst) {
+// ---------------------------------------------------------------------------
+// Out-of-line helpers for the rare paths (kept out of the kernel's instruction stream)
+// ---------------------------------------------------------------------------
+// One pixel of blend_at for any fill / blend mode.
+__device__ __noinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ st, const StopRec* __restrict__ stops,
+                                                   const uint16_t* __restrict__ texels, float fx, float fy_base, int l,
+                                                   float coverage, float clip, float4 dst) {
+    float fill[4];
+    if (st->fill_type == 0u) {
+        fill[0] = st->color[0]; fill[1] = st->color[1]; fill[2] = st->color[2]; fill[3] = st->color[3];
+    } else if (st->fill_type == 1u) {
+        gradient_at(*st, stops, fx, fy_base, l, fill);
+    } else {
+        texture_at(*st, texels, fx, fy_base, l, fill);
+    }
     float sa = fill[3] * coverage;
-    if (apply_clip) sa *= clip;
+    if (clip >= 0.0f) sa *= clip;  // clip < 0: no mask applies
     float bl[3];
-    vblend::blend(mode, dst.x, dst.y, dst.z, fill[0], fill[1], fill[2], bl);
+    vblend::blend(st->blend_mode, dst.x, dst.y, dst.z, fill[0], fill[1], fill[2], bl);
     float inv_dst_a = 1.0f - dst.w;
     float inv_dst_a_src_a = inv_dst_a * sa;
     float inv_src_a = 1.0f - sa;
@@ -119,96 +162,6 @@ __device__ __forceinline__ float4 blend_fill(uint32_t mode, const float fill[4],
                        fmaf(dst.w, inv_src_a, sa));
 }
 
-// One pixel of blend_at (cpu/painter/mod.rs:406-447) for any fill / blend
-// mode; only instantiated inside blend_column_generic (inlining it eight times
-// per layer into the kernel made the kernel 15k instructions long).
-__device__ __forceinline__ float4 blend_pixel_generic(const StyleRec* __restrict__ st, const StopRec* __restrict__ stops,
-                                                   const uint16_t* __restrict__ texels, float fx, float fy, int l,
-                                                   float coverage, bool apply_clip, float clip, float4 dst) {
-    float fill[4];
-    if (st->fill_type == 0u) {
-        fill[0] = st->color[0]; fill[1] = st->color[1]; fill[2] = st->color[2]; fill[3] = st->color[3];
-    } else if (st->fill_type == 1u) {
-        gradient_at(*st, stops, fx, fy, l, fill);
-    } else {
-        texture_at(*st, texels, fx, fy, l, fill);
-    }
-    return blend_fill(st->blend_mode, fill, coverage, apply_clip, clip, dst);
-}
-
-// The eight pixels of a lane (one f32x8) in one call: px = r[8] g[8] b[8] a[8] in
-// local memory. One call per layer instead of eight keeps the register
-// save / restore traffic around the call out of the pixel loop; the style record
-// (and, for gradients of up to four stops, the stops) are loaded once per call.
-__device__ __noinline__ void blend_column_generic(const StyleRec* __restrict__ st_ptr, const StopRec* __restrict__ stops,
-                                                  const uint16_t* __restrict__ texels, float fx, float fy,
-                                                  const float* __restrict__ cov, bool apply_clip,
-                                                  const float* __restrict__ clip /* stride 32 */, float* __restrict__ px) {
-    const StyleRec s = *st_ptr;
-    if (s.fill_type == 1u && s.stop_count <= 4u) {
-        const GradientSetup g = gradient_setup(s, stops);
-#pragma unroll 2  // measured: 1 -> 10.5 ms, 2 -> 7.4 ms, 4 -> 10.2 ms (spills) on circles8k
-        for (int l = 0; l < 8; ++l) {
-            float fill[4];
-            gradient_at_small(s, g, fx, fy, l, fill);
-            float4 d = blend_fill(s.blend_mode, fill, cov[l], apply_clip, apply_clip ? clip[l * 32] : 1.0f,
-                                  make_float4(px[l], px[8 + l], px[16 + l], px[24 + l]));
-            px[l] = d.x;
-            px[8 + l] = d.y;
-            px[16 + l] = d.z;
-            px[24 + l] = d.w;
-        }
-        return;
-    }
-#pragma unroll 2
-    for (int l = 0; l < 8; ++l) {
-        float4 d = make_float4(px[l], px[8 + l], px[16 + l], px[24 + l]);
-        d = blend_pixel_generic(&s, stops, texels, fx, fy, l, cov[l], apply_clip, apply_clip ? clip[l * 32] : 1.0f, d);
-        px[l] = d.x;
-        px[8 + l] = d.y;
-        px[16 + l] = d.z;
-        px[24 + l] = d.w;
-    }
-}
-
-// Slab mapping (paint_kernel<_, true>): the eight pixels of a lane lie in one row, pixel j
-// at x0 + 2 j; `active` bit j says whether this lane blends pixel j (its f32x8 of the
-// reference has a non-zero coverage, cpu/painter/mod.rs:317-319). (fy, l) is the f32x8 base
-// row and the row inside it, exactly the operands gradient_at / texture_at combine.
-__device__ __noinline__ void blend_row_generic(const StyleRec* __restrict__ st_ptr, const StopRec* __restrict__ stops,
-                                               const uint16_t* __restrict__ texels, uint32_t x0, float fy, int l,
-                                               const float* __restrict__ cov, uint32_t active, bool apply_clip,
-                                               const float* __restrict__ clip /* stride 32 */, float* __restrict__ px) {
-    const StyleRec s = *st_ptr;
-    if (s.fill_type == 1u && s.stop_count <= 4u) {
-        const GradientSetup g = gradient_setup(s, stops);
-#pragma unroll 2
-        for (int j = 0; j < 8; ++j) {
-            if (!((active >> j) & 1u)) continue;
-            float fill[4];
-            gradient_at_small(s, g, (float)(x0 + 2u * (uint32_t)j), fy, l, fill);
-            float4 d = blend_fill(s.blend_mode, fill, cov[j], apply_clip, apply_clip ? clip[j * 32] : 1.0f,
-                                  make_float4(px[j], px[8 + j], px[16 + j], px[24 + j]));
-            px[j] = d.x;
-            px[8 + j] = d.y;
-            px[16 + j] = d.z;
-            px[24 + j] = d.w;
-        }
-        return;
-    }
-#pragma unroll 2
-    for (int j = 0; j < 8; ++j) {
-        if (!((active >> j) & 1u)) continue;
-        float4 d = make_float4(px[j], px[8 + j], px[16 + j], px[24 + j]);
-        d = blend_pixel_generic(&s, stops, texels, (float)(x0 + 2u * (uint32_t)j), fy, l, cov[j], apply_clip,
-                                apply_clip ? clip[j * 32] : 1.0f, d);
-        px[j] = d.x;
-        px[8 + j] = d.y;
-        px[16 + j] = d.z;
-        px[24 + j] = d.w;
-    }
-}
-
 __device__ __noinline__ uint32_t srgb_bytes_any_order(float r, float g, float b, float a, const uint32_t* ch) {
     return pixel_to_srgb_bytes(r, g, b, a, ch);
 }
@@ -216,71 +169,167 @@ __device__ __noinline__ uint32_t srgb_bytes_any_order(float r, float g, float b,
 // The scalar blend of the solid-tile fold (all 16 modes) stays out of line too.
 __device__ __noinline__ Rgba blend_solid(uint32_t mode, Rgba dst, Rgba src) { return sblend::blend(mode, dst, src); }
 
-constexpr int kPaintWarpsPerBlock = 2;
+// sRGB encode of a pixel pair (compute_srgb, mod.rs:466-483), RGBA order.
+__device__ __forceinline__ f2 srgb2(f2 l) {
+    const f2 s = f2{sqrtf(l.x), sqrtf(l.y)};
+    const f2 s3 = mul2(l, s);
+    const f2 m = mul2(l, f2_splat(12.92f));
+    const f2 n = fma2(f2_splat(0.20101772f), s3,
+                      fma2(f2_splat(-0.51280147f), l, fma2(f2_splat(1.344401f), s, f2_splat(-0.030656587f))));
+    return f2{l.x <= 0.0031308f ? m.x : n.x, l.y <= 0.0031308f ? m.y : n.y};
+}
+__device__ __forceinline__ void to_byte2(f2 v, uint32_t& b0, uint32_t& b1) {
+    f2 sc = mul2(v, f2_splat(255.0f));
+    sc.x = d_clamp(sc.x, 0.0f, 255.0f);
+    sc.y = d_clamp(sc.y, 0.0f, 255.0f);
+    const f2 val = add2(sc, f2_splat(__uint_as_float(0x4B000000u)));
+    b0 = __float_as_uint(val.x) & 0xFFu;
+    b1 = __float_as_uint(val.y) & 0xFFu;
+}
 
-// kMinBlocks trades registers for resident warps (8 -> 128 regs, 10 -> 96 regs).
-//
-// kSlab selects the pixel <-> lane mapping of the per-entry work (everything per tile is the
-// same code):
-//   false  lane = (column x = lane / 2, rows 8 (lane % 2) .. +8): one f32x8 of the reference per
-//          lane; every entry costs the same ~550 warp instructions whatever it covers.
-//   true   lane = (column parity p = lane / 16, row r = lane % 16); the tile is walked in eight
-//          "slabs" of two columns, left to right, carrying the running cover of the lane's row
-//          in a register. Slabs left / right of the entry's segments only see the carry / the
-//          final cover, slabs without any coverage are skipped by the whole warp, and only the
-//          cells of touched slabs are read and re-zeroed: the cost follows the covered area
-//          (profiles/r1_paint_kernel_analysis.md). Per-pixel arithmetic is the same.
-//          EXPERIMENTAL: selected with FORMA_PAINT_KERNEL=slab only; written after the GPU
-//          budget of round 1 was spent, so it has not run on a device yet.
-template <int kMinBlocks, bool kSlab>
+__device__ __forceinline__ void store_tile_solid(const PaintScene& S, uint8_t* fb, uint32_t tx, uint32_t ty, uint32_t lane,
+                                                 uint32_t rgba, bool vec_ok) {
+    const uint32_t py = ty * 16u + (lane >> 1);
+    const uint32_t px0 = tx * 16u + (lane & 1u) * 8u;
+    if (py >= S.height || px0 >= S.width) return;
+    uint8_t* row = fb + (size_t)py * S.stride + (size_t)px0 * 4u;
+    if (vec_ok && px0 + 8u <= S.width) {
+        const uint4 v = make_uint4(rgba, rgba, rgba, rgba);
+        reinterpret_cast<uint4*>(row)[0] = v;
+        reinterpret_cast<uint4*>(row)[1] = v;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (px0 + (uint32_t)j < S.width) reinterpret_cast<uint32_t*>(row)[j] = rgba;
+    }
+}
+
+// Shared-memory word of pixel (local_x, local_y): lane = 2 ly + lx / 8 owns the eight cells
+// j = lx % 8 as two 16-byte words at [lane * 4 + j] (j < 4) and [128 + lane * 4 + j - 4]:
+// a warp-wide 16-byte access is conflict-free.
+__device__ __forceinline__ uint32_t cell_index(uint32_t lx, uint32_t ly) {
+    return ((lx & 4u) << 5) + (ly * 2u + (lx >> 3)) * 4u + (lx & 3u);
+}
+
+constexpr int kPaintWarpsPerBlock = 2;
+constexpr uint32_t kPackedSegLimit = 2016u;  // segments per normalisation round of the packed cells (< 2048)
+
+struct WarpSmem {
+    uint32_t cells[2][256];  // packed (area << 16) + cover, double-buffered by entry parity
+    float clip[256];         // clip mask, same layout
+    EntryRec hdr[32];        // the 32 entry records of the current group
+};
+
+// Scatter-adds the segments [s0, s1) of one entry into `cells` (acc_segment,
+// cpu/painter/mod.rs:257-271). `pre0` / `pre1` hold the first two 32-segment chunks.
+__device__ __forceinline__ void scatter_entry(const uint64_t* __restrict__ segs, uint32_t s0, uint32_t s1, uint64_t pre0,
+                                              uint64_t pre1, uint32_t* cells, uint32_t lane) {
+    uint32_t done = 0;
+    for (uint32_t i = s0 + lane; i < s1; i += 32u) {
+        const uint32_t chunk = (i - s0) >> 5;
+        const uint64_t s = chunk == 0u ? pre0 : (chunk == 1u ? pre1 : segs[i]);
+        const uint32_t cell = cell_index((uint32_t)(s >> 16) & 15u, (uint32_t)(s >> 12) & 15u);
+        const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+        const int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
+        atomicAdd(&cells[cell], (uint32_t)(((dam * cv) << 16) + cv));
+        done += 32u;
+        if (done >= kPackedSegLimit && i + 32u < s1) {
+            // Very long entry: fold the low halves back to i8 so that they cannot overflow
+            // 16 bits (areas wrap at i16, covers at i8, exactly like the reference's lanes).
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t w = cells[k * 32 + lane];
+                const int32_t lo = (int32_t)(int16_t)(w & 0xFFFFu);
+                const uint32_t area = (w - (uint32_t)lo) & 0xFFFF0000u;
+                cells[k * 32 + lane] = area + (uint32_t)(int32_t)(int8_t)lo;
+            }
+            __syncwarp();
+            done = 0;
+        }
+    }
+}
+
+template <int kMinBlocks>
 __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_kernel(PaintScene S, PaintInputs in, uint32_t n_tiles) {
-    __shared__ int32_t s_area[kPaintWarpsPerBlock][256];
-    __shared__ int32_t s_cover[kPaintWarpsPerBlock][256];
-    __shared__ float s_clip[kPaintWarpsPerBlock][256];
+    __shared__ __align__(16) WarpSmem s_warp[kPaintWarpsPerBlock];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    int32_t* area = s_area[warp];
-    int32_t* cover = s_cover[warp];
+    WarpSmem& W = s_warp[warp];
     const Rgba clear{S.clear[0], S.clear[1], S.clear[2], S.clear[3]};
     const bool rgba_order = S.channels[0] == 0u && S.channels[1] == 1u && S.channels[2] == 2u && S.channels[3] == 3u;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in.framebuffer) | (uintptr_t)S.stride) & 15u) == 0u;
     const uint32_t ntx = S.tx_hi - S.tx_lo;
-    const uint32_t x = lane >> 1, half = lane & 1u;
+    const uint32_t row = lane >> 1, hx = lane & 1u;
     // The cells of this warp start (and are kept) zeroed.
 #pragma unroll
-    for (int l = 0; l < 8; ++l) {
-        area[l * 32 + lane] = 0;
-        cover[l * 32 + lane] = 0;
+    for (int k = 0; k < 8; ++k) {
+        W.cells[0][k * 32 + lane] = 0u;
+        W.cells[1][k * 32 + lane] = 0u;
     }
     __syncwarp();
 
-    // Tile tickets are drawn two tiles ahead and the entry range of the next tile is
-    // loaded while the current one is painted, so a warp never waits for the
-    // counter or for tile_begin / tile_end between tiles.
-    uint32_t cur = 0, next_raw = 0, cur_b = 0, cur_e = 0;
-    if (lane == 0) cur = atomicAdd(in.tile_counter, 1u);
-    cur = __shfl_sync(kFullMask, cur, 0);
-    if (lane == 0) next_raw = atomicAdd(in.tile_counter, 1u);
-    if (cur < n_tiles) {
-        const uint32_t t0 = (S.ty_lo + cur / ntx) * S.tiles_x + S.tx_lo + cur % ntx;
-        cur_b = in.tile_begin[t0];
-        cur_e = in.tile_end[t0];
+    // Ticket -> tile. Tickets [0, H) walk the heavy-tile lists (largest class first), the
+    // remaining n_tiles tickets the tile rectangle in row-major order; a tile that is on a
+    // list is skipped there. Lists hold tiles of the whole frame: those outside this
+    // launch's rows / columns are skipped here.
+    uint32_t hcount[kHeavyClasses], H = 0;
+#pragma unroll
+    for (int c = 0; c < kHeavyClasses; ++c) {
+        hcount[c] = in.heavy ? in.heavy_count[c] : 0u;
+        H += hcount[c];
     }
-    while (cur < n_tiles) {
-        const uint32_t tile_lin = cur, b = cur_b, e = cur_e;
-        {
-            const uint32_t nxt = __shfl_sync(kFullMask, next_raw, 0);
-            uint32_t nb = 0, ne = 0;
-            if (nxt < n_tiles) {
-                const uint32_t t1 = (S.ty_lo + nxt / ntx) * S.tiles_x + S.tx_lo + nxt % ntx;
-                nb = in.tile_begin[t1];
-                ne = in.tile_end[t1];
+    const uint32_t n_tickets = H + n_tiles;
+    auto resolve = [&](uint32_t ticket, uint32_t& tid, uint32_t& b, uint32_t& e) -> bool {
+        if (ticket >= n_tickets) return false;
+        if (ticket < H) {
+            uint32_t t = ticket;
+            int c = kHeavyClasses - 1;
+#pragma unroll
+            for (int q = kHeavyClasses - 1; q > 0; --q)
+                if (c == q && t >= hcount[q]) {
+                    t -= hcount[q];
+                    c = q - 1;
+                }
+            tid = in.heavy[(size_t)c * in.n_tiles_total + t];
+            const uint32_t ty = tid / S.tiles_x, tx = tid - ty * S.tiles_x;
+            if (ty < S.ty_lo || ty >= S.ty_hi || tx < S.tx_lo || tx >= S.tx_hi) {
+                tid = 0xFFFFFFFFu;  // not this launch's tile
+                return true;
             }
-            if (lane == 0) next_raw = atomicAdd(in.tile_counter, 1u);
-            cur = nxt;
-            cur_b = nb;
-            cur_e = ne;
+            const uint2 r = in.tile_range[tid];
+            b = r.x;
+            e = r.y;
+            return true;
         }
-        const uint32_t ty = S.ty_lo + tile_lin / ntx, tx = S.tx_lo + tile_lin % ntx;
-        const uint32_t tid = ty * S.tiles_x + tx;
+        const uint32_t lin = ticket - H;
+        tid = (S.ty_lo + lin / ntx) * S.tiles_x + S.tx_lo + lin % ntx;
+        const uint2 r = in.tile_range[tid];
+        b = r.x;
+        e = r.y;
+        if (in.heavy && e - b >= kHeavyMin) tid = 0xFFFFFFFFu;  // painted from its list
+        return true;
+    };
+
+    // Tickets are drawn two tiles ahead and the entry range of the next tile is loaded while
+    // the current one is painted.
+    uint32_t next_ticket = 0, cur_tid = 0, cur_b = 0, cur_e = 0;
+    bool have = false;
+    {
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(in.tile_counter, 1u);
+        t0 = __shfl_sync(kFullMask, t0, 0);
+        if (lane == 0) next_ticket = atomicAdd(in.tile_counter, 1u);
+        have = resolve(t0, cur_tid, cur_b, cur_e);
+    }
+    while (have) {
+        const uint32_t tid = cur_tid, b = cur_b, e = cur_e;
+        {
+            const uint32_t nxt = __shfl_sync(kFullMask, next_ticket, 0);
+            have = resolve(nxt, cur_tid, cur_b, cur_e);
+            if (lane == 0) next_ticket = atomicAdd(in.tile_counter, 1u);
+        }
+        if (tid == 0xFFFFFFFFu) continue;
+        const uint32_t ty = tid / S.tiles_x, tx = tid - ty * S.tiles_x;
 
         // ---- optimizer passes (layer_workbench/passes/*.rs) ------------------
         // Pass A: per-entry facts, 32 entries at a time.
@@ -423,7 +472,7 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 // CachedTile::convert_optimizer_op (cpu/painter/mod.rs:686-704): the same
                 // solid colour as last frame is not written again.
                 const bool same = use_cache && ((cache_x >> 30) & 1u) && cache_solid == bytes;
-                if (!same) store_tile_solid(S, in.framebuffer, tx, ty, lane, bytes);
+                if (!same) store_tile_solid(S, in.framebuffer, tx, ty, lane, bytes, vec_ok);
                 if (lane == 0) {
                     if (use_cache) S.cache_tiles[tid] = make_uint2(cache_x | (1u << 30), bytes);
                     if (!same && S.written_list) S.written_list[atomicAdd(S.written_count, 1u)] = tid;
@@ -438,308 +487,267 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
         }
 
         // ---- paint (layer_workbench/mod.rs:301-337, cpu/painter/mod.rs:290-347) ---
-        float dr[8], dg[8], db[8], da[8];
+        // Pixel pair q = pixels 2 q, 2 q + 1 of the lane; (r, g, b, a) planes.
+        f2 dr[4], dg[4], db[4], da[4];
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            dr[l] = clear.r; dg[l] = clear.g; db[l] = clear.b; da[l] = clear.a;
+        for (int q = 0; q < 4; ++q) {
+            dr[q] = f2_splat(clear.r); dg[q] = f2_splat(clear.g); db[q] = f2_splat(clear.b); da[q] = f2_splat(clear.a);
         }
         bool clip_active = false;
         uint32_t clip_last = 0;
-        // The clip mask lives in shared memory (lane-private slots l*32 + lane): it
-        // is only touched by tiles that contain clip layers.
-        float* clip_mask = s_clip[warp] + lane;
-        const float fx = (float)(x + tx * 16u);
-        const float fy = (float)(half * 8u + ty * 16u);
+        const uint32_t x0 = tx * 16u + hx * 8u;          // first pixel column of the lane
+        const float fy8 = (float)(ty * 16u + (row & 8u));  // y of lane 0 of the reference's f32x8 holding this row
+        const int ly8 = (int)(row & 7u);                   // the row inside it
+        const uint32_t grp_shift = (lane & 16u) + hx;      // ballot bits of this lane's f32x8 group: grp_shift + 2 i
 
         for (uint32_t p0 = first_paint; p0 < e; p0 += 32u) {
             const uint32_t cnt = min(32u, e - p0);
-            EntryHdr mine{};
-            uint32_t my_flags = kFlagMaskedOut;
+            uint32_t my_flags = kFlagMaskedOut, my_s0 = 0, my_s1 = 0;
+            __syncwarp();  // the previous group's records are no longer read
             if (lane < cnt) {
-                mine = load_hdr(in, p0 + lane);
+                const uint4* src = reinterpret_cast<const uint4*>(in.recs + p0 + lane);
+                uint4* dstp = reinterpret_cast<uint4*>(&W.hdr[lane]);
+                const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+                dstp[0] = q0; dstp[1] = q1; dstp[2] = q2; dstp[3] = q3;
                 my_flags = in.eflags[p0 + lane];
+                my_s0 = q0.y;
+                my_s1 = q0.z;
+                if (my_flags & kFlagMaskedOut) my_s1 = my_s0;  // nothing to accumulate
             }
-            // Prefetch the first segment chunk of the first entry of this group.
-            uint32_t nflags = __shfl_sync(kFullMask, my_flags, 0);
-            uint64_t pre = 0;
+            __syncwarp();
+
+            // Pipeline prologue: entry 0 is accumulated now, the segments of entry 1 are requested.
+            uint64_t nx0 = 0, nx1 = 0;  // first two chunks of the entry after the one being accumulated
             {
-                uint32_t s0 = __shfl_sync(kFullMask, mine.seg0, 0), s1 = __shfl_sync(kFullMask, mine.seg1, 0);
-                if (!(nflags & kFlagMaskedOut) && s0 + lane < s1) pre = in.segs[s0 + lane];
+                const uint32_t s0 = __shfl_sync(kFullMask, my_s0, 0), s1 = __shfl_sync(kFullMask, my_s1, 0);
+                uint64_t a0 = 0, a1 = 0;
+                if (s0 + lane < s1) a0 = in.segs[s0 + lane];
+                if (s0 + 32u + lane < s1) a1 = in.segs[s0 + 32u + lane];
+                if (cnt > 1u) {
+                    const uint32_t t0 = __shfl_sync(kFullMask, my_s0, 1), t1 = __shfl_sync(kFullMask, my_s1, 1);
+                    if (t0 + lane < t1) nx0 = in.segs[t0 + lane];
+                    if (t0 + 32u + lane < t1) nx1 = in.segs[t0 + 32u + lane];
+                }
+                if (s1 > s0) scatter_entry(in.segs, s0, s1, a0, a1, W.cells[0], lane);
+                __syncwarp();
             }
 
             for (uint32_t k = 0; k < cnt; ++k) {
-                const uint32_t flags = nflags;
-                const uint64_t first_seg = pre;
-                if (k + 1 < cnt) {  // start fetching the next entry's segments
-                    nflags = __shfl_sync(kFullMask, my_flags, (int)k + 1);
-                    uint32_t s0 = __shfl_sync(kFullMask, mine.seg0, (int)k + 1);
-                    uint32_t s1 = __shfl_sync(kFullMask, mine.seg1, (int)k + 1);
-                    pre = 0;
-                    if (!(nflags & kFlagMaskedOut) && s0 + lane < s1) pre = in.segs[s0 + lane];
+                uint32_t* cells = W.cells[k & 1u];
+                // Request the segments of entry k + 2, accumulate entry k + 1 into the other buffer.
+                {
+                    const uint64_t c0 = nx0, c1 = nx1;
+                    nx0 = nx1 = 0;
+                    if (k + 2u < cnt) {
+                        const uint32_t t0 = __shfl_sync(kFullMask, my_s0, (int)k + 2), t1 = __shfl_sync(kFullMask, my_s1, (int)k + 2);
+                        if (t0 + lane < t1) nx0 = in.segs[t0 + lane];
+                        if (t0 + 32u + lane < t1) nx1 = in.segs[t0 + 32u + lane];
+                    }
+                    if (k + 1u < cnt) {
+                        const uint32_t s0 = __shfl_sync(kFullMask, my_s0, (int)k + 1), s1 = __shfl_sync(kFullMask, my_s1, (int)k + 1);
+                        if (s1 > s0) scatter_entry(in.segs, s0, s1, c0, c1, W.cells[(k + 1u) & 1u], lane);
+                    }
                 }
-                if (flags & kFlagMaskedOut) continue;
-                const EntryHdr er = bcast_hdr(mine, (int)k);
-                const uint32_t fill_rule = meta_fill_rule(er.meta);
+                const uint32_t flags = __shfl_sync(kFullMask, my_flags, (int)k);
+                if (flags & kFlagMaskedOut) {
+                    __syncwarp();
+                    continue;
+                }
+                const EntryRec& er = W.hdr[k];
+                const uint32_t meta = er.meta, layer = er.layer;
+                const uint32_t fill_rule = meta_fill_rule(meta);
+                const bool has_segs = er.seg1 > er.seg0;
 
-                if constexpr (kSlab) {
-                    // ---- slab walk (see the comment above the kernel) --------------------
-                    const uint32_t row = lane & 15u, par = lane >> 4;
-                    // acc_segment (cpu/painter/mod.rs:257-271) into column-major cells: the cell of
-                    // (column 2 j + par, row) is word 32 j + lane, so a slab is one conflict-free access.
-                    uint32_t x_lo = 16u, x_hi = 0u;  // columns this entry's segments touch
-                    if (er.seg1 > er.seg0) {
-                        for (uint32_t i = er.seg0 + lane; i < er.seg1; i += 32u) {
-                            uint64_t s = (i < er.seg0 + 32u) ? first_seg : in.segs[i];
-                            const uint32_t lx = (uint32_t)(s >> 16) & 15u, ly = (uint32_t)(s >> 12) & 15u;
-                            int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
-                            int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
-                            atomicAdd(&area[lx * 16u + ly], dam * cv);
-                            atomicAdd(&cover[lx * 16u + ly], cv);
-                            x_lo = min(x_lo, lx);
-                            x_hi = max(x_hi, lx);
-                        }
-                        x_lo = __reduce_min_sync(kFullMask, x_lo);
-                        x_hi = __reduce_max_sync(kFullMask, x_hi);
-                        __syncwarp();
-                    }
-                    const bool has_cells = x_lo <= x_hi;
-                    const uint32_t s_first = x_lo >> 1, s_last = x_hi >> 1;  // slabs with cells (if has_cells)
-
-                    if (clip_active && clip_last < er.layer) clip_active = false;  // mod.rs:302-306
-                    const bool is_clip = meta_func(er.meta) == 1u;
-                    if (is_clip && !clip_active) {  // clip_at, mod.rs:449-464
-                        clip_active = true;
-                        clip_last = er.layer + er.clip_layers;
-                    }
-                    const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
-                    const bool draws = !is_clip && !(apply_clip && !clip_active);  // mod.rs:321-323
-
-                    // Running cover of this lane's row over the columns left of the current slab
-                    // (i8, wrapping like the reference's lanes), starting from the carry-in.
-                    const uint32_t cw = row < 4u ? er.carry.x : row < 8u ? er.carry.y : row < 12u ? er.carry.z : er.carry.w;
-                    int32_t run = (int32_t)(int8_t)((cw >> (8u * (row & 3u))) & 0xFFu);
-                    // Slabs without cells see 32 * run only: one coverage before the cells, one after.
-                    float cov_flat = coverage_of(32 * run, fill_rule);
-                    uint32_t nz_flat = __ballot_sync(kFullMask, cov_flat != 0.0f);
-
-                    float cov[8];
-                    uint32_t act = 0u;  // bit j: this lane's f32x8 of slab j has a non-zero coverage
+                // Running cover of this lane's row left of its first pixel (i8, wrapping like the
+                // reference's lanes): the carry-in, plus the left half's covers for the right half.
+                const uint32_t cw = reinterpret_cast<const uint32_t*>(&er.carry)[row >> 2];
+                int32_t run = (int32_t)(int8_t)((cw >> (8u * (row & 3u))) & 0xFFu);
+                float cov[8];
+                if (has_segs) {
+                    // (the __syncwarp that ended the previous iteration made this buffer's atomics visible)
+                    uint4* c4 = reinterpret_cast<uint4*>(cells);
+                    const uint4 w0 = c4[lane], w1 = c4[32 + lane];
+                    c4[lane] = make_uint4(0u, 0u, 0u, 0u);
+                    c4[32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    int32_t area[8], cv[8], total = 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        uint32_t nz;
-                        if (has_cells && (uint32_t)j >= s_first && (uint32_t)j <= s_last) {
-                            const int idx = j * 32 + (int)lane;
-                            const int32_t a = (int32_t)(int16_t)area[idx];
-                            const int32_t c = (int32_t)(int8_t)cover[idx];
-                            area[idx] = 0;
-                            cover[idx] = 0;
-                            const int32_t c_other = __shfl_xor_sync(kFullMask, c, 16);
-                            // column 2 j sees the covers left of the slab, column 2 j + 1 also column 2 j's
-                            const int32_t here = (int32_t)(int8_t)(run + (par ? c_other : 0));
-                            cov[j] = coverage_of(32 * here + a, fill_rule);  // compute_doubled_areas, mod.rs:388-404
-                            run = (int32_t)(int8_t)(run + c + c_other);
-                            nz = __ballot_sync(kFullMask, cov[j] != 0.0f);
-                            if ((uint32_t)j == s_last) {  // right of the cells only the final cover counts
-                                cov_flat = coverage_of(32 * run, fill_rule);
-                                nz_flat = __ballot_sync(kFullMask, cov_flat != 0.0f);
-                            }
-                        } else {
-                            cov[j] = cov_flat;
-                            nz = nz_flat;
-                        }
-                        if (is_clip) clip_mask[j * 32] = cov[j];
-                        if ((nz >> (lane & 24u)) & 0xFFu) act |= 1u << j;
+                        const int32_t lo = (int32_t)(int16_t)(w[j] & 0xFFFFu);
+                        cv[j] = lo;
+                        area[j] = (int32_t)(w[j] - (uint32_t)lo) >> 16;  // i16, sign-extended
+                        total += lo;
                     }
-                    if (has_cells) __syncwarp();
-                    if (!draws) continue;
-                    const uint32_t slabs = __reduce_or_sync(kFullMask, act);  // slabs somebody covers (warp-uniform)
-                    if (!slabs) continue;
+                    const int32_t left = __shfl_xor_sync(kFullMask, total, 1);
+                    if (hx) run += left;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        // compute_doubled_areas, mod.rs:388-404: 32 * cover of the columns to the left + area
+                        cov[j] = coverage_of(32 * (int32_t)(int8_t)run + area[j], fill_rule);
+                        run += cv[j];
+                    }
+                } else {
+                    const float c = coverage_of(32 * run, fill_rule);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cov[j] = c;
+                }
 
-                    const uint32_t mode = meta_blend(er.meta);
-                    const uint32_t fill_type = meta_fill_type(er.meta);
-                    if (fill_type == 0u && mode == 0u) {  // blend_at, mod.rs:406-447, solid `Over`
+                if (clip_active && clip_last < layer) clip_active = false;  // mod.rs:302-306
+
+                if (meta_func(meta) == 1u) {  // clip_at, mod.rs:449-464
+                    if (!clip_active) {
+                        clip_active = true;
+                        clip_last = layer + er.clip_layers;
+                    }
+                    float4* m4 = reinterpret_cast<float4*>(W.clip);
+                    m4[lane] = make_float4(cov[0], cov[1], cov[2], cov[3]);
+                    m4[32 + lane] = make_float4(cov[4], cov[5], cov[6], cov[7]);
+                    __syncwarp();
+                    continue;
+                }
+                const bool apply_clip = meta_is_clipped(meta) && !(flags & kFlagSkipClip);
+                bool nonzero = false;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (!((slabs >> j) & 1u)) continue;  // nobody covers slab j: skipped by the whole warp
-                            if (!((act >> j) & 1u)) continue;    // this lane's f32x8 is all zero (mod.rs:317-319)
-                            float sa = er.color[3] * cov[j];
-                            if (apply_clip) sa *= clip_mask[j * 32];
-                            float inv_dst_a_src_a = (1.0f - da[j]) * sa;
-                            float inv_src_a = 1.0f - sa;
-                            float dst_a_src_a = da[j] * sa;
-                            float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
-                            float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
-                            float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
-                            dr[j] = fmaf(dr[j], inv_src_a, cr);
-                            dg[j] = fmaf(dg[j], inv_src_a, cg);
-                            db[j] = fmaf(db[j], inv_src_a, cb);
-                            da[j] = fmaf(da[j], inv_src_a, sa);
+                for (int j = 0; j < 8; ++j) nonzero = nonzero || cov[j] != 0.0f;
+                if (!__any_sync(kFullMask, nonzero) || (apply_clip && !clip_active)) {  // mod.rs:317-323
+                    __syncwarp();
+                    continue;
+                }
+                float clipv[8];
+                if (apply_clip) {
+                    const float4* m4 = reinterpret_cast<const float4*>(W.clip);
+                    const float4 m0 = m4[lane], m1 = m4[32 + lane];
+                    clipv[0] = m0.x; clipv[1] = m0.y; clipv[2] = m0.z; clipv[3] = m0.w;
+                    clipv[4] = m1.x; clipv[5] = m1.y; clipv[6] = m1.z; clipv[7] = m1.w;
+                }
+
+                const uint32_t mode = meta_blend(meta);
+                const uint32_t fill_type = meta_fill_type(meta);
+                if (fill_type == 0u && mode == 0u) {
+                    // blend_at (mod.rs:406-447) for a solid `Over` layer: blended == src, and zero
+                    // coverage leaves the pixel as it is, so no f32x8 bookkeeping is needed.
+                    const f2 cr = f2_splat(er.color[0]), cg = f2_splat(er.color[1]), cb = f2_splat(er.color[2]);
+                    const f2 ca = f2_splat(er.color[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        f2 sa = mul2(ca, f2{cov[2 * q], cov[2 * q + 1]});
+                        if (apply_clip) sa = mul2(sa, f2{clipv[2 * q], clipv[2 * q + 1]});
+                        const f2 inv_dst_a = sub2(f2_splat(1.0f), da[q]);
+                        const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
+                        const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
+                        const f2 dst_a_src_a = mul2(da[q], sa);
+                        dr[q] = compose2(dr[q], cr, cr, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                        dg[q] = compose2(dg[q], cg, cg, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                        db[q] = compose2(db[q], cb, cb, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                        da[q] = fma2(da[q], inv_src_a, sa);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+
+                // Everything else follows the reference's f32x8 rule exactly: a pixel is blended iff
+                // some pixel of its f32x8 (same column, same half of the tile) has non-zero coverage.
+                uint32_t active = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t bal = __ballot_sync(kFullMask, cov[j] != 0.0f);
+                    if ((bal >> grp_shift) & 0x5555u) active |= 1u << j;
+                }
+                const StyleRec* st = &S.styles[er.slot];
+                if (mode < 12u && (fill_type == 0u || (fill_type == 1u && st->stop_count <= 4u))) {
+                    // Separable blend of a solid colour or a small gradient, on pixel pairs.
+                    GradientSetup g;
+                    float gsx = 0.0f, gsy = 0.0f;
+                    uint32_t gtype = 0;
+                    if (fill_type == 1u) {
+                        g = gradient_setup(*st, S.stops);
+                        gsx = st->start[0];
+                        gsy = st->start[1];
+                        gtype = st->gradient_type;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (!((active >> (2 * q)) & 3u)) continue;
+                        f2 fr, fg, fb, fa;
+                        if (fill_type == 0u) {
+                            fr = f2_splat(er.color[0]); fg = f2_splat(er.color[1]); fb = f2_splat(er.color[2]); fa = f2_splat(er.color[3]);
+                        } else {
+                            float c0[4], c1[4];
+                            gradient_at_small_xy(g, gtype, gsx, gsy, (float)(x0 + 2u * (uint32_t)q), fy8, ly8, c0);
+                            gradient_at_small_xy(g, gtype, gsx, gsy, (float)(x0 + 2u * (uint32_t)q + 1u), fy8, ly8, c1);
+                            fr = f2{c0[0], c1[0]}; fg = f2{c0[1], c1[1]}; fb = f2{c0[2], c1[2]}; fa = f2{c0[3], c1[3]};
                         }
-                    } else if (act) {
-                        const StyleRec* st = &S.styles[er.slot];
-                        float px[32];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            px[j] = dr[j]; px[8 + j] = dg[j]; px[16 + j] = db[j]; px[24 + j] = da[j];
+                        f2 sa = mul2(fa, f2{cov[2 * q], cov[2 * q + 1]});
+                        if (apply_clip) sa = mul2(sa, f2{clipv[2 * q], clipv[2 * q + 1]});
+                        const f2 br = blend_sep2(mode, dr[q], fr), bg = blend_sep2(mode, dg[q], fg), bb = blend_sep2(mode, db[q], fb);
+                        const f2 inv_dst_a = sub2(f2_splat(1.0f), da[q]);
+                        const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
+                        const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
+                        const f2 dst_a_src_a = mul2(da[q], sa);
+                        const f2 nr = compose2(dr[q], fr, br, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                        const f2 ng = compose2(dg[q], fg, bg, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                        const f2 nb = compose2(db[q], fb, bb, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                        const f2 na = fma2(da[q], inv_src_a, sa);
+                        if ((active >> (2 * q)) & 1u) {
+                            dr[q].x = nr.x; dg[q].x = ng.x; db[q].x = nb.x; da[q].x = na.x;
                         }
-                        blend_row_generic(st, S.stops, S.texels, tx * 16u + par, (float)((row >> 3) * 8u + ty * 16u), (int)(row & 7u), cov,
-                                          act, apply_clip, clip_mask, px);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            dr[j] = px[j]; dg[j] = px[8 + j]; db[j] = px[16 + j]; da[j] = px[24 + j];
+                        if ((active >> (2 * q + 1)) & 1u) {
+                            dr[q].y = nr.y; dg[q].y = ng.y; db[q].y = nb.y; da[q].y = na.y;
                         }
                     }
                 } else {
-                    // acc_segment: scatter-add the cell's segments (cpu/painter/mod.rs:257-271).
-                    int32_t a8[8];
-                    uint32_t run_lo, run_hi;  // running covers of rows 0-3 / 4-7 of this lane's half, packed i8
-                    if (er.seg1 > er.seg0) {
-                        for (uint32_t i = er.seg0 + lane; i < er.seg1; i += 32u) {
-                            uint64_t s = (i < er.seg0 + 32u) ? first_seg : in.segs[i];
-                            uint32_t cell = cell_index((uint32_t)(s >> 16) & 15u, (uint32_t)(s >> 12) & 15u);
-                            int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
-                            int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
-                            atomicAdd(&area[cell], dam * cv);
-                            atomicAdd(&cover[cell], cv);
+                    // Textures, gradients with more than four stops, non-separable modes: one
+                    // out-of-line call per blended pixel.
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if ((active >> (2 * q)) & 1u) {
+                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, (float)(x0 + 2u * (uint32_t)q), fy8, ly8, cov[2 * q],
+                                                                 apply_clip ? clipv[2 * q] : -1.0f,
+                                                                 make_float4(dr[q].x, dg[q].x, db[q].x, da[q].x));
+                            dr[q].x = d.x; dg[q].x = d.y; db[q].x = d.z; da[q].x = d.w;
                         }
-                        __syncwarp();
-                        uint32_t c_lo = 0, c_hi = 0;
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) {
-                            int idx = l * 32 + (int)lane;  // == cell_index(x, half * 8 + l)
-                            a8[l] = (int32_t)(int16_t)area[idx];
-                            uint32_t cb = (uint32_t)cover[idx] & 0xFFu;
-                            if (l < 4) c_lo |= cb << (8 * l);
-                            else c_hi |= cb << (8 * (l - 4));
-                            area[idx] = 0;
-                            cover[idx] = 0;
-                        }
-                        // Exclusive prefix over columns x' < x (same half): lanes l-2, l-4, ...
-                        uint32_t i_lo = c_lo, i_hi = c_hi;
-#pragma unroll
-                        for (int o = 2; o < 32; o <<= 1) {
-                            uint32_t n_lo = __shfl_up_sync(kFullMask, i_lo, o);
-                            uint32_t n_hi = __shfl_up_sync(kFullMask, i_hi, o);
-                            if (lane >= (uint32_t)o) {
-                                i_lo = __vadd4(i_lo, n_lo);
-                                i_hi = __vadd4(i_hi, n_hi);
-                            }
-                        }
-                        uint32_t e_lo = __shfl_up_sync(kFullMask, i_lo, 2);
-                        uint32_t e_hi = __shfl_up_sync(kFullMask, i_hi, 2);
-                        if (lane < 2u) e_lo = e_hi = 0u;
-                        run_lo = __vadd4(e_lo, half ? er.carry.z : er.carry.x);
-                        run_hi = __vadd4(e_hi, half ? er.carry.w : er.carry.y);
-                        __syncwarp();
-                    } else {
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) a8[l] = 0;
-                        run_lo = half ? er.carry.z : er.carry.x;
-                        run_hi = half ? er.carry.w : er.carry.y;
-                    }
-
-                    if (clip_active && clip_last < er.layer) clip_active = false;  // mod.rs:302-306
-
-                    float cov[8];
-                    bool all_zero = true;
-#pragma unroll
-                    for (int l = 0; l < 8; ++l) {
-                        uint32_t byte = ((l < 4 ? run_lo : run_hi) >> (8 * (l & 3))) & 0xFFu;
-                        int32_t doubled = 32 * (int32_t)(int8_t)byte + a8[l];  // compute_doubled_areas, mod.rs:388-404
-                        cov[l] = coverage_of(doubled, fill_rule);
-                        all_zero = all_zero && (cov[l] == 0.0f);
-                    }
-
-                    if (meta_func(er.meta) == 1u) {  // clip_at, mod.rs:449-464
-                        if (!clip_active) {
-                            clip_active = true;
-                            clip_last = er.layer + er.clip_layers;
-                        }
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) clip_mask[l * 32] = cov[l];
-                        continue;
-                    }
-                    const bool apply_clip = meta_is_clipped(er.meta) && !(flags & kFlagSkipClip);
-                    if (all_zero) continue;                    // mod.rs:317-319 (whole f32x8 is zero)
-                    if (apply_clip && !clip_active) continue;  // mod.rs:321-323
-
-                    const uint32_t mode = meta_blend(er.meta);
-                    const uint32_t fill_type = meta_fill_type(er.meta);
-                    // blend_at, mod.rs:406-447. The mode / fill dispatch is hoisted out of
-                    // the pixel loop: a solid `Over` layer (by far the most common) is
-                    // straight-line code; everything else goes through one out-of-line
-                    // helper per pixel so that the kernel stays small enough for the
-                    // instruction cache.
-                    if (fill_type == 0u && mode == 0u) {
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) {
-                            float sa = er.color[3] * cov[l];
-                            if (apply_clip) sa *= clip_mask[l * 32];
-                            float inv_dst_a_src_a = (1.0f - da[l]) * sa;
-                            float inv_src_a = 1.0f - sa;
-                            float dst_a_src_a = da[l] * sa;
-                            float cr = fmaf(er.color[0], inv_dst_a_src_a, er.color[0] * dst_a_src_a);
-                            float cg = fmaf(er.color[1], inv_dst_a_src_a, er.color[1] * dst_a_src_a);
-                            float cb = fmaf(er.color[2], inv_dst_a_src_a, er.color[2] * dst_a_src_a);
-                            dr[l] = fmaf(dr[l], inv_src_a, cr);
-                            dg[l] = fmaf(dg[l], inv_src_a, cg);
-                            db[l] = fmaf(db[l], inv_src_a, cb);
-                            da[l] = fmaf(da[l], inv_src_a, sa);
-                        }
-                    } else {
-                        const StyleRec* st = &S.styles[er.slot];
-                        float px[32], cv[8];
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) {
-                            px[l] = dr[l]; px[8 + l] = dg[l]; px[16 + l] = db[l]; px[24 + l] = da[l];
-                            cv[l] = cov[l];
-                        }
-                        blend_column_generic(st, S.stops, S.texels, fx, fy, cv, apply_clip, clip_mask, px);
-#pragma unroll
-                        for (int l = 0; l < 8; ++l) {
-                            dr[l] = px[l]; dg[l] = px[8 + l]; db[l] = px[16 + l]; da[l] = px[24 + l];
+                        if ((active >> (2 * q + 1)) & 1u) {
+                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, (float)(x0 + 2u * (uint32_t)q + 1u), fy8, ly8,
+                                                                 cov[2 * q + 1], apply_clip ? clipv[2 * q + 1] : -1.0f,
+                                                                 make_float4(dr[q].y, dg[q].y, db[q].y, da[q].y));
+                            dr[q].y = d.x; dg[q].y = d.y; db[q].y = d.z; da[q].y = d.w;
                         }
                     }
                 }
+                __syncwarp();
             }
         }
 
         // compute_srgb + LinearLayout::write (mod.rs:466-483, layout/mod.rs:265-282).
-        if constexpr (kSlab) {
-            // Pixel j of a lane is (2 j + par, row): transpose through the (now idle) clip-mask
-            // words so that a store instruction writes two whole 64-byte tile rows.
-            uint32_t* stage = reinterpret_cast<uint32_t*>(s_clip[warp]);
-            const uint32_t row = lane & 15u, par = lane >> 4;
-            __syncwarp();
+        const uint32_t py = ty * 16u + row;
+        if (py < S.height && x0 < S.width) {
+            uint32_t out[8];
+            if (rgba_order) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                stage[row * 16u + 2u * (uint32_t)j + par] =
-                    rgba_order ? pixel_to_srgb_bytes_rgba(dr[j], dg[j], db[j], da[j])
-                               : srgb_bytes_any_order(dr[j], dg[j], db[j], da[j], S.channels);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t w = (uint32_t)k * 32u + lane;
-                const uint32_t py = ty * 16u + (w >> 4), qx = tx * 16u + (w & 15u);
-                if (qx < S.width && py < S.height)
-                    *reinterpret_cast<uint32_t*>(in.framebuffer + (size_t)py * S.stride + (size_t)qx * 4u) = stage[w];
-            }
-            __syncwarp();
-            continue;
-        }
-        const uint32_t px = tx * 16u + x;
-        if (px < S.width) {
-#pragma unroll
-            for (int l = 0; l < 8; ++l) {
-                uint32_t py = ty * 16u + half * 8u + l;
-                if (py < S.height) {
-                    // RGBA order (kernel-uniform) needs no channel selection; other orders take the
-                    // out-of-line generic conversion.
-                    uint32_t rgba = rgba_order ? pixel_to_srgb_bytes_rgba(dr[l], dg[l], db[l], da[l])
-                                               : srgb_bytes_any_order(dr[l], dg[l], db[l], da[l], S.channels);
-                    *reinterpret_cast<uint32_t*>(in.framebuffer + (size_t)py * S.stride + (size_t)px * 4u) = rgba;
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t r0, r1, g0, g1, b0, b1, a0, a1;
+                    to_byte2(srgb2(dr[q]), r0, r1);
+                    to_byte2(srgb2(dg[q]), g0, g1);
+                    to_byte2(srgb2(db[q]), b0, b1);
+                    to_byte2(da[q], a0, a1);
+                    out[2 * q] = r0 | (g0 << 8) | (b0 << 16) | (a0 << 24);
+                    out[2 * q + 1] = r1 | (g1 << 8) | (b1 << 16) | (a1 << 24);
                 }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    out[2 * q] = srgb_bytes_any_order(dr[q].x, dg[q].x, db[q].x, da[q].x, S.channels);
+                    out[2 * q + 1] = srgb_bytes_any_order(dr[q].y, dg[q].y, db[q].y, da[q].y, S.channels);
+                }
+            }
+            uint8_t* rowp = in.framebuffer + (size_t)py * S.stride + (size_t)x0 * 4u;
+            if (vec_ok && x0 + 8u <= S.width) {
+                reinterpret_cast<uint4*>(rowp)[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                reinterpret_cast<uint4*>(rowp)[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (x0 + (uint32_t)j < S.width) reinterpret_cast<uint32_t*>(rowp)[j] = out[j];
             }
         }
     }
@@ -769,38 +777,48 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const uint8_t* __rest
 }
 
 void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st) {
-    gather_tiles_kernel<<<148 * 4, 256, 0, st>>>(framebuffer, S.stride, S.width, S.height, S.tiles_x, S.written_list,
-                                                  S.written_count, packed);
+    gather_tiles_kernel<<<device_sm_count() * 4, 256, 0, st>>>(framebuffer, S.stride, S.width, S.height, S.tiles_x, S.written_list,
+                                                               S.written_count, packed);
 }
 
-void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint32_t* tile_begin,
-                  const uint32_t* tile_end, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st) {
+// Self-test of the packed fp32 arithmetic (forma_debug_selftest): every packed helper against
+// the scalar IEEE operation it stands for, on `n` operand triples. Returns mismatches in out[0].
+__global__ void f32x2_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                      uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
+    if (i + 1u >= n) return;
+    const f2 x{a[i], a[i + 1]}, y{b[i], b[i + 1]}, z{c[i], c[i + 1]};
+    uint32_t bad = 0;
+    auto same = [](float p, float q) { return __float_as_uint(p) == __float_as_uint(q) || (p != p && q != q); };
+    const f2 f = fma2(x, y, z), m = mul2(x, y), s = add2(x, y), d = sub2(x, y);
+    const f2 ms = add2(mul2(x, y), z);  // a product followed by a sum must stay two roundings
+    bad += !same(f.x, fmaf(x.x, y.x, z.x)) + !same(f.y, fmaf(x.y, y.y, z.y));
+    bad += !same(m.x, x.x * y.x) + !same(m.y, x.y * y.y);
+    bad += !same(s.x, x.x + y.x) + !same(s.y, x.y + y.y);
+    bad += !same(d.x, x.x - y.x) + !same(d.y, x.y - y.y);
+    bad += !same(ms.x, (x.x * y.x) + z.x) + !same(ms.y, (x.y * y.y) + z.y);
+    if (bad) atomicAdd(out, bad);
+}
+void launch_f32x2_selftest(const float* a, const float* b, const float* c, uint32_t n, uint32_t* out, cudaStream_t st) {
+    f32x2_selftest_kernel<<<(n / 2 + 255) / 256, 256, 0, st>>>(a, b, c, n, out);
+}
+
+void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint2* tile_range, const uint32_t* heavy,
+                  const uint32_t* heavy_count, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st) {
     if (S.tx_hi <= S.tx_lo || S.ty_hi <= S.ty_lo) return;
     uint32_t n_tiles = (S.tx_hi - S.tx_lo) * (S.ty_hi - S.ty_lo);
     cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
-    PaintInputs in{segs, recs, tile_begin, tile_end, eflags, framebuffer, tile_counter};
-    // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy.
-    // FORMA_PAINT_REGS=96 selects the 96-register build (default: 128 registers,
-    // measured 17 % faster on paris@4K: fewer spills beat the extra warps).
-    // FORMA_PAINT_KERNEL=slab selects the experimental slab mapping (see paint_kernel).
-    static int blocks_per_sm = 0, variant = 0;
-    if (!blocks_per_sm) {
-        const char* e = getenv("FORMA_PAINT_REGS");
-        const char* k = getenv("FORMA_PAINT_KERNEL");
-        variant = (k && !strcmp(k, "slab")) ? 1 : (e && atoi(e) == 96) ? 10 : 8;
-        if (variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8, false>, kPaintWarpsPerBlock * 32, 0);
-        else if (variant == 10) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<10, false>, kPaintWarpsPerBlock * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, paint_kernel<8, true>, kPaintWarpsPerBlock * 32, 0);
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    PaintInputs in{segs, recs, tile_range, heavy, heavy_count, S.tiles_x * S.tiles_y, eflags, framebuffer, tile_counter};
+    // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy (per device).
+    static int blocks_per_sm[kMaxDevices] = {0};
+    int& per_sm = blocks_per_sm[current_device_index()];
+    if (!per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
+        if (per_sm < 1) per_sm = 1;
     }
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    uint32_t want = (uint32_t)(blocks_per_sm * sms);
-    uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
-    if (variant == 8) paint_kernel<8, false><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
-    else if (variant == 10) paint_kernel<10, false><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
-    else paint_kernel<8, true><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    const uint32_t want = (uint32_t)(per_sm * device_sm_count());
+    const uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
+    paint_kernel<8><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
 }
 
 }  // namespace forma

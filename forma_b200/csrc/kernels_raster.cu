@@ -423,6 +423,28 @@ __global__ void __launch_bounds__(kRasterThreads)
     }
 }
 
+// Inspection only (forma_renderer_lines): the line records of segment.rs:298-383 as the
+// reference's SegmentBufferView holds them (segment.rs:530-545), one per point pair; the
+// render path itself never materialises them. `lengths` are per line (the host turns them
+// into the reference's inclusive prefix sums).
+__global__ void line_records_kernel(RasterArgs A, uint32_t n, uint32_t* __restrict__ orders, float* __restrict__ x0,
+                                    float* __restrict__ y0, float* __restrict__ dx, float* __restrict__ dy,
+                                    float* __restrict__ a, float* __restrict__ b, float* __restrict__ c,
+                                    float* __restrict__ d, uint32_t* __restrict__ lengths) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const LineParams L = line_setup(A, i);
+    orders[i] = L.order;
+    x0[i] = L.x0; y0[i] = L.y0; dx[i] = L.dx; dy[i] = L.dy;
+    a[i] = L.a; b[i] = L.b; c[i] = L.c; d[i] = L.d;
+    lengths[i] = L.length;
+}
+
+void launch_line_records(const RasterArgs& args, uint32_t n, uint32_t* orders, float* const f[8], uint32_t* lengths,
+                         cudaStream_t stream) {
+    if (n) line_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(args, n, orders, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], lengths);
+}
+
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------

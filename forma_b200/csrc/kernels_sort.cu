@@ -18,9 +18,9 @@
 // * Small sorts and (key, u32 payload) pairs (the painter's cell / gap tables):
 //   one upfront histogram kernel for all passes, then one single-sweep
 //   ("onesweep") kernel per pass with decoupled look-back (16 B/key per pass;
-//   latency-bound at these sizes). The persistent single-sweep kernel that
-//   preceded the reduce-then-scan passes is kept for A/B runs
-//   (FORMA_SORT_MODE=persistent).
+//   latency-bound at these sizes). A persistent single-sweep kernel for the large sorts
+//   was measured in round 1 (look-back-bound, 34 % of the HBM peak, profiles/r1_v2_*) and
+//   removed in favour of the reduce-then-scan passes.
 #include "cuda_common.cuh"
 #include "kernels.h"
 
@@ -277,19 +277,8 @@ __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
 }
 
 // ---------------------------------------------------------------------------
-// Persistent, TMA-staged variant for large key-only sorts (the main pixel
-// segment sort). CTA c owns tiles c, c + G, c + 2G, ... (G = resident CTAs), so
-// every tile's predecessors are being processed in the same or an earlier
-// round. While tile k is ranked and scattered, the keys of tile k + G are
-// already in flight: one thread issues a 32 KB `cp.async.bulk` (1-D TMA) into
-// the other shared-memory stage and the CTA later waits on its mbarrier. The
-// stage that delivered tile k doubles as the digit-order staging buffer of the
-// write-out, so the loads of the next tile, the ranking of this one and the
-// stores of this one overlap inside one CTA instead of relying on other CTAs.
+// 1-D TMA (cp.async.bulk) + mbarrier helpers used by the downsweep's tile staging.
 // ---------------------------------------------------------------------------
-constexpr int kPItems = 16;
-constexpr int kPTile = kSortThreads * kPItems;  // 4096 keys = 32 KB
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -311,146 +300,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-    }
-}
-
-struct PersistentSmem {
-    uint64_t stage[2][kPTile];              // 2 x 32 KB
-    uint32_t warp_hist[kSortWarps][kRadix]; // 8 KB
-    uint32_t digit_start[kRadix];
-    uint32_t global_base[kRadix];
-    uint32_t warp_tot[kSortWarps];
-    uint64_t bar[2];
-};
-
-__global__ void __launch_bounds__(kSortThreads, 2)
-    onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
-                               const uint32_t* __restrict__ global_offsets, uint32_t* __restrict__ lb, uint32_t tiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    PersistentSmem& S = *reinterpret_cast<PersistentSmem*>(smem_raw);
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
-    const uint32_t G = gridDim.x;
-    if (t == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](uint32_t tile, uint32_t st) {  // thread 0 only
-        uint32_t base = tile * (uint32_t)kPTile;
-        uint32_t valid = min((uint32_t)kPTile, n - base);
-        uint32_t bytes = ((valid + 1u) & ~1u) * 8u;  // multiple of 16 B (the buffers have one key of slack)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&S.bar[st], bytes);
-        tma_load_1d(&S.stage[st][0], keys_in + base, bytes, &S.bar[st]);
-    };
-
-    uint32_t tile = blockIdx.x;
-    if (tile >= tiles) return;
-    if (t == 0) issue(tile, 0);
-    uint32_t st = 0, phase0 = 0, phase1 = 0;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t max_digit = (1u << spec.bits) - 1u;
-
-    for (; tile < tiles; tile += G, st ^= 1u) {
-        if (t == 0 && tile + G < tiles) issue(tile + G, st ^ 1u);
-        for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&S.warp_hist[0][0])[i] = 0;
-        const uint32_t base = tile * (uint32_t)kPTile;
-        const uint32_t valid = min((uint32_t)kPTile, n - base);
-        if (st == 0) {
-            mbar_wait(&S.bar[0], phase0);
-            phase0 ^= 1u;
-        } else {
-            mbar_wait(&S.bar[1], phase1);
-            phase1 ^= 1u;
-        }
-        uint64_t* stage = S.stage[st];
-
-        // Keys from the staged tile, warp-striped like the one-shot kernel.
-        uint64_t key[kPItems];
-        const uint32_t wofs = warp * (32u * kPItems);
-#pragma unroll
-        for (int i = 0; i < kPItems; ++i) key[i] = stage[wofs + i * 32u + lane];
-        __syncthreads();  // everybody has its keys (and the zeroed histograms are visible)
-
-        uint32_t rank[kPItems];
-#pragma unroll
-        for (int i = 0; i < kPItems; ++i) {
-            uint32_t slot = wofs + i * 32u + lane;
-            uint32_t d = slot < valid ? digit_of(key[i], spec) : max_digit;
-            uint32_t peers = __match_any_sync(kFullMask, d);
-            uint32_t leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) {
-                old = S.warp_hist[warp][d];
-                S.warp_hist[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(kFullMask, old, leader);
-            rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
-            __syncwarp();
-        }
-        __syncthreads();
-
-        uint32_t count = 0;
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = S.warp_hist[w][t];
-            S.warp_hist[w][t] = count;
-            count += c;
-        }
-        uint32_t* my_slot = lb + (size_t)tile * kRadix + t;
-        if (tile != 0) st_relaxed(my_slot, kFlagAggregate | count);
-        uint32_t incl = warp_inclusive_scan(count);
-        if (lane == 31) S.warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t dstart = incl - count;
-        for (uint32_t w = 0; w < warp; ++w) dstart += S.warp_tot[w];
-        S.digit_start[t] = dstart;
-        {
-            uint32_t prefix = 0;
-            int32_t p = (int32_t)tile - 1;
-            bool done = p < 0;
-            while (!done) {
-                uint32_t v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    v[j] = (p - j >= 0) ? ld_relaxed(lb + (size_t)(p - j) * kRadix + t) : kFlagInclusive;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (done) break;
-                    uint32_t flag = v[j] & kFlagMask;
-                    if (flag == 0) {
-                        p -= j;
-                        goto retry;
-                    }
-                    prefix += v[j] & kValueMask;
-                    if (flag == kFlagInclusive) done = true;
-                }
-                p -= 4;
-            retry:;
-            }
-            st_relaxed(my_slot, kFlagInclusive | (prefix + count));
-            S.global_base[t] = global_offsets[t] + prefix - dstart;
-        }
-        __syncthreads();
-
-        // Digit-order staging in the buffer that delivered the tile, then coalesced write-out.
-#pragma unroll
-        for (int i = 0; i < kPItems; ++i) {
-            uint32_t d = rank[i] >> 16;
-            stage[S.digit_start[d] + S.warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kPItems; ++k) {
-            uint32_t p = t + k * kSortThreads;
-            if (p < valid) {
-                uint64_t kk = stage[p];
-                keys_out[S.global_base[digit_of(kk, spec)] + p] = kk;
-            }
-        }
-        __syncthreads();  // the stage is free again: the next iteration may refill it by TMA
     }
 }
 
@@ -545,210 +394,17 @@ __global__ void __launch_bounds__(kRadix) radix_tile_scan_kernel(uint32_t* __res
     }
 }
 
-__global__ void __launch_bounds__(kSortThreads, 3)
-    radix_downsweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
-                           const uint32_t* __restrict__ tile_base /*[tiles][256]: global offset per (tile, digit)*/) {
-    __shared__ uint64_t s_keys[kDsTile];
-    __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];
-    __shared__ uint32_t s_digit_start[kRadix];
-    __shared__ uint32_t s_global_base[kRadix];
-    __shared__ uint32_t s_warp_tot[kSortWarps];
-
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t gbase = tile_base[(size_t)tile * kRadix + t];  // consumed after the ranking
-    for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
-    const uint32_t base = tile * (uint32_t)kDsTile;
-    const uint32_t valid = min((uint32_t)kDsTile, n - base);
-
-    uint64_t key[kDsItems];
-    const uint32_t warp_base = base + warp * (32u * kDsItems);
-#pragma unroll
-    for (int i = 0; i < kDsItems; ++i) {
-        uint32_t idx = warp_base + i * 32u + lane;
-        key[i] = idx < n ? keys_in[idx] : ~0ull;
-    }
-    __syncthreads();
-
-    // Stable rank of every key among the keys of its warp with the same digit
-    // (out-of-range slots of the last tile take the largest digit: they rank last).
-    uint32_t rank[kDsItems];
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t max_digit = (1u << spec.bits) - 1u;
-#pragma unroll
-    for (int i = 0; i < kDsItems; ++i) {
-        uint32_t idx = warp_base + i * 32u + lane;
-        uint32_t d = idx < n ? digit_of(key[i], spec) : max_digit;
-        uint32_t peers = __match_any_sync(kFullMask, d);
-        uint32_t leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader) {
-            old = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = old + __popc(peers);
-        }
-        old = __shfl_sync(kFullMask, old, leader);
-        rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    uint32_t count = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-        uint32_t c = s_warp_hist[w][t];
-        s_warp_hist[w][t] = count;
-        count += c;
-    }
-    uint32_t incl = warp_inclusive_scan(count);
-    if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t dstart = incl - count;
-    for (uint32_t w = 0; w < warp; ++w) dstart += s_warp_tot[w];
-    s_digit_start[t] = dstart;
-    s_global_base[t] = gbase - dstart;
-    __syncthreads();
-
-#pragma unroll
-    for (int i = 0; i < kDsItems; ++i) {
-        uint32_t d = rank[i] >> 16;
-        s_keys[s_digit_start[d] + s_warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kDsItems; ++k) {
-        uint32_t p = t + k * kSortThreads;
-        if (p < valid) {
-            uint64_t kk = s_keys[p];
-            keys_out[s_global_base[digit_of(kk, spec)] + p] = kk;
-        }
-    }
-}
-
 // Persistent downsweep: CTA c owns tiles c, c + G, ...; the keys of the next
 // kDsStages - 1 tiles of the CTA are always in flight as 32 KB `cp.async.bulk`
 // (1-D TMA) copies into a shared-memory ring, so the HBM reads never wait for
 // the ranking or the stores of the current tile. The stage that delivered a
 // tile is reused as its digit-order staging buffer before the write-out.
 constexpr int kDsStages = 3;
-struct DownsweepSmem {
-    uint64_t stage[kDsStages][kDsTile];     // 3 x 32 KB
-    uint32_t warp_hist[kSortWarps][kRadix]; // 8 KB
-    uint32_t digit_start[kRadix];
-    uint32_t global_base[kRadix];
-    uint32_t warp_tot[kSortWarps];
-    uint64_t bar[kDsStages];
-};
-
-__global__ void __launch_bounds__(kSortThreads, 2)
-    radix_downsweep_tma_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out, uint32_t n, DigitSpec spec,
-                               const uint32_t* __restrict__ tile_base, uint32_t tiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    DownsweepSmem& S = *reinterpret_cast<DownsweepSmem*>(smem_raw);
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
-    const uint32_t G = gridDim.x;
-    if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < kDsStages; ++s) mbar_init(&S.bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](uint32_t tile, uint32_t st) {  // thread 0 only
-        uint32_t base = tile * (uint32_t)kDsTile;
-        uint32_t valid = min((uint32_t)kDsTile, n - base);
-        uint32_t bytes = ((valid + 1u) & ~1u) * 8u;  // multiple of 16 B (the buffers have one key of slack)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&S.bar[st], bytes);
-        tma_load_1d(&S.stage[st][0], keys_in + base, bytes, &S.bar[st]);
-    };
-
-    uint32_t tile = blockIdx.x;
-    if (tile >= tiles) return;
-    if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < kDsStages - 1; ++s)
-            if (tile + (uint32_t)s * G < tiles) issue(tile + (uint32_t)s * G, (uint32_t)s);
-    }
-    uint32_t st = 0, phases = 0;  // bit s of `phases` = parity to wait for on stage s
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t max_digit = (1u << spec.bits) - 1u;
-
-    for (; tile < tiles; tile += G) {
-        // The stage freed by the previous iteration receives the tile kDsStages - 1 rounds ahead.
-        if (t == 0 && tile + (uint32_t)(kDsStages - 1) * G < tiles)
-            issue(tile + (uint32_t)(kDsStages - 1) * G, (st + kDsStages - 1u) % kDsStages);
-        const uint32_t gbase = tile_base[(size_t)tile * kRadix + t];
-        for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&S.warp_hist[0][0])[i] = 0;
-        const uint32_t base = tile * (uint32_t)kDsTile;
-        const uint32_t valid = min((uint32_t)kDsTile, n - base);
-        mbar_wait(&S.bar[st], (phases >> st) & 1u);
-        phases ^= 1u << st;
-        uint64_t* stage = S.stage[st];
-
-        uint64_t key[kDsItems];
-        const uint32_t wofs = warp * (32u * kDsItems);
-#pragma unroll
-        for (int i = 0; i < kDsItems; ++i) key[i] = stage[wofs + i * 32u + lane];
-        __syncthreads();  // everybody has its keys (and the zeroed histograms are visible)
-
-        uint32_t rank[kDsItems];
-#pragma unroll
-        for (int i = 0; i < kDsItems; ++i) {
-            uint32_t slot = wofs + i * 32u + lane;
-            uint32_t d = slot < valid ? digit_of(key[i], spec) : max_digit;
-            uint32_t peers = __match_any_sync(kFullMask, d);
-            uint32_t leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) {
-                old = S.warp_hist[warp][d];
-                S.warp_hist[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(kFullMask, old, leader);
-            rank[i] = (old + __popc(peers & lt_mask)) | (d << 16);
-            __syncwarp();
-        }
-        __syncthreads();
-
-        uint32_t count = 0;
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t c = S.warp_hist[w][t];
-            S.warp_hist[w][t] = count;
-            count += c;
-        }
-        uint32_t incl = warp_inclusive_scan(count);
-        if (lane == 31) S.warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t dstart = incl - count;
-        for (uint32_t w = 0; w < warp; ++w) dstart += S.warp_tot[w];
-        S.digit_start[t] = dstart;
-        S.global_base[t] = gbase - dstart;
-        __syncthreads();
-
-#pragma unroll
-        for (int i = 0; i < kDsItems; ++i) {
-            uint32_t d = rank[i] >> 16;
-            stage[S.digit_start[d] + S.warp_hist[warp][d] + (rank[i] & 0xFFFFu)] = key[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kDsItems; ++k) {
-            uint32_t p = t + k * kSortThreads;
-            if (p < valid) {
-                uint64_t kk = stage[p];
-                keys_out[S.global_base[digit_of(kk, spec)] + p] = kk;
-            }
-        }
-        __syncthreads();  // the stage is free again: the next iteration refills it by TMA
-        st = (st + 1u) % kDsStages;
-    }
-}
-
-// Same tile (4096 keys) with 512 threads x 8 keys: the ranking chain per warp is
-// half as long and an SM holds 32 warps instead of 16 (2 CTAs, <= 64 registers),
-// which is what the profile of the 256-thread version asked for (short-scoreboard
-// and fixed-latency stalls at 24 % occupancy). Per-warp digit counters are u16
-// (a tile has 4096 keys) so that the shared memory still fits twice per SM.
+// 512 threads x 8 keys per 4096-key tile: the ranking chain per warp is short and an SM
+// holds 32 warps (2 CTAs, <= 64 registers) — a 256-thread x 16-key version measured
+// short-scoreboard / fixed-latency bound at 24 % occupancy (profiles/README.md, round 1).
+// Per-warp digit counters are u16 (a tile has 4096 keys) so that the shared memory still
+// fits twice per SM.
 constexpr int kWideThreads = 512;
 constexpr int kWideItems = 8;
 constexpr int kWideWarps = kWideThreads / 32;
@@ -880,27 +536,9 @@ __global__ void __launch_bounds__(kWideThreads, 2)
 static uint32_t tiles_for(uint32_t n, int items) { return (n + kSortThreads * items - 1) / (kSortThreads * items); }
 // Keys per thread: 4096-key tiles from 2^19 keys on (fewer tiles = a shorter look-back chain for
 // the single-sweep pair sorts, and the reduce-then-scan path for key-only sorts), 1024-key tiles
-// below that so that small sorts still spread over the SMs. FORMA_SORT_BIG_LOG2 overrides (A/B).
-static int items_for(uint32_t n) {
-    static int log2_big = 0;
-    if (!log2_big) {
-        const char* e = getenv("FORMA_SORT_BIG_LOG2");
-        log2_big = e ? atoi(e) : 19;  // measured: 2^17 costs paris@4K (230 k cells) 4 % of its table stage
-        if (log2_big < 10 || log2_big > 30) log2_big = 19;
-    }
-    return n >= (1u << log2_big) ? 16 : 4;
-}
-// Large key-only sorts: FORMA_SORT_MODE = scan (default: reduce-then-scan passes),
-// persistent (TMA-staged single sweep) or oneshot (single sweep), for A/B measurements.
-enum class BigSortMode { Scan, Persistent, OneShot };
-static BigSortMode big_sort_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("FORMA_SORT_MODE");
-        mode = (e && e[0] == 'p') ? 1 : (e && e[0] == 'o') ? 2 : 0;
-    }
-    return (BigSortMode)mode;
-}
+// below that so that small sorts still spread over the SMs (option sort_big_log2, default 19:
+// 2^17 measured 4 % slower on paris@4K's 230 k-cell tables).
+static int items_for(uint32_t n) { return n >= (1u << options().sort_big_log2) ? 16 : 4; }
 
 // scratch layout (u32 words): hist[6][256] | tile_counter[8] | lookback[6][tiles][256]
 // or, for the reduce-then-scan passes: totals[6][kTotalsRows][256] | tile_hist[tiles][256]
@@ -914,10 +552,11 @@ template <bool kPairs, int kItems>
 static void launch_passes(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
                           const SortPlan& plan, const uint32_t* hist, uint32_t* lookback, uint32_t* counters, uint32_t tiles,
                           cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {  // let several CTAs of 18-43 KB share one SM's shared memory
+    static bool configured[kMaxDevices] = {false};
+    const int dev = current_device_index();
+    if (!configured[dev]) {  // let several CTAs of 18-43 KB share one SM's shared memory
         cudaFuncSetAttribute(onesweep_pass_kernel<kPairs, kItems>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured = true;
+        configured[dev] = true;
     }
     for (uint32_t p = 0; p < plan.n_passes; ++p) {
         const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
@@ -935,60 +574,45 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     if (n < 2 || plan.n_passes == 0) return res;
     const int items = items_for(n);
     const uint32_t tiles = tiles_for(n, items);
-    if (!vals && items == 16 && big_sort_mode() == BigSortMode::Scan) {
-        const uint32_t tiles_per_chunk = (tiles + kMaxChunks - 1) / kMaxChunks;
-        const uint32_t chunks = (tiles + tiles_per_chunk - 1) / tiles_per_chunk;
-        uint32_t* chunk_totals = static_cast<uint32_t*>(scratch);
-        uint32_t* tile_hist = chunk_totals + (size_t)kMaxSortPasses * kTotalsRows * kRadix;
-        cudaMemsetAsync(chunk_totals, 0, (size_t)plan.n_passes * kTotalsRows * kRadix * sizeof(uint32_t), stream);
-        // Persistent TMA-staged downsweep unless FORMA_SORT_DS=simple (one CTA per tile).
-        static int ds_grid = -1, wide_grid = 0;
-        if (ds_grid < 0) {
-            const char* e = getenv("FORMA_SORT_DS");  // simple | tma256 | (default) wide
-            ds_grid = 0;
-            if (!e || (e[0] != 's' && e[0] != 't')) {
-                cudaFuncSetAttribute(radix_downsweep_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(DownsweepWideSmem));
-                int per_sm = 0, sms = 148, dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_wide_kernel, kWideThreads,
-                                                              sizeof(DownsweepWideSmem));
-                wide_grid = per_sm > 0 ? per_sm * sms : 0;
-            }
-            if (!wide_grid && !(e && e[0] == 's')) {
-                cudaFuncSetAttribute(radix_downsweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(DownsweepSmem));
-                int per_sm = 0, sms = 148, dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_tma_kernel, kSortThreads,
-                                                              sizeof(DownsweepSmem));
-                ds_grid = per_sm > 0 ? per_sm * sms : 0;
-            }
+    if (!vals && items == 16) {
+        // Persistent TMA-staged downsweep: 2 CTAs per SM (per-device attribute + grid).
+        static int wide_grids[kMaxDevices];
+        static bool ds_configured[kMaxDevices] = {false};
+        const int cur_dev = current_device_index();
+        int& wide_grid = wide_grids[cur_dev];
+        if (!ds_configured[cur_dev]) {
+            ds_configured[cur_dev] = true;
+            cudaFuncSetAttribute(radix_downsweep_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(DownsweepWideSmem));
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_wide_kernel, kWideThreads,
+                                                          sizeof(DownsweepWideSmem));
+            wide_grid = per_sm > 0 ? per_sm * device_sm_count() : 0;
         }
-        for (uint32_t p = 0; p < plan.n_passes; ++p) {
-            const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
-            uint64_t* kout = (p & 1u) ? keys : keys_tmp;
-            uint32_t* totals = chunk_totals + (size_t)p * kTotalsRows * kRadix;
-            if (pass_events) cudaEventRecord(pass_events[3 * p], stream);
-            radix_upsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, n, plan.pass[p], tile_hist, totals, tiles_per_chunk);
-            radix_tile_scan_kernel<<<chunks, kRadix, 0, stream>>>(tile_hist, totals, tiles, tiles_per_chunk);
-            if (pass_events) cudaEventRecord(pass_events[3 * p + 1], stream);
-            if (wide_grid > 0)
+        if (wide_grid > 0) {
+            const uint32_t tiles_per_chunk = (tiles + kMaxChunks - 1) / kMaxChunks;
+            const uint32_t chunks = (tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+            uint32_t* chunk_totals = static_cast<uint32_t*>(scratch);
+            uint32_t* tile_hist = chunk_totals + (size_t)kMaxSortPasses * kTotalsRows * kRadix;
+            cudaMemsetAsync(chunk_totals, 0, (size_t)plan.n_passes * kTotalsRows * kRadix * sizeof(uint32_t), stream);
+            for (uint32_t p = 0; p < plan.n_passes; ++p) {
+                const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
+                uint64_t* kout = (p & 1u) ? keys : keys_tmp;
+                uint32_t* totals = chunk_totals + (size_t)p * kTotalsRows * kRadix;
+                if (pass_events) cudaEventRecord(pass_events[3 * p], stream);
+                radix_upsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, n, plan.pass[p], tile_hist, totals, tiles_per_chunk);
+                radix_tile_scan_kernel<<<chunks, kRadix, 0, stream>>>(tile_hist, totals, tiles, tiles_per_chunk);
+                if (pass_events) cudaEventRecord(pass_events[3 * p + 1], stream);
                 radix_downsweep_wide_kernel<<<min(tiles, (uint32_t)wide_grid), kWideThreads, sizeof(DownsweepWideSmem), stream>>>(
                     kin, kout, n, plan.pass[p], tile_hist, tiles);
-            else if (ds_grid > 0)
-                radix_downsweep_tma_kernel<<<min(tiles, (uint32_t)ds_grid), kSortThreads, sizeof(DownsweepSmem), stream>>>(
-                    kin, kout, n, plan.pass[p], tile_hist, tiles);
-            else
-                radix_downsweep_kernel<<<tiles, kSortThreads, 0, stream>>>(kin, kout, n, plan.pass[p], tile_hist);
-            if (pass_events) cudaEventRecord(pass_events[3 * p + 2], stream);
+                if (pass_events) cudaEventRecord(pass_events[3 * p + 2], stream);
+            }
+            res.timed_passes = pass_events ? (int)plan.n_passes : 0;
+            res.launches = 3 * (int)plan.n_passes;
+            res.in_tmp = (plan.n_passes & 1u) != 0u;
+            return res;
         }
-        res.timed_passes = pass_events ? (int)plan.n_passes : 0;
-        res.launches = 3 * (int)plan.n_passes;
-        res.in_tmp = (plan.n_passes & 1u) != 0u;
-        return res;
+        // (occupancy query failed: fall through to the single-sweep passes)
     }
     uint32_t* hist = static_cast<uint32_t*>(scratch);
     uint32_t* counters = hist + kMaxSortPasses * kRadix;
@@ -1002,30 +626,6 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     if (vals) {
         if (items == 16) launch_passes<true, 16>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
         else launch_passes<true, 4>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
-    } else if (items == 16 && big_sort_mode() == BigSortMode::Persistent) {
-        // Large key-only sort: persistent CTAs with TMA-staged tiles.
-        static int resident = 0;
-        if (!resident) {
-            cudaFuncSetAttribute(onesweep_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(PersistentSmem));
-            int per_sm = 0, sms = 148, dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onesweep_persistent_kernel, kSortThreads,
-                                                          sizeof(PersistentSmem));
-            resident = per_sm > 0 ? per_sm * sms : 0;
-        }
-        if (resident > 0) {
-            uint32_t grid = min(tiles, (uint32_t)resident);  // all CTAs must be co-resident (look-back)
-            for (uint32_t p = 0; p < plan.n_passes; ++p) {
-                const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
-                uint64_t* kout = (p & 1u) ? keys : keys_tmp;
-                onesweep_persistent_kernel<<<grid, kSortThreads, sizeof(PersistentSmem), stream>>>(
-                    kin, kout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tiles);
-            }
-        } else {
-            launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);
-        }
     } else {
         if (items == 16) launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);
         else launch_passes<false, 4>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);

@@ -349,19 +349,33 @@ __global__ void merge_entries_kernel(PaintScene S, const uint64_t* __restrict__ 
     eflags[pos] = (uint8_t)flags;
 }
 
-// Per painted tile: [begin, end) of its entries in the sorted entry list.
-__global__ void tile_range_kernel(PaintScene S, const uint64_t* __restrict__ ekey, uint32_t n_entries,
-                                  uint32_t* __restrict__ tile_begin, uint32_t* __restrict__ tile_end) {
+// Per painted tile: [begin, end) of its entries in the sorted entry list, written by the
+// thread of the tile's last entry (which bisects for the first one); the same thread files
+// a tile with many entries in its class list (see paint_common.cuh: kHeavyMin).
+__global__ void tile_index_kernel(PaintScene S, const uint64_t* __restrict__ ekey, uint32_t n_entries,
+                                  uint2* __restrict__ tile_range, uint32_t* __restrict__ heavy /* [classes][tiles] or null */,
+                                  uint32_t* __restrict__ heavy_count) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_entries) return;
-    uint64_t k = ekey[p];
+    const uint64_t k = ekey[p];
     // Entries outside the render target (biased tile coordinate 0 = tile -1, or
     // beyond the last tile) belong to no painted tile.
     if (key_ty(k) == 0u || key_ty(k) > S.tiles_y || key_tx(k) == 0u || key_tx(k) > S.tiles_x) return;
-    uint64_t tile_bits = k >> 41;
-    uint32_t tid = (key_ty(k) - 1u) * S.tiles_x + (key_tx(k) - 1u);
-    if (p == 0 || (ekey[p - 1] >> 41) != tile_bits) tile_begin[tid] = p;
-    if (p + 1 == n_entries || (ekey[p + 1] >> 41) != tile_bits) tile_end[tid] = p + 1;
+    const uint64_t tile_bits = k >> 41;
+    if (p + 1 != n_entries && (ekey[p + 1] >> 41) == tile_bits) return;  // not the tile's last entry
+    uint32_t lo = 0, hi = p;  // first entry of the tile: the first q with ekey[q] >> 41 >= tile_bits
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((ekey[mid] >> 41) < tile_bits) lo = mid + 1u;
+        else hi = mid;
+    }
+    const uint32_t tid = (key_ty(k) - 1u) * S.tiles_x + (key_tx(k) - 1u);
+    tile_range[tid] = make_uint2(lo, p + 1u);
+    const uint32_t count = p + 1u - lo;
+    if (heavy && count >= kHeavyMin) {
+        const int c = heavy_class(count);
+        heavy[(size_t)c * S.tiles_x * S.tiles_y + atomicAdd(&heavy_count[c], 1u)] = tid;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -428,12 +442,11 @@ void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_
                                                                gap_carry, ekey, recs, eflags);
 }
 
-void launch_tile_ranges(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint32_t* tile_begin,
-                        uint32_t* tile_end, cudaStream_t st) {
-    size_t bytes = (size_t)S.tiles_x * S.tiles_y * sizeof(uint32_t);
-    cudaMemsetAsync(tile_begin, 0, bytes, st);
-    cudaMemsetAsync(tile_end, 0, bytes, st);
-    if (n_entries) tile_range_kernel<<<(n_entries + 255) / 256, 256, 0, st>>>(S, ekey, n_entries, tile_begin, tile_end);
+void launch_tile_index(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint2* tile_range, uint32_t* heavy,
+                       uint32_t* heavy_count, cudaStream_t st) {
+    cudaMemsetAsync(tile_range, 0, (size_t)S.tiles_x * S.tiles_y * sizeof(uint2), st);
+    cudaMemsetAsync(heavy_count, 0, kHeavyClasses * sizeof(uint32_t), st);
+    if (n_entries) tile_index_kernel<<<(n_entries + 255) / 256, 256, 0, st>>>(S, ekey, n_entries, tile_range, heavy, heavy_count);
 }
 
 

@@ -42,6 +42,15 @@ constexpr uint32_t kFlagClipish = 32;      // Func::Clip, or a Draw layer with i
 constexpr uint32_t kFlagOpaque = 64;       // Draw, solid fill, BlendMode::Over, alpha == 1
 constexpr uint32_t kFlagClippedDraw = 128; // Draw layer with is_clipped
 
+// Tiles with at least kHeavyMin entries are listed by class (class c: 2^(c+4) <= entries <
+// 2^(c+5), the last class open-ended) so that the painter starts them first.
+constexpr int kHeavyClasses = kHeavyListClasses;
+constexpr uint32_t kHeavyMin = 16;
+__device__ __forceinline__ int heavy_class(uint32_t entries) {
+    const int c = 27 - __clz((int)entries);  // floor(log2) - 4
+    return c > kHeavyClasses - 1 ? kHeavyClasses - 1 : c;
+}
+
 // packed style: fill_rule | func<<1 | is_clipped<<2 | fill_type<<3 | blend_mode<<5 | unchanged<<9
 __device__ __forceinline__ uint32_t pack_style_meta(const StyleRec& st, bool unchanged) {
     return (st.fill_rule & 1u) | ((st.func & 1u) << 1) | ((st.is_clipped ? 1u : 0u) << 2) | ((st.fill_type & 3u) << 3) |

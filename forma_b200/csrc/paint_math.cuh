@@ -424,6 +424,51 @@ __device__ __forceinline__ void gradient_at_small(const StyleRec& st, const Grad
     for (int k = 0; k < 4; ++k) out[k] = __uint_as_float(bits[k]);
 }
 
+// gradient_at_small with the style's start point and type passed in registers (the painter's
+// pixel-pair loop); identical operations in identical order.
+__device__ __forceinline__ void gradient_at_small_xy(const GradientSetup& g, uint32_t gradient_type, float sx, float sy, float x,
+                                                     float y_base, int lane, float out[4]) {
+    float t;
+    if (gradient_type == 0u) {
+        float tx = (x - sx) * g.dx * g.dot_recip;
+        float ty = y_base - sy;
+        t = fmaf(((float)lane + ty) * g.dy, g.dot_recip, tx);
+    } else {
+        float px = x - sx;
+        float px2 = px * px;
+        float py = (float)lane + (y_base - sy);
+        t = sqrtf(fmaf(py, py, px2) * g.dot_recip);
+    }
+    uint32_t bits[4] = {0u, 0u, 0u, 0u};
+    bool acc = t <= g.c[0].stop;
+    if (acc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits[k] |= __float_as_uint(g.c[0].color[k]);
+    }
+    float start_stop = 0.0f;
+#pragma unroll
+    for (uint32_t i = 1; i < 4u; ++i) {
+        if (i < g.count) {
+            bool mask = acc != (t < g.c[i].stop);
+            if (mask) {
+                float d = g.c[i].stop - start_stop;
+                float local_t = (t - start_stop) * d_rcp(d);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    bits[k] |= __float_as_uint(fmaf(local_t, g.c[i].color[k], fmaf(-local_t, g.c[i - 1].color[k], g.c[i - 1].color[k])));
+                acc = true;
+            }
+            start_stop = g.c[i].stop;
+        }
+    }
+    if (!acc) {  // g.c[3] is the last stop (padding repeats it)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits[k] |= __float_as_uint(g.c[3].color[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = __uint_as_float(bits[k]);
+}
+
 // Texture::color_at for one lane (cpu/painter/styling.rs:146-193).
 __device__ inline void texture_at(const StyleRec& st, const uint16_t* __restrict__ texels, float x, float y_base,
                                   int lane, float out[4]) {

@@ -5,11 +5,13 @@
 // every stage is a CUDA kernel sequence on one stream, and there is no CPU
 // fallback: without a usable sm_100 device forma_renderer_new() fails.
 #include <algorithm>
+#include <cctype>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
+#include <stdexcept>
 #include <string>
 
 #include "../../include/forma_b200.h"
@@ -31,6 +33,36 @@ void set_error(const char* fmt, ...) {
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     g_error = buf;
+}
+
+// ---------------------------------------------------------------------------
+// Options
+// ---------------------------------------------------------------------------
+struct OptionName {
+    const char* name;
+    int Options::*field;
+    int lo, hi;
+};
+static const OptionName kOptionNames[] = {
+    {"speculate", &Options::speculate, 0, 1},         {"band_copy", &Options::band_copy, 0, 1},
+    {"copy_bands", &Options::copy_bands, 1, 16},      {"sort_full_key", &Options::sort_full_key, 0, 1},
+    {"sort_big_log2", &Options::sort_big_log2, 10, 30}, {"test_gap_cap", &Options::test_gap_cap, 0, 1 << 30},
+    {"paint_lpt", &Options::paint_lpt, 0, 1},
+};
+Options& options() {
+    static Options o = [] {
+        Options v;
+        for (const OptionName& n : kOptionNames) {
+            std::string env = "FORMA_";
+            for (const char* c = n.name; *c; ++c) env += (char)toupper((unsigned char)*c);
+            if (const char* e = getenv(env.c_str())) {
+                long x = strtol(e, nullptr, 10);
+                if (x >= n.lo && x <= n.hi) v.*(n.field) = (int)x;
+            }
+        }
+        return v;
+    }();
+    return o;
 }
 
 // ---------------------------------------------------------------------------
@@ -83,6 +115,12 @@ void Composition::set_order(Layer* l, int64_t order) {  // layer.rs:148-158
 }
 
 Layer* Composition::insert(uint32_t order, Layer* layer) {  // mod.rs:121-138
+    // The reference takes the Layer by value: a layer cannot sit at two orders. Through
+    // the C ABI the same handle can be inserted again, which moves it.
+    if (layer->order >= 0 && (uint32_t)layer->order != order) {
+        auto at = layers.find((uint32_t)layer->order);
+        if (at != layers.end() && at->second == layer) layers.erase(at);
+    }
     set_order(layer, order);
     Layer* old = nullptr;
     auto it = layers.find(order);
@@ -136,6 +174,9 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
     const FlattenProgram& prog = path.data->program();
     uint32_t count = prog.n_points;
     if (count) {
+        if ((uint64_t)n_points + count >= (1ull << 32)) compact_geom();  // dead geometry counts until compacted
+        if ((uint64_t)n_points + count >= (1ull << 32))
+            throw std::length_error("segment buffer would exceed 2^32 points");
         PendingInsert job;
         job.data = path.data;
         job.has_xf = path.has_xf;
@@ -260,35 +301,24 @@ class Renderer {
     }
     DeviceBuffer<uint64_t> segs, segs_tmp;
     DeviceBuffer<uint8_t> sort_scratch;
-    DeviceBuffer<uint32_t> head_masks, cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, gid_tmp, tile_begin, tile_end;
+    DeviceBuffer<uint32_t> head_masks, cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, gid_tmp, heavy_tiles;
+    DeviceBuffer<uint2> tile_range;
     DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp, gkey_tmp;
     DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
     DeviceBuffer<uint8_t> eflags, framebuffer;
     DeviceBuffer<EntryRec> recs;
     // Band-wise copy-back of host frames (see render()).
     static constexpr uint32_t kMaxCopyBands = 16;
-    static uint32_t copy_bands() {  // FORMA_COPY_BANDS=n (1..16): number of paint / copy-back bands of a host frame
-        static const uint32_t n = [] {
-            const char* e = getenv("FORMA_COPY_BANDS");
-            long v = e ? strtol(e, nullptr, 10) : 4;
-            return (uint32_t)std::min<long>(std::max<long>(v, 1), kMaxCopyBands);
-        }();
-        return n;
-    }
+    static uint32_t copy_bands() { return (uint32_t)std::min(std::max(options().copy_bands, 1), (int)kMaxCopyBands); }
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t band_ev[kMaxCopyBands + 1];
     cudaEvent_t count_ev = nullptr;  // completion of a count read-back (waited on instead of the whole stream)
     cudaError_t ensure_count_event() {
         return count_ev ? cudaSuccess : cudaEventCreateWithFlags(&count_ev, cudaEventDisableTiming);
     }
-    static bool speculation_enabled() {  // FORMA_SPECULATE=0: never launch a kernel before its sizes are known on the host
-        static const bool on = !(getenv("FORMA_SPECULATE") && getenv("FORMA_SPECULATE")[0] == '0');
-        return on;
-    }
-    static bool band_copies_enabled() {  // FORMA_BAND_COPY=0 copies the frame in one piece after the paint kernel
-        static const bool on = !(getenv("FORMA_BAND_COPY") && getenv("FORMA_BAND_COPY")[0] == '0');
-        return on;
-    }
+    static bool speculation_enabled() { return options().speculate != 0; }
+    static size_t test_gap_cap_override() { return (size_t)std::max(options().test_gap_cap, 0); }
+    static bool band_copies_enabled() { return options().band_copy != 0; }
     // Layer-cache frames: per-slot `is_unchanged` flags, the list of written
     // tiles and their packed pixels (only these travel back to a host buffer).
     DeviceBuffer<uint8_t> d_unchanged;
@@ -305,6 +335,8 @@ class Renderer {
     DeviceBuffer<FlattenJob> up_jobs;
 
     uint32_t last_segments = 0, last_cells = 0, last_entries = 0, last_gaps = 0;
+    RasterArgs last_raster{};        // line-setup arguments of the last render (device pointers owned by its composition)
+    bool last_raster_valid = false;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied over PCIe since creation
     double stage_ms[8] = {0};               // see forma_renderer_stage_times
     double kernel_ms[4] = {0};              // see forma_renderer_kernel_times
@@ -599,7 +631,8 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
 // Stages 1½ + 2: fills `segs` with the unsorted pixel segments.
 int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, float band_lo, float band_hi,
                         uint32_t* n_out) {
-    RasterArgs ra;
+    RasterArgs& ra = last_raster;  // kept for forma_renderer_lines
+    last_raster_valid = true;
     ra.x = comp.d_x.ptr;
     ra.y = comp.d_y.ptr;
     ra.gid = comp.d_gid.ptr;
@@ -636,7 +669,7 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     n = pinned_totals[0];
     {
         // Already ordered by layer: no layer digits (see Composition::layers_in_order).
-        static const bool skip_layer_digits = !(getenv("FORMA_SORT_FULL_KEY") && getenv("FORMA_SORT_FULL_KEY")[0] == '1');
+        const bool skip_layer_digits = options().sort_full_key == 0;
         const uint64_t layer_bound = (comp.layers_in_order && skip_layer_digits) ? 0u : (comp.n_orders ? comp.n_orders - 1u : 0u);
         const uint64_t bound[3] = {layer_bound, pinned_totals[4], pinned_totals[5]};
         segment_plan = make_sort_plan(segment_key_layout(), bound);  // layer, tile_x, tile_y
@@ -773,8 +806,11 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
 
     // Stage 4: cells -> carries -> entries -> paint.
     size_t n_tiles_total = (size_t)S.tiles_x * S.tiles_y;
-    FORMA_CUDA_TRY(tile_begin.reserve(n_tiles_total));
-    FORMA_CUDA_TRY(tile_end.reserve(n_tiles_total));
+    FORMA_CUDA_TRY(tile_range.reserve(n_tiles_total));
+    FORMA_CUDA_TRY(heavy_tiles.reserve(n_tiles_total * kHeavyListClasses));
+    // Heavy tiles first (longest-processing-time order): their lists + counts (totals[8..11]).
+    uint32_t* const heavy_lists = options().paint_lpt ? heavy_tiles.ptr : nullptr;
+    uint32_t* const heavy_counts = totals.ptr + 8;
     uint8_t* fb = buffer;
     if (!buffer_on_device) {
         FORMA_CUDA_TRY(framebuffer.reserve((size_t)stride * height));
@@ -841,10 +877,14 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         // Same scheme for the number of carry-only entries: gap_fill runs ahead of the read-back.
         FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 2, totals.ptr + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
+        // The speculative output survives only if the reserve(n_gaps + 1) calls below do not
+        // reallocate: one element of every buffer is kept back (the sort's slack slot).
         size_t gap_cap = 0;
-        if (speculation_enabled())
-            gap_cap = std::min({ekey_tmp.capacity, eid_tmp.capacity, gap_carry.capacity,
-                                (size_t)last_gaps * 2u + 4096u /* also the number of threads launched */});
+        if (speculation_enabled()) {
+            const size_t room = std::min({ekey_tmp.capacity, eid_tmp.capacity, gap_carry.capacity});
+            gap_cap = std::min<size_t>(room ? room - 1u : 0u, (size_t)last_gaps * 2u + 4096u /* also the number of threads launched */);
+            if (test_gap_cap_override() && gap_cap) gap_cap = std::min<size_t>(gap_cap, test_gap_cap_override());
+        }
         if (gap_cap) {
             launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
                             ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, (uint32_t)gap_cap, (uint32_t)gap_cap, stream);
@@ -884,7 +924,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                              gap_carry.ptr, ekey.ptr, recs.ptr, eflags.ptr, stream);
         ++launches;
     }
-    launch_tile_ranges(S, ekey.ptr, n_entries, tile_begin.ptr, tile_end.ptr, stream);
+    launch_tile_index(S, ekey.ptr, n_entries, tile_range.ptr, heavy_lists, heavy_counts, stream);
     launches += n_entries ? 1 : 0;
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
     // Host frame without a layer cache: paint in bands of tile rows and copy each
@@ -904,7 +944,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             PaintScene Sb = S;
             Sb.ty_lo = S.ty_lo + paint_rows * k / kCopyBands;
             Sb.ty_hi = S.ty_lo + paint_rows * (k + 1u) / kCopyBands;
-            launch_paint(Sb, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
+            launch_paint(Sb, segs.ptr, recs.ptr, tile_range.ptr, heavy_lists, heavy_counts, eflags.ptr, fb, totals.ptr + 3, stream);
             ++launches;
             FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], stream));
             FORMA_CUDA_TRY(cudaStreamWaitEvent(copy_stream, band_ev[k], 0));
@@ -919,7 +959,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         paint_launches = kCopyBands;
         copied_in_bands = true;
     } else {
-        launch_paint(S, segs.ptr, recs.ptr, tile_begin.ptr, tile_end.ptr, eflags.ptr, fb, totals.ptr + 3, stream);
+        launch_paint(S, segs.ptr, recs.ptr, tile_range.ptr, heavy_lists, heavy_counts, eflags.ptr, fb, totals.ptr + 3, stream);
         ++launches;
     }
     FORMA_CUDA_TRY(cudaGetLastError());
@@ -1352,7 +1392,7 @@ static forma_renderer* renderer_new_impl(int device_ordinal) {
     }
     forma_renderer* r = new forma_renderer();
     r->r.device = device_ordinal;
-    if (cudaMallocHost(&r->r.pinned_totals, 8 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(8) != cudaSuccess ||
+    if (cudaMallocHost(&r->r.pinned_totals, 16 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(16) != cudaSuccess ||
         cudaMemset(r->r.totals.ptr, 0, r->r.totals.capacity * sizeof(uint32_t)) != cudaSuccess) {
         set_error("allocation of renderer state failed");
         delete r;
@@ -1449,6 +1489,76 @@ int forma_shared_frame_free(int device, void* device_ptr) {
     return FORMA_STATUS_OK;
 }
 
+int forma_set_option(const char* name, int value) {
+    if (name)
+        for (const OptionName& n : kOptionNames)
+            if (!strcmp(n.name, name)) {
+                if (value < n.lo || value > n.hi) break;
+                options().*(n.field) = value;
+                return FORMA_OK;
+            }
+    set_error("forma_set_option: unknown option or value out of range (%s = %d)", name ? name : "(null)", value);
+    return FORMA_ERR_INVALID_ARGUMENT;
+}
+int forma_get_option(const char* name, int* value) {
+    if (name && value)
+        for (const OptionName& n : kOptionNames)
+            if (!strcmp(n.name, name)) {
+                *value = options().*(n.field);
+                return FORMA_OK;
+            }
+    set_error("forma_get_option: unknown option %s", name ? name : "(null)");
+    return FORMA_ERR_INVALID_ARGUMENT;
+}
+
+// Packed-fp32 self-test (see kernels_painter.cu): random and special operands (zeros,
+// denormals, infinities, NaN, cancellation cases) through every packed helper of the painter.
+static int selftest_impl(int device, uint64_t* mismatches) {
+    if (!mismatches) return FORMA_ERR_INVALID_ARGUMENT;
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    const uint32_t n = 1u << 20;
+    std::vector<float> h(3u * n);
+    uint64_t sstate = 0x1234567ull;
+    auto next = [&] {
+        sstate += 0x9E3779B97F4A7C15ull;
+        uint64_t z = sstate;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    const uint32_t special[] = {0x00000000u, 0x80000000u, 0x00000001u, 0x007FFFFFu, 0x00800000u, 0x3F800000u, 0xBF800000u,
+                                0x3F7FFFFFu, 0x3F800001u, 0x7F7FFFFFu, 0x7F800000u, 0xFF800000u, 0x7FC00000u, 0x33800000u};
+    for (size_t i = 0; i < h.size(); ++i) {
+        const uint64_t r = next();
+        uint32_t bits;
+        switch (r & 7u) {
+            case 0: bits = special[(r >> 8) % (sizeof(special) / sizeof(special[0]))]; break;
+            case 1: bits = (uint32_t)(r >> 32); break;                                  // any bit pattern
+            case 2: bits = 0x3F800000u - (uint32_t)((r >> 32) & 0x3FFFFFu); break;      // just below 1
+            default: {                                                                  // [0, 1) colours / coverages
+                float f = (float)((r >> 40) & 0xFFFFFFu) / 16777216.0f;
+                std::memcpy(&bits, &f, 4);
+            }
+        }
+        std::memcpy(&h[i], &bits, 4);
+    }
+    DeviceBuffer<float> d;
+    DeviceBuffer<uint32_t> out;
+    FORMA_CUDA_TRY(d.reserve(h.size()));
+    FORMA_CUDA_TRY(out.reserve(1));
+    FORMA_CUDA_TRY(cudaMemcpy(d.ptr, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FORMA_CUDA_TRY(cudaMemset(out.ptr, 0, sizeof(uint32_t)));
+    launch_f32x2_selftest(d.ptr, d.ptr + n, d.ptr + 2u * n, n, out.ptr, 0);
+    FORMA_CUDA_TRY(cudaGetLastError());
+    uint32_t bad = 0;
+    FORMA_CUDA_TRY(cudaMemcpy(&bad, out.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    *mismatches = bad;
+    return FORMA_OK;
+}
+int forma_debug_selftest(int device, uint64_t* mismatches) {
+    return guarded((int)FORMA_ERR_CAPACITY, [&] { return selftest_impl(device, mismatches); });
+}
+
 uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.launches; }
 void forma_renderer_stage_times(const forma_renderer* r, double out_ms[8]) {
     for (int i = 0; i < 8; ++i) out_ms[i] = r->r.stage_ms[i];
@@ -1486,12 +1596,48 @@ void forma_path_builder_extend(forma_path_builder* pb, const uint8_t* cmds, uint
     });
 }
 
-uint64_t forma_renderer_lines(forma_renderer*, uint64_t, uint32_t*, float*, float*, float*, float*, float*, float*,
-                              float*, float*, uint32_t*) {
-    // Line records are never materialised: line setup is fused into the
-    // pixel-grid intersection kernel. Parity of this stage is observable through
-    // forma_renderer_rasterize_only (same segments, same order).
-    return 0;
+static uint64_t renderer_lines_impl(forma_renderer* r, uint64_t cap, uint32_t* orders, float* x0, float* y0, float* dx,
+                                    float* dy, float* a, float* b, float* c, float* d, uint32_t* lengths) {
+    // Line records are never materialised by render(): line setup is fused into the
+    // pixel-grid intersection kernel. For inspection they are produced here, by the same
+    // device function (line_setup), from the arguments of the last render; the composition
+    // of that render must still be alive.
+    Renderer& R = r->r;
+    if (!R.last_raster_valid || R.last_raster.n_points < 2) return 0;
+    const uint32_t n = R.last_raster.n_points - 1u;
+    if (!cap || !orders) return n;
+    if (cudaSetDevice(R.device) != cudaSuccess) return 0;
+    RasterArgs A = R.last_raster;
+    A.band_lo = -3.0e38f;  // the reference's records know no tile bands
+    A.band_hi = 3.0e38f;
+    DeviceBuffer<uint32_t> d_orders, d_lengths;
+    DeviceBuffer<float> d_f[8];
+    if (d_orders.reserve(n) != cudaSuccess || d_lengths.reserve(n) != cudaSuccess) return 0;
+    float* fp[8];
+    for (int k = 0; k < 8; ++k) {
+        if (d_f[k].reserve(n) != cudaSuccess) return 0;
+        fp[k] = d_f[k].ptr;
+    }
+    launch_line_records(A, n, d_orders.ptr, fp, d_lengths.ptr, R.stream);
+    const size_t m = (size_t)std::min<uint64_t>(cap, n);
+    float* out[8] = {x0, y0, dx, dy, a, b, c, d};
+    bool ok = cudaMemcpyAsync(orders, d_orders.ptr, m * 4, cudaMemcpyDeviceToHost, R.stream) == cudaSuccess &&
+              cudaMemcpyAsync(lengths, d_lengths.ptr, m * 4, cudaMemcpyDeviceToHost, R.stream) == cudaSuccess;
+    for (int k = 0; k < 8 && ok; ++k) ok = cudaMemcpyAsync(out[k], fp[k], m * 4, cudaMemcpyDeviceToHost, R.stream) == cudaSuccess;
+    if (!ok || cudaStreamSynchronize(R.stream) != cudaSuccess) {
+        set_error("forma_renderer_lines: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    uint32_t sum = 0;  // prefix_sum, segment.rs:90-98 (inclusive)
+    for (size_t i = 0; i < m; ++i) {
+        sum += lengths[i];
+        lengths[i] = sum;
+    }
+    return n;
+}
+uint64_t forma_renderer_lines(forma_renderer* r, uint64_t cap, uint32_t* orders, float* x0, float* y0, float* dx, float* dy,
+                              float* a, float* b, float* c, float* d, uint32_t* lengths) {
+    return guarded((uint64_t)0, [&] { return renderer_lines_impl(r, cap, orders, x0, y0, dx, dy, a, b, c, d, lengths); });
 }
 uint64_t forma_renderer_segments(forma_renderer* r, uint64_t cap, uint64_t* out) {
     uint64_t n = r->r.last_segments;
@@ -1531,8 +1677,8 @@ int forma_renderer_sort_u64(forma_renderer* r, uint64_t* keys, uint64_t n) {
     }
     if (n < 2) return FORMA_OK;
     FORMA_CUDA_TRY(cudaSetDevice(R.device));
-    FORMA_CUDA_TRY(R.segs.reserve(n));
-    FORMA_CUDA_TRY(R.segs_tmp.reserve(n));
+    FORMA_CUDA_TRY(R.segs.reserve(n + 1));  // one key of slack: the TMA downsweep copies an even number of keys
+    FORMA_CUDA_TRY(R.segs_tmp.reserve(n + 1));
     FORMA_CUDA_TRY(R.sort_scratch.reserve(radix_scratch_bytes((uint32_t)n)));
     FORMA_CUDA_TRY(cudaMemcpyAsync(R.segs.ptr, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, R.stream));
     // The caller's keys are on the host: take the field bounds from their OR.

@@ -242,14 +242,28 @@ void forma_renderer_kernel_times(const forma_renderer*, double out_ms[4], uint32
  * [6] tiles the last layer-cache render copied back to a host buffer, [7] 0. */
 void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
 
+/* Schedule switches of the library (process-wide; none changes results): "speculate",
+ * "band_copy", "copy_bands", "sort_full_key", "sort_big_log2", "paint_lpt", "test_gap_cap".
+ * Defaults come from the environment (FORMA_SPECULATE, ...); see DESIGN.md section 6. */
+int forma_set_option(const char* name, int value);
+int forma_get_option(const char* name, int* value);
+
+/* Device self-test of the painter's packed-fp32 (f32x2) arithmetic against the scalar IEEE
+ * operations it stands for (2^20 operand triples incl. zeros, denormals, infinities, NaN);
+ * *mismatches must come back 0. */
+int forma_debug_selftest(int device, uint64_t* mismatches);
+
 /* Number of CUDA kernels the renderer launched since it was created. */
 uint64_t forma_renderer_launch_count(const forma_renderer*);
 
 /* --- stage-level access (parity tests; the reference's own tests reach the
  *     same data through Rasterizer::segments(), cpu/rasterizer.rs:88) -------- */
 
-/* Copy the line records produced by the last render (SegmentBufferView of
- * segment.rs:530-545) to host arrays of capacity `cap`; returns the count. */
+/* The line records of the last render (SegmentBufferView of segment.rs:530-545: one
+ * record per point pair, `lengths` as inclusive prefix sums) in host arrays of capacity
+ * `cap`; returns the count (call with cap = 0 to size the arrays). render() never
+ * materialises them; they are recomputed here from the last render's composition, which
+ * must still be alive. */
 uint64_t forma_renderer_lines(forma_renderer*, uint64_t cap, uint32_t* orders, float* x0, float* y0,
                               float* dx, float* dy, float* a, float* b, float* c, float* d,
                               uint32_t* lengths);

@@ -38,6 +38,18 @@ def f32(v) -> float:
     return float(np.float32(v))
 
 
+def splitmix_uniform_block(seed: int, n: int) -> np.ndarray:
+    """The first n `SplitMix64(seed).uniform()` values (u in [0, 1), float64), vectorised:
+    the k-th output only depends on seed + k * gamma."""
+    with np.errstate(over="ignore"):
+        k = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed & MASK) + k * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+
+
 def circle_path(api, cx, cy, r):
     """Rational-quad circle (shape of e2e-tests/tests/tests.rs:80-105)."""
     w = f32(np.sqrt(np.float32(2.0)) / np.float32(2.0))
@@ -121,7 +133,42 @@ def random_mixed(api, comp, n_layers: int, width: int, height: int, seed: int):
 
 def random_circles(api, comp, n_layers: int, width: int, height: int, seed: int, r=(4.0, 40.0)):
     """BASELINE config 5 shape: rational-quad circles, 3-stop radial gradients
-    centred on the circle, blend mode = layer index mod 8 over separable modes."""
+    centred on the circle, blend mode = layer index mod 8 over separable modes.
+    Same random stream as 13 `SplitMix64.uniform` calls per circle (cx, cy, radius, alpha,
+    3 x rgb), drawn in one vectorised block: a 1 M-circle scene is built in seconds."""
+    modes = [BlendMode.Over, BlendMode.Multiply, BlendMode.Screen, BlendMode.Overlay, BlendMode.Darken,
+             BlendMode.Lighten, BlendMode.HardLight, BlendMode.Difference]
+    u = splitmix_uniform_block(seed, 13 * n_layers).reshape(n_layers, 13)
+
+    def rounded(v):  # float64 arithmetic, one rounding to f32 — what SplitMix64.uniform / f32() do
+        return v.astype(np.float32).astype(np.float64)
+    cx = rounded(0.0 + (float(width) - 0.0) * u[:, 0])
+    cy = rounded(0.0 + (float(height) - 0.0) * u[:, 1])
+    rad = rounded(r[0] + (r[1] - r[0]) * u[:, 2])
+    alpha = rounded(0.3 + (1.0 - 0.3) * u[:, 3])
+    rgb = rounded(u[:, 4:13])
+    xp, xm, yp, ym = rounded(cx + rad), rounded(cx - rad), rounded(cy + rad), rounded(cy - rad)
+    w = f32(np.sqrt(np.float32(2.0)) / np.float32(2.0))
+    cols = np.stack([cx, cy, xp, xm, yp, ym, alpha], axis=1).tolist()
+    rgb = rgb.tolist()
+    for i in range(n_layers):
+        x, y, x1, x0, y1, y0, a = cols[i]
+        c = rgb[i]
+        path = (api.PathBuilder().move_to(Point(x1, y))
+                .rat_quad_to(Point(x1, y0), Point(x, y0), w)
+                .rat_quad_to(Point(x0, y0), Point(x0, y), w)
+                .rat_quad_to(Point(x0, y1), Point(x, y1), w)
+                .rat_quad_to(Point(x1, y1), Point(x1, y), w).build())
+        gb = GradientBuilder(Point(x, y), Point(x1, y)).type(GradientType.Radial)
+        gb.color(Color(c[0], c[1], c[2], a))
+        gb.color(Color(c[3], c[4], c[5], a))
+        gb.color(Color(c[6], c[7], c[8], a))
+        comp.get_mut_or_insert_default(i).insert(path).set_props(
+            Props(func=Func.Draw(Style(fill=Fill.Gradient(gb.build()), blend_mode=modes[i % 8]))))
+
+
+def random_circles_scalar(api, comp, n_layers: int, width: int, height: int, seed: int, r=(4.0, 40.0)):
+    """The same scene drawn call by call (pins the vectorised generator in the CPU tests)."""
     rng = SplitMix64(seed)
     modes = [BlendMode.Over, BlendMode.Multiply, BlendMode.Screen, BlendMode.Overlay, BlendMode.Darken,
              BlendMode.Lighten, BlendMode.HardLight, BlendMode.Difference]

@@ -33,8 +33,11 @@ def check_reference_line(d, n_gpus, steps):
     assert d["metric"] == "frames/sec" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == n_gpus and d["steps"] == steps and d["warmup"] >= 3
     assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1.0
-    assert d["vs_baseline"] is None and d["config"]["workload"] == "smoke" and d["config"]["pixel_segments"] > 0
+    assert d["vs_baseline"] is None and d["config"]["workload"] == "smoke" and d["workload_stats"]["pixel_segments"] > 0
+    # `config` and `data` are what the driver compares between the two arms: only keys both arms can fill alike
+    assert set(d["config"]) == {"workload", "desc", "width", "height", "l2", "parallelism"} and d["data"] == "synthetic"
     cb = d["cpu_baseline"]
+    assert cb["cores"] <= cb["usable_cpus"] and cb["thread_candidates_ms"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "smoke" in cb["sample"]
     assert set(cb["stage_ms"]) == {"line_setup", "rasterize", "sort", "paint"}
     e = d["e2e"]

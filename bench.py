@@ -325,10 +325,13 @@ def bench_workload(env, args, name, steps, warmup, headline):
         torch.cuda.synchronize()
         costs = renderer.row_costs() if hasattr(renderer, "row_costs") else None
         if costs is not None and len(costs) and not args.equal_bands:
+            # + a floor per row: every tile of a row is at least cleared and stored
+            costs = [float(c) + 2.0 * ((w + 15) // 16) for c in costs]
             bd = bands.balanced_band(h, world, rank, costs)
             balance = "previous frame's per-row cost"
         else:
             balance = "equal rows"
+        comp.evict()  # from here on this rank only keeps its band's geometry resident
     r0, r1 = bd.tile_row0, bd.tile_row1
     crop = None if world == 1 else Rect((0, w), (bd.y0, max(bd.y1, bd.y0)))
     host = SharedHostFrame(torch, dist, h * stride, rank, world, name)
@@ -439,7 +442,10 @@ def bench_workload(env, args, name, steps, warmup, headline):
             torch.cuda.synchronize()
             assembled_ok = bool(torch.equal(ref[:, :w * 4], whole[:h, :w * 4]))
             del ref
+            comp.evict()  # the whole-frame render made everything resident again: back to the band
         dist.barrier()
+        frame_device()
+        torch.cuda.synchronize()
     c0 = renderer.counters()
     stage_acc = {k: 0.0 for k in renderer.STAGES}
     kern_acc, step_trace = {}, []

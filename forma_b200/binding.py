@@ -289,6 +289,13 @@ SIGNATURES = {
     "renderer_rasterize_only": (C.c_uint64, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u64p]),
     "renderer_sort_u64": (C.c_int, [_vp, _u64p, C.c_uint64]),
     "debug_selftest": (C.c_int, [C.c_int, _u64p]),
+    "renderer_multi_new": (_vp, [C.POINTER(C.c_int), C.c_int]),
+    "renderer_multi_free": (None, [_vp]),
+    "renderer_multi_device_count": (C.c_int, [_vp]),
+    "renderer_multi_render": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _fp, C.POINTER(_CRect), C.POINTER(_CTimings)]),
+    "renderer_multi_render_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, _fp, C.POINTER(_CRect), C.POINTER(_CTimings)]),
+    "renderer_multi_bands": (C.c_int, [_vp, _u32p, C.POINTER(C.c_double)]),
+    "renderer_row_costs": (C.c_uint64, [_vp, C.c_uint64, _u64p]),
     "set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
 }
@@ -335,6 +342,9 @@ class Api:
 
     def Renderer(self, device: int = 0) -> "Renderer":
         return Renderer(self, device)
+
+    def MultiRenderer(self, devices: Sequence[int]) -> "MultiRenderer":
+        return MultiRenderer(self, devices)
 
     def SharedFrame(self, device: int, nbytes: int, handle: Optional[bytes] = None) -> "SharedFrame":
         return SharedFrame(self, device, nbytes, handle)
@@ -690,6 +700,14 @@ class Renderer:
         return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries", "written_tiles"),
                         [int(v) for v in out]))
 
+    def row_costs(self) -> np.ndarray:
+        """Per-tile-row cost of the last render (forma_renderer_row_costs)."""
+        n = int(self._api.renderer_row_costs(self._h, 0, None))
+        out = np.zeros(n, np.uint64)
+        if n:
+            self._api.renderer_row_costs(self._h, n, out.ctypes.data_as(_u64p))
+        return out
+
     def set_stream(self, cuda_stream: int) -> None:
         self._api.renderer_set_stream(self._h, C.c_void_p(cuda_stream))
 
@@ -726,6 +744,56 @@ class Renderer:
     def __del__(self):
         try:
             self._api.renderer_free(self._h)
+        except Exception:
+            pass
+
+
+class MultiRenderer:
+    """One renderer over several GPUs of the box (forma_renderer_multi_*): `render` /
+    `render_device` have Renderer's arguments minus the layer cache; the frame is split into
+    cost-balanced bands of tile rows, one per device."""
+
+    def __init__(self, api: Api, devices: Sequence[int]):
+        self._api = api
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = api.renderer_multi_new(arr, len(devices))
+        if not self._h:
+            raise FormaError(f"MultiRenderer::new failed: {api.last_error().decode()}")
+        self.n = int(api.renderer_multi_device_count(self._h))
+
+    def _call(self, fn, what, composition, ptr, width, height, channels, clear_color, crop, stride):
+        stride = width * 4 if stride is None else stride
+        ch = (C.c_uint32 * 4)(*channels)
+        cc = (C.c_float * 4)(clear_color.r, clear_color.g, clear_color.b, clear_color.a)
+        rect = _CRect(crop.horizontal[0], crop.horizontal[1], crop.vertical[0], crop.vertical[1]) if crop is not None else None
+        t = _CTimings()
+        st = fn(self._h, composition._h, ptr, width, stride, height, ch, cc, C.byref(rect) if rect is not None else None, C.byref(t))
+        self._api.check(st, what)
+        return Timings(t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms, t.n_lines, t.n_segments)
+
+    def render(self, composition: "Composition", buffer: np.ndarray, width: int, height: int, channels=RGBA,
+               clear_color: Color = Color(1.0, 1.0, 1.0, 1.0), crop: Optional[Rect] = None, stride: Optional[int] = None) -> Timings:
+        s = width * 4 if stride is None else stride
+        assert buffer.dtype == np.uint8 and buffer.flags["C_CONTIGUOUS"] and buffer.size >= height * s
+        return self._call(self._api.renderer_multi_render, "MultiRenderer::render", composition,
+                          buffer.ctypes.data_as(C.c_void_p), width, height, channels, clear_color, crop, stride)
+
+    def render_device(self, composition: "Composition", device_ptr: int, width: int, height: int, channels=RGBA,
+                      clear_color: Color = Color(1.0, 1.0, 1.0, 1.0), crop: Optional[Rect] = None,
+                      stride: Optional[int] = None) -> Timings:
+        return self._call(self._api.renderer_multi_render_device, "MultiRenderer::render_device", composition,
+                          C.c_void_p(device_ptr), width, height, channels, clear_color, crop, stride)
+
+    def bands(self):
+        """(tile-row boundaries of the next frame's bands, ms of every band in the last frame)."""
+        b = (C.c_uint32 * (self.n + 1))()
+        ms = (C.c_double * self.n)()
+        self._api.renderer_multi_bands(self._h, b, ms)
+        return list(b), list(ms)
+
+    def __del__(self):
+        try:
+            self._api.renderer_multi_free(self._h)
         except Exception:
             pass
 

@@ -68,6 +68,11 @@ struct FlattenProgram {
     bool rational = false;        // some quadratic has a weight != 1
     uint32_t n_points = 0;        // output points
     uint32_t n_contour_ends = 0;  // points that end a contour, the last point of the program excluded
+    // Bounds of every point the program can emit: its literal points and the (projected)
+    // control points of its quadratics, whose convex hull contains the evaluated points.
+    // bounded == false when a weight is not positive (no hull property): never filter then.
+    bool bounded = true;
+    float min_x = 0.0f, min_y = 0.0f, max_x = 0.0f, max_y = 0.0f;
 };
 
 // A batch entry of flatten_eval_kernel: points [first, first+count) of the

@@ -170,6 +170,25 @@ class SplineBuilder {
             if (s.ends_contour && si + 1 < splines_.size()) out.n_contour_ends += 1;
         }
         out.n_points = (uint32_t)std::min<uint64_t>(pt, 0xFFFFFFFFull);
+        {  // bounds (see FlattenProgram)
+            float lo_x = INFINITY, lo_y = INFINITY, hi_x = -INFINITY, hi_y = -INFINITY;
+            auto take = [&](float px, float py) {
+                if (!(px == px) || !(py == py)) out.bounded = false;  // NaN
+                lo_x = std::fmin(lo_x, px); hi_x = std::fmax(hi_x, px);
+                lo_y = std::fmin(lo_y, py); hi_y = std::fmax(hi_y, py);
+            };
+            for (const SplineRec& r : out.splines) {
+                take(r.p0x, r.p0y);
+                take(r.p2x, r.p2y);
+            }
+            for (const QuadRec& q : out.quads)
+                for (int k = 0; k < 3; ++k) {
+                    if (!(q.pw[k] > 0.0f)) out.bounded = false;
+                    else take(q.px[k] / q.pw[k], q.py[k] / q.pw[k]);
+                }
+            if (out.splines.empty() && out.quads.empty()) lo_x = lo_y = hi_x = hi_y = 0.0f;
+            out.min_x = lo_x; out.min_y = lo_y; out.max_x = hi_x; out.max_y = hi_y;
+        }
         // Paths made of short line splines are smaller point by point (9 B / point
         // against 36 B / spline): expand the records on the host in that case.
         if (sizeof(SplineRec) * out.splines.size() > (sizeof(PointRec) + 1) * (size_t)out.n_points && pt < (1ull << 31)) {

@@ -44,8 +44,53 @@ struct PendingInsert {
     bool has_xf;
     float xf[6];
     uint32_t geom_id;  // Layer::dense_id at the time of the insert
-    uint32_t dst;    // first point in the segment buffer
+    uint32_t dst;    // first point in the (unfiltered) segment buffer
     uint32_t count;  // number of points
+    float y_min, y_max;  // rows the insert's points can take before the layer's transform (+- a safety margin)
+};
+
+// What one CUDA device holds of a composition: the evaluated points of the inserts that can
+// reach the rows it renders, the lookup tables, and the pinned staging of its uploads.
+struct CompDevice {
+    DeviceBuffer<float> d_x, d_y;
+    DeviceBuffer<uint32_t> d_gid;
+    uint32_t n_resident = 0;          // points evaluated on this device
+    size_t jobs_resident = 0;         // jobs [0, jobs_resident) were considered (evaluated, or left out by the band filter)
+    uint64_t geom_epoch = 0;          // Composition::geom_epoch these points belong to
+    // Band filter: when set, only inserts whose bounds meet the pixel rows [band_lo, band_hi) are
+    // resident (a GPU that paints a band of tile rows never needs the rest).
+    bool filtered = false;
+    float band_lo = 0.0f, band_hi = 0.0f;
+    // Pinned staging of the flatten programs of jobs [staged_from, staged_to) for this device.
+    PinnedBuffer<SplineRec> h_splines;
+    PinnedBuffer<PointRec> h_points;
+    PinnedBuffer<uint8_t> h_kinds;
+    PinnedBuffer<QuadUp> h_quads;
+    PinnedBuffer<FlattenJob> h_jobs;
+    bool staged_valid = false;
+    bool staged_rational = true;      // the staged quadratics are QuadUp (else QuadUpPoly)
+    bool staged_filtered = false;
+    float staged_lo = 0.0f, staged_hi = 0.0f;
+    size_t staged_from = 0, staged_to = 0, staged_jobs = 0, staged_splines = 0, staged_recs = 0, staged_quads = 0,
+           staged_points = 0;
+    // Tables.
+    uint64_t tables_version = 0;      // Composition::tables_version of the device copies (0 = none)
+    DeviceBuffer<uint32_t> d_layer_bits;
+    DeviceBuffer<int32_t> d_geom_slot;
+    DeviceBuffer<LayerRec> d_layers;
+    DeviceBuffer<StyleRec> d_styles;
+    DeviceBuffer<int32_t> d_order_to_style;
+    DeviceBuffer<StopRec> d_stops;
+    DeviceBuffer<uint16_t> d_texels;
+    // keep_staging: the pinned copies of the last batch stay valid (an evicted composition is
+    // re-uploaded from them without touching the host-side programs again).
+    void reset_residency(bool keep_staging = false) {
+        n_resident = 0;
+        jobs_resident = 0;
+        filtered = false;
+        if (!keep_staging) staged_valid = false;
+        tables_version = 0;
+    }
 };
 
 class Composition {
@@ -72,50 +117,35 @@ class Composition {
     uint64_t garbage_points = 0;      // points whose geometry id no longer maps to a layer
     void mark_dirty() { tables_dirty = true; }
 
-    // --- segment buffer (device) ------------------------------------------------
-    int device = -1;                  // bound at first render
-    uint32_t n_points = 0;            // points appended so far (incl. not yet resident)
+    // --- segment buffer ------------------------------------------------------------
+    uint32_t n_points = 0;            // points appended so far (dead geometry included until compacted)
     uint64_t some_ids = 0;            // SegmentBuffer::len(): ids that are Some
     std::vector<PendingInsert> jobs;  // every Layer::insert so far, in order
-    size_t jobs_resident = 0;         // jobs [0, jobs_resident) are evaluated in HBM
-    DeviceBuffer<float> d_x, d_y;
-    DeviceBuffer<uint32_t> d_gid;
-    uint32_t n_resident = 0;          // points already evaluated on the device
-    // Pinned staging of the flatten programs of jobs [staged_from, staged_to).
-    PinnedBuffer<SplineRec> h_splines;
-    PinnedBuffer<PointRec> h_points;
-    PinnedBuffer<uint8_t> h_kinds;
-    size_t staged_recs = 0;
-    bool staged_rational = true;      // the staged quadratics are QuadUp (else QuadUpPoly)
-    PinnedBuffer<QuadUp> h_quads;
-    PinnedBuffer<FlattenJob> h_jobs;
-    size_t staged_from = 0, staged_to = 0, staged_splines = 0, staged_quads = 0, staged_points = 0;
+    uint64_t geom_epoch = 1;          // bumped by compact_geom: device copies of an older epoch are stale
+    // Residency per CUDA device (one process may render the composition on several GPUs).
+    std::map<int, std::unique_ptr<CompDevice>> devices;
+    CompDevice& on(int device) {
+        auto& p = devices[device];
+        if (!p) p.reset(new CompDevice());
+        return *p;
+    }
     // Drops device residency: the next render re-uploads everything from pinned
     // host memory (used to measure the cold, end-to-end path).
     void evict() {
-        jobs_resident = 0;
-        n_resident = 0;
-        tables_resident = false;
+        for (auto& kv : devices) kv.second->reset_residency(true);
     }
 
-    // --- per-frame lookup tables (device), rebuilt when dirty ------------------
+    // --- per-frame lookup tables: pinned host copies, rebuilt when dirty -------------
     bool tables_dirty = true;         // host-side pinned copies are stale
-    bool tables_resident = false;     // device copies match the pinned copies
+    uint64_t tables_version = 0;      // bumped at every rebuild; a device copy of an older version is stale
     PinnedBuffer<LayerRec> h_layers;
     PinnedBuffer<uint32_t> h_layer_bits;  // order | enabled << 21: uploaded instead of h_layers when no layer has a transform
-    DeviceBuffer<uint32_t> d_layer_bits;
     bool layers_have_xf = false;
     PinnedBuffer<StyleRec> h_styles;
     PinnedBuffer<int32_t> h_order_to_style, h_geom_slot;
     PinnedBuffer<StopRec> h_stops;
     PinnedBuffer<uint16_t> h_texels;
     size_t n_layer_recs = 0, n_style_recs = 0, n_stops = 0, n_texels = 0;
-    DeviceBuffer<int32_t> d_geom_slot;
-    DeviceBuffer<LayerRec> d_layers;
-    DeviceBuffer<StyleRec> d_styles;
-    DeviceBuffer<int32_t> d_order_to_style;
-    DeviceBuffer<StopRec> d_stops;
-    DeviceBuffer<uint16_t> d_texels;
     uint32_t n_geoms = 0, n_orders = 0;
     // The inserts' layer orders never decrease along the segment buffer, so the
     // rasterizer emits the pixel segments already ordered by layer and the

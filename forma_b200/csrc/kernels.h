@@ -20,6 +20,7 @@ struct Options {
     int sort_big_log2 = 19;  // key count from which the 4096-key tiles / reduce-then-scan passes are used
     int test_gap_cap = 0;    // test hook: cap of the speculative carry-only-entry launch (0 = none)
     int paint_lpt = 1;       // heavy tiles first (longest-processing-time order) in the paint kernel
+    int band_filter = 1;     // a render cropped to a band of rows only makes the band's geometry resident
 };
 Options& options();
 
@@ -122,15 +123,16 @@ struct PaintScene {
 };
 
 uint32_t cell_num_blocks(uint32_t n);
-// block_counts: cell_num_blocks(n) entries -> exclusive offsets; total[0] = #cells.
-// head_masks: (n + 31) / 32 words, one bit per segment that starts a cell (read by launch_cell_write).
-void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* head_masks, uint32_t* total,
-                       cudaStream_t st);
-// Both read the cell count from device memory (n_cells_ptr) and are no-ops when it
-// exceeds `cap`, so that they can be launched before the host has read the count;
-// grid_cells sizes the cover grid (an upper bound of the count, or the count).
-void launch_cell_write(const uint32_t* head_masks, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
-                       const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st);
+// One pass over the sorted segments: cell_start[c] = first segment of cell c (for c < cap;
+// cell_start[#cells] = n when #cells < cap) and n_cells_out[0] = #cells. `state` needs
+// cells_scan_state_words(n) u64 words. May be launched before the host knows the count: it
+// reads nothing that depends on it.
+size_t cells_scan_state_words(uint32_t n);
+void launch_cells_scan(const uint64_t* segs, uint32_t n, unsigned long long* state, uint32_t* cell_start, uint32_t cap,
+                       uint32_t* n_cells_out, cudaStream_t st);
+// Reads the cell count from device memory (n_cells_ptr) and is a no-op when it exceeds
+// `cap`, so that it can be launched before the host has read the count; grid_cells sizes
+// the grid (an upper bound of the count, or the count).
 // Also writes cell_key (the key of each cell's first segment).
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, uint64_t* cell_key,
                        const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
@@ -142,7 +144,7 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
                        uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st);
 // Carry-only entries in (layer, tile_y, tile_x) order; payload = n_cells + gap id.
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
-                     const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
+                     const uint4* carry_after, const uint32_t* gap_offset /* scanned gap counts */, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
                      uint32_t grid_gaps /* threads to launch: >= the entry count */, cudaStream_t st);
 // One painter entry = one (tile, layer) pair with segments and / or a carried cover.
@@ -171,6 +173,9 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
                   const uint32_t* heavy_count, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st);
 // Packed fp32 (f32x2) arithmetic of the painter against scalar IEEE operations; mismatches are added to out[0].
 void launch_f32x2_selftest(const float* a, const float* b, const float* c, uint32_t n, uint32_t* out, cudaStream_t st);
+// out[row] = 32 x entries + pixel segments of tile row `row` (see row_cost_kernel).
+void launch_row_costs(const uint2* tile_range, uint32_t tiles_x, uint32_t tiles_y, const uint64_t* segs, uint32_t n,
+                      unsigned long long* out, cudaStream_t st);
 // Packs the tiles in S.written_list into `packed` (256 u32 per tile, row-major).
 void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st);
 

@@ -16,7 +16,7 @@
 //   staging in shared memory, coalesced scatter): 24 B/key per pass, and no CTA
 //   ever waits for another one (see the comment above those kernels).
 // * Small sorts and (key, u32 payload) pairs (the painter's cell / gap tables):
-//   one upfront histogram kernel for all passes, then one single-sweep
+//   one upfront histogram kernel for all passes (every pass CTA scans its 256 counts itself), then one single-sweep
 //   ("onesweep") kernel per pass with decoupled look-back (16 B/key per pass;
 //   latency-bound at these sizes). A persistent single-sweep kernel for the large sorts
 //   was measured in round 1 (look-back-bound, 34 % of the HBM peak, profiles/r1_v2_*) and
@@ -120,24 +120,11 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
     }
 }
 
-// Exclusive scan of each pass's 256-bin histogram (one CTA per pass).
-__global__ void __launch_bounds__(kRadix) radix_scan_hist_kernel(uint32_t* __restrict__ hist) {
-    __shared__ uint32_t warp_tot[kRadix / 32];
-    uint32_t* h = hist + blockIdx.x * kRadix;
-    uint32_t v = h[threadIdx.x];
-    uint32_t incl = warp_inclusive_scan(v);
-    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint32_t base = 0;
-    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) base += warp_tot[w];
-    h[threadIdx.x] = base + incl - v;
-}
-
 template <bool kPairs, int kItems>
 __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
     onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, uint32_t n, DigitSpec spec,
-                         const uint32_t* __restrict__ global_offsets /*[256], exclusive*/,
+                         const uint32_t* __restrict__ digit_counts /*[256]: keys per digit (radix_hist_kernel)*/,
                          uint32_t* __restrict__ lb /*[tiles][256], zeroed*/, uint32_t* __restrict__ tile_counter) {
     constexpr int kTileKeys = kSortThreads * kItems;
     __shared__ uint64_t s_keys[kTileKeys];
@@ -145,12 +132,19 @@ __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
     __shared__ uint32_t s_digit_start[kRadix];
     __shared__ uint32_t s_global_base[kRadix];
     __shared__ uint32_t s_warp_tot[kSortWarps];
+    __shared__ uint32_t s_hist_tot[kSortWarps];
     __shared__ uint32_t s_tile;
 
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
     if (t == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
+    // Every CTA turns the pass's digit counts into exclusive offsets itself (256 values).
+    const uint32_t hist_count = digit_counts[t];
+    const uint32_t hist_incl = warp_inclusive_scan(hist_count);
+    if (lane == 31) s_hist_tot[warp] = hist_incl;
     __syncthreads();
+    uint32_t digit_offset = hist_incl - hist_count;  // first output position of digit t
+    for (uint32_t w = 0; w < warp; ++w) digit_offset += s_hist_tot[w];
     const uint32_t tile = s_tile;
     const uint32_t base = tile * (uint32_t)kTileKeys;
     const uint32_t valid = min((uint32_t)kTileKeys, n - base);
@@ -233,7 +227,7 @@ __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
         retry:;
         }
         st_relaxed(my_slot, kFlagInclusive | (prefix + count));
-        s_global_base[t] = global_offsets[t] + prefix - dstart;
+        s_global_base[t] = digit_offset + prefix - dstart;
     }
     __syncthreads();
 
@@ -621,8 +615,7 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     cudaMemsetAsync(scratch, 0, total_words * sizeof(uint32_t), stream);
     uint32_t hist_blocks = min(tiles_for(n, 16) * 4u, 148u * 8u);
     radix_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, plan, hist);
-    radix_scan_hist_kernel<<<plan.n_passes, kRadix, 0, stream>>>(hist);
-    res.launches = 2;
+    res.launches = 1;
     if (vals) {
         if (items == 16) launch_passes<true, 16>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
         else launch_passes<true, 4>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);

@@ -7,8 +7,7 @@
 // independently the carries are materialised first:
 //
 //   cells     runs of sorted segments with equal (tile_y, tile_x, layer)
-//             (cell_count writes one head bit per segment, cell_write turns the
-//             bits into cell_start)
+//             (cells_scan: one pass, head bits -> cell_start by decoupled look-back)
 //   covers    per cell: sum of segment covers by local_y (wrapping i8), its key
 //   re-sort   cell ids stably by the layer bits only -> (layer, tile_y, tile_x)
 //   carries   per (tile_y, layer) group a running sum -> carry-in of every cell
@@ -40,61 +39,76 @@ __device__ __forceinline__ bool is_cell_head(const uint64_t* __restrict__ segs, 
 constexpr int kCellItems = 8;
 constexpr int kCellTile = kCellThreads * kCellItems;
 
-__global__ void __launch_bounds__(kCellThreads)
-    cell_count_kernel(const uint64_t* __restrict__ segs, uint32_t n, uint32_t* __restrict__ block_counts,
-                      uint32_t* __restrict__ head_masks /* one bit per segment: starts a cell */) {
-    __shared__ uint32_t warp_cnt[kCellThreads / 32];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t base = blockIdx.x * kCellTile + warp * (32u * kCellItems);
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int k = 0; k < kCellItems; ++k) {
-        uint32_t i = base + k * 32u + lane;
-        bool head = i < n && is_cell_head(segs, i);
-        uint32_t m = __ballot_sync(kFullMask, head);
-        if (lane == 0 && base + k * 32u < n) head_masks[(base + k * 32u) >> 5] = m;  // cell_write reads these, not the segments
-        cnt += __popc(m);
-    }
-    if (lane == 0) warp_cnt[warp] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t s = 0;
-        for (int w = 0; w < kCellThreads / 32; ++w) s += warp_cnt[w];
-        block_counts[blockIdx.x] = s;
-    }
-}
+// Single pass over the sorted segments: head bits (a segment starts a cell when its key
+// differs from its predecessor's), the cells' first segments (`cell_start`) and their number.
+// CTA tiles are taken by ticket; a tile's cell offset comes from its predecessors by
+// decoupled look-back (state[t] = flag | running count; state[tiles] = ticket counter).
+// Positions >= cap are not written: the kernel may be launched before the host knows how
+// many cells there are (Renderer::render repeats it after growing the buffers).
+constexpr unsigned long long kCellAggregate = 1ull << 62, kCellInclusive = 2ull << 62, kCellFlags = 3ull << 62;
 
 __global__ void __launch_bounds__(kCellThreads)
-    cell_write_kernel(const uint32_t* __restrict__ head_masks, uint32_t n, const uint32_t* __restrict__ block_offsets,
-                      uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ n_cells_ptr, uint32_t cap) {
+    cells_scan_kernel(const uint64_t* __restrict__ segs, uint32_t n, unsigned long long* __restrict__ state, uint32_t tiles,
+                      uint32_t* __restrict__ cell_start, uint32_t cap, uint32_t* __restrict__ n_cells_out) {
     __shared__ uint32_t warp_cnt[kCellThreads / 32];
-    // The cell count is read on the device: the kernel may be launched before the
-    // host knows it (Renderer::render); it does nothing if the buffers are too small.
-    const uint32_t n_cells = *n_cells_ptr;
-    if (n_cells > cap) return;
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t base = blockIdx.x * kCellTile + warp * (32u * kCellItems);
+    if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[tiles], 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kCellTile + warp * (32u * kCellItems);
     uint32_t masks[kCellItems];
     uint32_t cnt = 0;
 #pragma unroll
     for (int k = 0; k < kCellItems; ++k) {
-        masks[k] = base + k * 32u < n ? head_masks[(base + k * 32u) >> 5] : 0u;  // same word for the whole warp
+        const uint32_t i = base + k * 32u + lane;
+        const bool head = i < n && is_cell_head(segs, i);
+        masks[k] = __ballot_sync(kFullMask, head);
         cnt += __popc(masks[k]);
     }
     if (lane == 0) warp_cnt[warp] = cnt;
     __syncthreads();
-    uint32_t pos = block_offsets[blockIdx.x];
-    for (uint32_t w = 0; w < warp; ++w) pos += warp_cnt[w];
+    uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+    for (int w = 0; w < kCellThreads / 32; ++w) {
+        if ((uint32_t)w < warp) warp_off += warp_cnt[w];
+        tile_sum += warp_cnt[w];
+    }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = state;
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            st[0] = kCellInclusive | tile_sum;
+        } else {
+            st[tile] = kCellAggregate | tile_sum;
+            int32_t p = (int32_t)tile - 1;
+            while (true) {
+                const unsigned long long v = st[p];
+                if ((v & kCellFlags) == 0) continue;
+                prefix += v & ~kCellFlags;
+                if ((v & kCellFlags) == kCellInclusive) break;
+                --p;
+            }
+            st[tile] = kCellInclusive | (prefix + tile_sum);
+        }
+        s_prefix = prefix;
+        if (tile + 1 == tiles) {
+            const uint32_t total = (uint32_t)(prefix + tile_sum);
+            n_cells_out[0] = total;
+            if (total < cap) cell_start[total] = n;  // one-past-the-end sentinel
+        }
+    }
+    __syncthreads();
+    uint32_t pos = (uint32_t)s_prefix + warp_off;
 #pragma unroll
     for (int k = 0; k < kCellItems; ++k) {
         if ((masks[k] >> lane) & 1u) {
-            uint32_t i = base + k * 32u + lane;
-            uint32_t p = pos + __popc(masks[k] & ((1u << lane) - 1u));
-            cell_start[p] = i;
+            const uint32_t q = pos + __popc(masks[k] & ((1u << lane) - 1u));
+            if (q < cap) cell_start[q] = base + k * 32u + lane;
         }
         pos += __popc(masks[k]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[n_cells] = n;
 }
 
 // Per cell: sum of covers by local_y (acc_segment's cover part + cover_carry,
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(kCoverCells)
     __shared__ int32_t s_acc[kCoverCells][16];
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
     const uint32_t c0 = blockIdx.x * kCoverCells;
-    const uint32_t n_cells = *n_cells_ptr;  // see cell_write_kernel
+    const uint32_t n_cells = *n_cells_ptr;  // written by cells_scan_kernel; the host may not know it yet
     if (n_cells > cap || c0 >= n_cells) return;
     const uint32_t nc = min((uint32_t)kCoverCells, n_cells - c0);
     if (t <= nc) s_start[t] = cell_start[c0 + t];
@@ -238,7 +252,7 @@ __global__ void carry_scan_kernel(PaintScene S, const uint64_t* __restrict__ key
 // (tile_y, tile_x, layer).
 __global__ void gap_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2, const uint32_t* __restrict__ perm,
                                 const uint64_t* __restrict__ cell_key, const uint4* __restrict__ carry_after,
-                                const uint32_t* __restrict__ gap_count, const uint32_t* __restrict__ gap_offset,
+                                const uint32_t* __restrict__ gap_offset /* exclusive scan of the gap counts */,
                                 uint32_t n_cells, uint64_t* __restrict__ gkey, uint32_t* __restrict__ gid,
                                 uint4* __restrict__ gap_carry, const uint32_t* __restrict__ n_gaps_ptr, uint32_t cap) {
     // One thread per carry-only entry q: its source cell is the last one (in carry
@@ -246,7 +260,7 @@ __global__ void gap_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2,
     // offset with the next cell and sort before it.
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_gaps = *n_gaps_ptr;
-    if (n_gaps > cap || q >= n_gaps) return;  // cap: see cell_write_kernel
+    if (n_gaps > cap || q >= n_gaps) return;  // cap: launched before the host knows the count
     uint32_t lo = 0, hi = n_cells;  // first j with gap_offset[j] > q
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
@@ -378,21 +392,52 @@ __global__ void tile_index_kernel(PaintScene S, const uint64_t* __restrict__ eke
     }
 }
 
+// Cost of every tile row of the frame just rendered: 32 x its (tile, layer) entries + its
+// pixel segments (paint time follows the entries, sort / table time the segments). The
+// multi-GPU band split of the next frame is balanced on these. One warp per row.
+__global__ void row_cost_kernel(const uint2* __restrict__ tile_range, uint32_t tiles_x, uint32_t tiles_y,
+                                const uint64_t* __restrict__ segs, uint32_t n, unsigned long long* __restrict__ out) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (row >= tiles_y) return;
+    uint32_t entries = 0;
+    for (uint32_t tx = lane; tx < tiles_x; tx += 32u) {
+        const uint2 r = tile_range[(size_t)row * tiles_x + tx];
+        entries += r.y - r.x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) entries += __shfl_xor_sync(kFullMask, entries, o);
+    if (lane == 0) {
+        auto lower = [&](uint64_t key) {  // first segment with key >= `key`
+            uint32_t lo = 0, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (segs[mid] < key) lo = mid + 1u;
+                else hi = mid;
+            }
+            return lo;
+        };
+        const uint32_t s0 = lower((uint64_t)(row + 1u) << 53), s1 = lower((uint64_t)(row + 2u) << 53);
+        out[row] = 32ull * entries + (unsigned long long)(s1 - s0);
+    }
+}
+
+void launch_row_costs(const uint2* tile_range, uint32_t tiles_x, uint32_t tiles_y, const uint64_t* segs, uint32_t n,
+                      unsigned long long* out, cudaStream_t st) {
+    if (tiles_y) row_cost_kernel<<<(tiles_y + 7) / 8, 256, 0, st>>>(tile_range, tiles_x, tiles_y, segs, n, out);
+}
+
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
 uint32_t cell_num_blocks(uint32_t n) { return (n + kCellTile - 1) / kCellTile; }
 
-void launch_cell_count(const uint64_t* segs, uint32_t n, uint32_t* block_counts, uint32_t* head_masks, uint32_t* total,
-                       cudaStream_t st) {
-    uint32_t nb = cell_num_blocks(n);
-    cell_count_kernel<<<nb, kCellThreads, 0, st>>>(segs, n, block_counts, head_masks);
-    launch_scan_u32(block_counts, nb, total, nullptr, st);
-}
+size_t cells_scan_state_words(uint32_t n) { return (size_t)cell_num_blocks(n) + 2; }
 
-void launch_cell_write(const uint32_t* head_masks, uint32_t n, const uint32_t* block_offsets, uint32_t* cell_start,
-                       const uint32_t* n_cells_ptr, uint32_t cap, cudaStream_t st) {
-    cell_write_kernel<<<cell_num_blocks(n), kCellThreads, 0, st>>>(head_masks, n, block_offsets, cell_start, n_cells_ptr, cap);
+void launch_cells_scan(const uint64_t* segs, uint32_t n, unsigned long long* state, uint32_t* cell_start, uint32_t cap,
+                       uint32_t* n_cells_out, cudaStream_t st) {
+    const uint32_t tiles = cell_num_blocks(n);
+    cudaMemsetAsync(state, 0, (tiles + 1) * sizeof(unsigned long long), st);
+    cells_scan_kernel<<<tiles, kCellThreads, 0, st>>>(segs, n, state, tiles, cell_start, cap, n_cells_out);
 }
 
 void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, uint64_t* cell_key,
@@ -425,11 +470,11 @@ void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t
 }
 
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
-                     const uint4* carry_after, const uint32_t* gap_count, const uint32_t* gap_offset, uint32_t n_cells,
+                     const uint4* carry_after, const uint32_t* gap_offset, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
                      uint32_t grid_gaps, cudaStream_t st) {
     if (!grid_gaps || !n_cells) return;
-    gap_fill_kernel<<<(grid_gaps + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_count, gap_offset, n_cells,
+    gap_fill_kernel<<<(grid_gaps + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_offset, n_cells,
                                                               gkey, gid, gap_carry, n_gaps_ptr, cap);
 }
 

@@ -13,6 +13,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/forma_b200.h"
 #include "cuda_common.cuh"
@@ -47,7 +48,7 @@ static const OptionName kOptionNames[] = {
     {"speculate", &Options::speculate, 0, 1},         {"band_copy", &Options::band_copy, 0, 1},
     {"copy_bands", &Options::copy_bands, 1, 16},      {"sort_full_key", &Options::sort_full_key, 0, 1},
     {"sort_big_log2", &Options::sort_big_log2, 10, 30}, {"test_gap_cap", &Options::test_gap_cap, 0, 1 << 30},
-    {"paint_lpt", &Options::paint_lpt, 0, 1},
+    {"paint_lpt", &Options::paint_lpt, 0, 1},         {"band_filter", &Options::band_filter, 0, 1},
 };
 Options& options() {
     static Options o = [] {
@@ -184,6 +185,30 @@ void Composition::layer_insert(Layer* layer, const Path& path) {
         job.geom_id = layer->dense_id;
         job.dst = n_points;
         job.count = count;
+        // Rows the insert can reach (for the band filter of multi-GPU frames): the program's
+        // bounds through the path's transform, widened by half a pixel plus a relative term
+        // that covers the rounding of the evaluation; infinite when the hull argument fails.
+        job.y_min = -INFINITY;
+        job.y_max = INFINITY;
+        if (prog.bounded) {
+            float lo = prog.min_y, hi = prog.max_y;
+            if (path.has_xf) {  // ty = fma(uy, x, fma(vy, y, t.y)) over the four corners
+                lo = INFINITY;
+                hi = -INFINITY;
+                for (int cx = 0; cx < 2; ++cx)
+                    for (int cy = 0; cy < 2; ++cy) {
+                        const float px = cx ? prog.max_x : prog.min_x, py = cy ? prog.max_y : prog.min_y;
+                        const float ty = fmaf(path.xf[1], px, fmaf(path.xf[3], py, path.xf[5]));
+                        lo = std::fmin(lo, ty);
+                        hi = std::fmax(hi, ty);
+                    }
+            }
+            if (lo == lo && hi == hi && std::isfinite(lo) && std::isfinite(hi)) {
+                const float margin = 0.5f + 1e-4f * std::fmax(std::fabs(lo), std::fabs(hi));
+                job.y_min = lo - margin;
+                job.y_max = hi + margin;
+            }
+        }
         jobs.push_back(std::move(job));
         // ids that are Some: every point that does not end a contour, except the
         // last point of the insert (its id is the trailing None).
@@ -236,10 +261,7 @@ void Composition::compact_geom() {
     next_dense_id = next;
     n_points = (uint32_t)pts;
     garbage_points = 0;
-    jobs_resident = 0;  // everything is evaluated again into the re-packed buffer
-    n_resident = 0;
-    staged_from = staged_to = 0;
-    staged_splines = staged_recs = staged_quads = staged_points = 0;
+    ++geom_epoch;  // everything is evaluated again into the re-packed buffers (see Renderer::flush_geometry)
     tables_dirty = true;
 }
 
@@ -285,6 +307,7 @@ class Renderer {
    public:
     int device = 0;
     cudaStream_t stream = 0;
+    bool owns_stream = false;
     uint64_t launches = 0;
     uint32_t caches_in_use = 0;
     Timer timer;
@@ -301,7 +324,7 @@ class Renderer {
     }
     DeviceBuffer<uint64_t> segs, segs_tmp;
     DeviceBuffer<uint8_t> sort_scratch;
-    DeviceBuffer<uint32_t> head_masks, cell_start, perm, perm_tmp, gap_count, gap_offset, eid, eid_tmp, gid_tmp, heavy_tiles;
+    DeviceBuffer<uint32_t> cell_start, perm, perm_tmp, gap_count, eid, eid_tmp, gid_tmp, heavy_tiles;
     DeviceBuffer<uint2> tile_range;
     DeviceBuffer<uint64_t> cell_key, key2, key2_tmp, ekey, ekey_tmp, gkey_tmp;
     DeviceBuffer<uint4> cell_cover, carry_in, carry_after, gap_carry;
@@ -335,6 +358,7 @@ class Renderer {
     DeviceBuffer<FlattenJob> up_jobs;
 
     uint32_t last_segments = 0, last_cells = 0, last_entries = 0, last_gaps = 0;
+    uint32_t last_tiles_x = 0, last_tiles_y = 0;  // tile grid of the last render (forma_renderer_row_costs)
     RasterArgs last_raster{};        // line-setup arguments of the last render (device pointers owned by its composition)
     bool last_raster_valid = false;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied over PCIe since creation
@@ -354,10 +378,13 @@ class Renderer {
             for (auto& e : timer.ev) cudaEventDestroy(e);
             for (auto& e : timer.sort_ev) cudaEventDestroy(e);
         }
+        if (owns_stream && stream) cudaStreamDestroy(stream);
     }
 
-    int flush_geometry(Composition& comp);
+    int flush_geometry(Composition& comp, float band_lo = 0.0f, float band_hi = 0.0f, bool band_is_partial = false);
     int upload_tables(Composition& comp, int64_t cache_id);
+    static int rebuild_tables(Composition& comp, int64_t cache_id);
+    int upload_tables_device(Composition& comp, CompDevice& cd);
     int read_total(uint32_t slot, uint32_t* out);
     int rasterize(Composition& comp, uint32_t width, uint32_t height, float band_lo, float band_hi, uint32_t* n_out);
     int render(Composition& comp, uint8_t* buffer, bool buffer_on_device, uint64_t width, uint64_t stride,
@@ -386,52 +413,72 @@ static QuadUp quad_upload(const QuadRec& q) {
     return u;
 }
 
-// Evaluates the Layer::insert jobs that are not resident yet into the device
-// segment buffer: one batched upload from pinned staging + one kernel.
-int Renderer::flush_geometry(Composition& comp) {
-    if (comp.device < 0) comp.device = device;
-    if (comp.device != device) {
-        set_error("composition is resident on device %d, renderer uses device %d", comp.device, device);
-        return FORMA_STATUS_INVALID;
-    }
+// Evaluates the Layer::insert jobs that are not resident on this device yet into its
+// segment buffer: one batched upload from pinned staging + one kernel. With a band
+// ([band_lo, band_hi) in pixel rows, narrower than the frame) and no layer transform in
+// the composition, inserts that cannot reach the band are left out: a GPU that paints a
+// band of tile rows then uploads, evaluates and scans only the geometry of its band.
+int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bool band_is_partial) {
     comp.compact_geom();
-    const size_t from = comp.jobs_resident, to = comp.jobs.size();
+    CompDevice& cd = comp.on(device);
+    if (cd.geom_epoch != comp.geom_epoch) {  // compacted since: the resident points are stale
+        cd.reset_residency();
+        cd.geom_epoch = comp.geom_epoch;
+    }
+    // The filter only holds while no layer moves its geometry (a layer transform would have to be
+    // applied to the bounds, and changes from frame to frame): fall back to everything otherwise.
+    bool any_layer_xf = false;
+    for (auto& kv : comp.layers) any_layer_xf = any_layer_xf || kv.second->has_xf;
+    const bool want_filter = band_is_partial && !any_layer_xf && options().band_filter != 0;
+    if (cd.jobs_resident > 0) {
+        // What is resident must cover what this render needs.
+        const bool covers = !cd.filtered || (want_filter && band_lo >= cd.band_lo && band_hi <= cd.band_hi);
+        if (!covers) cd.reset_residency();
+    }
+    if (cd.jobs_resident == 0) {
+        cd.filtered = want_filter;
+        cd.band_lo = band_lo;
+        cd.band_hi = band_hi;
+    }
+    const size_t from = cd.jobs_resident, to = comp.jobs.size();
     if (from == to) return FORMA_STATUS_OK;
     if (to - from >= (1u << 30)) {
         set_error("too many inserts in one batch");
         return FORMA_STATUS_CAPACITY;
     }
-    FORMA_CUDA_TRY(comp.d_x.reserve(comp.n_points, true, stream));
-    FORMA_CUDA_TRY(comp.d_y.reserve(comp.n_points, true, stream));
-    FORMA_CUDA_TRY(comp.d_gid.reserve(comp.n_points, true, stream));
+    auto wanted = [&](const PendingInsert& p) { return !cd.filtered || !(p.y_min >= cd.band_hi || p.y_max <= cd.band_lo); };
 
-    if (comp.staged_from != from || comp.staged_to != to) {
-        // (Re)build the pinned staging copy of the flatten programs of jobs [from, to).
-        size_t n_splines = 0, n_quads = 0, n_pts = 0, n_recs = 0;
+    if (!cd.staged_valid || cd.staged_from != from || cd.staged_to != to || cd.staged_filtered != cd.filtered ||
+        (cd.filtered && (cd.staged_lo != cd.band_lo || cd.staged_hi != cd.band_hi))) {
+        // (Re)build the pinned staging copy of the flatten programs of the wanted jobs in [from, to).
+        size_t n_jobs = 0, n_splines = 0, n_quads = 0, n_pts = 0, n_recs = 0;
         bool rational = false;  // any weight != 1 in the batch: 48-byte QuadUp, else 36-byte QuadUpPoly
         for (size_t j = from; j < to; ++j) {
+            if (!wanted(comp.jobs[j])) continue;
             const FlattenProgram& prog = comp.jobs[j].data->program();
             rational = rational || prog.rational;
+            ++n_jobs;
             n_splines += prog.splines.size();
             n_recs += prog.points.size();
             n_quads += prog.quads.size();
             n_pts += prog.n_points;
         }
-        if (n_pts >= (1ull << 32)) {
-            set_error("too many points in one batch");
+        if ((uint64_t)cd.n_resident + n_pts >= (1ull << 32)) {
+            set_error("too many points in the segment buffer");
             return FORMA_STATUS_CAPACITY;
         }
         FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // staging may still be in flight
-        FORMA_CUDA_TRY(comp.h_splines.reserve(n_splines + 1));
-        FORMA_CUDA_TRY(comp.h_points.reserve(n_recs + 1));
-        FORMA_CUDA_TRY(comp.h_kinds.reserve(n_recs + 1));
-        FORMA_CUDA_TRY(comp.h_quads.reserve(n_quads + 1));
-        FORMA_CUDA_TRY(comp.h_jobs.reserve(to - from));
-        size_t si = 0, qi = 0, pi = 0, ri = 0;
+        FORMA_CUDA_TRY(cd.h_splines.reserve(n_splines + 1));
+        FORMA_CUDA_TRY(cd.h_points.reserve(n_recs + 1));
+        FORMA_CUDA_TRY(cd.h_kinds.reserve(n_recs + 1));
+        FORMA_CUDA_TRY(cd.h_quads.reserve(n_quads + 1));
+        FORMA_CUDA_TRY(cd.h_jobs.reserve(n_jobs + 1));
+        size_t ji = 0, si = 0, qi = 0, pi = 0, ri = 0;
         for (size_t j = from; j < to; ++j) {
             const PendingInsert& p = comp.jobs[j];
+            if (!wanted(p)) continue;
             const FlattenProgram& prog = p.data->program();
-            FlattenJob& job = comp.h_jobs.ptr[j - from];
+            FlattenJob& job = cd.h_jobs.ptr[ji++];
             job.first_point = (uint32_t)pi;
             job.count = p.count;
             job.quad_base = (uint32_t)qi;
@@ -440,18 +487,18 @@ int Renderer::flush_geometry(Composition& comp) {
             job.geom_id = p.geom_id;
             job.has_xf = p.has_xf ? 1u : 0u;
             std::memcpy(job.xf, p.xf, sizeof(job.xf));
-            job.dst = p.dst;
+            job.dst = cd.n_resident + (uint32_t)pi;  // device-local: the resident inserts are packed
             if (!prog.splines.empty())
-                std::memcpy(comp.h_splines.ptr + si, prog.splines.data(), prog.splines.size() * sizeof(SplineRec));
+                std::memcpy(cd.h_splines.ptr + si, prog.splines.data(), prog.splines.size() * sizeof(SplineRec));
             if (!prog.points.empty()) {
-                std::memcpy(comp.h_points.ptr + ri, prog.points.data(), prog.points.size() * sizeof(PointRec));
-                std::memcpy(comp.h_kinds.ptr + ri, prog.kinds.data(), prog.kinds.size());
+                std::memcpy(cd.h_points.ptr + ri, prog.points.data(), prog.points.size() * sizeof(PointRec));
+                std::memcpy(cd.h_kinds.ptr + ri, prog.kinds.data(), prog.kinds.size());
                 ri += prog.points.size();
             }
             if (rational) {
-                for (size_t q = 0; q < prog.quads.size(); ++q) comp.h_quads.ptr[qi + q] = quad_upload(prog.quads[q]);
+                for (size_t q = 0; q < prog.quads.size(); ++q) cd.h_quads.ptr[qi + q] = quad_upload(prog.quads[q]);
             } else {  // the pinned buffer is sized for QuadUp; the smaller records share it
-                QuadUpPoly* poly = reinterpret_cast<QuadUpPoly*>(comp.h_quads.ptr);
+                QuadUpPoly* poly = reinterpret_cast<QuadUpPoly*>(cd.h_quads.ptr);
                 for (size_t q = 0; q < prog.quads.size(); ++q) {
                     const QuadRec& s = prog.quads[q];
                     QuadUpPoly& u = poly[qi + q];
@@ -468,48 +515,65 @@ int Renderer::flush_geometry(Composition& comp) {
             qi += prog.quads.size();
             pi += prog.n_points;
         }
-        comp.staged_from = from;
-        comp.staged_to = to;
-        comp.staged_splines = n_splines;
-        comp.staged_recs = n_recs;
-        comp.staged_quads = n_quads;
-        comp.staged_points = n_pts;
-        comp.staged_rational = rational;
+        cd.staged_valid = true;
+        cd.staged_from = from;
+        cd.staged_to = to;
+        cd.staged_filtered = cd.filtered;
+        cd.staged_lo = cd.band_lo;
+        cd.staged_hi = cd.band_hi;
+        cd.staged_jobs = n_jobs;
+        cd.staged_splines = n_splines;
+        cd.staged_recs = n_recs;
+        cd.staged_quads = n_quads;
+        cd.staged_points = n_pts;
+        cd.staged_rational = rational;
+    } else {
+        // Same batch as last time (evicted composition): only the destinations depend on what is resident.
+        uint32_t pi = 0;
+        for (size_t k = 0; k < cd.staged_jobs; ++k) {
+            cd.h_jobs.ptr[k].dst = cd.n_resident + pi;
+            pi += cd.h_jobs.ptr[k].count;
+        }
     }
-    const size_t quad_bytes = comp.staged_rational ? sizeof(QuadUp) : sizeof(QuadUpPoly);
-    FORMA_CUDA_TRY(up_splines.reserve(comp.staged_splines + 1));
-    FORMA_CUDA_TRY(up_points.reserve(comp.staged_recs + 1));
-    FORMA_CUDA_TRY(up_kinds.reserve(comp.staged_recs + 1));
-    FORMA_CUDA_TRY(up_quads.reserve(comp.staged_quads + 1));
-    FORMA_CUDA_TRY(up_jobs.reserve(to - from));
-    if (comp.staged_splines)
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_splines.ptr, comp.h_splines.ptr, comp.staged_splines * sizeof(SplineRec),
+    cd.jobs_resident = to;
+    if (!cd.staged_jobs) return FORMA_STATUS_OK;
+    const uint32_t n_after = cd.n_resident + (uint32_t)cd.staged_points;
+    FORMA_CUDA_TRY(cd.d_x.reserve(n_after, true, stream));
+    FORMA_CUDA_TRY(cd.d_y.reserve(n_after, true, stream));
+    FORMA_CUDA_TRY(cd.d_gid.reserve(n_after, true, stream));
+    const size_t quad_bytes = cd.staged_rational ? sizeof(QuadUp) : sizeof(QuadUpPoly);
+    FORMA_CUDA_TRY(up_splines.reserve(cd.staged_splines + 1));
+    FORMA_CUDA_TRY(up_points.reserve(cd.staged_recs + 1));
+    FORMA_CUDA_TRY(up_kinds.reserve(cd.staged_recs + 1));
+    FORMA_CUDA_TRY(up_quads.reserve(cd.staged_quads + 1));
+    FORMA_CUDA_TRY(up_jobs.reserve(cd.staged_jobs));
+    if (cd.staged_splines)
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_splines.ptr, cd.h_splines.ptr, cd.staged_splines * sizeof(SplineRec),
                                        cudaMemcpyHostToDevice, stream));
-    if (comp.staged_recs) {
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_points.ptr, comp.h_points.ptr, comp.staged_recs * sizeof(PointRec), cudaMemcpyHostToDevice,
+    if (cd.staged_recs) {
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_points.ptr, cd.h_points.ptr, cd.staged_recs * sizeof(PointRec), cudaMemcpyHostToDevice,
                                        stream));
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, comp.h_kinds.ptr, comp.staged_recs, cudaMemcpyHostToDevice, stream));
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, cd.h_kinds.ptr, cd.staged_recs, cudaMemcpyHostToDevice, stream));
     }
-    if (comp.staged_quads) {
-        FORMA_CUDA_TRY(up_quads_raw.reserve(comp.staged_quads + 1));
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, comp.h_quads.ptr, comp.staged_quads * quad_bytes, cudaMemcpyHostToDevice,
+    if (cd.staged_quads) {
+        FORMA_CUDA_TRY(up_quads_raw.reserve(cd.staged_quads + 1));
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, cd.h_quads.ptr, cd.staged_quads * quad_bytes, cudaMemcpyHostToDevice,
                                        stream));
-        if (comp.staged_rational)
-            launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)comp.staged_quads, stream);
+        if (cd.staged_rational)
+            launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)cd.staged_quads, stream);
         else
             launch_quad_expand_poly(reinterpret_cast<const QuadUpPoly*>(up_quads_raw.ptr), up_quads.ptr,
-                                    (uint32_t)comp.staged_quads, stream);
+                                    (uint32_t)cd.staged_quads, stream);
         ++launches;
     }
-    FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, comp.h_jobs.ptr, (to - from) * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
-    h2d_bytes += comp.staged_splines * sizeof(SplineRec) + comp.staged_recs * (sizeof(PointRec) + 1) +
-                 comp.staged_quads * quad_bytes + (to - from) * sizeof(FlattenJob);
-    launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)(to - from),
-                        (uint32_t)comp.staged_points, comp.d_x.ptr, comp.d_y.ptr, comp.d_gid.ptr, stream);
+    FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, cd.h_jobs.ptr, cd.staged_jobs * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
+    h2d_bytes += cd.staged_splines * sizeof(SplineRec) + cd.staged_recs * (sizeof(PointRec) + 1) +
+                 cd.staged_quads * quad_bytes + cd.staged_jobs * sizeof(FlattenJob);
+    launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)cd.staged_jobs,
+                        (uint32_t)cd.staged_points, cd.d_x.ptr, cd.d_y.ptr, cd.d_gid.ptr, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
-    comp.n_resident = comp.n_points;
-    comp.jobs_resident = to;
+    cd.n_resident = n_after;
     return FORMA_STATUS_OK;
 }
 
@@ -517,7 +581,20 @@ int Renderer::flush_geometry(Composition& comp) {
 // these look-ups per point). The pinned host copies are rebuilt when the
 // composition changed and re-uploaded when they are not resident.
 int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
+    CompDevice& cd = comp.on(device);
     if (comp.tables_dirty || comp.tables_cache_id != cache_id) {
+        FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // an upload from the pinned tables may still be in flight
+        int st = rebuild_tables(comp, cache_id);
+        if (st) return st;
+    }
+    if (cd.tables_version == comp.tables_version) return FORMA_STATUS_OK;
+    return upload_tables_device(comp, cd);
+}
+
+// Host part: the pinned copies of the tables (no CUDA work besides pinned allocations). A
+// caller that renders one composition on several devices runs it once before its workers start.
+int Renderer::rebuild_tables(Composition& comp, int64_t cache_id) {
+    {
         std::vector<StopRec> stops;
         std::vector<uint16_t> texels;
         std::unordered_map<const void*, uint32_t> tex_offsets;
@@ -525,7 +602,6 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         for (auto& kv : comp.layers) max_order = std::max(max_order, kv.first);
         uint32_t n_orders = comp.layers.empty() ? 0u : max_order + 1u;
         uint32_t n_geoms = comp.next_dense_id;
-        FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
         FORMA_CUDA_TRY(comp.h_layers.reserve(comp.layers.size() + 1));
         FORMA_CUDA_TRY(comp.h_styles.reserve(comp.layers.size() + 1));
         FORMA_CUDA_TRY(comp.h_order_to_style.reserve(n_orders + 1));
@@ -607,9 +683,12 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         comp.n_orders = n_orders;
         comp.tables_dirty = false;
         comp.tables_cache_id = cache_id;
-        comp.tables_resident = false;
+        ++comp.tables_version;
     }
-    if (comp.tables_resident) return FORMA_STATUS_OK;
+    return FORMA_STATUS_OK;
+}
+
+int Renderer::upload_tables_device(Composition& comp, CompDevice& cd) {
     auto up = [&](auto& dbuf, const auto& hbuf, size_t n) -> cudaError_t {
         cudaError_t e = dbuf.reserve(n + 1);
         if (e != cudaSuccess || n == 0) return e;
@@ -617,14 +696,14 @@ int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
         return cudaMemcpyAsync(dbuf.ptr, hbuf.ptr, n * sizeof(*hbuf.ptr), cudaMemcpyHostToDevice, stream);
     };
     // Layers without transforms (the common case) travel as 4 bytes each instead of 36.
-    if (comp.layers_have_xf) FORMA_CUDA_TRY(up(comp.d_layers, comp.h_layers, comp.n_layer_recs));
-    else FORMA_CUDA_TRY(up(comp.d_layer_bits, comp.h_layer_bits, comp.n_layer_recs));
-    FORMA_CUDA_TRY(up(comp.d_styles, comp.h_styles, comp.n_style_recs));
-    FORMA_CUDA_TRY(up(comp.d_stops, comp.h_stops, comp.n_stops));
-    FORMA_CUDA_TRY(up(comp.d_texels, comp.h_texels, comp.n_texels));
-    FORMA_CUDA_TRY(up(comp.d_order_to_style, comp.h_order_to_style, comp.n_orders));
-    FORMA_CUDA_TRY(up(comp.d_geom_slot, comp.h_geom_slot, comp.n_geoms));
-    comp.tables_resident = true;
+    if (comp.layers_have_xf) FORMA_CUDA_TRY(up(cd.d_layers, comp.h_layers, comp.n_layer_recs));
+    else FORMA_CUDA_TRY(up(cd.d_layer_bits, comp.h_layer_bits, comp.n_layer_recs));
+    FORMA_CUDA_TRY(up(cd.d_styles, comp.h_styles, comp.n_style_recs));
+    FORMA_CUDA_TRY(up(cd.d_stops, comp.h_stops, comp.n_stops));
+    FORMA_CUDA_TRY(up(cd.d_texels, comp.h_texels, comp.n_texels));
+    FORMA_CUDA_TRY(up(cd.d_order_to_style, comp.h_order_to_style, comp.n_orders));
+    FORMA_CUDA_TRY(up(cd.d_geom_slot, comp.h_geom_slot, comp.n_geoms));
+    cd.tables_version = comp.tables_version;
     return FORMA_STATUS_OK;
 }
 
@@ -633,14 +712,15 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
                         uint32_t* n_out) {
     RasterArgs& ra = last_raster;  // kept for forma_renderer_lines
     last_raster_valid = true;
-    ra.x = comp.d_x.ptr;
-    ra.y = comp.d_y.ptr;
-    ra.gid = comp.d_gid.ptr;
-    ra.n_points = comp.n_resident;
-    ra.geom_slot = comp.d_geom_slot.ptr;
+    CompDevice& cd = comp.on(device);
+    ra.x = cd.d_x.ptr;
+    ra.y = cd.d_y.ptr;
+    ra.gid = cd.d_gid.ptr;
+    ra.n_points = cd.n_resident;
+    ra.geom_slot = cd.d_geom_slot.ptr;
     ra.n_geoms = comp.n_geoms;
-    ra.layers = comp.layers_have_xf ? comp.d_layers.ptr : nullptr;
-    ra.layer_bits = comp.d_layer_bits.ptr;
+    ra.layers = comp.layers_have_xf ? cd.d_layers.ptr : nullptr;
+    ra.layer_bits = cd.d_layer_bits.ptr;
     ra.width = (float)width;
     ra.height = (float)height;
     ra.band_lo = band_lo;
@@ -734,15 +814,21 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
 
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
-    int st = flush_geometry(comp);
+    // Lines entirely above / below the painted tile rows cannot reach a painted tile: they are
+    // culled per line (rasterize), and whole inserts are left out of the device's segment
+    // buffer when the band is narrower than the frame (flush_geometry).
+    const float band_lo = (float)(S.ty_lo * 16u), band_hi = (float)std::min<uint64_t>((uint64_t)S.ty_hi * 16u, height);
+    const bool band_is_partial = S.ty_lo > 0u || S.ty_hi < S.tiles_y;
+    int st = flush_geometry(comp, band_lo, band_hi, band_is_partial);
     if (st) return st;
     st = upload_tables(comp, -1);
     if (st) return st;
-    S.styles = comp.d_styles.ptr;
-    S.order_to_style = comp.d_order_to_style.ptr;
+    CompDevice& cd = comp.on(device);
+    S.styles = cd.d_styles.ptr;
+    S.order_to_style = cd.d_order_to_style.ptr;
     S.n_orders = comp.n_orders;
-    S.stops = comp.d_stops.ptr;
-    S.texels = comp.d_texels.ptr;
+    S.stops = cd.d_stops.ptr;
+    S.texels = cd.d_texels.ptr;
 
     const bool pack_written = cache && !buffer_on_device;
     if (cache) {  // renderer.rs:94-110
@@ -784,9 +870,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
 
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[7], stream));
     uint32_t n = 0;
-    // Lines entirely above / below the painted tile rows cannot reach a painted
-    // tile; culling them is what lets several GPUs split a frame by tile bands.
-    st = rasterize(comp, S.width, S.height, (float)(S.ty_lo * 16u), (float)std::min<uint64_t>((uint64_t)S.ty_hi * 16u, height), &n);
+    st = rasterize(comp, S.width, S.height, band_lo, band_hi, &n);
     if (st) return st;
 
     // Stage 3: sort.
@@ -806,6 +890,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
 
     // Stage 4: cells -> carries -> entries -> paint.
     size_t n_tiles_total = (size_t)S.tiles_x * S.tiles_y;
+    last_tiles_x = S.tiles_x;
+    last_tiles_y = S.tiles_y;
     FORMA_CUDA_TRY(tile_range.reserve(n_tiles_total));
     FORMA_CUDA_TRY(heavy_tiles.reserve(n_tiles_total * kHeavyListClasses));
     // Heavy tiles first (longest-processing-time order): their lists + counts (totals[8..11]).
@@ -818,28 +904,29 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     uint32_t n_cells = 0, n_gaps = 0, n_entries = 0;
     if (n > 0) {
-        uint32_t nb = cell_num_blocks(n);
-        FORMA_CUDA_TRY(block_sums.reserve(nb + 1));
-        FORMA_CUDA_TRY(head_masks.reserve(n / 32 + 2));
-        launch_cell_count(segs.ptr, n, block_sums.ptr, head_masks.ptr, totals.ptr + 1, stream);
-        launches += 2;
-        // Read the cell count back; meanwhile the next two kernels already run with
-        // the count taken from device memory, into the buffers of the previous frames
-        // (they do nothing if those are too small, and are then repeated below).
-        FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 1, totals.ptr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
-        size_t cell_cap = 0;
-        if (speculation_enabled() && cell_start.capacity > 1)
+        // Cells: one pass finds the cell heads and counts them. The count is read back, but
+        // nothing waits for it: the pass itself and the cover kernel run into the buffers of
+        // the previous frames (the count is taken from device memory, writes beyond the
+        // capacity are dropped) and are repeated below only if those turn out too small.
+        FORMA_CUDA_TRY(scan_state.reserve(std::max(cells_scan_state_words(n), scan_state_words(n))));
+        FORMA_CUDA_TRY(cell_start.reserve(4096));
+        size_t cell_cap = 0;  // cells the cover kernel may handle speculatively
+        if (speculation_enabled() && cell_key.capacity)
             cell_cap = std::min({cell_start.capacity - 1, cell_key.capacity, cell_cover.capacity, key2.capacity, perm.capacity,
                                  (size_t)0xFFFFFFFFu});
+        launch_cells_scan(segs.ptr, n, scan_state.ptr, cell_start.ptr, (uint32_t)std::min<size_t>(cell_start.capacity, 0xFFFFFFFFu),
+                          totals.ptr + 1, stream);
+        ++launches;
+        FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 1, totals.ptr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
         if (cell_cap) {
-            launch_cell_write(head_masks.ptr, n, block_sums.ptr, cell_start.ptr, totals.ptr + 1, (uint32_t)cell_cap, stream);
             launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, (uint32_t)cell_cap,
                               (uint32_t)std::min<size_t>(cell_cap, n), cell_cover.ptr, key2.ptr, perm.ptr, stream);
-            launches += 2;
+            ++launches;
         }
         FORMA_CUDA_TRY(cudaEventSynchronize(count_ev));
         n_cells = pinned_totals[1];
+        const bool cells_fit = (size_t)n_cells + 1 <= cell_start.capacity;
         FORMA_CUDA_TRY(cell_start.reserve(n_cells + 1));
         FORMA_CUDA_TRY(cell_key.reserve(n_cells));
         FORMA_CUDA_TRY(cell_cover.reserve(n_cells));
@@ -850,12 +937,15 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(perm.reserve(n_cells));
         FORMA_CUDA_TRY(perm_tmp.reserve(n_cells));
         FORMA_CUDA_TRY(gap_count.reserve(n_cells));
-        FORMA_CUDA_TRY(gap_offset.reserve(n_cells));
-        if (!cell_cap || n_cells > cell_cap) {
-            launch_cell_write(head_masks.ptr, n, block_sums.ptr, cell_start.ptr, totals.ptr + 1, n_cells, stream);
+        if (!cells_fit) {  // cell_start was too small: the pass dropped the overflow
+            launch_cells_scan(segs.ptr, n, scan_state.ptr, cell_start.ptr, (uint32_t)std::min<size_t>(cell_start.capacity, 0xFFFFFFFFu),
+                              totals.ptr + 1, stream);
+            ++launches;
+        }
+        if (!cells_fit || !cell_cap || n_cells > cell_cap) {
             launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, n_cells, n_cells, cell_cover.ptr, key2.ptr,
                               perm.ptr, stream);
-            launches += 2;
+            ++launches;
         }
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_cells)));
         {
@@ -869,10 +959,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         }
         launch_carry_scan(S, key2.ptr, perm.ptr, cell_cover.ptr, n_cells, carry_in.ptr, carry_after.ptr, gap_count.ptr,
                           stream);
-        FORMA_CUDA_TRY(cudaMemcpyAsync(gap_offset.ptr, gap_count.ptr, n_cells * sizeof(uint32_t),
-                                       cudaMemcpyDeviceToDevice, stream));
-        FORMA_CUDA_TRY(scan_state.reserve(scan_state_words(n_cells)));
-        launch_scan_u32(gap_offset.ptr, n_cells, totals.ptr + 2, scan_state.ptr, stream);
+        // gap_count -> exclusive offsets, in place (gap_fill only needs the offsets).
+        launch_scan_u32(gap_count.ptr, n_cells, totals.ptr + 2, scan_state.ptr, stream);
         launches += 2;
         // Same scheme for the number of carry-only entries: gap_fill runs ahead of the read-back.
         FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 2, totals.ptr + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -886,7 +974,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             if (test_gap_cap_override() && gap_cap) gap_cap = std::min<size_t>(gap_cap, test_gap_cap_override());
         }
         if (gap_cap) {
-            launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
+            launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, n_cells,
                             ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, (uint32_t)gap_cap, (uint32_t)gap_cap, stream);
             ++launches;
         }
@@ -907,7 +995,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         if (n_gaps) {
             FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_gaps)));
             if (!gap_cap || n_gaps > gap_cap) {
-                launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, gap_offset.ptr, n_cells,
+                launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, n_cells,
                                 ekey_tmp.ptr, eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, n_gaps, n_gaps, stream);
                 ++launches;
             }
@@ -1044,7 +1132,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         timings->rasterize_ms = stage_ms[2];
         timings->sort_ms = stage_ms[3];
         timings->paint_ms = stage_ms[4] + stage_ms[5];
-        timings->n_lines = comp.n_resident ? comp.n_resident - 1 : 0;
+        timings->n_lines = cd.n_resident ? cd.n_resident - 1 : 0;
         timings->n_segments = n;
     }
     if (cache) {  // renderer.rs:217-223
@@ -1487,6 +1575,234 @@ int forma_shared_frame_free(int device, void* device_ptr) {
     FORMA_CUDA_TRY(cudaSetDevice(device));
     FORMA_CUDA_TRY(cudaFree(device_ptr));
     return FORMA_STATUS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Several GPUs behind one renderer (single process): tile-row bands, one worker thread and
+// one forma_renderer per device. Every device makes the geometry of its band resident
+// (flush_geometry's band filter), rasterizes, sorts and paints its band, and either copies
+// the band's rows to the caller's host buffer or stores them into the frame in the first
+// device's memory over NVLink (peer access). No collective: the bands are disjoint row
+// ranges of one frame. The bands of the next frame are balanced on this frame's row costs.
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+#include <thread>
+
+struct forma_renderer_multi {
+    std::vector<forma_renderer*> dev;
+    std::vector<uint32_t> bounds;  // tile rows: band i = [bounds[i], bounds[i + 1])
+    uint32_t bounds_lo = 0, bounds_hi = 0;
+    bool peer_ok = true;           // every device may store into the first device's memory
+    std::vector<double> last_ms;   // device-timeline ms of each band in the last frame
+};
+
+static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint8_t* buffer, bool on_device, uint64_t width,
+                             uint64_t stride, uint64_t height, const uint32_t channels[4], const float clear[4],
+                             const forma_rect* crop, forma_timings* timings) {
+    const size_t n = m->dev.size();
+    if (!n || !width || !height || width > FORMA_MAX_WIDTH || height > FORMA_MAX_HEIGHT) {
+        set_error("forma_renderer_multi_render: invalid arguments");
+        return FORMA_STATUS_INVALID;
+    }
+    if (on_device && n > 1 && !m->peer_ok) {
+        set_error("forma_renderer_multi_render_device: peer access to the first device is not available");
+        return FORMA_STATUS_INVALID;
+    }
+    Composition& comp = c->c;
+    // Tile rows to paint (crop is tile-granular like cpu/renderer.rs:43-52).
+    const uint32_t tiles_y = (uint32_t)((height + 15u) / 16u);
+    uint32_t row_lo = 0, row_hi = tiles_y;
+    forma_rect full{0, width, 0, height};
+    if (crop) {
+        full = *crop;
+        row_lo = (uint32_t)std::min<uint64_t>(crop->vert_start / 16u, tiles_y);
+        row_hi = (uint32_t)std::min<uint64_t>((crop->vert_end + 15u) / 16u, tiles_y);
+        if (row_hi < row_lo) row_hi = row_lo;
+    }
+    if (m->bounds.size() != n + 1 || m->bounds_lo != row_lo || m->bounds_hi != row_hi) {  // first frame / new target: equal bands
+        m->bounds.assign(n + 1, row_lo);
+        for (size_t i = 0; i <= n; ++i) m->bounds[i] = row_lo + (uint32_t)(((uint64_t)(row_hi - row_lo) * i) / n);
+        m->bounds_lo = row_lo;
+        m->bounds_hi = row_hi;
+    }
+    // Host-side preparation, once: compaction, the pinned tables, the per-device records.
+    comp.compact_geom();
+    if (comp.tables_dirty || comp.tables_cache_id != -1) {
+        for (forma_renderer* r : m->dev) {
+            FORMA_CUDA_TRY(cudaSetDevice(r->r.device));
+            FORMA_CUDA_TRY(cudaStreamSynchronize(r->r.stream));
+        }
+        int st = Renderer::rebuild_tables(comp, -1);
+        if (st) return st;
+    }
+    for (forma_renderer* r : m->dev) comp.on(r->r.device);
+
+    std::vector<int> status(n, FORMA_STATUS_OK);
+    std::vector<std::string> errors(n);
+    std::vector<forma_timings> tms(n);
+    std::vector<std::vector<uint64_t>> costs(n);
+    m->last_ms.assign(n, 0.0);
+    auto work = [&](size_t i) {
+        const uint32_t r0 = m->bounds[i], r1 = m->bounds[i + 1];
+        std::memset(&tms[i], 0, sizeof(forma_timings));
+        if (r1 <= r0) return;
+        forma_rect band = full;
+        band.vert_start = std::max<uint64_t>(full.vert_start, (uint64_t)r0 * 16u);
+        band.vert_end = std::min<uint64_t>(std::min<uint64_t>(full.vert_end, height), (uint64_t)r1 * 16u);
+        if (band.vert_end <= band.vert_start) return;
+        Renderer& R = m->dev[i]->r;
+        status[i] = guarded((int)FORMA_ERR_CAPACITY, [&] {
+            return R.render(comp, buffer, on_device, width, stride, height, channels, clear, &band, nullptr, &tms[i]);
+        });
+        if (status[i]) {
+            errors[i] = forma_last_error();
+            return;
+        }
+        m->last_ms[i] = R.stage_ms[7];
+        costs[i].assign(tiles_y, 0);
+        forma_renderer_row_costs(m->dev[i], tiles_y, costs[i].data());
+    };
+    if (n == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (size_t i = 0; i < n; ++i) threads.emplace_back(work, i);
+        for (std::thread& t : threads) t.join();
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (status[i]) {
+            set_error("device %d: %s", m->dev[i]->r.device, errors[i].c_str());
+            return status[i];
+        }
+    if (timings) {
+        std::memset(timings, 0, sizeof(*timings));
+        for (size_t i = 0; i < n; ++i) {  // stages: the slowest band; sizes: the whole frame
+            timings->line_setup_ms = std::max(timings->line_setup_ms, tms[i].line_setup_ms);
+            timings->rasterize_ms = std::max(timings->rasterize_ms, tms[i].rasterize_ms);
+            timings->sort_ms = std::max(timings->sort_ms, tms[i].sort_ms);
+            timings->paint_ms = std::max(timings->paint_ms, tms[i].paint_ms);
+            timings->n_lines += tms[i].n_lines;
+            timings->n_segments += tms[i].n_segments;
+        }
+    }
+    // Next frame's bands: equal shares of this frame's row costs (+ a floor per row: every
+    // tile is at least cleared and stored).
+    if (n > 1 && row_hi > row_lo) {
+        std::vector<double> cost(tiles_y, 0.0);
+        const double floor_cost = 2.0 * (double)((width + 15u) / 16u);
+        for (size_t i = 0; i < n; ++i)
+            for (uint32_t r = m->bounds[i]; r < m->bounds[i + 1] && r < (uint32_t)costs[i].size(); ++r)
+                cost[r] = (double)costs[i][r];
+        double total = 0.0;
+        for (uint32_t r = row_lo; r < row_hi; ++r) total += (cost[r] += floor_cost);
+        std::vector<uint32_t> nb(1, row_lo);
+        double run = 0.0;
+        size_t k = 1;
+        for (uint32_t r = row_lo; r < row_hi; ++r) {
+            while (k < n && run + 0.5 * cost[r] >= total * (double)k / (double)n) {
+                nb.push_back(r);
+                ++k;
+            }
+            run += cost[r];
+        }
+        while (nb.size() < n) nb.push_back(row_hi);
+        nb.push_back(row_hi);
+        m->bounds = nb;
+    }
+    return FORMA_STATUS_OK;
+}
+
+extern "C" {
+
+forma_renderer_multi* forma_renderer_multi_new(const int* devices, int n) {
+    return guarded((forma_renderer_multi*)nullptr, [&]() -> forma_renderer_multi* {
+        if (!devices || n < 1 || n > 64) {
+            set_error("forma_renderer_multi_new: need 1..64 device ordinals");
+            return nullptr;
+        }
+        std::unique_ptr<forma_renderer_multi> m(new forma_renderer_multi());
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < i; ++j)
+                if (devices[j] == devices[i]) {
+                    set_error("forma_renderer_multi_new: device %d listed twice", devices[i]);
+                    for (forma_renderer* r : m->dev) forma_renderer_free(r);
+                    return nullptr;
+                }
+            forma_renderer* r = forma_renderer_new(devices[i]);
+            if (!r) {
+                for (forma_renderer* q : m->dev) forma_renderer_free(q);
+                return nullptr;
+            }
+            // Each device renders on its own (non-blocking) stream.
+            cudaStream_t st = nullptr;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess) {
+                r->r.stream = st;
+                r->r.owns_stream = true;
+            }
+            m->dev.push_back(r);
+        }
+        for (int i = 1; i < n; ++i) {  // stores into the first device's frame go over NVLink
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) != cudaSuccess || !can) {
+                m->peer_ok = false;
+                continue;
+            }
+            cudaSetDevice(devices[i]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->peer_ok = false;
+            cudaGetLastError();
+        }
+        return m.release();
+    });
+}
+void forma_renderer_multi_free(forma_renderer_multi* m) {
+    if (!m) return;
+    for (forma_renderer* r : m->dev) forma_renderer_free(r);
+    delete m;
+}
+int forma_renderer_multi_device_count(const forma_renderer_multi* m) { return m ? (int)m->dev.size() : 0; }
+int forma_renderer_multi_render(forma_renderer_multi* m, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
+                                uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
+                                forma_timings* timings) {
+    return guarded((int)FORMA_ERR_CAPACITY,
+                   [&] { return multi_render_impl(m, c, buffer, false, width, stride, height, channels, clear, crop, timings); });
+}
+int forma_renderer_multi_render_device(forma_renderer_multi* m, forma_composition* c, uint8_t* buffer_on_first_device,
+                                       uint64_t width, uint64_t stride, uint64_t height, const uint32_t channels[4],
+                                       const float clear[4], const forma_rect* crop, forma_timings* timings) {
+    return guarded((int)FORMA_ERR_CAPACITY, [&] {
+        return multi_render_impl(m, c, buffer_on_first_device, true, width, stride, height, channels, clear, crop, timings);
+    });
+}
+/* Tile-row boundaries of the bands the next frame will use (n + 1 values) and the
+ * device-timeline ms every band took in the last frame (n values). */
+int forma_renderer_multi_bands(const forma_renderer_multi* m, uint32_t* bounds, double* band_ms) {
+    if (!m) return 0;
+    for (size_t i = 0; bounds && i < m->bounds.size(); ++i) bounds[i] = m->bounds[i];
+    for (size_t i = 0; band_ms && i < m->last_ms.size(); ++i) band_ms[i] = m->last_ms[i];
+    return (int)m->dev.size();
+}
+
+static uint64_t row_costs_impl(forma_renderer* r, uint64_t cap, uint64_t* out) {
+    Renderer& R = r->r;
+    const uint32_t rows = R.last_tiles_y;
+    if (!rows || !cap || !out) return rows;
+    if (cudaSetDevice(R.device) != cudaSuccess) return 0;
+    DeviceBuffer<unsigned long long> d;
+    if (d.reserve(rows) != cudaSuccess) return 0;
+    launch_row_costs(R.tile_range.ptr, R.last_tiles_x, rows, R.segs.ptr, R.last_segments, d.ptr, R.stream);
+    std::vector<unsigned long long> h(rows);
+    if (cudaMemcpyAsync(h.data(), d.ptr, rows * sizeof(unsigned long long), cudaMemcpyDeviceToHost, R.stream) != cudaSuccess ||
+        cudaStreamSynchronize(R.stream) != cudaSuccess) {
+        set_error("forma_renderer_row_costs: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    for (uint64_t i = 0; i < std::min<uint64_t>(cap, rows); ++i) out[i] = h[i];
+    return rows;
+}
+uint64_t forma_renderer_row_costs(forma_renderer* r, uint64_t cap, uint64_t* out) {
+    return guarded((uint64_t)0, [&] { return row_costs_impl(r, cap, out); });
 }
 
 int forma_set_option(const char* name, int value) {

@@ -206,6 +206,28 @@ int forma_renderer_render_device(forma_renderer*, forma_composition*, uint8_t* d
  * instead of the default stream. */
 void forma_renderer_set_stream(forma_renderer*, void* cuda_stream);
 
+/* Several GPUs behind one renderer, single process (Renderer::new for a multi-GPU box):
+ * `render` has the contract of forma_renderer_render, `render_device` that of
+ * forma_renderer_render_device with the frame in the FIRST listed device's memory (the other
+ * devices store their rows into it over NVLink; needs peer access). The frame is split into
+ * bands of tile rows, one per device, rebalanced every frame on the previous frame's row
+ * costs; each device keeps only its band's geometry resident. Layer caches are not
+ * supported here (cache = NULL semantics). Every listed device must be an sm_100 GPU. */
+typedef struct forma_renderer_multi forma_renderer_multi;
+forma_renderer_multi* forma_renderer_multi_new(const int* device_ordinals, int n);
+void forma_renderer_multi_free(forma_renderer_multi*);
+int forma_renderer_multi_device_count(const forma_renderer_multi*);
+int forma_renderer_multi_render(forma_renderer_multi*, forma_composition*, uint8_t* buffer, uint64_t width,
+                                uint64_t width_stride, uint64_t height, const uint32_t channels[4],
+                                const float clear_color[4], const forma_rect* crop, forma_timings* timings);
+int forma_renderer_multi_render_device(forma_renderer_multi*, forma_composition*, uint8_t* buffer_on_first_device,
+                                       uint64_t width, uint64_t width_stride, uint64_t height,
+                                       const uint32_t channels[4], const float clear_color[4],
+                                       const forma_rect* crop, forma_timings* timings);
+/* bounds[n + 1]: tile-row boundaries of the bands the next frame will use; band_ms[n]:
+ * device-timeline ms of every band in the last frame. Returns n. */
+int forma_renderer_multi_bands(const forma_renderer_multi*, uint32_t* bounds, double* band_ms);
+
 /* Multi-GPU frame assembly without a copy (one process per GPU, tile-row bands,
  * SURVEY.md §8e): the process that owns the frame allocates it with
  * forma_shared_frame_create and passes the 64-byte handle to the others (any
@@ -242,8 +264,15 @@ void forma_renderer_kernel_times(const forma_renderer*, double out_ms[4], uint32
  * [6] tiles the last layer-cache render copied back to a host buffer, [7] 0. */
 void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
 
+/* Cost of every tile row of the last render (32 x its (tile, layer) entries + its pixel
+ * segments; rows outside the rendered crop cost 0): what a caller balances the tile-row
+ * bands of the next multi-GPU frame on. Returns the number of tile rows;
+ * call with cap = 0 to size `out`. */
+uint64_t forma_renderer_row_costs(forma_renderer*, uint64_t cap, uint64_t* out);
+
 /* Schedule switches of the library (process-wide; none changes results): "speculate",
- * "band_copy", "copy_bands", "sort_full_key", "sort_big_log2", "paint_lpt", "test_gap_cap".
+ * "band_copy", "copy_bands", "sort_full_key", "sort_big_log2", "paint_lpt", "band_filter",
+ * "test_gap_cap".
  * Defaults come from the environment (FORMA_SPECULATE, ...); see DESIGN.md section 6. */
 int forma_set_option(const char* name, int value);
 int forma_get_option(const char* name, int* value);

@@ -122,4 +122,18 @@ struct StopRec {
     float stop;
 };
 
+// A gradient of at most four stops, ready for the painter (built on the device from the
+// StyleRec and its stops whenever the tables are uploaded): the per-gradient terms of
+// Gradient::get_t and color_at (cpu/painter/styling.rs:59-143) that do not depend on the pixel.
+struct GradRec {  // 128 B: one float per lane of a warp
+    float sx, sy, dx, dy;   // start, end - start
+    float dot_recip;        // (dx * dx + dy * dy).recip()
+    uint32_t type;          // 0 linear, 1 radial
+    uint32_t count;         // stops (2..4); 0xFFFFFFFF = not a small gradient
+    uint32_t pad;
+    float color[4][4];      // stop colours; entries past the last stop repeat it
+    float stop[4];
+    float rcp_d[4];         // [i - 1] = (stop[i] - start_stop).recip(), start_stop = 0 for i = 1, else stop[i - 1]
+};
+
 }  // namespace forma

@@ -81,6 +81,7 @@ struct CompDevice {
     DeviceBuffer<StyleRec> d_styles;
     DeviceBuffer<int32_t> d_order_to_style;
     DeviceBuffer<StopRec> d_stops;
+    DeviceBuffer<GradRec> d_grads;    // built on the device from d_styles / d_stops (grad_setup_kernel)
     DeviceBuffer<uint16_t> d_texels;
     // keep_staging: the pinned copies of the last batch stay valid (an evicted composition is
     // re-uploaded from them without touching the host-side programs again).

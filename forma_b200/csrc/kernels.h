@@ -106,6 +106,7 @@ struct PaintScene {
     const int32_t* order_to_style;// layer id (order) -> style slot
     uint32_t n_orders;
     const StopRec* stops;
+    const GradRec* grads;         // per style slot (valid where the style is a gradient of <= 4 stops)
     const uint16_t* texels;       // RGBA f16 (styling.rs:224-249), 4 per texel
     float clear[4];
     uint32_t channels[4];         // already upgraded Alpha -> One when clear.a == 1
@@ -171,6 +172,8 @@ void launch_tile_index(const PaintScene& S, const uint64_t* ekey, uint32_t n_ent
                        uint32_t* heavy_count, cudaStream_t st);
 void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint2* tile_range, const uint32_t* heavy,
                   const uint32_t* heavy_count, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st);
+// GradRec of every style slot (see device_types.h).
+void launch_grad_setup(const StyleRec* styles, const StopRec* stops, uint32_t n_styles, GradRec* grads, cudaStream_t st);
 // Packed fp32 (f32x2) arithmetic of the painter against scalar IEEE operations; mismatches are added to out[0].
 void launch_f32x2_selftest(const float* a, const float* b, const float* c, uint32_t n, uint32_t* out, cudaStream_t st);
 // out[row] = 32 x entries + pixel segments of tile row `row` (see row_cost_kernel).

@@ -204,11 +204,88 @@ __device__ __forceinline__ void store_tile_solid(const PaintScene& S, uint8_t* f
     }
 }
 
-// Shared-memory word of pixel (local_x, local_y): lane = 2 ly + lx / 8 owns the eight cells
-// j = lx % 8 as two 16-byte words at [lane * 4 + j] (j < 4) and [128 + lane * 4 + j - 4]:
-// a warp-wide 16-byte access is conflict-free.
-__device__ __forceinline__ uint32_t cell_index(uint32_t lx, uint32_t ly) {
-    return ((lx & 4u) << 5) + (ly * 2u + (lx >> 3)) * 4u + (lx & 3u);
+// Shared-memory word of pixel (local_x, local_y): row-major, ly * 16 + lx, i.e. the segment's
+// (local_x, local_y) byte with its nibbles swapped. Lane l = 2 ly + lx / 8 owns the eight
+// consecutive words l * 8 .. + 8 (two 16-byte accesses, two-way bank conflict: negligible
+// next to the index arithmetic a swizzle would cost per segment).
+__device__ __forceinline__ uint32_t cell_index_of(uint64_t s) {
+    const uint32_t t = (uint32_t)(s >> 12);  // bits 7..4 local_x, 3..0 local_y
+    return ((t & 15u) << 4) | ((t >> 4) & 15u);
+}
+
+// doubled_area_to_coverage (cpu/painter/mod.rs:76-94) by fill rule. The clamp of the
+// non-zero rule only ever sees a non-negative, non-NaN value: min(v, 1) is the same result.
+__device__ __forceinline__ float coverage_non_zero(int32_t doubled_area) {
+    return fminf(fabsf((float)doubled_area * (1.0f / 512.0f)), 1.0f);
+}
+__device__ __forceinline__ float coverage_even_odd(int32_t doubled_area) {
+    return (float)(512 - abs((doubled_area & 1023) - 512)) * (1.0f / 512.0f);
+}
+
+template <class T>
+__device__ __forceinline__ void rotate4(T (&v)[4]) {
+    const T t = v[0];
+    v[0] = v[1];
+    v[1] = v[2];
+    v[2] = v[3];
+    v[3] = t;
+}
+
+// Gradient::color_at (cpu/painter/styling.rs:58-144) for the pixel pair (x, x + 1) of one row,
+// from the per-style record in shared memory. Same operations in the same order as
+// gradient_at (paint_math.cuh); d.recip() of every stop interval comes precomputed.
+__device__ __forceinline__ void gradient_pair(const GradRec& g, float x, float y_base, int lane_in_f32x8, f2& r, f2& gg, f2& b, f2& a) {
+    f2 t;
+    const f2 xs = f2{x, x + 1.0f};
+    if (g.type == 0u) {
+        // tx = (x - sx) * dx * dot_recip; t = fma((lane + (y_base - sy)) * dy, dot_recip, tx)
+        const f2 tx = mul2(mul2(sub2(xs, f2_splat(g.sx)), f2_splat(g.dx)), f2_splat(g.dot_recip));
+        const float ty = y_base - g.sy;
+        t = fma2(f2_splat(((float)lane_in_f32x8 + ty) * g.dy), f2_splat(g.dot_recip), tx);
+    } else {
+        const f2 px = sub2(xs, f2_splat(g.sx));
+        const f2 px2 = mul2(px, px);
+        const float py = (float)lane_in_f32x8 + (y_base - g.sy);
+        const f2 q = mul2(fma2(f2_splat(py), f2_splat(py), px2), f2_splat(g.dot_recip));
+        t = f2{sqrtf(q.x), sqrtf(q.y)};
+    }
+    uint32_t bx[4] = {0u, 0u, 0u, 0u}, by[4] = {0u, 0u, 0u, 0u};
+    bool accx = t.x <= g.stop[0], accy = t.y <= g.stop[0];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (accx) bx[k] = __float_as_uint(g.color[0][k]);
+        if (accy) by[k] = __float_as_uint(g.color[0][k]);
+    }
+    float start = 0.0f;
+#pragma unroll
+    for (uint32_t i = 1; i < 4u; ++i) {
+        if (i < g.count) {
+            const bool mx = accx != (t.x < g.stop[i]), my = accy != (t.y < g.stop[i]);
+            if (mx || my) {
+                const f2 local_t = mul2(sub2(t, f2_splat(start)), f2_splat(g.rcp_d[i - 1]));
+                const f2 neg_t = neg2(local_t);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const f2 c0 = f2_splat(g.color[i - 1][k]);
+                    const f2 v = fma2(local_t, f2_splat(g.color[i][k]), fma2(neg_t, c0, c0));
+                    if (mx) bx[k] |= __float_as_uint(v.x);
+                    if (my) by[k] |= __float_as_uint(v.y);
+                }
+                accx = accx || mx;
+                accy = accy || my;
+            }
+            start = g.stop[i];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // color[3] is the last stop (padding repeats it)
+        if (!accx) bx[k] |= __float_as_uint(g.color[3][k]);
+        if (!accy) by[k] |= __float_as_uint(g.color[3][k]);
+    }
+    r = f2{__uint_as_float(bx[0]), __uint_as_float(by[0])};
+    gg = f2{__uint_as_float(bx[1]), __uint_as_float(by[1])};
+    b = f2{__uint_as_float(bx[2]), __uint_as_float(by[2])};
+    a = f2{__uint_as_float(bx[3]), __uint_as_float(by[3])};
 }
 
 constexpr int kPaintWarpsPerBlock = 2;
@@ -217,7 +294,8 @@ constexpr uint32_t kPackedSegLimit = 2016u;  // segments per normalisation round
 struct WarpSmem {
     uint32_t cells[2][256];  // packed (area << 16) + cover, double-buffered by entry parity
     float clip[256];         // clip mask, same layout
-    EntryRec hdr[32];        // the 32 entry records of the current group
+    EntryRec hdr[32];        // the 32 entry records of the current group (pad = current optimizer flags)
+    GradRec grad;            // gradient of the entry being blended
 };
 
 // Scatter-adds the segments [s0, s1) of one entry into `cells` (acc_segment,
@@ -228,10 +306,10 @@ __device__ __forceinline__ void scatter_entry(const uint64_t* __restrict__ segs,
     for (uint32_t i = s0 + lane; i < s1; i += 32u) {
         const uint32_t chunk = (i - s0) >> 5;
         const uint64_t s = chunk == 0u ? pre0 : (chunk == 1u ? pre1 : segs[i]);
-        const uint32_t cell = cell_index((uint32_t)(s >> 16) & 15u, (uint32_t)(s >> 12) & 15u);
+        const uint32_t cell = cell_index_of(s);
         const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
         const int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
-        atomicAdd(&cells[cell], (uint32_t)(((dam * cv) << 16) + cv));
+        atomicAdd(&cells[cell], (uint32_t)((dam * cv) * 65536 + cv));
         done += 32u;
         if (done >= kPackedSegLimit && i + 32u < s1) {
             // Very long entry: fold the low halves back to i8 so that they cannot overflow
@@ -495,101 +573,117 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
         }
         bool clip_active = false;
         uint32_t clip_last = 0;
-        const uint32_t x0 = tx * 16u + hx * 8u;          // first pixel column of the lane
+        const uint32_t x0 = tx * 16u + hx * 8u;            // first pixel column of the lane
         const float fy8 = (float)(ty * 16u + (row & 8u));  // y of lane 0 of the reference's f32x8 holding this row
         const int ly8 = (int)(row & 7u);                   // the row inside it
         const uint32_t grp_shift = (lane & 16u) + hx;      // ballot bits of this lane's f32x8 group: grp_shift + 2 i
+        const uint4* hdr4 = reinterpret_cast<const uint4*>(W.hdr);
 
         for (uint32_t p0 = first_paint; p0 < e; p0 += 32u) {
             const uint32_t cnt = min(32u, e - p0);
-            uint32_t my_flags = kFlagMaskedOut, my_s0 = 0, my_s1 = 0;
             __syncwarp();  // the previous group's records are no longer read
             if (lane < cnt) {
+                // Stage the record; its spare word carries the (possibly updated) optimizer flags,
+                // and a masked-out entry gets an empty segment range: nothing to accumulate.
                 const uint4* src = reinterpret_cast<const uint4*>(in.recs + p0 + lane);
                 uint4* dstp = reinterpret_cast<uint4*>(&W.hdr[lane]);
-                const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+                uint4 q0 = src[0];
+                const uint4 q1 = src[1], q2 = src[2];
+                uint4 q3 = src[3];
+                q3.w = in.eflags[p0 + lane];
+                if (q3.w & kFlagMaskedOut) q0.z = q0.y;
                 dstp[0] = q0; dstp[1] = q1; dstp[2] = q2; dstp[3] = q3;
-                my_flags = in.eflags[p0 + lane];
-                my_s0 = q0.y;
-                my_s1 = q0.z;
-                if (my_flags & kFlagMaskedOut) my_s1 = my_s0;  // nothing to accumulate
             }
             __syncwarp();
 
             // Pipeline prologue: entry 0 is accumulated now, the segments of entry 1 are requested.
             uint64_t nx0 = 0, nx1 = 0;  // first two chunks of the entry after the one being accumulated
+            uint32_t grad_word = 0, grad_next = 0;
             {
-                const uint32_t s0 = __shfl_sync(kFullMask, my_s0, 0), s1 = __shfl_sync(kFullMask, my_s1, 0);
+                const uint4 h = hdr4[0];
+                if (h.w & kMetaSmallGradient) grad_next = reinterpret_cast<const uint32_t*>(&S.grads[hdr4[3].x])[lane];
+                const uint32_t s0 = h.y, s1 = h.z;
                 uint64_t a0 = 0, a1 = 0;
                 if (s0 + lane < s1) a0 = in.segs[s0 + lane];
                 if (s0 + 32u + lane < s1) a1 = in.segs[s0 + 32u + lane];
                 if (cnt > 1u) {
-                    const uint32_t t0 = __shfl_sync(kFullMask, my_s0, 1), t1 = __shfl_sync(kFullMask, my_s1, 1);
-                    if (t0 + lane < t1) nx0 = in.segs[t0 + lane];
-                    if (t0 + 32u + lane < t1) nx1 = in.segs[t0 + 32u + lane];
+                    const uint4 g = hdr4[4];
+                    if (g.y + lane < g.z) nx0 = in.segs[g.y + lane];
+                    if (g.y + 32u + lane < g.z) nx1 = in.segs[g.y + 32u + lane];
                 }
                 if (s1 > s0) scatter_entry(in.segs, s0, s1, a0, a1, W.cells[0], lane);
                 __syncwarp();
             }
 
             for (uint32_t k = 0; k < cnt; ++k) {
-                uint32_t* cells = W.cells[k & 1u];
                 // Request the segments of entry k + 2, accumulate entry k + 1 into the other buffer.
                 {
                     const uint64_t c0 = nx0, c1 = nx1;
                     nx0 = nx1 = 0;
                     if (k + 2u < cnt) {
-                        const uint32_t t0 = __shfl_sync(kFullMask, my_s0, (int)k + 2), t1 = __shfl_sync(kFullMask, my_s1, (int)k + 2);
-                        if (t0 + lane < t1) nx0 = in.segs[t0 + lane];
-                        if (t0 + 32u + lane < t1) nx1 = in.segs[t0 + 32u + lane];
+                        const uint4 g = hdr4[(k + 2u) * 4u];
+                        if (g.y + lane < g.z) nx0 = in.segs[g.y + lane];
+                        if (g.y + 32u + lane < g.z) nx1 = in.segs[g.y + 32u + lane];
                     }
+                    grad_word = grad_next;  // word `lane` of this entry's gradient record (if it has one)
                     if (k + 1u < cnt) {
-                        const uint32_t s0 = __shfl_sync(kFullMask, my_s0, (int)k + 1), s1 = __shfl_sync(kFullMask, my_s1, (int)k + 1);
-                        if (s1 > s0) scatter_entry(in.segs, s0, s1, c0, c1, W.cells[(k + 1u) & 1u], lane);
+                        const uint4 g = hdr4[(k + 1u) * 4u];
+                        if (g.w & kMetaSmallGradient)
+                            grad_next = reinterpret_cast<const uint32_t*>(&S.grads[hdr4[(k + 1u) * 4u + 3u].x])[lane];
+                        if (g.z > g.y) scatter_entry(in.segs, g.y, g.z, c0, c1, W.cells[(k + 1u) & 1u], lane);
                     }
                 }
-                const uint32_t flags = __shfl_sync(kFullMask, my_flags, (int)k);
+                const uint4 h0 = hdr4[k * 4u], h3 = hdr4[k * 4u + 3u];  // layer, seg0, seg1, meta | slot, clip_layers, flags0, flags
+                const uint32_t flags = h3.w;
                 if (flags & kFlagMaskedOut) {
                     __syncwarp();
                     continue;
                 }
-                const EntryRec& er = W.hdr[k];
-                const uint32_t meta = er.meta, layer = er.layer;
+                const uint32_t meta = h0.w, layer = h0.x;
                 const uint32_t fill_rule = meta_fill_rule(meta);
-                const bool has_segs = er.seg1 > er.seg0;
 
                 // Running cover of this lane's row left of its first pixel (i8, wrapping like the
                 // reference's lanes): the carry-in, plus the left half's covers for the right half.
-                const uint32_t cw = reinterpret_cast<const uint32_t*>(&er.carry)[row >> 2];
+                const uint32_t cw = reinterpret_cast<const uint32_t*>(&W.hdr[k].carry)[row >> 2];
                 int32_t run = (int32_t)(int8_t)((cw >> (8u * (row & 3u))) & 0xFFu);
-                float cov[8];
-                if (has_segs) {
+                f2 cov[4];  // coverage of the lane's pixel pairs
+                f2 clip2[4] = {f2_splat(1.0f), f2_splat(1.0f), f2_splat(1.0f), f2_splat(1.0f)};  // clip mask of the pairs (when it applies)
+                if (h0.z > h0.y) {
                     // (the __syncwarp that ended the previous iteration made this buffer's atomics visible)
-                    uint4* c4 = reinterpret_cast<uint4*>(cells);
-                    const uint4 w0 = c4[lane], w1 = c4[32 + lane];
-                    c4[lane] = make_uint4(0u, 0u, 0u, 0u);
-                    c4[32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+                    uint4* c4 = reinterpret_cast<uint4*>(W.cells[k & 1u]);
+                    const uint4 w0 = c4[2u * lane], w1 = c4[2u * lane + 1u];
+                    c4[2u * lane] = make_uint4(0u, 0u, 0u, 0u);
+                    c4[2u * lane + 1u] = make_uint4(0u, 0u, 0u, 0u);
                     const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                     int32_t area[8], cv[8], total = 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int32_t lo = (int32_t)(int16_t)(w[j] & 0xFFFFu);
-                        cv[j] = lo;
-                        area[j] = (int32_t)(w[j] - (uint32_t)lo) >> 16;  // i16, sign-extended
-                        total += lo;
+                        cv[j] = (int32_t)(int16_t)(w[j] & 0xFFFFu);
+                        area[j] = (int32_t)(w[j] + 0x8000u) >> 16;  // == (w - cover) >> 16: the high half as i16
+                        total += cv[j];
                     }
                     const int32_t left = __shfl_xor_sync(kFullMask, total, 1);
                     if (hx) run += left;
+                    // compute_doubled_areas, mod.rs:388-404: 32 * cover of the columns to the left + area
+                    int32_t dbl[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        // compute_doubled_areas, mod.rs:388-404: 32 * cover of the columns to the left + area
-                        cov[j] = coverage_of(32 * (int32_t)(int8_t)run + area[j], fill_rule);
+                        dbl[j] = 32 * (int32_t)(int8_t)run + area[j];
                         run += cv[j];
                     }
-                } else {
-                    const float c = coverage_of(32 * run, fill_rule);
+                    if (fill_rule == 0u) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) cov[j] = c;
+                        for (int q = 0; q < 4; ++q)
+                            cov[q] = f2{coverage_non_zero(dbl[2 * q]), coverage_non_zero(dbl[2 * q + 1])};
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            cov[q] = f2{coverage_even_odd(dbl[2 * q]), coverage_even_odd(dbl[2 * q + 1])};
+                    }
+                } else {
+                    const float c = fill_rule == 0u ? coverage_non_zero(32 * run) : coverage_even_odd(32 * run);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cov[q] = f2_splat(c);
                 }
 
                 if (clip_active && clip_last < layer) clip_active = false;  // mod.rs:302-306
@@ -597,41 +691,40 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 if (meta_func(meta) == 1u) {  // clip_at, mod.rs:449-464
                     if (!clip_active) {
                         clip_active = true;
-                        clip_last = layer + er.clip_layers;
+                        clip_last = layer + h3.y;
                     }
                     float4* m4 = reinterpret_cast<float4*>(W.clip);
-                    m4[lane] = make_float4(cov[0], cov[1], cov[2], cov[3]);
-                    m4[32 + lane] = make_float4(cov[4], cov[5], cov[6], cov[7]);
+                    m4[2u * lane] = make_float4(cov[0].x, cov[0].y, cov[1].x, cov[1].y);
+                    m4[2u * lane + 1u] = make_float4(cov[2].x, cov[2].y, cov[3].x, cov[3].y);
                     __syncwarp();
                     continue;
                 }
                 const bool apply_clip = meta_is_clipped(meta) && !(flags & kFlagSkipClip);
                 bool nonzero = false;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) nonzero = nonzero || cov[j] != 0.0f;
+                for (int q = 0; q < 4; ++q) nonzero = nonzero || cov[q].x != 0.0f || cov[q].y != 0.0f;
                 if (!__any_sync(kFullMask, nonzero) || (apply_clip && !clip_active)) {  // mod.rs:317-323
                     __syncwarp();
                     continue;
                 }
-                float clipv[8];
-                if (apply_clip) {
+                if (apply_clip) {  // the mask multiplies the source alpha: fold it into the coverage's place
                     const float4* m4 = reinterpret_cast<const float4*>(W.clip);
-                    const float4 m0 = m4[lane], m1 = m4[32 + lane];
-                    clipv[0] = m0.x; clipv[1] = m0.y; clipv[2] = m0.z; clipv[3] = m0.w;
-                    clipv[4] = m1.x; clipv[5] = m1.y; clipv[6] = m1.z; clipv[7] = m1.w;
+                    const float4 m0 = m4[2u * lane], m1 = m4[2u * lane + 1u];
+                    clip2[0] = f2{m0.x, m0.y}; clip2[1] = f2{m0.z, m0.w}; clip2[2] = f2{m1.x, m1.y}; clip2[3] = f2{m1.z, m1.w};
                 }
 
                 const uint32_t mode = meta_blend(meta);
                 const uint32_t fill_type = meta_fill_type(meta);
+                const uint4 h2 = hdr4[k * 4u + 2u];  // the solid colour
                 if (fill_type == 0u && mode == 0u) {
                     // blend_at (mod.rs:406-447) for a solid `Over` layer: blended == src, and zero
                     // coverage leaves the pixel as it is, so no f32x8 bookkeeping is needed.
-                    const f2 cr = f2_splat(er.color[0]), cg = f2_splat(er.color[1]), cb = f2_splat(er.color[2]);
-                    const f2 ca = f2_splat(er.color[3]);
+                    const f2 cr = f2_splat(__uint_as_float(h2.x)), cg = f2_splat(__uint_as_float(h2.y));
+                    const f2 cb = f2_splat(__uint_as_float(h2.z)), ca = f2_splat(__uint_as_float(h2.w));
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        f2 sa = mul2(ca, f2{cov[2 * q], cov[2 * q + 1]});
-                        if (apply_clip) sa = mul2(sa, f2{clipv[2 * q], clipv[2 * q + 1]});
+                        f2 sa = mul2(ca, cov[q]);
+                        if (apply_clip) sa = mul2(sa, clip2[q]);
                         const f2 inv_dst_a = sub2(f2_splat(1.0f), da[q]);
                         const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
                         const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
@@ -649,69 +742,73 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 // some pixel of its f32x8 (same column, same half of the tile) has non-zero coverage.
                 uint32_t active = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t bal = __ballot_sync(kFullMask, cov[j] != 0.0f);
-                    if ((bal >> grp_shift) & 0x5555u) active |= 1u << j;
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t b0 = __ballot_sync(kFullMask, cov[q].x != 0.0f), b1 = __ballot_sync(kFullMask, cov[q].y != 0.0f);
+                    if ((b0 >> grp_shift) & 0x5555u) active |= 1u << (2 * q);
+                    if ((b1 >> grp_shift) & 0x5555u) active |= 2u << (2 * q);
                 }
-                const StyleRec* st = &S.styles[er.slot];
-                if (mode < 12u && (fill_type == 0u || (fill_type == 1u && st->stop_count <= 4u))) {
-                    // Separable blend of a solid colour or a small gradient, on pixel pairs.
-                    GradientSetup g;
-                    float gsx = 0.0f, gsy = 0.0f;
-                    uint32_t gtype = 0;
-                    if (fill_type == 1u) {
-                        g = gradient_setup(*st, S.stops);
-                        gsx = st->start[0];
-                        gsy = st->start[1];
-                        gtype = st->gradient_type;
+                const int32_t slot = (int32_t)h3.x;
+                const bool small_gradient = (meta & kMetaSmallGradient) != 0u;
+                if (mode < 12u && (fill_type == 0u || small_gradient)) {
+                    // Separable blend of a solid colour or a gradient of up to four stops. The pair
+                    // loop is NOT unrolled (the planes rotate through slot 0 instead): twelve blend
+                    // modes and the gradient, inlined four times, do not fit the instruction cache.
+                    if (small_gradient) {
+                        // The layer's gradient record (128 bytes, requested one entry ago) -> shared memory.
+                        __syncwarp();
+                        reinterpret_cast<uint32_t*>(&W.grad)[lane] = grad_word;
+                        __syncwarp();
                     }
-#pragma unroll
+                    const f2 solid_r = f2_splat(__uint_as_float(h2.x)), solid_g = f2_splat(__uint_as_float(h2.y));
+                    const f2 solid_b = f2_splat(__uint_as_float(h2.z)), solid_a = f2_splat(__uint_as_float(h2.w));
+                    float px = (float)x0;
+#pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
-                        if (!((active >> (2 * q)) & 3u)) continue;
-                        f2 fr, fg, fb, fa;
-                        if (fill_type == 0u) {
-                            fr = f2_splat(er.color[0]); fg = f2_splat(er.color[1]); fb = f2_splat(er.color[2]); fa = f2_splat(er.color[3]);
-                        } else {
-                            float c0[4], c1[4];
-                            gradient_at_small_xy(g, gtype, gsx, gsy, (float)(x0 + 2u * (uint32_t)q), fy8, ly8, c0);
-                            gradient_at_small_xy(g, gtype, gsx, gsy, (float)(x0 + 2u * (uint32_t)q + 1u), fy8, ly8, c1);
-                            fr = f2{c0[0], c1[0]}; fg = f2{c0[1], c1[1]}; fb = f2{c0[2], c1[2]}; fa = f2{c0[3], c1[3]};
+                        if (active & 3u) {
+                            f2 fr = solid_r, fg = solid_g, fb = solid_b, fa = solid_a;
+                            if (small_gradient) gradient_pair(W.grad, px, fy8, ly8, fr, fg, fb, fa);
+                            f2 sa = mul2(fa, cov[0]);
+                            if (apply_clip) sa = mul2(sa, clip2[0]);
+                            const f2 br = blend_sep2(mode, dr[0], fr), bg = blend_sep2(mode, dg[0], fg), bb = blend_sep2(mode, db[0], fb);
+                            const f2 inv_dst_a = sub2(f2_splat(1.0f), da[0]);
+                            const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
+                            const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
+                            const f2 dst_a_src_a = mul2(da[0], sa);
+                            const f2 nr = compose2(dr[0], fr, br, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                            const f2 ng = compose2(dg[0], fg, bg, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                            const f2 nb = compose2(db[0], fb, bb, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+                            const f2 na = fma2(da[0], inv_src_a, sa);
+                            if (active & 1u) {
+                                dr[0].x = nr.x; dg[0].x = ng.x; db[0].x = nb.x; da[0].x = na.x;
+                            }
+                            if (active & 2u) {
+                                dr[0].y = nr.y; dg[0].y = ng.y; db[0].y = nb.y; da[0].y = na.y;
+                            }
                         }
-                        f2 sa = mul2(fa, f2{cov[2 * q], cov[2 * q + 1]});
-                        if (apply_clip) sa = mul2(sa, f2{clipv[2 * q], clipv[2 * q + 1]});
-                        const f2 br = blend_sep2(mode, dr[q], fr), bg = blend_sep2(mode, dg[q], fg), bb = blend_sep2(mode, db[q], fb);
-                        const f2 inv_dst_a = sub2(f2_splat(1.0f), da[q]);
-                        const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
-                        const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
-                        const f2 dst_a_src_a = mul2(da[q], sa);
-                        const f2 nr = compose2(dr[q], fr, br, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
-                        const f2 ng = compose2(dg[q], fg, bg, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
-                        const f2 nb = compose2(db[q], fb, bb, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
-                        const f2 na = fma2(da[q], inv_src_a, sa);
-                        if ((active >> (2 * q)) & 1u) {
-                            dr[q].x = nr.x; dg[q].x = ng.x; db[q].x = nb.x; da[q].x = na.x;
-                        }
-                        if ((active >> (2 * q + 1)) & 1u) {
-                            dr[q].y = nr.y; dg[q].y = ng.y; db[q].y = nb.y; da[q].y = na.y;
-                        }
+                        // rotate: pair q + 1 moves into slot 0 (after four rounds everything is back in place)
+                        rotate4(dr); rotate4(dg); rotate4(db); rotate4(da); rotate4(cov); rotate4(clip2);
+                        active >>= 2;
+                        px += 2.0f;
                     }
                 } else {
                     // Textures, gradients with more than four stops, non-separable modes: one
                     // out-of-line call per blended pixel.
-#pragma unroll
+                    const StyleRec* st = &S.styles[slot];
+#pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
-                        if ((active >> (2 * q)) & 1u) {
-                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, (float)(x0 + 2u * (uint32_t)q), fy8, ly8, cov[2 * q],
-                                                                 apply_clip ? clipv[2 * q] : -1.0f,
-                                                                 make_float4(dr[q].x, dg[q].x, db[q].x, da[q].x));
-                            dr[q].x = d.x; dg[q].x = d.y; db[q].x = d.z; da[q].x = d.w;
+                        const float fx = (float)(x0 + 2u * (uint32_t)q);
+                        if (active & 1u) {
+                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, fx, fy8, ly8, cov[0].x, apply_clip ? clip2[0].x : -1.0f,
+                                                                 make_float4(dr[0].x, dg[0].x, db[0].x, da[0].x));
+                            dr[0].x = d.x; dg[0].x = d.y; db[0].x = d.z; da[0].x = d.w;
                         }
-                        if ((active >> (2 * q + 1)) & 1u) {
-                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, (float)(x0 + 2u * (uint32_t)q + 1u), fy8, ly8,
-                                                                 cov[2 * q + 1], apply_clip ? clipv[2 * q + 1] : -1.0f,
-                                                                 make_float4(dr[q].y, dg[q].y, db[q].y, da[q].y));
-                            dr[q].y = d.x; dg[q].y = d.y; db[q].y = d.z; da[q].y = d.w;
+                        if (active & 2u) {
+                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, fx + 1.0f, fy8, ly8, cov[0].y,
+                                                                 apply_clip ? clip2[0].y : -1.0f, make_float4(dr[0].y, dg[0].y, db[0].y, da[0].y));
+                            dr[0].y = d.x; dg[0].y = d.y; db[0].y = d.z; da[0].y = d.w;
                         }
+                        rotate4(dr); rotate4(dg); rotate4(db); rotate4(da); rotate4(cov); rotate4(clip2);
+                        active >>= 2;
                     }
                 }
                 __syncwarp();
@@ -779,6 +876,56 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const uint8_t* __rest
 void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st) {
     gather_tiles_kernel<<<device_sm_count() * 4, 256, 0, st>>>(framebuffer, S.stride, S.width, S.height, S.tiles_x, S.written_list,
                                                                S.written_count, packed);
+}
+
+// One thread per style slot: the GradRec of a gradient of up to four stops, with the very
+// operations Gradient::get_t / color_at perform per call (styling.rs:59-66,107-108).
+__global__ void grad_setup_kernel(const StyleRec* __restrict__ styles, const StopRec* __restrict__ stops, uint32_t n,
+                                  GradRec* __restrict__ grads) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const StyleRec st = styles[i];
+    GradRec g;
+    g.pad = 0u;
+    if (st.fill_type != 1u || st.stop_count < 2u || st.stop_count > 4u) {
+        g.sx = g.sy = g.dx = g.dy = g.dot_recip = 0.0f;
+        g.type = 0u;
+        g.count = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g.stop[k] = g.rcp_d[k] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g.color[k][c] = 0.0f;
+        }
+        grads[i] = g;
+        return;
+    }
+    g.sx = st.start[0];
+    g.sy = st.start[1];
+    g.dx = st.end[0] - st.start[0];
+    g.dy = st.end[1] - st.start[1];
+    const float dot = g.dx * g.dx + g.dy * g.dy;
+    g.dot_recip = d_rcp(dot);
+    g.type = st.gradient_type;
+    g.count = st.stop_count;
+    const StopRec* sp = stops + st.stop_first;
+    float start_stop = 0.0f;
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; ++k) {
+        const StopRec s = sp[k < st.stop_count ? k : st.stop_count - 1u];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) g.color[k][c] = s.color[c];
+        g.stop[k] = s.stop;
+        if (k >= 1u) {
+            g.rcp_d[k - 1u] = d_rcp(s.stop - start_stop);
+            start_stop = s.stop;
+        }
+    }
+    g.rcp_d[3] = 0.0f;
+    grads[i] = g;
+}
+void launch_grad_setup(const StyleRec* styles, const StopRec* stops, uint32_t n_styles, GradRec* grads, cudaStream_t st) {
+    if (n_styles) grad_setup_kernel<<<(n_styles + 127) / 128, 128, 0, st>>>(styles, stops, n_styles, grads);
 }
 
 // Self-test of the packed fp32 arithmetic (forma_debug_selftest): every packed helper against

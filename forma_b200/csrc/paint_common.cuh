@@ -51,10 +51,13 @@ __device__ __forceinline__ int heavy_class(uint32_t entries) {
     return c > kHeavyClasses - 1 ? kHeavyClasses - 1 : c;
 }
 
-// packed style: fill_rule | func<<1 | is_clipped<<2 | fill_type<<3 | blend_mode<<5 | unchanged<<9
+// packed style: fill_rule | func<<1 | is_clipped<<2 | fill_type<<3 | blend_mode<<5 | unchanged<<9 |
+//               small gradient (<= 4 stops: the painter uses its GradRec)<<10
+constexpr uint32_t kMetaSmallGradient = 1u << 10;
 __device__ __forceinline__ uint32_t pack_style_meta(const StyleRec& st, bool unchanged) {
     return (st.fill_rule & 1u) | ((st.func & 1u) << 1) | ((st.is_clipped ? 1u : 0u) << 2) | ((st.fill_type & 3u) << 3) |
-           ((st.blend_mode & 15u) << 5) | (unchanged ? (1u << 9) : 0u);
+           ((st.blend_mode & 15u) << 5) | (unchanged ? (1u << 9) : 0u) |
+           ((st.fill_type == 1u && st.stop_count >= 2u && st.stop_count <= 4u) ? kMetaSmallGradient : 0u);
 }
 
 __device__ __forceinline__ uint32_t fill_rule_of(const PaintScene& S, uint32_t layer) {

@@ -703,6 +703,12 @@ int Renderer::upload_tables_device(Composition& comp, CompDevice& cd) {
     FORMA_CUDA_TRY(up(cd.d_texels, comp.h_texels, comp.n_texels));
     FORMA_CUDA_TRY(up(cd.d_order_to_style, comp.h_order_to_style, comp.n_orders));
     FORMA_CUDA_TRY(up(cd.d_geom_slot, comp.h_geom_slot, comp.n_geoms));
+    // Gradient records of the styles (only when some style is a gradient: n_stops > 0).
+    FORMA_CUDA_TRY(cd.d_grads.reserve(comp.n_style_recs + 1));
+    if (comp.n_stops) {
+        launch_grad_setup(cd.d_styles.ptr, cd.d_stops.ptr, (uint32_t)comp.n_style_recs, cd.d_grads.ptr, stream);
+        ++launches;
+    }
     cd.tables_version = comp.tables_version;
     return FORMA_STATUS_OK;
 }
@@ -828,6 +834,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     S.order_to_style = cd.d_order_to_style.ptr;
     S.n_orders = comp.n_orders;
     S.stops = cd.d_stops.ptr;
+    S.grads = cd.d_grads.ptr;
     S.texels = cd.d_texels.ptr;
 
     const bool pack_written = cache && !buffer_on_device;

@@ -3,7 +3,7 @@
 # GPU parity suite (all failures listed), then one bench line per workload (no CPU leg, no extras).
 mkdir -p gpurun_out
 R=$1; shift
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -40 > gpurun_out/${R}_gpu_tests.txt
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -40 > gpurun_out/${R}_gpu_tests.txt
 for w in "$@"; do
   timeout 120 python bench.py --no-cpu --no-extra --workload $w > gpurun_out/${R}_bench_${w}.json 2> gpurun_out/${R}_bench_${w}.err
 done

@@ -512,25 +512,37 @@ __global__ void __launch_bounds__(kScanThreads) chained_scan_kernel(uint32_t* __
         if ((uint32_t)w < warp) warp_off += warp_tot[w];
         tile_sum += warp_tot[w];
     }
-    if (t == 0) {
+    if (warp == 0) {  // decoupled look-back, 32 predecessors per round
         volatile unsigned long long* st = state;
         unsigned long long prefix = 0;
         if (tile == 0) {
-            st[0] = kScanInclusive | tile_sum;
+            if (lane == 0) st[0] = kScanInclusive | tile_sum;
         } else {
-            st[tile] = kScanAggregate | tile_sum;
+            if (lane == 0) st[tile] = kScanAggregate | tile_sum;
             int32_t p = (int32_t)tile - 1;
             while (true) {
-                unsigned long long s = st[p];
-                if ((s & kScanFlags) == 0) continue;
-                prefix += s & ~kScanFlags;
-                if ((s & kScanFlags) == kScanInclusive) break;
-                --p;
+                const int32_t idx = p - (int32_t)lane;
+                unsigned long long v = kScanInclusive;
+                if (idx >= 0) {
+                    do {
+                        v = st[idx];
+                    } while ((v & kScanFlags) == 0);
+                }
+                const uint32_t incl = __ballot_sync(kFullMask, (v & kScanFlags) == kScanInclusive);
+                const uint32_t upto = incl ? (uint32_t)__ffs((int)incl) : 32u;
+                unsigned long long part = lane < upto ? (v & ~kScanFlags) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+                prefix += part;
+                if (incl) break;
+                p -= 32;
             }
-            st[tile] = kScanInclusive | (prefix + tile_sum);
+            if (lane == 0) st[tile] = kScanInclusive | (prefix + tile_sum);
         }
-        s_prefix = prefix;
-        if (tile + 1 == tiles) total[0] = (uint32_t)(prefix + tile_sum);
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile + 1 == tiles) total[0] = (uint32_t)(prefix + tile_sum);
+        }
     }
     __syncthreads();
     const uint32_t add = (uint32_t)s_prefix + warp_off;

@@ -75,28 +75,42 @@ __global__ void __launch_bounds__(kCellThreads)
         if ((uint32_t)w < warp) warp_off += warp_cnt[w];
         tile_sum += warp_cnt[w];
     }
-    if (threadIdx.x == 0) {
+    // Decoupled look-back by the first warp: 32 predecessors per round, until one of them
+    // already holds an inclusive prefix.
+    if (warp == 0) {
         volatile unsigned long long* st = state;
         unsigned long long prefix = 0;
         if (tile == 0) {
-            st[0] = kCellInclusive | tile_sum;
+            if (lane == 0) st[0] = kCellInclusive | tile_sum;
         } else {
-            st[tile] = kCellAggregate | tile_sum;
+            if (lane == 0) st[tile] = kCellAggregate | tile_sum;
             int32_t p = (int32_t)tile - 1;
             while (true) {
-                const unsigned long long v = st[p];
-                if ((v & kCellFlags) == 0) continue;
-                prefix += v & ~kCellFlags;
-                if ((v & kCellFlags) == kCellInclusive) break;
-                --p;
+                const int32_t idx = p - (int32_t)lane;
+                unsigned long long v = kCellInclusive;  // before the first tile: an inclusive prefix of 0
+                if (idx >= 0) {
+                    do {
+                        v = st[idx];
+                    } while ((v & kCellFlags) == 0);
+                }
+                const uint32_t incl = __ballot_sync(kFullMask, (v & kCellFlags) == kCellInclusive);
+                const uint32_t upto = incl ? (uint32_t)__ffs((int)incl) : 32u;  // lanes [0, upto) count
+                unsigned long long part = lane < upto ? (v & ~kCellFlags) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFullMask, part, o);
+                prefix += part;
+                if (incl) break;
+                p -= 32;
             }
-            st[tile] = kCellInclusive | (prefix + tile_sum);
+            if (lane == 0) st[tile] = kCellInclusive | (prefix + tile_sum);
         }
-        s_prefix = prefix;
-        if (tile + 1 == tiles) {
-            const uint32_t total = (uint32_t)(prefix + tile_sum);
-            n_cells_out[0] = total;
-            if (total < cap) cell_start[total] = n;  // one-past-the-end sentinel
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile + 1 == tiles) {
+                const uint32_t total = (uint32_t)(prefix + tile_sum);
+                n_cells_out[0] = total;
+                if (total < cap) cell_start[total] = n;  // one-past-the-end sentinel
+            }
         }
     }
     __syncthreads();

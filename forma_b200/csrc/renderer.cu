@@ -427,9 +427,8 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
     }
     // The filter only holds while no layer moves its geometry (a layer transform would have to be
     // applied to the bounds, and changes from frame to frame): fall back to everything otherwise.
-    bool any_layer_xf = false;
-    for (auto& kv : comp.layers) any_layer_xf = any_layer_xf || kv.second->has_xf;
-    const bool want_filter = band_is_partial && !any_layer_xf && options().band_filter != 0;
+    // (comp.layers_have_xf is maintained by rebuild_tables, which every caller runs first.)
+    const bool want_filter = band_is_partial && !comp.layers_have_xf && options().band_filter != 0;
     if (cd.jobs_resident > 0) {
         // What is resident must cover what this render needs.
         const bool covers = !cd.filtered || (want_filter && band_lo >= cd.band_lo && band_hi <= cd.band_hi);
@@ -581,6 +580,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
 // these look-ups per point). The pinned host copies are rebuilt when the
 // composition changed and re-uploaded when they are not resident.
 int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
+    comp.compact_geom();  // renumbers the geometry ids the tables are built from (no-op unless half of the points are dead)
     CompDevice& cd = comp.on(device);
     if (comp.tables_dirty || comp.tables_cache_id != cache_id) {
         FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // an upload from the pinned tables may still be in flight
@@ -825,9 +825,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     // buffer when the band is narrower than the frame (flush_geometry).
     const float band_lo = (float)(S.ty_lo * 16u), band_hi = (float)std::min<uint64_t>((uint64_t)S.ty_hi * 16u, height);
     const bool band_is_partial = S.ty_lo > 0u || S.ty_hi < S.tiles_y;
-    int st = flush_geometry(comp, band_lo, band_hi, band_is_partial);
+    int st = upload_tables(comp, -1);
     if (st) return st;
-    st = upload_tables(comp, -1);
+    st = flush_geometry(comp, band_lo, band_hi, band_is_partial);
     if (st) return st;
     CompDevice& cd = comp.on(device);
     S.styles = cd.d_styles.ptr;
@@ -1977,7 +1977,7 @@ static uint64_t rasterize_only_impl(forma_renderer* r, forma_composition* c, uin
                                     uint64_t cap, uint64_t* out) {
     Renderer& R = r->r;
     if (cudaSetDevice(R.device) != cudaSuccess) return 0;
-    if (R.flush_geometry(c->c) || R.upload_tables(c->c, -1)) return 0;
+    if (R.upload_tables(c->c, -1) || R.flush_geometry(c->c)) return 0;
     uint32_t n = 0;
     if (R.rasterize(c->c, (uint32_t)std::min<uint64_t>(width, 0xFFFFFFFFu), (uint32_t)std::min<uint64_t>(height, 0xFFFFFFFFu),
                     -3.0e38f, 3.0e38f, &n))

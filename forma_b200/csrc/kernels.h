@@ -124,20 +124,16 @@ struct PaintScene {
 };
 
 uint32_t cell_num_blocks(uint32_t n);
-// One pass over the sorted segments: cell_start[c] = first segment of cell c (for c < cap;
-// cell_start[#cells] = n when #cells < cap) and n_cells_out[0] = #cells. `state` needs
-// cells_scan_state_words(n) u64 words. May be launched before the host knows the count: it
-// reads nothing that depends on it.
-size_t cells_scan_state_words(uint32_t n);
-void launch_cells_scan(const uint64_t* segs, uint32_t n, unsigned long long* state, uint32_t* cell_start, uint32_t cap,
-                       uint32_t* n_cells_out, cudaStream_t st);
-// Reads the cell count from device memory (n_cells_ptr) and is a no-op when it exceeds
-// `cap`, so that it can be launched before the host has read the count; grid_cells sizes
-// the grid (an upper bound of the count, or the count).
-// Also writes cell_key (the key of each cell's first segment).
-void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, uint64_t* cell_key,
-                       const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
-                       uint32_t* perm, cudaStream_t st);
+// Cells in one pass over the sorted segments (+ a small kernel for the cells that cross a
+// CTA tile): cell_start[c] = first segment of cell c (cell_start[#cells] = n), the cell's
+// cover (16 x i8 by local_y), its key, the (tile_y, layer, tile_x) key of the carry pass and
+// perm[c] = c, for every c < cap - 1; n_cells_out[0] = #cells. All five arrays need `cap`
+// entries. `state`: cells_state_words(n) u64 words. May be launched before the host knows the
+// count; the caller repeats it if #cells >= cap.
+size_t cells_state_words(uint32_t n);
+void launch_cells(const PaintScene& S, const uint64_t* segs, uint32_t n, unsigned long long* state, uint32_t* cell_start,
+                  uint32_t cap, uint32_t* n_cells_out, uint64_t* cell_key, uint4* cell_cover, uint64_t* key2, uint32_t* perm,
+                  cudaStream_t st);
 // Plans of the painter's two pair sorts (their key bounds are host-known).
 SortPlan carry_sort_plan(const PaintScene& S);
 SortPlan gap_sort_plan(const PaintScene& S);

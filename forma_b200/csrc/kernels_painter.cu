@@ -222,70 +222,110 @@ __device__ __forceinline__ float coverage_even_odd(int32_t doubled_area) {
     return (float)(512 - abs((doubled_area & 1023) - 512)) * (1.0f / 512.0f);
 }
 
-template <class T>
-__device__ __forceinline__ void rotate4(T (&v)[4]) {
-    const T t = v[0];
-    v[0] = v[1];
-    v[1] = v[2];
-    v[2] = v[3];
-    v[3] = t;
-}
-
 // Gradient::color_at (cpu/painter/styling.rs:58-144) for the pixel pair (x, x + 1) of one row,
-// from the per-style record in shared memory. Same operations in the same order as
-// gradient_at (paint_math.cuh); d.recip() of every stop interval comes precomputed.
-__device__ __forceinline__ void gradient_pair(const GradRec& g, float x, float y_base, int lane_in_f32x8, f2& r, f2& gg, f2& b, f2& a) {
+// from the per-style record in shared memory (read as eight 16-byte words). Same operations
+// in the same order as gradient_at (paint_math.cuh); d.recip() of every stop interval comes
+// precomputed.
+__device__ __forceinline__ void gradient_pair(const GradRec* gp, float x, float y_base, int lane_in_f32x8, f2& r, f2& gg, f2& b, f2& a) {
+    const float4* gv = reinterpret_cast<const float4*>(gp);
+    const float4 geo = gv[0];                                      // sx, sy, dx, dy
+    const float4 hdr = gv[1];                                      // dot_recip, type, count, -
+    const uint32_t type = __float_as_uint(hdr.y), count = __float_as_uint(hdr.z);
+    const float4 st4 = gv[6], rc4 = gv[7];
+    const float stop[4] = {st4.x, st4.y, st4.z, st4.w}, rcp_d[3] = {rc4.x, rc4.y, rc4.z};
     f2 t;
     const f2 xs = f2{x, x + 1.0f};
-    if (g.type == 0u) {
+    if (type == 0u) {
         // tx = (x - sx) * dx * dot_recip; t = fma((lane + (y_base - sy)) * dy, dot_recip, tx)
-        const f2 tx = mul2(mul2(sub2(xs, f2_splat(g.sx)), f2_splat(g.dx)), f2_splat(g.dot_recip));
-        const float ty = y_base - g.sy;
-        t = fma2(f2_splat(((float)lane_in_f32x8 + ty) * g.dy), f2_splat(g.dot_recip), tx);
+        const f2 tx = mul2(mul2(sub2(xs, f2_splat(geo.x)), f2_splat(geo.z)), f2_splat(hdr.x));
+        const float ty = y_base - geo.y;
+        t = fma2(f2_splat(((float)lane_in_f32x8 + ty) * geo.w), f2_splat(hdr.x), tx);
     } else {
-        const f2 px = sub2(xs, f2_splat(g.sx));
+        const f2 px = sub2(xs, f2_splat(geo.x));
         const f2 px2 = mul2(px, px);
-        const float py = (float)lane_in_f32x8 + (y_base - g.sy);
-        const f2 q = mul2(fma2(f2_splat(py), f2_splat(py), px2), f2_splat(g.dot_recip));
+        const float py = (float)lane_in_f32x8 + (y_base - geo.y);
+        const f2 q = mul2(fma2(f2_splat(py), f2_splat(py), px2), f2_splat(hdr.x));
         t = f2{sqrtf(q.x), sqrtf(q.y)};
     }
-    uint32_t bx[4] = {0u, 0u, 0u, 0u}, by[4] = {0u, 0u, 0u, 0u};
-    bool accx = t.x <= g.stop[0], accy = t.y <= g.stop[0];
+    float4 c_prev = gv[2];
+    const float cp0[4] = {c_prev.x, c_prev.y, c_prev.z, c_prev.w};
+    uint32_t bx[4], by[4];
+    bool accx = t.x <= stop[0], accy = t.y <= stop[0];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (accx) bx[k] = __float_as_uint(g.color[0][k]);
-        if (accy) by[k] = __float_as_uint(g.color[0][k]);
+        bx[k] = accx ? __float_as_uint(cp0[k]) : 0u;
+        by[k] = accy ? __float_as_uint(cp0[k]) : 0u;
     }
     float start = 0.0f;
 #pragma unroll
     for (uint32_t i = 1; i < 4u; ++i) {
-        if (i < g.count) {
-            const bool mx = accx != (t.x < g.stop[i]), my = accy != (t.y < g.stop[i]);
+        if (i < count) {
+            const float4 c_cur = gv[2 + i];
+            const bool mx = accx != (t.x < stop[i]), my = accy != (t.y < stop[i]);
             if (mx || my) {
-                const f2 local_t = mul2(sub2(t, f2_splat(start)), f2_splat(g.rcp_d[i - 1]));
+                const f2 local_t = mul2(sub2(t, f2_splat(start)), f2_splat(rcp_d[i - 1]));
                 const f2 neg_t = neg2(local_t);
+                const float c0[4] = {c_prev.x, c_prev.y, c_prev.z, c_prev.w}, c1[4] = {c_cur.x, c_cur.y, c_cur.z, c_cur.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const f2 c0 = f2_splat(g.color[i - 1][k]);
-                    const f2 v = fma2(local_t, f2_splat(g.color[i][k]), fma2(neg_t, c0, c0));
+                    const f2 s0 = f2_splat(c0[k]);
+                    const f2 v = fma2(local_t, f2_splat(c1[k]), fma2(neg_t, s0, s0));
                     if (mx) bx[k] |= __float_as_uint(v.x);
                     if (my) by[k] |= __float_as_uint(v.y);
                 }
                 accx = accx || mx;
                 accy = accy || my;
             }
-            start = g.stop[i];
+            start = stop[i];
+            c_prev = c_cur;
         }
     }
+    {
+        const float4 c_last = gv[5];  // color[3] is the last stop (padding repeats it)
+        const float cl[4] = {c_last.x, c_last.y, c_last.z, c_last.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {  // color[3] is the last stop (padding repeats it)
-        if (!accx) bx[k] |= __float_as_uint(g.color[3][k]);
-        if (!accy) by[k] |= __float_as_uint(g.color[3][k]);
+        for (int k = 0; k < 4; ++k) {
+            if (!accx) bx[k] |= __float_as_uint(cl[k]);
+            if (!accy) by[k] |= __float_as_uint(cl[k]);
+        }
     }
     r = f2{__uint_as_float(bx[0]), __uint_as_float(by[0])};
     gg = f2{__uint_as_float(bx[1]), __uint_as_float(by[1])};
     b = f2{__uint_as_float(bx[2]), __uint_as_float(by[2])};
     a = f2{__uint_as_float(bx[3]), __uint_as_float(by[3])};
+}
+
+// blend_at (cpu/painter/mod.rs:406-447) for one pixel pair of a layer with a separable blend mode
+// and a solid or small-gradient fill. One out-of-line copy for the whole kernel: the twelve modes
+// and the gradient, inlined per pair, do not fit the instruction cache. Arguments and result
+// travel in registers.
+//   ctl: blend mode | apply_clip << 8 | gradient fill << 9 | blend pixel x << 16 | blend pixel y << 17
+struct PairPlanes {
+    f2 r, g, b, a;
+};
+__device__ __noinline__ PairPlanes blend_pair_separable(PairPlanes d, f2 cov, f2 clip, uint32_t ctl, float x, float y_base,
+                                                       int lane_in_f32x8, const GradRec* grad, float4 solid) {
+    f2 fr = f2_splat(solid.x), fg = f2_splat(solid.y), fb = f2_splat(solid.z), fa = f2_splat(solid.w);
+    if (ctl & 0x200u) gradient_pair(grad, x, y_base, lane_in_f32x8, fr, fg, fb, fa);
+    f2 sa = mul2(fa, cov);
+    if (ctl & 0x100u) sa = mul2(sa, clip);
+    const uint32_t mode = ctl & 15u;
+    const f2 br = blend_sep2(mode, d.r, fr), bg = blend_sep2(mode, d.g, fg), bb = blend_sep2(mode, d.b, fb);
+    const f2 inv_dst_a = sub2(f2_splat(1.0f), d.a);
+    const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
+    const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
+    const f2 dst_a_src_a = mul2(d.a, sa);
+    const f2 nr = compose2(d.r, fr, br, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+    const f2 ng = compose2(d.g, fg, bg, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+    const f2 nb = compose2(d.b, fb, bb, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
+    const f2 na = fma2(d.a, inv_src_a, sa);
+    if (ctl & 0x10000u) {
+        d.r.x = nr.x; d.g.x = ng.x; d.b.x = nb.x; d.a.x = na.x;
+    }
+    if (ctl & 0x20000u) {
+        d.r.y = nr.y; d.g.y = ng.y; d.b.y = nb.y; d.a.y = na.y;
+    }
+    return d;
 }
 
 constexpr int kPaintWarpsPerBlock = 2;
@@ -298,22 +338,23 @@ struct WarpSmem {
     GradRec grad;            // gradient of the entry being blended
 };
 
-// Scatter-adds the segments [s0, s1) of one entry into `cells` (acc_segment,
-// cpu/painter/mod.rs:257-271). `pre0` / `pre1` hold the first two 32-segment chunks.
-__device__ __forceinline__ void scatter_entry(const uint64_t* __restrict__ segs, uint32_t s0, uint32_t s1, uint64_t pre0,
-                                              uint64_t pre1, uint32_t* cells, uint32_t lane) {
-    uint32_t done = 0;
-    for (uint32_t i = s0 + lane; i < s1; i += 32u) {
-        const uint32_t chunk = (i - s0) >> 5;
-        const uint64_t s = chunk == 0u ? pre0 : (chunk == 1u ? pre1 : segs[i]);
-        const uint32_t cell = cell_index_of(s);
-        const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
-        const int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
-        atomicAdd(&cells[cell], (uint32_t)((dam * cv) * 65536 + cv));
+// acc_segment (cpu/painter/mod.rs:257-271) for one segment: area and cover into the packed cell.
+__device__ __forceinline__ void scatter_one(uint32_t* cells, uint64_t s) {
+    const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
+    const int32_t dam = (int32_t)((uint32_t)(s >> 6) & 0x3Fu);
+    atomicAdd(&cells[cell_index_of(s)], (uint32_t)((dam * cv) * 65536 + cv));
+}
+
+// Segments 64.. of a long entry (about one entry in ten has more than 64). Every
+// kPackedSegLimit segments the low halves are folded back to i8 so that they cannot overflow
+// 16 bits (areas wrap at i16, covers at i8, exactly like the reference's lanes).
+__device__ __noinline__ void scatter_rest(const uint64_t* __restrict__ segs, uint32_t from, uint32_t s1, uint32_t* cells,
+                                          uint32_t lane) {
+    uint32_t done = 64u;
+    for (uint32_t i0 = from; i0 < s1; i0 += 32u) {
+        if (i0 + lane < s1) scatter_one(cells, segs[i0 + lane]);
         done += 32u;
-        if (done >= kPackedSegLimit && i + 32u < s1) {
-            // Very long entry: fold the low halves back to i8 so that they cannot overflow
-            // 16 bits (areas wrap at i16, covers at i8, exactly like the reference's lanes).
+        if (done >= kPackedSegLimit && i0 + 32u < s1) {
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -326,6 +367,16 @@ __device__ __forceinline__ void scatter_entry(const uint64_t* __restrict__ segs,
             done = 0;
         }
     }
+}
+
+// Scatter-adds the segments [s0, s1) of one entry into `cells`. `pre0` / `pre1` hold the
+// first two 32-segment chunks (requested one entry earlier).
+__device__ __forceinline__ void scatter_entry(const uint64_t* __restrict__ segs, uint32_t s0, uint32_t s1, uint64_t pre0,
+                                              uint64_t pre1, uint32_t* cells, uint32_t lane) {
+    const uint32_t n = s1 - s0;
+    if (lane < n) scatter_one(cells, pre0);
+    if (lane + 32u < n) scatter_one(cells, pre1);
+    if (n > 64u) scatter_rest(segs, s0 + 64u, s1, cells, lane);
 }
 
 template <int kMinBlocks>
@@ -750,65 +801,42 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 const int32_t slot = (int32_t)h3.x;
                 const bool small_gradient = (meta & kMetaSmallGradient) != 0u;
                 if (mode < 12u && (fill_type == 0u || small_gradient)) {
-                    // Separable blend of a solid colour or a gradient of up to four stops. The pair
-                    // loop is NOT unrolled (the planes rotate through slot 0 instead): twelve blend
-                    // modes and the gradient, inlined four times, do not fit the instruction cache.
+                    // Separable blend of a solid colour or a gradient of up to four stops: one
+                    // out-of-line call per pixel pair that has a pixel to blend.
                     if (small_gradient) {
                         // The layer's gradient record (128 bytes, requested one entry ago) -> shared memory.
                         __syncwarp();
                         reinterpret_cast<uint32_t*>(&W.grad)[lane] = grad_word;
                         __syncwarp();
                     }
-                    const f2 solid_r = f2_splat(__uint_as_float(h2.x)), solid_g = f2_splat(__uint_as_float(h2.y));
-                    const f2 solid_b = f2_splat(__uint_as_float(h2.z)), solid_a = f2_splat(__uint_as_float(h2.w));
-                    float px = (float)x0;
-#pragma unroll 1
+                    const float4 solid = make_float4(__uint_as_float(h2.x), __uint_as_float(h2.y), __uint_as_float(h2.z), __uint_as_float(h2.w));
+                    const uint32_t ctl = mode | (apply_clip ? 0x100u : 0u) | (small_gradient ? 0x200u : 0u);
+#pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        if (active & 3u) {
-                            f2 fr = solid_r, fg = solid_g, fb = solid_b, fa = solid_a;
-                            if (small_gradient) gradient_pair(W.grad, px, fy8, ly8, fr, fg, fb, fa);
-                            f2 sa = mul2(fa, cov[0]);
-                            if (apply_clip) sa = mul2(sa, clip2[0]);
-                            const f2 br = blend_sep2(mode, dr[0], fr), bg = blend_sep2(mode, dg[0], fg), bb = blend_sep2(mode, db[0], fb);
-                            const f2 inv_dst_a = sub2(f2_splat(1.0f), da[0]);
-                            const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
-                            const f2 inv_src_a = sub2(f2_splat(1.0f), sa);
-                            const f2 dst_a_src_a = mul2(da[0], sa);
-                            const f2 nr = compose2(dr[0], fr, br, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
-                            const f2 ng = compose2(dg[0], fg, bg, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
-                            const f2 nb = compose2(db[0], fb, bb, inv_dst_a_src_a, dst_a_src_a, inv_src_a);
-                            const f2 na = fma2(da[0], inv_src_a, sa);
-                            if (active & 1u) {
-                                dr[0].x = nr.x; dg[0].x = ng.x; db[0].x = nb.x; da[0].x = na.x;
-                            }
-                            if (active & 2u) {
-                                dr[0].y = nr.y; dg[0].y = ng.y; db[0].y = nb.y; da[0].y = na.y;
-                            }
+                        const uint32_t act = (active >> (2 * q)) & 3u;
+                        if (act) {
+                            const PairPlanes d = blend_pair_separable(PairPlanes{dr[q], dg[q], db[q], da[q]}, cov[q], clip2[q], ctl | (act << 16),
+                                                                      (float)(x0 + 2u * (uint32_t)q), fy8, ly8, &W.grad, solid);
+                            dr[q] = d.r; dg[q] = d.g; db[q] = d.b; da[q] = d.a;
                         }
-                        // rotate: pair q + 1 moves into slot 0 (after four rounds everything is back in place)
-                        rotate4(dr); rotate4(dg); rotate4(db); rotate4(da); rotate4(cov); rotate4(clip2);
-                        active >>= 2;
-                        px += 2.0f;
                     }
                 } else {
                     // Textures, gradients with more than four stops, non-separable modes: one
                     // out-of-line call per blended pixel.
                     const StyleRec* st = &S.styles[slot];
-#pragma unroll 1
+#pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float fx = (float)(x0 + 2u * (uint32_t)q);
-                        if (active & 1u) {
-                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, fx, fy8, ly8, cov[0].x, apply_clip ? clip2[0].x : -1.0f,
-                                                                 make_float4(dr[0].x, dg[0].x, db[0].x, da[0].x));
-                            dr[0].x = d.x; dg[0].x = d.y; db[0].x = d.z; da[0].x = d.w;
+                        if ((active >> (2 * q)) & 1u) {
+                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, fx, fy8, ly8, cov[q].x, apply_clip ? clip2[q].x : -1.0f,
+                                                                 make_float4(dr[q].x, dg[q].x, db[q].x, da[q].x));
+                            dr[q].x = d.x; dg[q].x = d.y; db[q].x = d.z; da[q].x = d.w;
                         }
-                        if (active & 2u) {
-                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, fx + 1.0f, fy8, ly8, cov[0].y,
-                                                                 apply_clip ? clip2[0].y : -1.0f, make_float4(dr[0].y, dg[0].y, db[0].y, da[0].y));
-                            dr[0].y = d.x; dg[0].y = d.y; db[0].y = d.z; da[0].y = d.w;
+                        if ((active >> (2 * q + 1)) & 1u) {
+                            const float4 d = blend_pixel_generic(st, S.stops, S.texels, fx + 1.0f, fy8, ly8, cov[q].y,
+                                                                 apply_clip ? clip2[q].y : -1.0f, make_float4(dr[q].y, dg[q].y, db[q].y, da[q].y));
+                            dr[q].y = d.x; dg[q].y = d.y; db[q].y = d.z; da[q].y = d.w;
                         }
-                        rotate4(dr); rotate4(dg); rotate4(db); rotate4(da); rotate4(cov); rotate4(clip2);
-                        active >>= 2;
                     }
                 }
                 __syncwarp();

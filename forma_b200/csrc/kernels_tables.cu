@@ -8,7 +8,7 @@
 //
 //   cells     runs of sorted segments with equal (tile_y, tile_x, layer)
 //             (cells_scan: one pass, head bits -> cell_start by decoupled look-back)
-//   covers    per cell: sum of segment covers by local_y (wrapping i8), its key
+//   covers    per cell: sum of segment covers by local_y (wrapping i8), its key (same pass)
 //   re-sort   cell ids stably by the layer bits only -> (layer, tile_y, tile_x)
 //   carries   per (tile_y, layer) group a running sum -> carry-in of every cell
 //             and "carry-only" entries for the tiles a layer spans without
@@ -39,33 +39,72 @@ __device__ __forceinline__ bool is_cell_head(const uint64_t* __restrict__ segs, 
 constexpr int kCellItems = 8;
 constexpr int kCellTile = kCellThreads * kCellItems;
 
-// Single pass over the sorted segments: head bits (a segment starts a cell when its key
-// differs from its predecessor's), the cells' first segments (`cell_start`) and their number.
-// CTA tiles are taken by ticket; a tile's cell offset comes from its predecessors by
-// decoupled look-back (state[t] = flag | running count; state[tiles] = ticket counter).
-// Positions >= cap are not written: the kernel may be launched before the host knows how
-// many cells there are (Renderer::render repeats it after growing the buffers).
+// Cells in one pass over the sorted segments. A CTA takes a tile of 2048 segments (by
+// ticket), keeps them in registers and
+//   1. marks the heads (a segment starts a cell when its key differs from its predecessor's),
+//   2. gets the number of cells before its tile by decoupled look-back (state[t] = flag |
+//      running count; state[tiles] = ticket counter; 32 predecessors per round),
+//   3. writes cell_start for its heads,
+//   4. sums the covers of every cell that lies entirely inside the tile, by local_y, in shared
+//      memory (acc_segment's cover part + cover_carry, cpu/painter/mod.rs:257-271,
+//      layer_workbench/mod.rs:218-224) and writes the cell's records: its cover (16 x i8),
+//      its key and the (tile_y, layer, tile_x) key of the carry pass.
+// Cells that cross a tile boundary (at most two per tile) are left to cells_boundary_kernel.
+// Positions >= cap are not written: the kernel may run before the host knows the cell count
+// (Renderer::render repeats both kernels after growing the buffers if it was too small).
 constexpr unsigned long long kCellAggregate = 1ull << 62, kCellInclusive = 2ull << 62, kCellFlags = 3ull << 62;
+constexpr uint32_t kCellSlots = 512;  // cells accumulated per round (a tile with more takes several rounds)
+
+__device__ __forceinline__ void write_cell_records(const PaintScene& S, uint32_t c, uint64_t first_seg, const int32_t* acc16,
+                                                   uint64_t* __restrict__ cell_key, uint4* __restrict__ cell_cover,
+                                                   uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        w[q] = ((uint32_t)acc16[4 * q] & 0xFFu) | (((uint32_t)acc16[4 * q + 1] & 0xFFu) << 8) |
+               (((uint32_t)acc16[4 * q + 2] & 0xFFu) << 16) | (((uint32_t)acc16[4 * q + 3] & 0xFFu) << 24);
+    const uint64_t ck = (first_seg >> kSortShift) << kSortShift;  // the cell's key = its first segment's
+    cell_key[c] = ck;
+    const int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
+    const bool relevant = !(ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi);
+    perm[c] = c;
+    cell_cover[c] = make_uint4(w[0], w[1], w[2], w[3]);
+    key2[c] = relevant ? make_key2(ck) : sentinel_key(S.tiles_y);
+}
 
 __global__ void __launch_bounds__(kCellThreads)
-    cells_scan_kernel(const uint64_t* __restrict__ segs, uint32_t n, unsigned long long* __restrict__ state, uint32_t tiles,
-                      uint32_t* __restrict__ cell_start, uint32_t cap, uint32_t* __restrict__ n_cells_out) {
+    cells_kernel(PaintScene S, const uint64_t* __restrict__ segs, uint32_t n, unsigned long long* __restrict__ state,
+                 uint32_t tiles, uint32_t* __restrict__ cell_start, uint32_t cap, uint32_t* __restrict__ n_cells_out,
+                 uint64_t* __restrict__ cell_key, uint4* __restrict__ cell_cover, uint64_t* __restrict__ key2,
+                 uint32_t* __restrict__ perm) {
     __shared__ uint32_t warp_cnt[kCellThreads / 32];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_prefix;
+    __shared__ int32_t s_acc[kCellSlots][16];
+    __shared__ uint64_t s_first[kCellSlots];  // first segment of the cell in each slot
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&state[tiles], 1ull);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t base = tile * kCellTile + warp * (32u * kCellItems);
+    const uint32_t tile_base = tile * kCellTile;
+    const uint32_t base = tile_base + warp * (32u * kCellItems);
+    // 1. segments -> registers, heads
+    uint64_t seg[kCellItems];
     uint32_t masks[kCellItems];
     uint32_t cnt = 0;
+    uint64_t carry_key = ~0ull;  // key of the element before the warp's first (none: every key differs from it)
+    if (base > 0 && base < n) carry_key = segs[base - 1] >> kSortShift;
 #pragma unroll
     for (int k = 0; k < kCellItems; ++k) {
         const uint32_t i = base + k * 32u + lane;
-        const bool head = i < n && is_cell_head(segs, i);
+        seg[k] = i < n ? segs[i] : 0ull;
+        const uint64_t key = seg[k] >> kSortShift;
+        uint64_t prev = __shfl_up_sync(kFullMask, key, 1);
+        if (lane == 0) prev = carry_key;
+        const bool head = i < n && (i == 0 || key != prev);
         masks[k] = __ballot_sync(kFullMask, head);
         cnt += __popc(masks[k]);
+        carry_key = __shfl_sync(kFullMask, key, 31);
     }
     if (lane == 0) warp_cnt[warp] = cnt;
     __syncthreads();
@@ -75,8 +114,7 @@ __global__ void __launch_bounds__(kCellThreads)
         if ((uint32_t)w < warp) warp_off += warp_cnt[w];
         tile_sum += warp_cnt[w];
     }
-    // Decoupled look-back by the first warp: 32 predecessors per round, until one of them
-    // already holds an inclusive prefix.
+    // 2. look-back (first warp)
     if (warp == 0) {
         volatile unsigned long long* st = state;
         unsigned long long prefix = 0;
@@ -114,102 +152,90 @@ __global__ void __launch_bounds__(kCellThreads)
         }
     }
     __syncthreads();
-    uint32_t pos = (uint32_t)s_prefix + warp_off;
+    const uint32_t cells_before = (uint32_t)s_prefix;
+    // 3. cell_start of the heads; rank of every element's cell inside the tile (-1: the cell
+    //    that continues from the previous tile)
+    int32_t local[kCellItems];
+    {
+        uint32_t pos = warp_off;
 #pragma unroll
-    for (int k = 0; k < kCellItems; ++k) {
-        if ((masks[k] >> lane) & 1u) {
-            const uint32_t q = pos + __popc(masks[k] & ((1u << lane) - 1u));
-            if (q < cap) cell_start[q] = base + k * 32u + lane;
+        for (int k = 0; k < kCellItems; ++k) {
+            const uint32_t upto = __popc(masks[k] & (0xFFFFFFFFu >> (31u - lane)));  // heads at or before this lane
+            local[k] = (int32_t)(pos + upto) - 1;
+            if ((masks[k] >> lane) & 1u) {
+                const uint32_t q = cells_before + pos + upto - 1u;
+                if (q < cap) cell_start[q] = base + k * 32u + lane;
+            }
+            pos += __popc(masks[k]);
         }
-        pos += __popc(masks[k]);
+    }
+    // 4. covers of the cells that lie inside the tile. The tile's last cell is complete iff the
+    //    next tile starts with a head (or there is no next element).
+    const uint32_t tile_end = min(tile_base + (uint32_t)kCellTile, n);
+    bool last_complete = true;
+    if (tile_end < n) last_complete = (segs[tile_end] >> kSortShift) != (segs[tile_end - 1u] >> kSortShift);
+    const uint32_t n_complete = tile_sum - ((tile_sum > 0u && !last_complete) ? 1u : 0u);  // cells [0, n_complete) of the tile
+    for (uint32_t r0 = 0; r0 < n_complete; r0 += kCellSlots) {
+        const uint32_t nr = min(kCellSlots, n_complete - r0);
+        for (uint32_t i = threadIdx.x; i < nr * 16u; i += kCellThreads) (&s_acc[0][0])[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kCellItems; ++k) {
+            const uint32_t i = base + k * 32u + lane;
+            const int32_t slot = local[k] - (int32_t)r0;
+            if (i < n && slot >= 0 && slot < (int32_t)nr) {
+                const uint64_t sg = seg[k];
+                const uint32_t ly = (uint32_t)(sg >> 12) & 15u;
+                const int32_t cv = (int32_t)(((uint32_t)sg & 0x3Fu) ^ 0x20u) - 0x20;
+                atomicAdd(&s_acc[slot][ly], cv);
+                if ((masks[k] >> lane) & 1u) s_first[slot] = sg;
+            }
+        }
+        __syncthreads();
+        for (uint32_t sl = threadIdx.x; sl < nr; sl += kCellThreads) {
+            const uint32_t c = cells_before + r0 + sl;
+            if (c < cap) write_cell_records(S, c, s_first[sl], s_acc[sl], cell_key, cell_cover, key2, perm);
+        }
+        __syncthreads();
     }
 }
 
-// Per cell: sum of covers by local_y (acc_segment's cover part + cover_carry,
-// cpu/painter/mod.rs:257-271, layer_workbench/mod.rs:218-224), and the
-// (tile_y, layer, tile_x) key for the carry pass.
-
-// A CTA owns 256 consecutive cells, i.e. one contiguous range of the sorted
-// segments: its warps stream that range with coalesced loads, find each
-// segment's cell from the run boundaries (ballot of key changes) and add its
-// cover to the cell's row counter in shared memory.
-constexpr int kCoverCells = 256;
-
-__global__ void __launch_bounds__(kCoverCells)
-    cell_cover_kernel(PaintScene S, const uint64_t* __restrict__ segs, const uint32_t* __restrict__ cell_start,
-                      uint64_t* __restrict__ cell_key, const uint32_t* __restrict__ n_cells_ptr, uint32_t cap,
-                      uint4* __restrict__ cell_cover, uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
-    __shared__ uint32_t s_start[kCoverCells + 1];
-    __shared__ int32_t s_acc[kCoverCells][16];
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
-    const uint32_t c0 = blockIdx.x * kCoverCells;
-    const uint32_t n_cells = *n_cells_ptr;  // written by cells_scan_kernel; the host may not know it yet
-    if (n_cells > cap || c0 >= n_cells) return;
-    const uint32_t nc = min((uint32_t)kCoverCells, n_cells - c0);
-    if (t <= nc) s_start[t] = cell_start[c0 + t];
-    if (t == 0) s_start[nc] = cell_start[c0 + nc];
+// The cells that cross a tile boundary of cells_kernel: one warp per boundary b (between
+// tiles b - 1 and b). The warp acts when the element after the boundary continues a cell whose
+// head lies in tile b - 1 (a cell that spans whole tiles is taken at its first boundary only)
+// and sums the covers over the cell's whole segment range.
+__global__ void __launch_bounds__(kCellThreads)
+    cells_boundary_kernel(PaintScene S, const uint64_t* __restrict__ segs, uint32_t n, const unsigned long long* __restrict__ state,
+                          uint32_t tiles, const uint32_t* __restrict__ cell_start, uint32_t cap,
+                          const uint32_t* __restrict__ n_cells_ptr, uint64_t* __restrict__ cell_key, uint4* __restrict__ cell_cover,
+                          uint64_t* __restrict__ key2, uint32_t* __restrict__ perm) {
+    const uint32_t b = blockIdx.x * (kCellThreads / 32) + (threadIdx.x >> 5) + 1u, lane = threadIdx.x & 31u;
+    if (b >= tiles) return;
+    const uint32_t n_cells = *n_cells_ptr;
+    if (n_cells >= cap) return;  // cell_start is incomplete: the host repeats both kernels
+    const uint32_t first = b * kCellTile;  // first element after the boundary
+    if (first >= n || (segs[first] >> kSortShift) != (segs[first - 1u] >> kSortShift)) return;  // a head: nothing crosses
+    const uint32_t incl_prev = (uint32_t)(state[b - 1u] & ~kCellFlags);                       // cells through tile b - 1
+    const uint32_t incl_prev2 = b >= 2u ? (uint32_t)(state[b - 2u] & ~kCellFlags) : 0u;
+    if (incl_prev == incl_prev2) return;  // tile b - 1 holds no head: an earlier boundary owns this cell
+    const uint32_t c = incl_prev - 1u;
+    const uint32_t s0 = cell_start[c], s1 = cell_start[c + 1u];
+    int32_t acc[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s_acc[t][r] = 0;
-    __syncthreads();
-
-    const uint32_t s0 = s_start[0], s1 = s_start[nc];
-    const uint32_t span = (((s1 - s0) + 7u) / 8u + 31u) & ~31u;  // per warp, a multiple of 32
-    const uint32_t w0 = s0 + warp * span, w1 = min(s1, w0 + span);
-    if (w0 < w1) {
-        uint32_t lo = 0, hi = nc;  // largest cell with s_start[cell] <= w0
-        while (hi - lo > 1u) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (s_start[mid] <= w0) lo = mid;
-            else hi = mid;
-        }
-        uint32_t base = lo - (s_start[lo] == w0 ? 1u : 0u);  // cell index before the first head (may wrap to ~0)
-        // Key of the segment before the span (a span that starts a cell differs from it by construction).
-        uint64_t carry = w0 > 0u ? (segs[w0 - 1u] >> kSortShift) : ~0ull;
-        const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
-        for (uint32_t i0 = w0; i0 < w1; i0 += 128u) {
-            uint64_t sv[4];  // four coalesced loads in flight per lane
+    for (int r = 0; r < 16; ++r) acc[r] = 0;
+    for (uint32_t i = s0 + lane; i < s1; i += 32u) {
+        const uint64_t sg = segs[i];
+        const uint32_t ly = (uint32_t)(sg >> 12) & 15u;
+        const int32_t cv = (int32_t)(((uint32_t)sg & 0x3Fu) ^ 0x20u) - 0x20;
 #pragma unroll
-            for (uint32_t u = 0; u < 4u; ++u) {
-                const uint32_t i = i0 + u * 32u + lane;
-                sv[u] = i < w1 ? segs[i] : 0ull;
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < 4u; ++u) {
-                const uint32_t i = i0 + u * 32u + lane;
-                const bool valid = i < w1;
-                const uint64_t s = sv[u];
-                const uint64_t k = s >> kSortShift;
-                uint64_t kp = __shfl_up_sync(kFullMask, k, 1);
-                if (lane == 0) kp = carry;
-                const uint32_t heads = __ballot_sync(kFullMask, valid && k != kp);
-                if (valid) {
-                    const uint32_t cell = base + __popc(heads & le_mask);
-                    const uint32_t ly = (uint32_t)(s >> 12) & 15u;
-                    const int32_t cv = (int32_t)(((uint32_t)s & 0x3Fu) ^ 0x20u) - 0x20;
-                    atomicAdd(&s_acc[cell][ly], cv);
-                }
-                base += __popc(heads);
-                carry = __shfl_sync(kFullMask, k, 31);
-            }
-        }
+        for (int r = 0; r < 16; ++r) acc[r] += (ly == (uint32_t)r) ? cv : 0;
     }
-    __syncthreads();
-
-    if (t < nc) {
-        const uint32_t c = c0 + t;
-        uint32_t w[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            w[q] = ((uint32_t)s_acc[t][4 * q] & 0xFFu) | (((uint32_t)s_acc[t][4 * q + 1] & 0xFFu) << 8) |
-                   (((uint32_t)s_acc[t][4 * q + 2] & 0xFFu) << 16) | (((uint32_t)s_acc[t][4 * q + 3] & 0xFFu) << 24);
-        const uint64_t ck = (segs[s_start[t]] >> kSortShift) << kSortShift;  // the cell's key = its first segment's
-        cell_key[c] = ck;
-        const int32_t ty = (int32_t)key_ty(ck) - 1, tx = (int32_t)key_tx(ck) - 1;
-        const bool relevant = !(ty < (int32_t)S.ty_lo || ty >= (int32_t)S.ty_hi || tx >= (int32_t)S.tx_hi);
-        perm[c] = c;
-        cell_cover[c] = make_uint4(w[0], w[1], w[2], w[3]);
-        key2[c] = relevant ? make_key2(ck) : sentinel_key(S.tiles_y);
+    for (int r = 0; r < 16; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(kFullMask, acc[r], o);
     }
+    if (lane == 0) write_cell_records(S, c, segs[s0], acc, cell_key, cell_cover, key2, perm);
 }
 
 // ---------------------------------------------------------------------------
@@ -445,21 +471,18 @@ void launch_row_costs(const uint2* tile_range, uint32_t tiles_x, uint32_t tiles_
 // ---------------------------------------------------------------------------
 uint32_t cell_num_blocks(uint32_t n) { return (n + kCellTile - 1) / kCellTile; }
 
-size_t cells_scan_state_words(uint32_t n) { return (size_t)cell_num_blocks(n) + 2; }
+size_t cells_state_words(uint32_t n) { return (size_t)cell_num_blocks(n) + 2; }
 
-void launch_cells_scan(const uint64_t* segs, uint32_t n, unsigned long long* state, uint32_t* cell_start, uint32_t cap,
-                       uint32_t* n_cells_out, cudaStream_t st) {
+void launch_cells(const PaintScene& S, const uint64_t* segs, uint32_t n, unsigned long long* state, uint32_t* cell_start,
+                  uint32_t cap, uint32_t* n_cells_out, uint64_t* cell_key, uint4* cell_cover, uint64_t* key2, uint32_t* perm,
+                  cudaStream_t st) {
     const uint32_t tiles = cell_num_blocks(n);
     cudaMemsetAsync(state, 0, (tiles + 1) * sizeof(unsigned long long), st);
-    cells_scan_kernel<<<tiles, kCellThreads, 0, st>>>(segs, n, state, tiles, cell_start, cap, n_cells_out);
-}
-
-void launch_cell_cover(const PaintScene& S, const uint64_t* segs, const uint32_t* cell_start, uint64_t* cell_key,
-                       const uint32_t* n_cells_ptr, uint32_t cap, uint32_t grid_cells, uint4* cell_cover, uint64_t* key2,
-                       uint32_t* perm, cudaStream_t st) {
-    if (grid_cells)
-        cell_cover_kernel<<<(grid_cells + kCoverCells - 1) / kCoverCells, kCoverCells, 0, st>>>(
-            S, segs, cell_start, cell_key, n_cells_ptr, cap, cell_cover, key2, perm);
+    cells_kernel<<<tiles, kCellThreads, 0, st>>>(S, segs, n, state, tiles, cell_start, cap, n_cells_out, cell_key, cell_cover, key2,
+                                                 perm);
+    if (tiles > 1)
+        cells_boundary_kernel<<<(tiles - 1 + kCellThreads / 32 - 1) / (kCellThreads / 32), kCellThreads, 0, st>>>(
+            S, segs, n, state, tiles, cell_start, cap, n_cells_out, cell_key, cell_cover, key2, perm);
 }
 
 // Largest values the three key fields can take in the pair sorts (sentinel

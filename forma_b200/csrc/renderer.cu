@@ -333,7 +333,8 @@ class Renderer {
     // Band-wise copy-back of host frames (see render()).
     static constexpr uint32_t kMaxCopyBands = 16;
     static uint32_t copy_bands() { return (uint32_t)std::min(std::max(options().copy_bands, 1), (int)kMaxCopyBands); }
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t band_stream[kMaxCopyBands];
+    bool band_streams_ok = false;
     cudaEvent_t band_ev[kMaxCopyBands + 1];
     cudaEvent_t count_ev = nullptr;  // completion of a count read-back (waited on instead of the whole stream)
     cudaError_t ensure_count_event() {
@@ -370,9 +371,9 @@ class Renderer {
     ~Renderer() {
         if (pinned_totals) cudaFreeHost(pinned_totals);
         if (count_ev) cudaEventDestroy(count_ev);
-        if (copy_stream) {
+        if (band_streams_ok) {
             for (auto& e : band_ev) cudaEventDestroy(e);
-            cudaStreamDestroy(copy_stream);
+            for (auto& bs : band_stream) cudaStreamDestroy(bs);
         }
         if (timer.ok) {
             for (auto& e : timer.ev) cudaEventDestroy(e);
@@ -911,48 +912,47 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     uint32_t n_cells = 0, n_gaps = 0, n_entries = 0;
     if (n > 0) {
-        // Cells: one pass finds the cell heads and counts them. The count is read back, but
-        // nothing waits for it: the pass itself and the cover kernel run into the buffers of
-        // the previous frames (the count is taken from device memory, writes beyond the
-        // capacity are dropped) and are repeated below only if those turn out too small.
-        FORMA_CUDA_TRY(scan_state.reserve(std::max(cells_scan_state_words(n), scan_state_words(n))));
-        FORMA_CUDA_TRY(cell_start.reserve(4096));
-        size_t cell_cap = 0;  // cells the cover kernel may handle speculatively
-        if (speculation_enabled() && cell_key.capacity)
-            cell_cap = std::min({cell_start.capacity - 1, cell_key.capacity, cell_cover.capacity, key2.capacity, perm.capacity,
-                                 (size_t)0xFFFFFFFFu});
-        launch_cells_scan(segs.ptr, n, scan_state.ptr, cell_start.ptr, (uint32_t)std::min<size_t>(cell_start.capacity, 0xFFFFFFFFu),
-                          totals.ptr + 1, stream);
-        ++launches;
+        // Cells: one pass finds the cell heads, counts them and sums their covers. The count is
+        // read back, but nothing waits for it: the pass runs into the buffers of the previous
+        // frames (writes beyond their capacity are dropped) and is repeated below only if
+        // those turn out too small.
+        FORMA_CUDA_TRY(scan_state.reserve(std::max(cells_state_words(n), scan_state_words(n))));
+        if (!cell_start.capacity) {  // first frame: a guess that usually holds (cells ~ segments / 20)
+            const size_t guess = (size_t)n / 8u + 4096u;
+            FORMA_CUDA_TRY(cell_start.reserve(guess));
+            FORMA_CUDA_TRY(cell_key.reserve(guess));
+            FORMA_CUDA_TRY(cell_cover.reserve(guess));
+            FORMA_CUDA_TRY(key2.reserve(guess));
+            FORMA_CUDA_TRY(perm.reserve(guess));
+        }
+        auto cells_capacity = [&] {
+            return (uint32_t)std::min({cell_start.capacity, cell_key.capacity, cell_cover.capacity, key2.capacity, perm.capacity,
+                                       (size_t)0xFFFFFFFFu});
+        };
+        uint32_t cell_cap = cells_capacity();
+        launch_cells(S, segs.ptr, n, scan_state.ptr, cell_start.ptr, cell_cap, totals.ptr + 1, cell_key.ptr, cell_cover.ptr,
+                     key2.ptr, perm.ptr, stream);
+        launches += 2;
         FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 1, totals.ptr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         FORMA_CUDA_TRY(cudaEventRecord(count_ev, stream));
-        if (cell_cap) {
-            launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, (uint32_t)cell_cap,
-                              (uint32_t)std::min<size_t>(cell_cap, n), cell_cover.ptr, key2.ptr, perm.ptr, stream);
-            ++launches;
-        }
         FORMA_CUDA_TRY(cudaEventSynchronize(count_ev));
         n_cells = pinned_totals[1];
-        const bool cells_fit = (size_t)n_cells + 1 <= cell_start.capacity;
+        const bool cells_fit = (size_t)n_cells + 1 <= cell_cap;
         FORMA_CUDA_TRY(cell_start.reserve(n_cells + 1));
-        FORMA_CUDA_TRY(cell_key.reserve(n_cells));
-        FORMA_CUDA_TRY(cell_cover.reserve(n_cells));
+        FORMA_CUDA_TRY(cell_key.reserve(n_cells + 1));
+        FORMA_CUDA_TRY(cell_cover.reserve(n_cells + 1));
         FORMA_CUDA_TRY(carry_in.reserve(n_cells));
         FORMA_CUDA_TRY(carry_after.reserve(n_cells));
-        FORMA_CUDA_TRY(key2.reserve(n_cells));
-        FORMA_CUDA_TRY(key2_tmp.reserve(n_cells));
-        FORMA_CUDA_TRY(perm.reserve(n_cells));
-        FORMA_CUDA_TRY(perm_tmp.reserve(n_cells));
+        FORMA_CUDA_TRY(key2.reserve(n_cells + 1));
+        FORMA_CUDA_TRY(key2_tmp.reserve(n_cells + 1));
+        FORMA_CUDA_TRY(perm.reserve(n_cells + 1));
+        FORMA_CUDA_TRY(perm_tmp.reserve(n_cells + 1));
         FORMA_CUDA_TRY(gap_count.reserve(n_cells));
-        if (!cells_fit) {  // cell_start was too small: the pass dropped the overflow
-            launch_cells_scan(segs.ptr, n, scan_state.ptr, cell_start.ptr, (uint32_t)std::min<size_t>(cell_start.capacity, 0xFFFFFFFFu),
-                              totals.ptr + 1, stream);
-            ++launches;
-        }
-        if (!cells_fit || !cell_cap || n_cells > cell_cap) {
-            launch_cell_cover(S, segs.ptr, cell_start.ptr, cell_key.ptr, totals.ptr + 1, n_cells, n_cells, cell_cover.ptr, key2.ptr,
-                              perm.ptr, stream);
-            ++launches;
+        if (!cells_fit) {  // the buffers were too small: the pass dropped the overflow
+            cell_cap = cells_capacity();
+            launch_cells(S, segs.ptr, n, scan_state.ptr, cell_start.ptr, cell_cap, totals.ptr + 1, cell_key.ptr, cell_cover.ptr,
+                         key2.ptr, perm.ptr, stream);
+            launches += 2;
         }
         FORMA_CUDA_TRY(sort_scratch.reserve(radix_scratch_bytes(n_cells)));
         {
@@ -1022,35 +1022,40 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     launch_tile_index(S, ekey.ptr, n_entries, tile_range.ptr, heavy_lists, heavy_counts, stream);
     launches += n_entries ? 1 : 0;
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
-    // Host frame without a layer cache: paint in bands of tile rows and copy each
-    // band back on a second stream while the next one is painted, so most of the
-    // PCIe transfer overlaps the paint kernel.
+    // Host frame without a layer cache: paint in bands of tile rows, every band on its own
+    // stream followed by the copy of its rows to the host buffer. The band kernels are
+    // persistent (one CTA per resident slot), so the CTAs of band k + 1 start as the warps of
+    // band k run dry: the kernels overlap at their tails, and the PCIe transfer of a band
+    // overlaps the painting of the following ones.
     bool copied_in_bands = false;
     uint32_t paint_launches = 1;
     const uint32_t paint_rows = S.ty_hi - S.ty_lo;
     if (!buffer_on_device && !cache && paint_rows >= 32u && S.tx_hi > S.tx_lo && band_copies_enabled()) {
-        if (!copy_stream) {
-            FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        if (!band_streams_ok) {
+            for (auto& bs : band_stream) FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&bs, cudaStreamNonBlocking));
             for (auto& e : band_ev) FORMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            band_streams_ok = true;
         }
         const uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
         const uint32_t kCopyBands = std::min(copy_bands(), paint_rows / 8u);
+        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], stream));  // the tables are ready
         for (uint32_t k = 0; k < kCopyBands; ++k) {
             PaintScene Sb = S;
             Sb.ty_lo = S.ty_lo + paint_rows * k / kCopyBands;
             Sb.ty_hi = S.ty_lo + paint_rows * (k + 1u) / kCopyBands;
-            launch_paint(Sb, segs.ptr, recs.ptr, tile_range.ptr, heavy_lists, heavy_counts, eflags.ptr, fb, totals.ptr + 3, stream);
+            cudaStream_t bs = band_stream[k];
+            FORMA_CUDA_TRY(cudaStreamWaitEvent(bs, band_ev[kMaxCopyBands], 0));
+            launch_paint(Sb, segs.ptr, recs.ptr, tile_range.ptr, heavy_lists, heavy_counts, eflags.ptr, fb, totals.ptr + 16 + k, bs);
             ++launches;
-            FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], stream));
-            FORMA_CUDA_TRY(cudaStreamWaitEvent(copy_stream, band_ev[k], 0));
             const uint64_t y0 = (uint64_t)Sb.ty_lo * 16u, y1 = std::min<uint64_t>((uint64_t)Sb.ty_hi * 16u, height);
             if (x1 > x0 && y1 > y0) {
                 FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
-                                                 (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, copy_stream));
+                                                 (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, bs));
                 d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
             }
+            FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], bs));
         }
-        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], copy_stream));
+        for (uint32_t k = 0; k < kCopyBands; ++k) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[k], 0));
         paint_launches = kCopyBands;
         copied_in_bands = true;
     } else {
@@ -1059,7 +1064,6 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[5], stream));
-    if (copied_in_bands) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[kMaxCopyBands], 0));
 
     last_written_tiles = 0;
     if (pack_written) {
@@ -1487,7 +1491,7 @@ static forma_renderer* renderer_new_impl(int device_ordinal) {
     }
     forma_renderer* r = new forma_renderer();
     r->r.device = device_ordinal;
-    if (cudaMallocHost(&r->r.pinned_totals, 16 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(16) != cudaSuccess ||
+    if (cudaMallocHost(&r->r.pinned_totals, 16 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(64) != cudaSuccess ||
         cudaMemset(r->r.totals.ptr, 0, r->r.totals.capacity * sizeof(uint32_t)) != cudaSuccess) {
         set_error("allocation of renderer state failed");
         delete r;

@@ -15,7 +15,7 @@ namespace forma {
 struct Options {
     int speculate = 1;       // launch kernels ahead of their count read-backs (0: strictly after)
     int band_copy = 1;       // host frames: paint / copy back in bands of tile rows
-    int copy_bands = 4;      //   ... how many (1..16)
+    int copy_bands = 8;      //   ... how many (1..16; measured on paris@4K: 1 -> 481, 2 -> 492, 4 -> 484, 8 -> 511 frames/s end to end)
     int sort_full_key = 0;   // 1: sort the layer digits even when the inserts are in layer order
     int sort_big_log2 = 19;  // key count from which the 4096-key tiles / reduce-then-scan passes are used
     int test_gap_cap = 0;    // test hook: cap of the speculative carry-only-entry launch (0 = none)

@@ -114,14 +114,53 @@ __global__ void __launch_bounds__(kCellThreads)
         if ((uint32_t)w < warp) warp_off += warp_cnt[w];
         tile_sum += warp_cnt[w];
     }
-    // 2. look-back (first warp)
+    // 2. publish this tile's count at once: successors can start summing while we accumulate
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = state;
+        st[tile] = (tile == 0 ? kCellInclusive : kCellAggregate) | tile_sum;
+    }
+    // rank of every element's cell inside the tile (-1: the cell that continues from the previous tile)
+    int32_t local[kCellItems];
+    {
+        uint32_t pos = warp_off;
+#pragma unroll
+        for (int k = 0; k < kCellItems; ++k) {
+            local[k] = (int32_t)(pos + __popc(masks[k] & (0xFFFFFFFFu >> (31u - lane)))) - 1;  // heads at or before this lane
+            pos += __popc(masks[k]);
+        }
+    }
+    // The tile's last cell is complete iff the next tile starts with a head (or there is no next element).
+    const uint32_t tile_end = min(tile_base + (uint32_t)kCellTile, n);
+    bool last_complete = true;
+    if (tile_end < n) last_complete = (segs[tile_end] >> kSortShift) != (segs[tile_end - 1u] >> kSortShift);
+    const uint32_t n_complete = tile_sum - ((tile_sum > 0u && !last_complete) ? 1u : 0u);  // cells [0, n_complete) of the tile
+
+    // 3. covers of the first kCellSlots complete cells — before the look-back: its latency hides behind this
+    auto accumulate = [&](uint32_t r0, uint32_t nr) {
+        for (uint32_t i = threadIdx.x; i < nr * 16u; i += kCellThreads) (&s_acc[0][0])[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kCellItems; ++k) {
+            const uint32_t i = base + k * 32u + lane;
+            const int32_t slot = local[k] - (int32_t)r0;
+            if (i < n && slot >= 0 && slot < (int32_t)nr) {
+                const uint64_t sg = seg[k];
+                const uint32_t ly = (uint32_t)(sg >> 12) & 15u;
+                const int32_t cv = (int32_t)(((uint32_t)sg & 0x3Fu) ^ 0x20u) - 0x20;
+                atomicAdd(&s_acc[slot][ly], cv);
+                if ((masks[k] >> lane) & 1u) s_first[slot] = sg;
+            }
+        }
+        __syncthreads();
+    };
+    const uint32_t nr0 = min(kCellSlots, n_complete);
+    accumulate(0u, nr0);
+
+    // 4. look-back (first warp): 32 predecessors per round, until one holds an inclusive prefix
     if (warp == 0) {
         volatile unsigned long long* st = state;
         unsigned long long prefix = 0;
-        if (tile == 0) {
-            if (lane == 0) st[0] = kCellInclusive | tile_sum;
-        } else {
-            if (lane == 0) st[tile] = kCellAggregate | tile_sum;
+        if (tile != 0) {
             int32_t p = (int32_t)tile - 1;
             while (true) {
                 const int32_t idx = p - (int32_t)lane;
@@ -153,45 +192,18 @@ __global__ void __launch_bounds__(kCellThreads)
     }
     __syncthreads();
     const uint32_t cells_before = (uint32_t)s_prefix;
-    // 3. cell_start of the heads; rank of every element's cell inside the tile (-1: the cell
-    //    that continues from the previous tile)
-    int32_t local[kCellItems];
-    {
-        uint32_t pos = warp_off;
+
+    // 5. cell_start of the heads, records of the complete cells
 #pragma unroll
-        for (int k = 0; k < kCellItems; ++k) {
-            const uint32_t upto = __popc(masks[k] & (0xFFFFFFFFu >> (31u - lane)));  // heads at or before this lane
-            local[k] = (int32_t)(pos + upto) - 1;
-            if ((masks[k] >> lane) & 1u) {
-                const uint32_t q = cells_before + pos + upto - 1u;
-                if (q < cap) cell_start[q] = base + k * 32u + lane;
-            }
-            pos += __popc(masks[k]);
+    for (int k = 0; k < kCellItems; ++k) {
+        if ((masks[k] >> lane) & 1u) {
+            const uint32_t q = cells_before + (uint32_t)local[k];
+            if (q < cap) cell_start[q] = base + k * 32u + lane;
         }
     }
-    // 4. covers of the cells that lie inside the tile. The tile's last cell is complete iff the
-    //    next tile starts with a head (or there is no next element).
-    const uint32_t tile_end = min(tile_base + (uint32_t)kCellTile, n);
-    bool last_complete = true;
-    if (tile_end < n) last_complete = (segs[tile_end] >> kSortShift) != (segs[tile_end - 1u] >> kSortShift);
-    const uint32_t n_complete = tile_sum - ((tile_sum > 0u && !last_complete) ? 1u : 0u);  // cells [0, n_complete) of the tile
     for (uint32_t r0 = 0; r0 < n_complete; r0 += kCellSlots) {
         const uint32_t nr = min(kCellSlots, n_complete - r0);
-        for (uint32_t i = threadIdx.x; i < nr * 16u; i += kCellThreads) (&s_acc[0][0])[i] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kCellItems; ++k) {
-            const uint32_t i = base + k * 32u + lane;
-            const int32_t slot = local[k] - (int32_t)r0;
-            if (i < n && slot >= 0 && slot < (int32_t)nr) {
-                const uint64_t sg = seg[k];
-                const uint32_t ly = (uint32_t)(sg >> 12) & 15u;
-                const int32_t cv = (int32_t)(((uint32_t)sg & 0x3Fu) ^ 0x20u) - 0x20;
-                atomicAdd(&s_acc[slot][ly], cv);
-                if ((masks[k] >> lane) & 1u) s_first[slot] = sg;
-            }
-        }
-        __syncthreads();
+        if (r0) accumulate(r0, nr);  // a tile with more than kCellSlots cells: further rounds
         for (uint32_t sl = threadIdx.x; sl < nr; sl += kCellThreads) {
             const uint32_t c = cells_before + r0 + sl;
             if (c < cap) write_cell_records(S, c, s_first[sl], s_acc[sl], cell_key, cell_cover, key2, perm);

@@ -698,7 +698,6 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                 const uint32_t cw = reinterpret_cast<const uint32_t*>(&W.hdr[k].carry)[row >> 2];
                 int32_t run = (int32_t)(int8_t)((cw >> (8u * (row & 3u))) & 0xFFu);
                 f2 cov[4];  // coverage of the lane's pixel pairs
-                f2 clip2[4] = {f2_splat(1.0f), f2_splat(1.0f), f2_splat(1.0f), f2_splat(1.0f)};  // clip mask of the pairs (when it applies)
                 if (h0.z > h0.y) {
                     // (the __syncwarp that ended the previous iteration made this buffer's atomics visible)
                     uint4* c4 = reinterpret_cast<uint4*>(W.cells[k & 1u]);
@@ -758,10 +757,13 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                     __syncwarp();
                     continue;
                 }
-                if (apply_clip) {  // the mask multiplies the source alpha: fold it into the coverage's place
+                f2 clip2[4];  // clip mask of the pairs; only read when apply_clip
+                if (apply_clip) {
                     const float4* m4 = reinterpret_cast<const float4*>(W.clip);
                     const float4 m0 = m4[2u * lane], m1 = m4[2u * lane + 1u];
                     clip2[0] = f2{m0.x, m0.y}; clip2[1] = f2{m0.z, m0.w}; clip2[2] = f2{m1.x, m1.y}; clip2[3] = f2{m1.z, m1.w};
+                } else {
+                    clip2[0] = clip2[1] = clip2[2] = clip2[3] = f2_splat(0.0f);
                 }
 
                 const uint32_t mode = meta_blend(meta);
@@ -772,10 +774,16 @@ __global__ void __launch_bounds__(kPaintWarpsPerBlock * 32, kMinBlocks) paint_ke
                     // coverage leaves the pixel as it is, so no f32x8 bookkeeping is needed.
                     const f2 cr = f2_splat(__uint_as_float(h2.x)), cg = f2_splat(__uint_as_float(h2.y));
                     const f2 cb = f2_splat(__uint_as_float(h2.z)), ca = f2_splat(__uint_as_float(h2.w));
+                    if (apply_clip) {  // src_a = fill.a * coverage * mask (mod.rs:425-429)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cov[q] = mul2(mul2(ca, cov[q]), clip2[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cov[q] = mul2(ca, cov[q]);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        f2 sa = mul2(ca, cov[q]);
-                        if (apply_clip) sa = mul2(sa, clip2[q]);
+                        const f2 sa = cov[q];
                         const f2 inv_dst_a = sub2(f2_splat(1.0f), da[q]);
                         const f2 inv_dst_a_src_a = mul2(inv_dst_a, sa);
                         const f2 inv_src_a = sub2(f2_splat(1.0f), sa);

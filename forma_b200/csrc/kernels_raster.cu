@@ -90,8 +90,8 @@ void launch_quad_expand_poly(const QuadUpPoly* in, QuadRec* out, uint32_t n, cud
 __global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const PointRec* __restrict__ points,
                                     const uint8_t* __restrict__ kinds, const QuadRec* __restrict__ quads,
                                     const FlattenJob* __restrict__ jobs, uint32_t n_jobs, uint32_t n_points,
-                                    float* __restrict__ out_x, float* __restrict__ out_y,
-                                    uint32_t* __restrict__ out_gid) {
+                                    uint32_t dst_base /* added to every job's dst */, float* __restrict__ out_x,
+                                    float* __restrict__ out_y, uint32_t* __restrict__ out_gid) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_points) return;
     uint32_t lo = 0, hi = n_jobs - 1u;  // last job with first_point <= i
@@ -166,7 +166,7 @@ __global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const
         px = tx;
         py = ty;
     }
-    uint32_t dst = job.dst + local;
+    uint32_t dst = dst_base + job.dst + local;
     // ids: None at contour ends; the id of the last point of an insert is
     // replaced by the trailing None (segment.rs:181-198).
     bool none = kind == 1u || local + 1u == job.count;
@@ -449,11 +449,11 @@ void launch_line_records(const RasterArgs& args, uint32_t n, uint32_t* orders, f
 // Host launchers
 // ---------------------------------------------------------------------------
 void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const uint8_t* kinds, const QuadRec* quads,
-                         const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, float* x, float* y, uint32_t* gid,
-                         cudaStream_t stream) {
+                         const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, uint32_t dst_base, float* x, float* y,
+                         uint32_t* gid, cudaStream_t stream) {
     if (!n_points || !n_jobs) return;
-    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, points, kinds, quads, jobs, n_jobs, n_points, x, y,
-                                                                    gid);
+    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, points, kinds, quads, jobs, n_jobs, n_points, dst_base,
+                                                                    x, y, gid);
 }
 
 uint32_t raster_num_blocks(uint32_t n_points) { return n_points ? (n_points + kRasterThreads - 1) / kRasterThreads : 0; }

@@ -487,7 +487,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
             job.geom_id = p.geom_id;
             job.has_xf = p.has_xf ? 1u : 0u;
             std::memcpy(job.xf, p.xf, sizeof(job.xf));
-            job.dst = cd.n_resident + (uint32_t)pi;  // device-local: the resident inserts are packed
+            job.dst = (uint32_t)pi;  // relative to the batch; the batch lands at the device's resident point count
             if (!prog.splines.empty())
                 std::memcpy(cd.h_splines.ptr + si, prog.splines.data(), prog.splines.size() * sizeof(SplineRec));
             if (!prog.points.empty()) {
@@ -527,14 +527,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
         cd.staged_quads = n_quads;
         cd.staged_points = n_pts;
         cd.staged_rational = rational;
-    } else {
-        // Same batch as last time (evicted composition): only the destinations depend on what is resident.
-        uint32_t pi = 0;
-        for (size_t k = 0; k < cd.staged_jobs; ++k) {
-            cd.h_jobs.ptr[k].dst = cd.n_resident + pi;
-            pi += cd.h_jobs.ptr[k].count;
-        }
-    }
+    }  // else: the same batch as last time (an evicted composition) is uploaded again from the same staging
     cd.jobs_resident = to;
     if (!cd.staged_jobs) return FORMA_STATUS_OK;
     const uint32_t n_after = cd.n_resident + (uint32_t)cd.staged_points;
@@ -570,7 +563,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
     h2d_bytes += cd.staged_splines * sizeof(SplineRec) + cd.staged_recs * (sizeof(PointRec) + 1) +
                  cd.staged_quads * quad_bytes + cd.staged_jobs * sizeof(FlattenJob);
     launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)cd.staged_jobs,
-                        (uint32_t)cd.staged_points, cd.d_x.ptr, cd.d_y.ptr, cd.d_gid.ptr, stream);
+                        (uint32_t)cd.staged_points, cd.n_resident, cd.d_x.ptr, cd.d_y.ptr, cd.d_gid.ptr, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
     cd.n_resident = n_after;
@@ -1305,7 +1298,7 @@ static int path_segments_impl(forma_path* p, const float** x, const float** y, c
         FORMA_CUDA_TRY(cudaDeviceSynchronize());
     }
     FORMA_CUDA_TRY(cudaMemcpy(dj.ptr, &job, sizeof(job), cudaMemcpyHostToDevice));
-    launch_flatten_eval(dc.ptr, dp.ptr, dk.ptr, dq.ptr, dj.ptr, 1, count, dx.ptr, dy.ptr, dg.ptr, 0);
+    launch_flatten_eval(dc.ptr, dp.ptr, dk.ptr, dq.ptr, dj.ptr, 1, count, 0, dx.ptr, dy.ptr, dg.ptr, 0);
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaMemcpy(p->x.data(), dx.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
     FORMA_CUDA_TRY(cudaMemcpy(p->y.data(), dy.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));

@@ -20,6 +20,7 @@ struct Options {
     int sort_big_log2 = 19;  // key count from which the 4096-key tiles / reduce-then-scan passes are used
     int test_gap_cap = 0;    // test hook: cap of the speculative carry-only-entry launch (0 = none)
     int paint_lpt = 1;       // heavy tiles first (longest-processing-time order) in the paint kernel
+    int paint_wide = 0;      // 1: the paint kernel built for 6 CTAs / SM (up to 168 registers) instead of 8 (128)
     int band_filter = 1;     // a render cropped to a band of rows only makes the band's geometry resident
 };
 Options& options();

@@ -993,15 +993,19 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
     cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
     PaintInputs in{segs, recs, tile_range, heavy, heavy_count, S.tiles_x * S.tiles_y, eflags, framebuffer, tile_counter};
     // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy (per device).
-    static int blocks_per_sm[kMaxDevices] = {0};
-    int& per_sm = blocks_per_sm[current_device_index()];
+    // Option paint_wide = 1 selects the build with up to 168 registers (6 CTAs / SM) instead of 128 (8 CTAs / SM).
+    static int blocks_per_sm[2][kMaxDevices] = {{0}};
+    const int wide = options().paint_wide ? 1 : 0;
+    int& per_sm = blocks_per_sm[wide][current_device_index()];
     if (!per_sm) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
+        if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paint_kernel<6>, kPaintWarpsPerBlock * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
         if (per_sm < 1) per_sm = 1;
     }
     const uint32_t want = (uint32_t)(per_sm * device_sm_count());
     const uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;
-    paint_kernel<8><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    if (wide) paint_kernel<6><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
+    else paint_kernel<8><<<min(want, need), kPaintWarpsPerBlock * 32, 0, st>>>(S, in, n_tiles);
 }
 
 }  // namespace forma

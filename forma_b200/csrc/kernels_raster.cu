@@ -9,10 +9,11 @@
 // The reference materialises a 40 B/line SoA between line setup and
 // rasterization and finds each pixel segment's line with a binary search over
 // the prefix sums (utils/prefix_scan.rs). Here both stages are fused: the line
-// parameters live in shared memory for the 256 lines of a CTA and each warp
-// expands its 32 lines into pixel segments with a warp scan that allocates the
-// output slots, so global traffic is 12 B/point in (twice) and 8 B/segment out,
-// emitted in exactly the reference's (line, k) order with coalesced stores.
+// parameters live in shared memory for the 256 lines of a CTA and the CTA's
+// threads share out the block's pixel segments evenly (bisection over the block's
+// prefix of line lengths), so global traffic is 12 B/point in (twice) and
+// 8 B/segment out, emitted in exactly the reference's (line, k) order with
+// coalesced stores.
 #include "cuda_common.cuh"
 #include "kernels.h"
 #include "quad_math.h"
@@ -350,10 +351,15 @@ struct SharedLines {
     float a[kRasterThreads], b[kRasterThreads], c[kRasterThreads], d[kRasterThreads];
     double a_over[kRasterThreads], b_over[kRasterThreads], cd_over[kRasterThreads];
     uint32_t order[kRasterThreads];
-    uint32_t excl[kRasterThreads];  // exclusive offset of the line inside its warp
+    uint32_t excl[kRasterThreads + 1];  // exclusive offset of the line inside its CTA (one spare slot: the bisection probes index 256 - 1 at most)
 };
 
-// Pass 2: recompute the CTA's 256 lines, then each warp expands its 32 lines.
+// Pass 2: recompute the CTA's 256 lines, then the CTA expands them together: pixel segment s
+// of the block (0 <= s < block total) goes to thread s % 256, which finds its line by
+// bisection over the block's exclusive prefix of the line lengths. A line of several thousand
+// segments (a long diagonal) is thus spread over the whole CTA instead of keeping one warp busy
+// for its whole length (measured on paris@4K: the kernel's time was one warp's tail — it did
+// not shrink when seven eighths of the lines were culled).
 __global__ void __launch_bounds__(kRasterThreads)
     raster_emit_kernel(RasterArgs A, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ out, uint32_t cap) {
     __shared__ SharedLines S;
@@ -364,7 +370,6 @@ __global__ void __launch_bounds__(kRasterThreads)
     LineParams L = line_setup(A, i);
     uint32_t incl = warp_inclusive_scan(L.length);
     if (lane == 31) warp_sums[warp] = incl;
-    S.excl[t] = incl - L.length;
     if (L.length) {
         S.x0[t] = L.x0; S.y0[t] = L.y0; S.dx[t] = L.dx; S.dy[t] = L.dy;
         S.a[t] = L.a; S.b[t] = L.b; S.c[t] = L.c; S.d[t] = L.d;
@@ -376,22 +381,27 @@ __global__ void __launch_bounds__(kRasterThreads)
         S.cd_over[t] = ((double)L.c - (double)L.d) * sum_recip;
     }
     __syncthreads();
-    uint32_t warp_base = block_offsets[blockIdx.x];
-    for (uint32_t w = 0; w < warp; ++w) warp_base += warp_sums[w];
-    const uint32_t warp_total = warp_sums[warp];
-    const uint32_t* excl = S.excl + warp * 32u;
+    uint32_t before = 0, block_total = 0;  // segments of the warps before this one / of the whole block
+#pragma unroll
+    for (uint32_t w = 0; w < (uint32_t)(kRasterThreads / 32); ++w) {
+        if (w < warp) before += warp_sums[w];
+        block_total += warp_sums[w];
+    }
+    S.excl[t] = before + incl - L.length;  // exclusive prefix over the block's 256 lines
+    __syncthreads();
+    const uint32_t block_base = block_offsets[blockIdx.x];
 
-    for (uint32_t s = lane; s < warp_total; s += 32u) {
-        // Largest j in [0, 32) with excl[j] <= s (zero-length lines share their
+    for (uint32_t s = t; s < block_total; s += kRasterThreads) {
+        // Largest j in [0, 256) with excl[j] <= s (zero-length lines share their
         // successor's offset and are skipped by taking the largest such j).
         uint32_t j = 0;
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
+        for (int step = kRasterThreads / 2; step > 0; step >>= 1) {
             uint32_t cand = j + step;
-            if (excl[cand] <= s) j = cand;
+            if (S.excl[cand] <= s) j = cand;
         }
-        const uint32_t li = warp * 32u + j;
-        const uint32_t k = s - excl[j];
+        const uint32_t li = j;
+        const uint32_t k = s - S.excl[j];
         const float a = S.a[li], b = S.b[li], c = S.c[li], d = S.d[li];
         // rasterizer.rs:63-76
         int32_t ii = (int32_t)k - (c != 0.0f ? 1 : 0) - (d != 0.0f ? 1 : 0);
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(kRasterThreads)
         uint64_t v = (ty << 53) | (tx << 41) | ((uint64_t)(S.order[li] & 0x1FFFFFu) << 20) | ((uint64_t)local_x << 16) |
                      ((uint64_t)local_y << 12) | ((uint64_t)(dam & 0x3Fu) << 6) | ((uint64_t)((uint32_t)cover & 0x3Fu));
         // `cap` guards a speculative launch made before the segment count is known on the host.
-        if (warp_base + s < cap) out[(uint64_t)warp_base + s] = v;
+        if (block_base + s < cap) out[(uint64_t)block_base + s] = v;
     }
 }
 

@@ -568,7 +568,7 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     if (n < 2 || plan.n_passes == 0) return res;
     const int items = items_for(n);
     const uint32_t tiles = tiles_for(n, items);
-    if (!vals && items == 16) {
+    if (!vals && items == 16 && n >= (1u << options().sort_scan_log2)) {
         // Persistent TMA-staged downsweep: 2 CTAs per SM (per-device attribute + grid).
         static int wide_grids[kMaxDevices];
         static bool ds_configured[kMaxDevices] = {false};

@@ -31,3 +31,9 @@ run(None, "whole")
 run(Rect((0, w), (0, h // 2 // 16 * 16)), "top half")
 run(Rect((0, w), (h // 2 // 16 * 16, h)), "bottom half")
 run(Rect((0, w), (h // 16 // 8 * 3 * 16, h // 16 // 8 * 4 * 16)), "one eighth")
+for v in (20, 21, 22, 23):
+    api.set_option("sort_scan_log2", v)
+    print("sort_scan_log2 =", v)
+    run(None, " whole")
+    run(Rect((0, w), (0, h // 2 // 16 * 16)), " top half")
+    run(Rect((0, w), (h // 16 // 8 * 3 * 16, h // 16 // 8 * 4 * 16)), " one eighth")

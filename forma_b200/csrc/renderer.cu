@@ -334,6 +334,8 @@ class Renderer {
     // Band-wise copy-back of host frames (see render()).
     static constexpr uint32_t kMaxCopyBands = 16;
     static uint32_t copy_bands() { return (uint32_t)std::min(std::max(options().copy_bands, 1), (int)kMaxCopyBands); }
+    cudaStream_t aux_stream = nullptr;  // side stream of the geometry upload (see flush_geometry)
+    cudaEvent_t aux_ev[2];
     cudaStream_t band_stream[kMaxCopyBands];
     bool band_streams_ok = false;
     cudaEvent_t band_ev[kMaxCopyBands + 1];
@@ -379,6 +381,11 @@ class Renderer {
         if (timer.ok) {
             for (auto& e : timer.ev) cudaEventDestroy(e);
             for (auto& e : timer.sort_ev) cudaEventDestroy(e);
+        }
+        if (aux_stream) {
+            cudaEventDestroy(aux_ev[0]);
+            cudaEventDestroy(aux_ev[1]);
+            cudaStreamDestroy(aux_stream);
         }
         if (owns_stream && stream) cudaStreamDestroy(stream);
     }
@@ -541,6 +548,29 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
     FORMA_CUDA_TRY(up_kinds.reserve(cd.staged_recs + 1));
     FORMA_CUDA_TRY(up_quads.reserve(cd.staged_quads + 1));
     FORMA_CUDA_TRY(up_jobs.reserve(cd.staged_jobs));
+    // The quadratics go first: their expansion kernel runs on a side stream while the copy
+    // engine keeps sending the other records.
+    bool expanding = false;
+    if (cd.staged_quads) {
+        FORMA_CUDA_TRY(up_quads_raw.reserve(cd.staged_quads + 1));
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, cd.h_quads.ptr, cd.staged_quads * quad_bytes, cudaMemcpyHostToDevice,
+                                       stream));
+        if (!aux_stream) {
+            FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+            FORMA_CUDA_TRY(cudaEventCreateWithFlags(&aux_ev[0], cudaEventDisableTiming));
+            FORMA_CUDA_TRY(cudaEventCreateWithFlags(&aux_ev[1], cudaEventDisableTiming));
+        }
+        FORMA_CUDA_TRY(cudaEventRecord(aux_ev[0], stream));
+        FORMA_CUDA_TRY(cudaStreamWaitEvent(aux_stream, aux_ev[0], 0));
+        if (cd.staged_rational)
+            launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)cd.staged_quads, aux_stream);
+        else
+            launch_quad_expand_poly(reinterpret_cast<const QuadUpPoly*>(up_quads_raw.ptr), up_quads.ptr,
+                                    (uint32_t)cd.staged_quads, aux_stream);
+        FORMA_CUDA_TRY(cudaEventRecord(aux_ev[1], aux_stream));
+        expanding = true;
+        ++launches;
+    }
     if (cd.staged_splines)
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_splines.ptr, cd.h_splines.ptr, cd.staged_splines * sizeof(SplineRec),
                                        cudaMemcpyHostToDevice, stream));
@@ -549,20 +579,10 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
                                        stream));
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, cd.h_kinds.ptr, cd.staged_recs, cudaMemcpyHostToDevice, stream));
     }
-    if (cd.staged_quads) {
-        FORMA_CUDA_TRY(up_quads_raw.reserve(cd.staged_quads + 1));
-        FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, cd.h_quads.ptr, cd.staged_quads * quad_bytes, cudaMemcpyHostToDevice,
-                                       stream));
-        if (cd.staged_rational)
-            launch_quad_expand(up_quads_raw.ptr, up_quads.ptr, (uint32_t)cd.staged_quads, stream);
-        else
-            launch_quad_expand_poly(reinterpret_cast<const QuadUpPoly*>(up_quads_raw.ptr), up_quads.ptr,
-                                    (uint32_t)cd.staged_quads, stream);
-        ++launches;
-    }
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, cd.h_jobs.ptr, cd.staged_jobs * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
     h2d_bytes += cd.staged_splines * sizeof(SplineRec) + cd.staged_recs * (sizeof(PointRec) + 1) +
                  cd.staged_quads * quad_bytes + cd.staged_jobs * sizeof(FlattenJob);
+    if (expanding) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, aux_ev[1], 0));
     launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)cd.staged_jobs,
                         (uint32_t)cd.staged_points, cd.n_resident, cd.d_x.ptr, cd.d_y.ptr, cd.d_gid.ptr, stream);
     ++launches;
@@ -1043,8 +1063,11 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
             ++launches;
             const uint64_t y0 = (uint64_t)Sb.ty_lo * 16u, y1 = std::min<uint64_t>((uint64_t)Sb.ty_hi * 16u, height);
             if (x1 > x0 && y1 > y0) {
-                FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
-                                                 (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, bs));
+                if (x0 == 0 && x1 * 4 == stride)  // whole rows without padding: one contiguous copy
+                    FORMA_CUDA_TRY(cudaMemcpyAsync(buffer + y0 * stride, fb + y0 * stride, (y1 - y0) * stride, cudaMemcpyDeviceToHost, bs));
+                else
+                    FORMA_CUDA_TRY(cudaMemcpy2DAsync(buffer + y0 * stride + x0 * 4, stride, fb + y0 * stride + x0 * 4, stride,
+                                                     (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, bs));
                 d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
             }
             FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], bs));

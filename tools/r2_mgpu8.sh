@@ -7,7 +7,7 @@ nvidia-smi topo -m >> gpurun_out/${R}_gpus.txt 2>&1
 (nproc; cat /sys/fs/cgroup/cpu.max) >> gpurun_out/${R}_gpus.txt 2>&1
 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 300 2>&1 | tail -8 > gpurun_out/${R}_multi_tests.txt
 cat gpurun_out/${R}_multi_tests.txt
-for N in 8 4; do
+for N in ${NS:-8 4}; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
     bench.py --gpus $N > gpurun_out/${R}_bench_n$N.json 2> gpurun_out/${R}_bench_n$N.err
 python - gpurun_out/${R}_bench_n$N.json <<'PY'

@@ -220,11 +220,16 @@ __device__ __forceinline__ LineParams line_setup(const RasterArgs& A, uint32_t i
         float by = fmaf(lay.uy, p1x, fmaf(lay.vy, p1y, lay.ty));
         p0x = ax; p0y = ay; p1x = bx; p1y = by;
     }
-    // skip_line, segment.rs:41-52 (+ the tile-band cull used when the frame is
-    // split over several GPUs; band == [0, height) on a single GPU).
+    // skip_line, segment.rs:41-52, + the cull of lines that cannot produce a pixel segment in the
+    // rows [band_lo, band_hi) this render paints (a crop, or one GPU's band of a multi-GPU frame).
+    // A segment's row is min(y0, y1) of its end points rounded to 1/16 pixel (rasterizer.rs:
+    // 111-156): rows >= band_hi follow from both end points >= band_hi; rows < band_lo need both
+    // end points below band_lo by more than the rounding (1/32) — 1/16 is used. With these two
+    // rules a culled line has no segment in a painted row, so a band render equals the whole
+    // frame's rows exactly (cells, optimiser decisions and pixels alike).
     bool skip = p0y == p1y || (p0y >= A.height && p1y >= A.height) || (p0x >= A.width && p1x >= A.width) ||
                 (p0y <= 0.0f && p1y <= 0.0f) || (p0y >= A.band_hi && p1y >= A.band_hi) ||
-                (p0y <= A.band_lo && p1y <= A.band_lo);
+                (p0y <= A.band_lo - 0.0625f && p1y <= A.band_lo - 0.0625f);
     if (skip) return L;
     float dx = p1x - p0x, dy = p1y - p0y;
     float dx_recip = d_rcp(dx), dy_recip = d_rcp(dy);

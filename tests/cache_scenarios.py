@@ -152,6 +152,44 @@ def animated_scene(api, frames=6, w=200, h=120):
     return f.shots
 
 
+def crop_with_layers_left_of_the_crop(api):
+    """Not a reference test, but the reference's rule (cpu/painter/mod.rs:501-522): with a crop,
+    every layer that has segments LEFT of the first cropped tile is queued for that tile even when
+    its cover sums to zero there, and is counted in the tile's cached layer count. Removing such a
+    layer therefore damages the first cropped tile of its tile row (and nothing else). The frames
+    carry a prefill, so which tiles a frame wrote is part of what is compared with the oracle."""
+    from forma_b200.binding import Point, Rect
+    f = Frames(api)
+    comp = api.Composition()
+    cache = f.r.create_buffer_layer_cache()
+    w, h = 4 * T, 2 * T
+    box = lambda x0, y0, x1, y1: (api.PathBuilder().move_to(Point(x0, y0)).line_to(Point(x0, y1)).line_to(Point(x1, y1))
+                                  .line_to(Point(x1, y0)).build())
+    comp.insert(0, comp.create_layer().insert(box(0.0, 0.0, float(w), float(h))).set_props(solid(GREEN)))   # covers everything
+    comp.insert(1, comp.create_layer().insert(box(3.0, 3.0, 9.0, 12.0)).set_props(solid(RED)))             # closed, inside tile (0, 0)
+    comp.insert(2, comp.create_layer().insert(box(20.0, T + 2.0, 2.5 * T, T + 9.0)).set_props(solid(RED)))  # row 1: reaches into the crop
+    crop = Rect((2 * T, 4 * T), (0, 2 * T))
+    buf = np.array([0x11, 0x22, 0x33, 0x44] * (w * h), np.uint8)
+
+    def frame():
+        f.r.render(comp, buf, w, h, RGBA, BLACK, crop, cache)
+        f.shots.append(buf.copy())
+        buf[:] = np.array([0x11, 0x22, 0x33, 0x44] * (w * h), np.uint8)
+        return f.shots[-1].reshape(h, w, 4)
+    img = frame()
+    assert px(img, 0) == [0x11, 0x22, 0x33, 0x44]            # left of the crop: untouched
+    assert px(img, 2 * T) == GREEN_SRGB and px(img, 2 * T + 2, T + 4) == RED_SRGB
+    img = frame()
+    assert (img == np.array([0x11, 0x22, 0x33, 0x44], np.uint8)).all()   # nothing changed: nothing written
+    comp.remove(1)                                             # the zero-cover layer left of the crop goes away
+    frame()
+    comp.remove(2)                                             # and the one that really reaches into the crop
+    img = frame()
+    assert px(img, 2 * T + 2, T + 4) == GREEN_SRGB
+    frame()
+    return f.shots
+
+
 SCENARIOS = [background_color_clear_when_changed, render_changed_layers_only,
              insert_remove_same_order_will_not_render_again, clear_emptied_tiles, separate_layer_caches,
-             draw_if_width_or_height_change]
+             draw_if_width_or_height_change, crop_with_layers_left_of_the_crop]

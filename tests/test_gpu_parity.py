@@ -121,7 +121,9 @@ def test_rasterize_axis_aligned_and_degenerate(cuda_api, oracle_api, cuda_render
 
 
 # --- stage 3: sort ---------------------------------------------------------------------
-@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 100_000, 3_000_001])
+# 4 194 303 / 4 194 305: either side of the single-sweep / reduce-then-scan switch (sort_scan_log2 = 22);
+# 40 M: the bench's sort size (100 k cubics), all 44 key bits incl. the full 21-bit layer field in play.
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 100_000, 3_000_001, 4_194_303, 4_194_305, 40_000_000])
 def test_sort_u64_stable_on_top_44_bits(cuda_renderer, n):
     rng = np.random.default_rng(n)
     keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)

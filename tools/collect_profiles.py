@@ -27,7 +27,7 @@ def run(args):
 
 
 for f in sorted(glob.glob(os.path.join(SRC, f"{TAG}_bench_*.json")) + glob.glob(os.path.join(SRC, f"{TAG}_gpu_tests.txt")) +
-                glob.glob(os.path.join(SRC, "mgpu_*.json"))):
+                (glob.glob(os.path.join(SRC, "mgpu_*.json")) if TAG == "r1" else [])):  # r1's multi-GPU files had no tag
     if os.path.getsize(f):
         name = os.path.basename(f)
         shutil.copy(f, os.path.join(DST, name if name.startswith(TAG) else f"{TAG}_{name}"))

@@ -697,7 +697,8 @@ class Renderer:
     def counters(self) -> dict:
         out = (C.c_uint64 * 8)()
         self._api.renderer_counters(self._h, out)
-        return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries", "written_tiles"),
+        return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries", "written_tiles",
+                         "tables_mode"),  # tables_mode: 0 counts read back, 1 sync-free, 2 sync-free attempt redone
                         [int(v) for v in out]))
 
     def row_costs(self) -> np.ndarray:

@@ -23,6 +23,8 @@ struct Options {
     int paint_lpt = 1;       // heavy tiles first (longest-processing-time order) in the paint kernel
     int paint_wide = 0;      // 1: the paint kernel built for 6 CTAs / SM (up to 168 registers) instead of 8 (128)
     int band_filter = 1;     // a render cropped to a band of rows only makes the band's geometry resident
+    int sync_free = 1;       // painter tables without count read-backs when the previous frame's counts bound this one's (redone the slow way if they do not)
+    int test_fast_shrink = 0;  // test hook: halve the bounds of the sync-free tables (forces the redo)
 };
 Options& options();
 
@@ -61,7 +63,9 @@ void launch_line_records(const RasterArgs& args, uint32_t n, uint32_t* orders, f
 // In-place exclusive scan of n u32 values; total[0] = sum. `state` (scan_state_words(n)
 // u64 words) enables the multi-CTA look-back scan for large n; nullptr = one CTA.
 size_t scan_state_words(uint32_t n);
-void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long long* state, cudaStream_t stream);
+// `n_dev` (optional): the element count in device memory, `n` then being its upper bound.
+void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long long* state, cudaStream_t stream,
+                     const uint32_t* n_dev = nullptr);
 
 // ---- kernels_sort.cu --------------------------------------------------------
 // LSD radix sort of u64 keys on bits [kSortShift, 64) (+ optional u32 payload).
@@ -100,7 +104,9 @@ struct SortResult {
 size_t radix_scratch_bytes(uint32_t n);
 SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
                              const SortPlan& plan, void* scratch, cudaStream_t stream,
-                             cudaEvent_t* pass_events = nullptr /* 3 per pass: before upsweep, before / after downsweep */);
+                             cudaEvent_t* pass_events = nullptr /* 3 per pass: before upsweep, before / after downsweep */,
+                             const uint32_t* n_dev = nullptr /* the key count in device memory; `n` is then its upper bound
+                                                                (single-sweep passes only) */);
 
 // ---- kernels_paint.cu -------------------------------------------------------
 struct PaintScene {
@@ -139,13 +145,24 @@ void launch_cells(const PaintScene& S, const uint64_t* segs, uint32_t n, unsigne
 // Plans of the painter's two pair sorts (their key bounds are host-known).
 SortPlan carry_sort_plan(const PaintScene& S);
 SortPlan gap_sort_plan(const PaintScene& S);
+// Cell / carry-only-entry counts that stay on the device (frames whose tables are built without a
+// host read-back, Options::sync_free): with `cells` set, the n_cells / n_gaps arguments of the
+// launchers below are upper bounds (grid sizes) and the kernels read the counts here; a count
+// above its bound makes them no-ops (the host then rebuilds the tables with known counts).
+struct DevCounts {
+    const uint32_t* cells = nullptr;
+    const uint32_t* gaps = nullptr;
+    uint32_t cell_bound = 0, gap_bound = 0;
+};
 void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
-                       uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st);
+                       uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st,
+                       const DevCounts& dc = DevCounts());
 // Carry-only entries in (layer, tile_y, tile_x) order; payload = n_cells + gap id.
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_offset /* scanned gap counts */, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
-                     uint32_t grid_gaps /* threads to launch: >= the entry count */, cudaStream_t st);
+                     uint32_t grid_gaps /* threads to launch: >= the entry count */, cudaStream_t st,
+                     const DevCounts& dc = DevCounts());
 // One painter entry = one (tile, layer) pair with segments and / or a carried cover.
 struct EntryRec {  // 64 B
     uint32_t layer, seg0, seg1;  // layer order; [seg0, seg1) in the sorted segments (empty for carry-only entries)
@@ -161,13 +178,14 @@ struct EntryRec {  // 64 B
 // initial flags of the n_cells + n_gaps entries, ordered by (tile_y, tile_x, layer).
 void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,
                           const uint32_t* gid, uint32_t n_gaps, const uint32_t* cell_start, const uint4* carry_in,
-                          const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st);
+                          const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st,
+                          const DevCounts& dc = DevCounts());
 // Per-tile entry ranges (zero for tiles without entries) and, when `heavy` is not null, the
 // lists of tiles with many entries: kHeavyListClasses arrays of tiles_x * tiles_y ids each,
 // their lengths in heavy_count[kHeavyListClasses] (both written here).
 constexpr int kHeavyListClasses = 4;
 void launch_tile_index(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint2* tile_range, uint32_t* heavy,
-                       uint32_t* heavy_count, cudaStream_t st);
+                       uint32_t* heavy_count, cudaStream_t st, const DevCounts& dc = DevCounts());
 void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* recs, const uint2* tile_range, const uint32_t* heavy,
                   const uint32_t* heavy_count, uint8_t* eflags, uint8_t* framebuffer, uint32_t* tile_counter, cudaStream_t st);
 // GradRec of every style slot (see device_types.h).

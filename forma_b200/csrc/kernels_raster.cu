@@ -299,7 +299,9 @@ __global__ void __launch_bounds__(kRasterThreads) line_count_kernel(RasterArgs A
 // of the producing kernel, a few thousand); writes the grand total to
 // total[0]. 1024 threads, each owning a contiguous chunk.
 __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restrict__ data, uint32_t n,
-                                                              uint32_t* __restrict__ total) {
+                                                              uint32_t* __restrict__ total,
+                                                              const uint32_t* __restrict__ n_dev = nullptr) {
+    if (n_dev) n = min(n, *n_dev);
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry, round_total;
     if (threadIdx.x == 0) carry = 0;
@@ -499,7 +501,9 @@ constexpr unsigned long long kScanAggregate = 1ull << 62, kScanInclusive = 2ull 
 
 __global__ void __launch_bounds__(kScanThreads) chained_scan_kernel(uint32_t* __restrict__ data, uint32_t n,
                                                                   unsigned long long* __restrict__ state, uint32_t tiles,
-                                                                  uint32_t* __restrict__ total) {
+                                                                  uint32_t* __restrict__ total,
+                                                                  const uint32_t* __restrict__ n_dev) {
+    if (n_dev) n = min(n, *n_dev);  // elements past the device-side count read as 0; every tile still takes part
     __shared__ uint32_t warp_tot[kScanThreads / 32];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_prefix;
@@ -570,14 +574,15 @@ __global__ void __launch_bounds__(kScanThreads) chained_scan_kernel(uint32_t* __
 
 size_t scan_state_words(uint32_t n) { return (size_t)(n + kScanTile - 1) / kScanTile + 2; }
 
-void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long long* state, cudaStream_t stream) {
+void launch_scan_u32(uint32_t* data, uint32_t n, uint32_t* total, unsigned long long* state, cudaStream_t stream,
+                     const uint32_t* n_dev) {
     if (n <= 16384u || !state) {
-        scan_block_sums_kernel<<<1, 1024, 0, stream>>>(data, n, total);
+        scan_block_sums_kernel<<<1, 1024, 0, stream>>>(data, n, total, n_dev);
         return;
     }
     uint32_t tiles = (n + kScanTile - 1) / kScanTile;
     cudaMemsetAsync(state, 0, (tiles + 1) * sizeof(unsigned long long), stream);
-    chained_scan_kernel<<<tiles, kScanThreads, 0, stream>>>(data, n, state, tiles, total);
+    chained_scan_kernel<<<tiles, kScanThreads, 0, stream>>>(data, n, state, tiles, total, n_dev);
 }
 
 }  // namespace forma

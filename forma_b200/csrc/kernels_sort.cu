@@ -100,8 +100,12 @@ SortPlan make_sort_plan(const KeyLayout& layout, const uint64_t bound[3]) {
 }
 
 // Counts every digit of every planned pass in one read of the keys.
+// `n_dev` (optional): the key count in device memory; `n` is then only its upper bound (the
+// count may not be known on the host when the sort is launched, see Renderer::render).
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, SortPlan plan,
-                                                                uint32_t* __restrict__ hist /*[passes][256]*/) {
+                                                                uint32_t* __restrict__ hist /*[passes][256]*/,
+                                                                const uint32_t* __restrict__ n_dev) {
+    if (n_dev) n = min(n, *n_dev);
     __shared__ uint32_t s_hist[kMaxSortPasses][kRadix];
     for (int i = threadIdx.x; i < kMaxSortPasses * kRadix; i += kSortThreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -125,7 +129,9 @@ __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
     onesweep_pass_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, uint32_t n, DigitSpec spec,
                          const uint32_t* __restrict__ digit_counts /*[256]: keys per digit (radix_hist_kernel)*/,
-                         uint32_t* __restrict__ lb /*[tiles][256], zeroed*/, uint32_t* __restrict__ tile_counter) {
+                         uint32_t* __restrict__ lb /*[tiles][256], zeroed*/, uint32_t* __restrict__ tile_counter,
+                         const uint32_t* __restrict__ n_dev) {
+    if (n_dev) n = min(n, *n_dev);
     constexpr int kTileKeys = kSortThreads * kItems;
     __shared__ uint64_t s_keys[kTileKeys];
     __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(kSortThreads, kItems == 16 ? 3 : 6)
     for (uint32_t w = 0; w < warp; ++w) digit_offset += s_hist_tot[w];
     const uint32_t tile = s_tile;
     const uint32_t base = tile * (uint32_t)kTileKeys;
+    if (base >= n) return;  // a tile beyond the (device-side) key count: tiles are taken in order, nobody waits for it
     const uint32_t valid = min((uint32_t)kTileKeys, n - base);
 
     // Warp-striped load: warp w owns keys [w*32*kItems, (w+1)*32*kItems) of the tile.
@@ -545,7 +552,7 @@ size_t radix_scratch_bytes(uint32_t n) {
 template <bool kPairs, int kItems>
 static void launch_passes(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
                           const SortPlan& plan, const uint32_t* hist, uint32_t* lookback, uint32_t* counters, uint32_t tiles,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const uint32_t* n_dev) {
     static bool configured[kMaxDevices] = {false};
     const int dev = current_device_index();
     if (!configured[dev]) {  // let several CTAs of 18-43 KB share one SM's shared memory
@@ -558,17 +565,18 @@ static void launch_passes(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, ui
         const uint32_t* vin = (p & 1u) ? vals_tmp : vals;
         uint32_t* vout = (p & 1u) ? vals : vals_tmp;
         onesweep_pass_kernel<kPairs, kItems><<<tiles, kSortThreads, 0, stream>>>(
-            kin, kout, vin, vout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, counters + p);
+            kin, kout, vin, vout, n, plan.pass[p], hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, counters + p, n_dev);
     }
 }
 
 SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, uint32_t n,
-                             const SortPlan& plan, void* scratch, cudaStream_t stream, cudaEvent_t* pass_events) {
+                             const SortPlan& plan, void* scratch, cudaStream_t stream, cudaEvent_t* pass_events,
+                             const uint32_t* n_dev) {
     SortResult res{0, false};
     if (n < 2 || plan.n_passes == 0) return res;
     const int items = items_for(n);
     const uint32_t tiles = tiles_for(n, items);
-    if (!vals && items == 16 && n >= (1u << options().sort_scan_log2)) {
+    if (!vals && items == 16 && n >= (1u << options().sort_scan_log2) && !n_dev) {
         // Persistent TMA-staged downsweep: 2 CTAs per SM (per-device attribute + grid).
         static int wide_grids[kMaxDevices];
         static bool ds_configured[kMaxDevices] = {false};
@@ -614,14 +622,14 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
     size_t total_words = (size_t)kMaxSortPasses * kRadix + 8 + (size_t)plan.n_passes * tiles * kRadix;
     cudaMemsetAsync(scratch, 0, total_words * sizeof(uint32_t), stream);
     uint32_t hist_blocks = min(tiles_for(n, 16) * 4u, 148u * 8u);
-    radix_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, plan, hist);
+    radix_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(keys, n, plan, hist, n_dev);
     res.launches = 1;
     if (vals) {
-        if (items == 16) launch_passes<true, 16>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
-        else launch_passes<true, 4>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream);
+        if (items == 16) launch_passes<true, 16>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream, n_dev);
+        else launch_passes<true, 4>(keys, keys_tmp, vals, vals_tmp, n, plan, hist, lookback, counters, tiles, stream, n_dev);
     } else {
-        if (items == 16) launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);
-        else launch_passes<false, 4>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream);
+        if (items == 16) launch_passes<false, 16>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream, n_dev);
+        else launch_passes<false, 4>(keys, keys_tmp, nullptr, nullptr, n, plan, hist, lookback, counters, tiles, stream, n_dev);
     }
     res.launches += (int)plan.n_passes;
     res.in_tmp = (plan.n_passes & 1u) != 0u;

@@ -253,12 +253,30 @@ __global__ void __launch_bounds__(kCellThreads)
 // ---------------------------------------------------------------------------
 // Carries
 // ---------------------------------------------------------------------------
+// Counts kept on the device (DevCounts, kernels.h): a frame whose tables are built without a
+// host read-back launches the kernels below over upper bounds and lets them pick up the real
+// counts here. A count above its bound (the buffers are too small) turns every later kernel of
+// the frame into a no-op; the host sees it at the end of the frame and builds the tables again.
+__device__ __forceinline__ void resolve_cells(const DevCounts& dc, uint32_t& n_cells) {
+    if (!dc.cells) return;
+    const uint32_t c = *dc.cells;
+    n_cells = c > dc.cell_bound ? 0u : c;
+}
+__device__ __forceinline__ void resolve_counts(const DevCounts& dc, uint32_t& n_cells, uint32_t& n_gaps) {
+    if (!dc.cells) return;
+    const uint32_t c = *dc.cells, g = *dc.gaps;
+    const bool ok = c <= dc.cell_bound && g <= dc.gap_bound;
+    n_cells = ok ? c : 0u;
+    n_gaps = ok ? g : 0u;
+}
+
 // One thread per (tile_y, layer) group head walks its group (cells sorted by
 // tile_x), producing each cell's carry-in, the running carry after it and the
 // number of carry-only entries to create before the next cell.
 __global__ void carry_scan_kernel(PaintScene S, const uint64_t* __restrict__ key2, const uint32_t* __restrict__ perm,
                                   const uint4* __restrict__ cell_cover, uint32_t n_cells, uint4* __restrict__ carry_in,
-                                  uint4* __restrict__ carry_after, uint32_t* __restrict__ gap_count) {
+                                  uint4* __restrict__ carry_after, uint32_t* __restrict__ gap_count, DevCounts dc) {
+    resolve_cells(dc, n_cells);
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_cells) return;
     uint64_t k = key2[j];
@@ -306,13 +324,16 @@ __global__ void gap_fill_kernel(PaintScene S, const uint64_t* __restrict__ key2,
                                 const uint64_t* __restrict__ cell_key, const uint4* __restrict__ carry_after,
                                 const uint32_t* __restrict__ gap_offset /* exclusive scan of the gap counts */,
                                 uint32_t n_cells, uint64_t* __restrict__ gkey, uint32_t* __restrict__ gid,
-                                uint4* __restrict__ gap_carry, const uint32_t* __restrict__ n_gaps_ptr, uint32_t cap) {
+                                uint4* __restrict__ gap_carry, const uint32_t* __restrict__ n_gaps_ptr, uint32_t cap,
+                                DevCounts dc) {
     // One thread per carry-only entry q: its source cell is the last one (in carry
     // order) whose exclusive offset is <= q — cells without entries share their
     // offset with the next cell and sort before it.
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_gaps = *n_gaps_ptr;
     if (n_gaps > cap || q >= n_gaps) return;  // cap: launched before the host knows the count
+    resolve_cells(dc, n_cells);
+    if (n_cells == 0u) return;
     uint32_t lo = 0, hi = n_cells;  // first j with gap_offset[j] > q
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
@@ -349,13 +370,15 @@ __global__ void merge_entries_kernel(PaintScene S, const uint64_t* __restrict__ 
                                      const uint64_t* __restrict__ gkey, const uint32_t* __restrict__ gid, uint32_t n_gaps,
                                      const uint32_t* __restrict__ cell_start, const uint4* __restrict__ carry_in,
                                      const uint4* __restrict__ gap_carry, uint64_t* __restrict__ ekey,
-                                     EntryRec* __restrict__ recs, uint8_t* __restrict__ eflags) {
+                                     EntryRec* __restrict__ recs, uint8_t* __restrict__ eflags, DevCounts dc) {
+    resolve_counts(dc, n_cells, n_gaps);
     // Merge-path style partition: the keys of a CTA's 256 consecutive elements of
     // one list bracket a short range of the other list, found once per CTA (two
     // full bisections by threads 0 and 1); every thread then bisects that range only.
     __shared__ uint32_t s_bound[2];
     const uint32_t i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x;
     const uint32_t n_all = n_cells + n_gaps;
+    if (i0 >= n_all) return;  // (whole CTA; only with device-side counts)
     const bool cell_block = i0 + blockDim.x <= n_cells, gap_block = i0 >= n_cells;  // else: the one mixed CTA
     if (threadIdx.x < 2u) {
         const uint32_t last = min(i0 + blockDim.x, n_all) - 1u;
@@ -420,7 +443,12 @@ __global__ void merge_entries_kernel(PaintScene S, const uint64_t* __restrict__ 
 // a tile with many entries in its class list (see paint_common.cuh: kHeavyMin).
 __global__ void tile_index_kernel(PaintScene S, const uint64_t* __restrict__ ekey, uint32_t n_entries,
                                   uint2* __restrict__ tile_range, uint32_t* __restrict__ heavy /* [classes][tiles] or null */,
-                                  uint32_t* __restrict__ heavy_count) {
+                                  uint32_t* __restrict__ heavy_count, DevCounts dc) {
+    if (dc.cells) {
+        uint32_t c = 0, g = 0;
+        resolve_counts(dc, c, g);
+        n_entries = c + g;
+    }
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_entries) return;
     const uint64_t k = ekey[p];
@@ -513,34 +541,37 @@ SortPlan gap_sort_plan(const PaintScene& S) {  // layer, tile_x, tile_y
 }
 
 void launch_carry_scan(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint4* cell_cover,
-                       uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st) {
+                       uint32_t n_cells, uint4* carry_in, uint4* carry_after, uint32_t* gap_count, cudaStream_t st,
+                       const DevCounts& dc) {
     carry_scan_kernel<<<(n_cells + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_cover, n_cells, carry_in, carry_after,
-                                                              gap_count);
+                                                              gap_count, dc);
 }
 
 void launch_gap_fill(const PaintScene& S, const uint64_t* key2, const uint32_t* perm, const uint64_t* cell_key,
                      const uint4* carry_after, const uint32_t* gap_offset, uint32_t n_cells,
                      uint64_t* gkey, uint32_t* gid, uint4* gap_carry, const uint32_t* n_gaps_ptr, uint32_t cap,
-                     uint32_t grid_gaps, cudaStream_t st) {
+                     uint32_t grid_gaps, cudaStream_t st, const DevCounts& dc) {
     if (!grid_gaps || !n_cells) return;
     gap_fill_kernel<<<(grid_gaps + 127) / 128, 128, 0, st>>>(S, key2, perm, cell_key, carry_after, gap_offset, n_cells,
-                                                              gkey, gid, gap_carry, n_gaps_ptr, cap);
+                                                              gkey, gid, gap_carry, n_gaps_ptr, cap, dc);
 }
 
 void launch_merge_entries(const PaintScene& S, const uint64_t* cell_key, uint32_t n_cells, const uint64_t* gkey,
                           const uint32_t* gid, uint32_t n_gaps, const uint32_t* cell_start, const uint4* carry_in,
-                          const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st) {
+                          const uint4* gap_carry, uint64_t* ekey, EntryRec* recs, uint8_t* eflags, cudaStream_t st,
+                          const DevCounts& dc) {
     uint32_t n = n_cells + n_gaps;
     if (n)
         merge_entries_kernel<<<(n + 255) / 256, 256, 0, st>>>(S, cell_key, n_cells, gkey, gid, n_gaps, cell_start, carry_in,
-                                                               gap_carry, ekey, recs, eflags);
+                                                               gap_carry, ekey, recs, eflags, dc);
 }
 
 void launch_tile_index(const PaintScene& S, const uint64_t* ekey, uint32_t n_entries, uint2* tile_range, uint32_t* heavy,
-                       uint32_t* heavy_count, cudaStream_t st) {
+                       uint32_t* heavy_count, cudaStream_t st, const DevCounts& dc) {
     cudaMemsetAsync(tile_range, 0, (size_t)S.tiles_x * S.tiles_y * sizeof(uint2), st);
     cudaMemsetAsync(heavy_count, 0, kHeavyClasses * sizeof(uint32_t), st);
-    if (n_entries) tile_index_kernel<<<(n_entries + 255) / 256, 256, 0, st>>>(S, ekey, n_entries, tile_range, heavy, heavy_count);
+    if (n_entries)
+        tile_index_kernel<<<(n_entries + 255) / 256, 256, 0, st>>>(S, ekey, n_entries, tile_range, heavy, heavy_count, dc);
 }
 
 

@@ -50,6 +50,7 @@ static const OptionName kOptionNames[] = {
     {"sort_big_log2", &Options::sort_big_log2, 10, 30}, {"test_gap_cap", &Options::test_gap_cap, 0, 1 << 30},
     {"paint_lpt", &Options::paint_lpt, 0, 1},         {"band_filter", &Options::band_filter, 0, 1},
     {"paint_wide", &Options::paint_wide, 0, 1},       {"sort_scan_log2", &Options::sort_scan_log2, 10, 31},
+    {"sync_free", &Options::sync_free, 0, 1},         {"test_fast_shrink", &Options::test_fast_shrink, 0, 1},
 };
 Options& options() {
     static Options o = [] {
@@ -362,6 +363,7 @@ class Renderer {
     DeviceBuffer<FlattenJob> up_jobs;
 
     uint32_t last_segments = 0, last_cells = 0, last_entries = 0, last_gaps = 0;
+    bool last_tables_sync_free = false, last_tables_redone = false;  // how the last frame's painter tables were built
     uint32_t last_tiles_x = 0, last_tiles_y = 0;  // tile grid of the last render (forma_renderer_row_costs)
     RasterArgs last_raster{};        // line-setup arguments of the last render (device pointers owned by its composition)
     bool last_raster_valid = false;
@@ -897,6 +899,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
 
     // Stage 3: sort.
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[2], stream));
+    const uint32_t prev_cells = last_cells, prev_gaps = last_gaps;  // of this renderer's previous frame
     last_cells = last_entries = 0;
     int timed_sort_passes = 0;
     if (n > 1) {
@@ -924,8 +927,84 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         FORMA_CUDA_TRY(framebuffer.reserve((size_t)stride * height));
         fb = framebuffer.ptr;
     }
+    uint32_t paint_launches = 1;
+    // Tables + paint + copy-back, once or (rarely) twice. fast = without count read-backs: the
+    // tables of a frame are normally about as large as those of the frame before, so every
+    // kernel is launched over bounds derived from the previous counts (+ 25 % + 4096) and reads
+    // the real counts from device memory (DevCounts); the host looks at them only after the
+    // frame's final synchronisation. A count above its bound (the kernels then did nothing,
+    // the frame holds the clear colour) sends the frame through the known-count path below.
+    uint32_t fast_cell_bound = 0, fast_gap_bound = 0;
+    auto tables_and_paint = [&](const bool fast) -> int {
     uint32_t n_cells = 0, n_gaps = 0, n_entries = 0;
-    if (n > 0) {
+    DevCounts dc;
+    if (n > 0 && fast) {
+        const uint64_t shrink = options().test_fast_shrink ? 2u : 1u;
+        const uint32_t cell_bound = fast_cell_bound =
+            (uint32_t)std::min<uint64_t>(((uint64_t)prev_cells + prev_cells / 4u + 4096u) / shrink, n);
+        const uint32_t gap_bound = fast_gap_bound =
+            (uint32_t)std::min<uint64_t>(((uint64_t)prev_gaps + prev_gaps / 4u + 4096u) / shrink, 0x7FFFFFFFu);
+        FORMA_CUDA_TRY(scan_state.reserve(std::max({cells_state_words(n), scan_state_words(n), scan_state_words(cell_bound)})));
+        FORMA_CUDA_TRY(cell_start.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(cell_key.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(cell_cover.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(carry_in.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(carry_after.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(key2.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(key2_tmp.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(perm.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(perm_tmp.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(gap_count.reserve((size_t)cell_bound + 1));
+        FORMA_CUDA_TRY(ekey_tmp.reserve((size_t)gap_bound + 1));
+        FORMA_CUDA_TRY(eid_tmp.reserve((size_t)gap_bound + 1));
+        FORMA_CUDA_TRY(gkey_tmp.reserve((size_t)gap_bound + 1));
+        FORMA_CUDA_TRY(gid_tmp.reserve((size_t)gap_bound + 1));
+        FORMA_CUDA_TRY(gap_carry.reserve((size_t)gap_bound + 1));
+        const size_t entry_bound = (size_t)cell_bound + gap_bound;
+        FORMA_CUDA_TRY(ekey.reserve(entry_bound));
+        FORMA_CUDA_TRY(eid.reserve(entry_bound));
+        FORMA_CUDA_TRY(eflags.reserve(entry_bound));
+        FORMA_CUDA_TRY(recs.reserve(entry_bound));
+        FORMA_CUDA_TRY(sort_scratch.reserve(std::max(radix_scratch_bytes(cell_bound), radix_scratch_bytes(gap_bound))));
+        dc.cells = totals.ptr + 1;
+        dc.gaps = totals.ptr + 2;
+        dc.cell_bound = cell_bound;
+        dc.gap_bound = gap_bound;
+        // Cells beyond cell_bound + 1 are dropped by the pass; the count it leaves in totals[1] is the real one.
+        launch_cells(S, segs.ptr, n, scan_state.ptr, cell_start.ptr, cell_bound + 1u, totals.ptr + 1, cell_key.ptr,
+                     cell_cover.ptr, key2.ptr, perm.ptr, stream);
+        launches += 2;
+        {
+            SortResult sr = launch_radix_sort(key2.ptr, key2_tmp.ptr, perm.ptr, perm_tmp.ptr, cell_bound, carry_sort_plan(S),
+                                              sort_scratch.ptr, stream, nullptr, dc.cells);
+            launches += sr.launches;
+            if (sr.in_tmp) {
+                swap_buffers(key2, key2_tmp);
+                swap_buffers(perm, perm_tmp);
+            }
+        }
+        launch_carry_scan(S, key2.ptr, perm.ptr, cell_cover.ptr, cell_bound, carry_in.ptr, carry_after.ptr, gap_count.ptr,
+                          stream, dc);
+        launch_scan_u32(gap_count.ptr, cell_bound, totals.ptr + 2, scan_state.ptr, stream, dc.cells);
+        launch_gap_fill(S, key2.ptr, perm.ptr, cell_key.ptr, carry_after.ptr, gap_count.ptr, cell_bound, ekey_tmp.ptr,
+                        eid_tmp.ptr, gap_carry.ptr, totals.ptr + 2, gap_bound, gap_bound, stream, dc);
+        launches += 3;
+        {
+            SortResult sr = launch_radix_sort(ekey_tmp.ptr, gkey_tmp.ptr, eid_tmp.ptr, gid_tmp.ptr, gap_bound, gap_sort_plan(S),
+                                              sort_scratch.ptr, stream, nullptr, dc.gaps);
+            launches += sr.launches;
+            if (sr.in_tmp) {
+                swap_buffers(ekey_tmp, gkey_tmp);
+                swap_buffers(eid_tmp, gid_tmp);
+            }
+        }
+        launch_merge_entries(S, cell_key.ptr, cell_bound, ekey_tmp.ptr, eid_tmp.ptr, gap_bound, cell_start.ptr, carry_in.ptr,
+                             gap_carry.ptr, ekey.ptr, recs.ptr, eflags.ptr, stream, dc);
+        ++launches;
+        n_entries = cell_bound + gap_bound;  // grid of the tile index pass
+        // The counts travel to the host behind everything else of the frame.
+        FORMA_CUDA_TRY(cudaMemcpyAsync(pinned_totals + 1, totals.ptr + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    } else if (n > 0) {
         // Cells: one pass finds the cell heads, counts them and sums their covers. The count is
         // read back, but nothing waits for it: the pass runs into the buffers of the previous
         // frames (writes beyond their capacity are dropped) and is repeated below only if
@@ -1033,7 +1112,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                              gap_carry.ptr, ekey.ptr, recs.ptr, eflags.ptr, stream);
         ++launches;
     }
-    launch_tile_index(S, ekey.ptr, n_entries, tile_range.ptr, heavy_lists, heavy_counts, stream);
+    launch_tile_index(S, ekey.ptr, n_entries, tile_range.ptr, heavy_lists, heavy_counts, stream, dc);
     launches += n_entries ? 1 : 0;
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
     // Host frame without a layer cache: paint in bands of tile rows, every band on its own
@@ -1042,7 +1121,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     // band k run dry: the kernels overlap at their tails, and the PCIe transfer of a band
     // overlaps the painting of the following ones.
     bool copied_in_bands = false;
-    uint32_t paint_launches = 1;
+    paint_launches = 1;
     const uint32_t paint_rows = S.ty_hi - S.ty_lo;
     if (!buffer_on_device && !cache && paint_rows >= 32u && S.tx_hi > S.tx_lo && band_copies_enabled()) {
         if (!band_streams_ok) {
@@ -1129,6 +1208,24 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[6], stream));
     FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (fast && n > 0) {
+        last_cells = pinned_totals[1];
+        last_gaps = pinned_totals[2];
+        last_entries = last_cells + last_gaps;
+    }
+    return FORMA_STATUS_OK;
+    };  // tables_and_paint
+    // (pack_written: the host scatter of the written tiles must not see a frame that is redone.)
+    bool fast = options().sync_free && n > 0 && prev_cells > 0 && !pack_written;
+    st = tables_and_paint(fast);
+    if (st) return st;
+    last_tables_redone = false;
+    if (fast && n > 0 && (last_cells > fast_cell_bound || last_gaps > fast_gap_bound)) {
+        last_tables_redone = true;
+        st = tables_and_paint(false);
+        if (st) return st;
+    }
+    last_tables_sync_free = fast && !last_tables_redone;
     {
         auto el = [&](int a, int b) {
             float ms = 0;
@@ -1915,7 +2012,7 @@ void forma_renderer_kernel_times(const forma_renderer* r, double out_ms[4], uint
 }
 void forma_renderer_counters(const forma_renderer* r, uint64_t out[8]) {
     out[6] = r->r.last_written_tiles;
-    out[7] = 0;
+    out[7] = r->r.last_tables_redone ? 2u : r->r.last_tables_sync_free ? 1u : 0u;
     out[0] = r->r.launches;
     out[1] = r->r.h2d_bytes;
     out[2] = r->r.d2h_bytes;

@@ -261,7 +261,10 @@ void forma_renderer_stage_times(const forma_renderer*, double out_ms[8]);
 void forma_renderer_kernel_times(const forma_renderer*, double out_ms[4], uint32_t out_launches[4]);
 /* [0] kernel launches, [1] host->device bytes, [2] device->host bytes (all
  * since creation), [3] pixel segments, [4] cells, [5] entries of the last render,
- * [6] tiles the last layer-cache render copied back to a host buffer, [7] 0. */
+ * [6] tiles the last layer-cache render copied back to a host buffer, [7] how the last
+ * render built its painter tables: 0 = with the cell / entry counts read back on the way,
+ * 1 = without a read-back (kernels sized by the previous frame's counts, option sync_free),
+ * 2 = attempted without, counts exceeded the bounds, tables and paint repeated as 0. */
 void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
 
 /* Cost of every tile row of the last render (32 x its (tile, layer) entries + its pixel

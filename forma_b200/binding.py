@@ -276,6 +276,7 @@ SIGNATURES = {
     "renderer_launch_count": (C.c_uint64, [_vp]),
     "renderer_stage_times": (None, [_vp, C.POINTER(C.c_double)]),
     "renderer_counters": (None, [_vp, _u64p]),
+    "renderer_host_slices": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "renderer_kernel_times": (None, [_vp, C.POINTER(C.c_double), _u32p]),
     "renderer_set_stream": (None, [_vp, _vp]),
     "shared_frame_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
@@ -700,6 +701,12 @@ class Renderer:
         return dict(zip(("launches", "h2d_bytes", "d2h_bytes", "segments", "cells", "entries", "written_tiles",
                          "tables_mode"),  # tables_mode: 0 counts read back, 1 sync-free, 2 sync-free attempt redone
                         [int(v) for v in out]))
+
+    def host_slices(self) -> list:
+        """Device-timeline ms of every slice of the last host frame ([] = rendered as one piece)."""
+        ms = (C.c_double * 16)()
+        n = int(self._api.renderer_host_slices(self._h, ms))
+        return [float(ms[i]) for i in range(n)]
 
     def row_costs(self) -> np.ndarray:
         """Per-tile-row cost of the last render (forma_renderer_row_costs)."""

@@ -25,6 +25,9 @@ struct Options {
     int band_filter = 1;     // a render cropped to a band of rows only makes the band's geometry resident
     int sync_free = 1;       // painter tables without count read-backs when the previous frame's counts bound this one's (redone the slow way if they do not)
     int test_fast_shrink = 0;  // test hook: halve the bounds of the sync-free tables (forces the redo)
+    int host_slices = 4;     // host frames: tile-row slices rendered as independent upload -> render -> copy-back pipelines on their own streams (1 = off)
+    int slice_bands = 2;     //   ... copy bands inside a slice
+    int slice_min_points = 65536;  //   ... only for compositions of at least this many points
 };
 Options& options();
 
@@ -194,7 +197,7 @@ void launch_grad_setup(const StyleRec* styles, const StopRec* stops, uint32_t n_
 void launch_f32x2_selftest(const float* a, const float* b, const float* c, uint32_t n, uint32_t* out, cudaStream_t st);
 // out[row] = 32 x entries + pixel segments of tile row `row` (see row_cost_kernel).
 void launch_row_costs(const uint2* tile_range, uint32_t tiles_x, uint32_t tiles_y, const uint64_t* segs, uint32_t n,
-                      unsigned long long* out, cudaStream_t st);
+                      unsigned long long* out, cudaStream_t st, unsigned long long* seg_out = nullptr);
 // Packs the tiles in S.written_list into `packed` (256 u32 per tile, row-major).
 void launch_gather_tiles(const PaintScene& S, const uint8_t* framebuffer, uint32_t* packed, cudaStream_t st);
 

@@ -476,7 +476,8 @@ __global__ void tile_index_kernel(PaintScene S, const uint64_t* __restrict__ eke
 // pixel segments (paint time follows the entries, sort / table time the segments). The
 // multi-GPU band split of the next frame is balanced on these. One warp per row.
 __global__ void row_cost_kernel(const uint2* __restrict__ tile_range, uint32_t tiles_x, uint32_t tiles_y,
-                                const uint64_t* __restrict__ segs, uint32_t n, unsigned long long* __restrict__ out) {
+                                const uint64_t* __restrict__ segs, uint32_t n, unsigned long long* __restrict__ out,
+                                unsigned long long* __restrict__ seg_out) {
     const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (row >= tiles_y) return;
     uint32_t entries = 0;
@@ -498,12 +499,15 @@ __global__ void row_cost_kernel(const uint2* __restrict__ tile_range, uint32_t t
         };
         const uint32_t s0 = lower((uint64_t)(row + 1u) << 53), s1 = lower((uint64_t)(row + 2u) << 53);
         out[row] = 32ull * entries + (unsigned long long)(s1 - s0);
+        // Pixel segments of the row; the last row also takes those below the frame (they sort
+        // behind every painted tile), so that the rows of a frame add up to its segment count.
+        if (seg_out) seg_out[row] = (row + 1u == tiles_y ? n : s1) - s0;
     }
 }
 
 void launch_row_costs(const uint2* tile_range, uint32_t tiles_x, uint32_t tiles_y, const uint64_t* segs, uint32_t n,
-                      unsigned long long* out, cudaStream_t st) {
-    if (tiles_y) row_cost_kernel<<<(tiles_y + 7) / 8, 256, 0, st>>>(tile_range, tiles_x, tiles_y, segs, n, out);
+                      unsigned long long* out, cudaStream_t st, unsigned long long* seg_out) {
+    if (tiles_y) row_cost_kernel<<<(tiles_y + 7) / 8, 256, 0, st>>>(tile_range, tiles_x, tiles_y, segs, n, out, seg_out);
 }
 
 // ---------------------------------------------------------------------------

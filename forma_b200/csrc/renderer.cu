@@ -6,13 +6,17 @@
 // fallback: without a usable sm_100 device forma_renderer_new() fails.
 #include <algorithm>
 #include <cctype>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/forma_b200.h"
@@ -51,6 +55,8 @@ static const OptionName kOptionNames[] = {
     {"paint_lpt", &Options::paint_lpt, 0, 1},         {"band_filter", &Options::band_filter, 0, 1},
     {"paint_wide", &Options::paint_wide, 0, 1},       {"sort_scan_log2", &Options::sort_scan_log2, 10, 31},
     {"sync_free", &Options::sync_free, 0, 1},         {"test_fast_shrink", &Options::test_fast_shrink, 0, 1},
+    {"host_slices", &Options::host_slices, 1, 16},    {"slice_bands", &Options::slice_bands, 1, 16},
+    {"slice_min_points", &Options::slice_min_points, 0, 1 << 30},
 };
 Options& options() {
     static Options o = [] {
@@ -308,6 +314,9 @@ struct Timer {
 class Renderer {
    public:
     int device = 0;
+    int res_key = 0;  // key of this renderer's residency record in a Composition: the device ordinal, or
+                      // device + 4096 * (k + 1) for the k-th slice renderer of a host-frame pipeline
+    int copy_bands_override = 0;  // slice renderers: copy bands inside the slice (0 = option copy_bands)
     cudaStream_t stream = 0;
     bool owns_stream = false;
     uint64_t launches = 0;
@@ -334,7 +343,9 @@ class Renderer {
     DeviceBuffer<EntryRec> recs;
     // Band-wise copy-back of host frames (see render()).
     static constexpr uint32_t kMaxCopyBands = 16;
-    static uint32_t copy_bands() { return (uint32_t)std::min(std::max(options().copy_bands, 1), (int)kMaxCopyBands); }
+    uint32_t copy_bands() const {
+        return (uint32_t)std::min(std::max(copy_bands_override ? copy_bands_override : options().copy_bands, 1), (int)kMaxCopyBands);
+    }
     cudaStream_t aux_stream = nullptr;  // side stream of the geometry upload (see flush_geometry)
     cudaEvent_t aux_ev[2];
     cudaStream_t band_stream[kMaxCopyBands];
@@ -372,6 +383,13 @@ class Renderer {
     double kernel_ms[4] = {0};              // see forma_renderer_kernel_times
     uint32_t kernel_launches[4] = {0};
     uint32_t* pinned_totals = nullptr;  // 4 x u32 pinned host words for count read-backs
+    // Renderers of a multi-device / sliced frame: the per-row costs of the frame (see
+    // row_cost_kernel) travel back behind the frame itself, without a synchronisation of their own.
+    bool track_row_costs = false;
+    DeviceBuffer<unsigned long long> d_row_costs;
+    PinnedBuffer<unsigned long long> h_row_costs;
+    uint32_t row_costs_rows = 0;  // rows of h_row_costs that belong to the last render (0 = none)
+    uint32_t last_slices = 0;     // slices of the last host frame (0 = rendered as one piece)
 
     ~Renderer() {
         if (pinned_totals) cudaFreeHost(pinned_totals);
@@ -431,7 +449,7 @@ static QuadUp quad_upload(const QuadRec& q) {
 // band of tile rows then uploads, evaluates and scans only the geometry of its band.
 int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bool band_is_partial) {
     comp.compact_geom();
-    CompDevice& cd = comp.on(device);
+    CompDevice& cd = comp.on(res_key);
     if (cd.geom_epoch != comp.geom_epoch) {  // compacted since: the resident points are stale
         cd.reset_residency();
         cd.geom_epoch = comp.geom_epoch;
@@ -598,7 +616,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
 // composition changed and re-uploaded when they are not resident.
 int Renderer::upload_tables(Composition& comp, int64_t cache_id) {
     comp.compact_geom();  // renumbers the geometry ids the tables are built from (no-op unless half of the points are dead)
-    CompDevice& cd = comp.on(device);
+    CompDevice& cd = comp.on(res_key);
     if (comp.tables_dirty || comp.tables_cache_id != cache_id) {
         FORMA_CUDA_TRY(cudaStreamSynchronize(stream));  // an upload from the pinned tables may still be in flight
         int st = rebuild_tables(comp, cache_id);
@@ -735,7 +753,7 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
                         uint32_t* n_out) {
     RasterArgs& ra = last_raster;  // kept for forma_renderer_lines
     last_raster_valid = true;
-    CompDevice& cd = comp.on(device);
+    CompDevice& cd = comp.on(res_key);
     ra.x = cd.d_x.ptr;
     ra.y = cd.d_y.ptr;
     ra.gid = cd.d_gid.ptr;
@@ -804,6 +822,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         return FORMA_STATUS_INVALID;
     }
     FORMA_CUDA_TRY(cudaSetDevice(device));
+    last_slices = 0;
     if (!timer.ok) {
         for (auto& e : timer.ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
         for (auto& e : timer.sort_ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
@@ -846,7 +865,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     if (st) return st;
     st = flush_geometry(comp, band_lo, band_hi, band_is_partial);
     if (st) return st;
-    CompDevice& cd = comp.on(device);
+    CompDevice& cd = comp.on(res_key);
     S.styles = cd.d_styles.ptr;
     S.order_to_style = cd.d_order_to_style.ptr;
     S.n_orders = comp.n_orders;
@@ -1114,6 +1133,16 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     launch_tile_index(S, ekey.ptr, n_entries, tile_range.ptr, heavy_lists, heavy_counts, stream, dc);
     launches += n_entries ? 1 : 0;
+    row_costs_rows = 0;
+    if (track_row_costs && n > 0) {
+        FORMA_CUDA_TRY(d_row_costs.reserve(2u * S.tiles_y));  // costs, then pixel segments per row
+        FORMA_CUDA_TRY(h_row_costs.reserve(2u * S.tiles_y));
+        launch_row_costs(tile_range.ptr, S.tiles_x, S.tiles_y, segs.ptr, n, d_row_costs.ptr, stream, d_row_costs.ptr + S.tiles_y);
+        ++launches;
+        FORMA_CUDA_TRY(cudaMemcpyAsync(h_row_costs.ptr, d_row_costs.ptr, 2u * S.tiles_y * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, stream));
+        row_costs_rows = S.tiles_y;
+    }
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[4], stream));
     // Host frame without a layer cache: paint in bands of tile rows, every band on its own
     // stream followed by the copy of its rows to the host buffer. The band kernels are
@@ -1123,14 +1152,14 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     bool copied_in_bands = false;
     paint_launches = 1;
     const uint32_t paint_rows = S.ty_hi - S.ty_lo;
-    if (!buffer_on_device && !cache && paint_rows >= 32u && S.tx_hi > S.tx_lo && band_copies_enabled()) {
+    if (!buffer_on_device && !cache && paint_rows >= (copy_bands_override ? 8u : 32u) && S.tx_hi > S.tx_lo && band_copies_enabled()) {
         if (!band_streams_ok) {
             for (auto& bs : band_stream) FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&bs, cudaStreamNonBlocking));
             for (auto& e : band_ev) FORMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             band_streams_ok = true;
         }
         const uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
-        const uint32_t kCopyBands = std::min(copy_bands(), paint_rows / 8u);
+        const uint32_t kCopyBands = std::max(1u, std::min(copy_bands(), paint_rows / 8u));
         FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], stream));  // the tables are ready
         for (uint32_t k = 0; k < kCopyBands; ++k) {
             PaintScene Sb = S;
@@ -1282,7 +1311,14 @@ struct forma_path_builder { PathBuilder b; };
 struct forma_path { Path p; std::vector<float> x, y; std::vector<uint8_t> c; };
 struct forma_composition { Composition c; };
 struct forma_layer;  // == forma::Layer
-struct forma_renderer { Renderer r; };
+struct forma_renderer_multi;
+struct forma_renderer {
+    Renderer r;
+    // Host-frame pipeline (forma_renderer_render): slice renderers on this renderer's device,
+    // created at the first frame that is sliced.
+    forma_renderer_multi* slicer = nullptr;
+    ~forma_renderer();
+};
 struct forma_layer_cache { LayerCache c; };
 
 static Layer* L(forma_layer* l) { return reinterpret_cast<Layer*>(l); }
@@ -1291,6 +1327,12 @@ static forma_layer* H(Layer* l) { return reinterpret_cast<forma_layer*>(l); }
 // No C++ exception crosses the C ABI: a failed host allocation (std::bad_alloc
 // from the containers behind these calls) is reported through the call's error
 // value and forma_last_error() like any other failure.
+// Host-frame pipeline (defined next to the multi-device renderer): returns -1 when the frame is
+// not sliced and the plain path has to render it.
+static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
+                              uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
+                              forma_timings* timings);
+
 template <class R, class F>
 static R guarded(R on_error, F&& f) noexcept {
     try {
@@ -1605,6 +1647,7 @@ static forma_renderer* renderer_new_impl(int device_ordinal) {
     }
     forma_renderer* r = new forma_renderer();
     r->r.device = device_ordinal;
+    r->r.res_key = device_ordinal;
     if (cudaMallocHost(&r->r.pinned_totals, 16 * sizeof(uint32_t)) != cudaSuccess || r->r.totals.reserve(64) != cudaSuccess ||
         cudaMemset(r->r.totals.ptr, 0, r->r.totals.capacity * sizeof(uint32_t)) != cudaSuccess) {
         set_error("allocation of renderer state failed");
@@ -1647,6 +1690,10 @@ int forma_renderer_render(forma_renderer* r, forma_composition* c, uint8_t* buff
                           uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
                           forma_layer_cache* cache, forma_timings* timings) {
     return guarded((int)FORMA_ERR_CAPACITY, [&] {
+        if (!cache) {
+            const int st = sliced_host_render(r, c, buffer, width, stride, height, channels, clear, crop, timings);
+            if (st >= 0) return st;
+        }
         return r->r.render(c->c, buffer, false, width, stride, height, channels, clear, crop, cache ? &cache->c : nullptr,
                            timings);
     });
@@ -1712,7 +1759,74 @@ int forma_shared_frame_free(int device, void* device_ptr) {
 // ---------------------------------------------------------------------------
 }  // extern "C"
 
-#include <thread>
+// Persistent worker threads of a multi-device (or sliced) renderer: run(n, f) executes f(0) on
+// the calling thread and f(1) ... f(n - 1) on workers that live as long as the pool, so a frame
+// of a millisecond does not pay for thread creation.
+class WorkerPool {
+   public:
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (std::thread& t : threads) t.join();
+    }
+    void run(size_t n, const std::function<void(size_t)>& f) {
+        if (n == 0) return;
+        while (threads.size() + 1 < n) {
+            const size_t index = threads.size() + 1;
+            uint64_t seen;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                seen = generation;
+            }
+            threads.emplace_back([this, index, seen] { worker(index, seen); });
+        }
+        if (n > 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            job = &f;
+            active = n;
+            pending = threads.size();
+            ++generation;
+        }
+        if (n > 1) cv_work.notify_all();
+        f(0);
+        if (n > 1) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return pending == 0; });
+            job = nullptr;
+        }
+    }
+
+   private:
+    void worker(size_t index, uint64_t seen) {
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            const std::function<void(size_t)>* f = job;
+            const size_t n = active;
+            lk.unlock();
+            if (index < n && f) {
+                try {
+                    (*f)(index);
+                } catch (...) {  // jobs report through their own status words
+                }
+            }
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(size_t)>* job = nullptr;
+    size_t active = 0, pending = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+};
 
 struct forma_renderer_multi {
     std::vector<forma_renderer*> dev;
@@ -1720,12 +1834,16 @@ struct forma_renderer_multi {
     uint32_t bounds_lo = 0, bounds_hi = 0;
     bool peer_ok = true;           // every device may store into the first device's memory
     std::vector<double> last_ms;   // device-timeline ms of each band in the last frame
+    size_t active = 0;             // bands used by the last frame (a sliced host frame may use fewer than dev.size())
+    uint64_t last_own_segments = 0;  // pixel segments of the last frame, every band counting its own rows only
+    WorkerPool pool;
 };
 
 static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint8_t* buffer, bool on_device, uint64_t width,
                              uint64_t stride, uint64_t height, const uint32_t channels[4], const float clear[4],
-                             const forma_rect* crop, forma_timings* timings) {
-    const size_t n = m->dev.size();
+                             const forma_rect* crop, forma_timings* timings, size_t n_use = 0) {
+    const size_t n = n_use ? std::min(n_use, m->dev.size()) : m->dev.size();
+    m->active = n;
     if (!n || !width || !height || width > FORMA_MAX_WIDTH || height > FORMA_MAX_HEIGHT) {
         set_error("forma_renderer_multi_render: invalid arguments");
         return FORMA_STATUS_INVALID;
@@ -1761,12 +1879,13 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
         int st = Renderer::rebuild_tables(comp, -1);
         if (st) return st;
     }
-    for (forma_renderer* r : m->dev) comp.on(r->r.device);
+    for (forma_renderer* r : m->dev) comp.on(r->r.res_key);  // the workers only look their records up
 
     std::vector<int> status(n, FORMA_STATUS_OK);
     std::vector<std::string> errors(n);
     std::vector<forma_timings> tms(n);
     std::vector<std::vector<uint64_t>> costs(n);
+    std::vector<uint64_t> own_segments(n, 0);
     m->last_ms.assign(n, 0.0);
     auto work = [&](size_t i) {
         const uint32_t r0 = m->bounds[i], r1 = m->bounds[i + 1];
@@ -1785,16 +1904,26 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
             return;
         }
         m->last_ms[i] = R.stage_ms[7];
-        costs[i].assign(tiles_y, 0);
-        forma_renderer_row_costs(m->dev[i], tiles_y, costs[i].data());
+        costs[i].assign(tiles_y, 0);  // the frame's row costs came back behind the frame (track_row_costs)
+        for (uint32_t r = 0; r < std::min(R.row_costs_rows, tiles_y); ++r) costs[i][r] = R.h_row_costs.ptr[r];
+        // A line that crosses a band boundary is rasterized by both neighbours: the frame's
+        // segment count is the sum of the segments every band has in its own rows.
+        if (R.row_costs_rows == tiles_y) {
+            uint64_t own = 0;
+            for (uint32_t r = r0; r < std::min(r1, tiles_y); ++r) own += R.h_row_costs.ptr[tiles_y + r];
+            own_segments[i] = own;
+        } else {
+            own_segments[i] = R.last_segments;
+        }
     };
-    if (n == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> threads;
-        for (size_t i = 0; i < n; ++i) threads.emplace_back(work, i);
-        for (std::thread& t : threads) t.join();
-    }
+    m->pool.run(n, [&](size_t i) {
+        try {
+            work(i);
+        } catch (const std::exception& e) {
+            status[i] = FORMA_STATUS_CAPACITY;
+            errors[i] = e.what();
+        }
+    });
     for (size_t i = 0; i < n; ++i)
         if (status[i]) {
             set_error("device %d: %s", m->dev[i]->r.device, errors[i].c_str());
@@ -1808,9 +1937,11 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
             timings->sort_ms = std::max(timings->sort_ms, tms[i].sort_ms);
             timings->paint_ms = std::max(timings->paint_ms, tms[i].paint_ms);
             timings->n_lines += tms[i].n_lines;
-            timings->n_segments += tms[i].n_segments;
+            timings->n_segments += own_segments[i];
         }
     }
+    m->last_own_segments = 0;
+    for (size_t i = 0; i < n; ++i) m->last_own_segments += own_segments[i];
     // Next frame's bands: equal shares of this frame's row costs (+ a floor per row: every
     // tile is at least cleared and stored).
     if (n > 1 && row_hi > row_lo) {
@@ -1821,6 +1952,15 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
                 cost[r] = (double)costs[i][r];
         double total = 0.0;
         for (uint32_t r = row_lo; r < row_hi; ++r) total += (cost[r] += floor_cost);
+        // Bands that are still within 8 % of an equal share stay as they are: moving a boundary
+        // makes the devices on both sides re-stage and re-upload their geometry.
+        double worst = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            double band = 0.0;
+            for (uint32_t r = m->bounds[i]; r < m->bounds[i + 1]; ++r) band += cost[r];
+            worst = std::max(worst, band);
+        }
+        if (worst * (double)n <= 1.08 * total) return FORMA_STATUS_OK;
         std::vector<uint32_t> nb(1, row_lo);
         double run = 0.0;
         size_t k = 1;
@@ -1865,6 +2005,7 @@ forma_renderer_multi* forma_renderer_multi_new(const int* devices, int n) {
                 r->r.stream = st;
                 r->r.owns_stream = true;
             }
+            r->r.track_row_costs = true;
             m->dev.push_back(r);
         }
         for (int i = 1; i < n; ++i) {  // stores into the first device's frame go over NVLink
@@ -1886,6 +2027,135 @@ void forma_renderer_multi_free(forma_renderer_multi* m) {
     for (forma_renderer* r : m->dev) forma_renderer_free(r);
     delete m;
 }
+}  // extern "C"
+
+forma_renderer::~forma_renderer() {
+    if (slicer) forma_renderer_multi_free(slicer);
+}
+
+// Host frames as a pipeline of tile-row slices. A host frame is upload (the geometry that is not
+// resident) -> line setup / rasterize / sort / tables -> paint -> copy-back; on one stream the
+// copy engines idle while the SMs work and the other way round, and PCIe carries one direction
+// at a time. Here the frame is cut into `host_slices` bands of tile rows; every slice is a
+// renderer of its own on this device (own stream, own scratch, own residency record with the
+// band filter of the multi-GPU path, so it uploads and evaluates only the geometry that can
+// reach its rows) driven by its own host thread: slice k + 1 uploads while slice k computes
+// and slice k - 1 copies back, and the two PCIe directions run at the same time. The slices are
+// balanced on the previous frame's row costs like the bands of a multi-GPU frame. Results are
+// those of a band render (tests/test_gpu_bench_scale.py: bands == whole frame).
+// Not sliced: frames with a layer cache (the cache records belong to one renderer), layers with
+// transforms (no band filter: every slice would upload everything), small compositions, short frames.
+static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
+                              uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
+                              forma_timings* timings) {
+    Renderer& P = r->r;
+    const int want = options().host_slices;
+    if (want < 2 || !buffer || !width || !height || width > FORMA_MAX_WIDTH || height > FORMA_MAX_HEIGHT || width * 4 > stride)
+        return -1;  // (invalid targets are reported by the plain path)
+    for (int k = 0; k < 4; ++k)
+        if (channels[k] > 5u) return -1;
+    Composition& comp = c->c;
+    if ((uint64_t)comp.n_points < (uint64_t)std::max(options().slice_min_points, 0)) return -1;
+    const uint32_t tiles_y = (uint32_t)((height + 15u) / 16u);
+    uint32_t row_lo = 0, row_hi = tiles_y;
+    if (crop) {
+        row_lo = (uint32_t)std::min<uint64_t>(crop->vert_start / 16u, tiles_y);
+        row_hi = (uint32_t)std::min<uint64_t>((crop->vert_end + 15u) / 16u, tiles_y);
+        if (crop->hor_end <= crop->hor_start) return -1;
+    }
+    if (row_hi <= row_lo) return -1;
+    const size_t n = std::min<size_t>((size_t)want, (row_hi - row_lo) / 16u);  // at least 16 tile rows per slice
+    if (n < 2) return -1;
+    if (cudaSetDevice(P.device) != cudaSuccess) return -1;
+    // The tables are rebuilt here (the slices find them clean) so that layers_have_xf is known.
+    comp.compact_geom();
+    if (comp.tables_dirty || comp.tables_cache_id != -1) {
+        FORMA_CUDA_TRY(cudaStreamSynchronize(P.stream));
+        if (r->slicer)
+            for (forma_renderer* q : r->slicer->dev) FORMA_CUDA_TRY(cudaStreamSynchronize(q->r.stream));
+        const int st = Renderer::rebuild_tables(comp, -1);
+        if (st) return st;
+    }
+    if (comp.layers_have_xf) return -1;
+    if (!r->slicer || r->slicer->dev.size() < n) {
+        if (r->slicer) forma_renderer_multi_free(r->slicer);
+        r->slicer = nullptr;
+        std::unique_ptr<forma_renderer_multi> m(new forma_renderer_multi());
+        for (size_t i = 0; i < (size_t)want; ++i) {
+            forma_renderer* q = forma_renderer_new(P.device);
+            if (!q) {
+                for (forma_renderer* x : m->dev) forma_renderer_free(x);
+                return FORMA_STATUS_CUDA;
+            }
+            cudaStream_t st = nullptr;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+                forma_renderer_free(q);
+                for (forma_renderer* x : m->dev) forma_renderer_free(x);
+                set_error("sliced host frame: cannot create a stream");
+                return FORMA_STATUS_CUDA;
+            }
+            q->r.stream = st;
+            q->r.owns_stream = true;
+            q->r.res_key = P.device + 4096 * (int)(i + 1);
+            q->r.track_row_costs = true;
+            m->dev.push_back(q);
+        }
+        r->slicer = m.release();
+    }
+    forma_renderer_multi* m = r->slicer;
+    // The slices start behind whatever the caller has queued on this renderer's stream.
+    if (!P.count_ev) FORMA_CUDA_TRY(P.ensure_count_event());
+    FORMA_CUDA_TRY(cudaEventRecord(P.count_ev, P.stream));
+    struct Before { uint64_t launches, h2d, d2h; };
+    std::vector<Before> before(n);
+    for (size_t i = 0; i < n; ++i) {
+        Renderer& Q = m->dev[i]->r;
+        Q.copy_bands_override = std::max(options().slice_bands, 1);
+        FORMA_CUDA_TRY(cudaStreamWaitEvent(Q.stream, P.count_ev, 0));
+        before[i] = {Q.launches, Q.h2d_bytes, Q.d2h_bytes};
+    }
+    const int st = multi_render_impl(m, c, buffer, false, width, stride, height, channels, clear, crop, timings, n);
+    if (st) return st;
+    // What the caller reads from this renderer after a frame: sums over the slices; stage times:
+    // the slowest slice (the slices overlap, so their sum means nothing).
+    P.last_segments = P.last_cells = P.last_entries = 0;
+    for (double& v : P.stage_ms) v = 0.0;
+    bool redone = false, all_fast = true;
+    for (size_t i = 0; i < n; ++i) {
+        const Renderer& Q = m->dev[i]->r;
+        P.launches += Q.launches - before[i].launches;
+        P.h2d_bytes += Q.h2d_bytes - before[i].h2d;
+        P.d2h_bytes += Q.d2h_bytes - before[i].d2h;
+        P.last_cells += Q.last_cells;
+        P.last_entries += Q.last_entries;
+        for (int k = 0; k < 8; ++k) P.stage_ms[k] = std::max(P.stage_ms[k], Q.stage_ms[k]);
+        redone = redone || Q.last_tables_redone;
+        all_fast = all_fast && Q.last_tables_sync_free;
+    }
+    for (int k = 0; k < 4; ++k) {
+        P.kernel_ms[k] = 0.0;
+        P.kernel_launches[k] = 0;
+    }
+    P.last_tables_redone = redone;
+    P.last_tables_sync_free = all_fast && !redone;
+    P.last_raster_valid = false;  // forma_renderer_lines describes the last unsliced render only
+    P.last_written_tiles = 0;
+    P.last_tiles_x = P.last_tiles_y = 0;
+    P.last_segments = (uint32_t)std::min<uint64_t>(m->last_own_segments, 0xFFFFFFFFu);
+    P.last_slices = (uint32_t)n;
+    return FORMA_STATUS_OK;
+}
+
+extern "C" {
+
+/* Slices of this renderer's last host frame (0 = rendered as one piece); out_ms (may be null,
+ * room for 16) receives the device-timeline ms of every slice. */
+int forma_renderer_host_slices(const forma_renderer* r, double* out_ms) {
+    if (!r || !r->r.last_slices || !r->slicer) return 0;
+    for (size_t i = 0; out_ms && i < r->slicer->last_ms.size() && i < 16; ++i) out_ms[i] = r->slicer->last_ms[i];
+    return (int)r->r.last_slices;
+}
+
 int forma_renderer_multi_device_count(const forma_renderer_multi* m) { return m ? (int)m->dev.size() : 0; }
 int forma_renderer_multi_render(forma_renderer_multi* m, forma_composition* c, uint8_t* buffer, uint64_t width, uint64_t stride,
                                 uint64_t height, const uint32_t channels[4], const float clear[4], const forma_rect* crop,
@@ -2081,6 +2351,11 @@ uint64_t forma_renderer_lines(forma_renderer* r, uint64_t cap, uint32_t* orders,
     return guarded((uint64_t)0, [&] { return renderer_lines_impl(r, cap, orders, x0, y0, dx, dy, a, b, c, d, lengths); });
 }
 uint64_t forma_renderer_segments(forma_renderer* r, uint64_t cap, uint64_t* out) {
+    if (r->r.last_slices) {
+        set_error("forma_renderer_segments: the last host frame was rendered in %u slices (option host_slices); "
+                  "there is no single sorted segment array to inspect", r->r.last_slices);
+        return 0;
+    }
     uint64_t n = r->r.last_segments;
     if (out && cap && n) {
         cudaError_t e = cudaMemcpy(out, r->r.segs.ptr, std::min<uint64_t>(cap, n) * sizeof(uint64_t), cudaMemcpyDeviceToHost);

@@ -266,6 +266,13 @@ void forma_renderer_kernel_times(const forma_renderer*, double out_ms[4], uint32
  * 1 = without a read-back (kernels sized by the previous frame's counts, option sync_free),
  * 2 = attempted without, counts exceeded the bounds, tables and paint repeated as 0. */
 void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
+/* Host frames (forma_renderer_render without a layer cache) of compositions whose layers carry no
+ * transform are rendered as a pipeline of tile-row slices on the renderer's device (option
+ * host_slices): slice k + 1 uploads its band's geometry while slice k computes and slice k - 1
+ * copies its rows back. Returns the number of slices of the last host frame (0 = one piece);
+ * out_ms (may be null, room for 16) receives each slice's device-timeline ms. After a sliced
+ * frame the counters above are sums over the slices and the stage times those of the slowest. */
+int forma_renderer_host_slices(const forma_renderer*, double* out_ms);
 
 /* Cost of every tile row of the last render (32 x its (tile, layer) entries + its pixel
  * segments; rows outside the rendered crop cost 0): what a caller balances the tile-row
@@ -274,8 +281,9 @@ void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
 uint64_t forma_renderer_row_costs(forma_renderer*, uint64_t cap, uint64_t* out);
 
 /* Schedule switches of the library (process-wide; none changes results): "speculate",
- * "band_copy", "copy_bands", "sort_full_key", "sort_big_log2", "paint_lpt", "band_filter",
- * "test_gap_cap".
+ * "band_copy", "copy_bands", "sort_full_key", "sort_big_log2", "sort_scan_log2", "paint_lpt",
+ * "paint_wide", "band_filter", "sync_free", "host_slices", "slice_bands", "slice_min_points",
+ * "test_gap_cap", "test_fast_shrink".
  * Defaults come from the environment (FORMA_SPECULATE, ...); see DESIGN.md section 6. */
 int forma_set_option(const char* name, int value);
 int forma_get_option(const char* name, int* value);

@@ -33,3 +33,14 @@ def cuda_renderer(cuda_api):
 @pytest.fixture(scope="session")
 def oracle_renderer(oracle_api):
     return oracle_api.Renderer(0)
+
+
+@pytest.fixture()
+def unsliced(cuda_api):
+    """Host frames rendered as one piece (option host_slices = 1): for tests that inspect the
+    stages of the last render (sorted segments, table modes, upload bytes of one renderer) -
+    a sliced host frame is rendered by one renderer per slice."""
+    saved = cuda_api.get_option("host_slices")
+    cuda_api.set_option("host_slices", 1)
+    yield
+    cuda_api.set_option("host_slices", saved)

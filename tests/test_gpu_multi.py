@@ -81,7 +81,7 @@ def test_multi_renderer_rejects_bad_device_lists(cuda_api):
         cuda_api.MultiRenderer([99])
 
 
-def test_band_render_keeps_only_the_bands_geometry(cuda_api, cuda_renderer, oracle_api):
+def test_band_render_keeps_only_the_bands_geometry(cuda_api, cuda_renderer, oracle_api, unsliced):
     """A render cropped to a band uploads only the inserts that can reach the band (h2d bytes
     well below the whole composition's), and frames rendered afterwards with other bands or the
     whole frame are still exact."""

@@ -135,7 +135,7 @@ def test_sort_u64_stable_on_top_44_bits(cuda_renderer, n):
     assert np.array_equal(out, keys[order])  # LSD radix is stable: a legal (and unique) outcome
 
 
-def test_pipeline_sorted_segments_match_oracle(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
+def test_pipeline_sorted_segments_match_oracle(cuda_api, oracle_api, cuda_renderer, oracle_renderer, unsliced):
     res = []
     for api, r in ((cuda_api, cuda_renderer), (oracle_api, oracle_renderer)):
         comp = api.Composition()
@@ -336,7 +336,7 @@ def test_order_limit_and_bad_arguments(cuda_api, cuda_renderer):
         cuda_renderer.render(comp, buf, 2, 2, RGBA, Color(), stride=4)  # width * 4 > stride
 
 
-def test_large_frame_properties(cuda_api, cuda_renderer):
+def test_large_frame_properties(cuda_api, cuda_renderer, unsliced):
     """Full-size checks that do not need the oracle: sortedness, idempotence,
     and a layer-order-independent checksum (opaque disjoint rectangles)."""
     w, h = 3840, 2160

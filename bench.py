@@ -476,6 +476,7 @@ def bench_workload(env, args, name, steps, warmup, headline):
             e2e_stage_acc[k] += v
     e2e_dev_ms, e2e_wall_ms = timed(frame_e2e_acc, steps)
     c3 = renderer.counters()
+    slice_ms = renderer.host_slices() if hasattr(renderer, "host_slices") else []
 
     def reduce_ranks(v, op):
         if world == 1:
@@ -559,7 +560,10 @@ def bench_workload(env, args, name, steps, warmup, headline):
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": T_e2e / steps,
                 "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total, "bytes_counted_by": "the library, summed over ranks",
                 "gpu_launches": launches_e2e, "host_frame": "pinned" if world == 1 else ("shared, page-locked per rank" if host.registered else "shared, pageable"),
-                "stage_ms": {k: round(v / steps, 4) for k, v in e2e_stage_acc.items()}},
+                "stage_ms": {k: round(v / steps, 4) for k, v in e2e_stage_acc.items()},
+                # host frames are rendered as a pipeline of tile-row slices (upload / compute / copy-back of
+                # neighbouring slices overlap); stage_ms then holds the slowest slice's stages, which overlap the others'
+                "host_slices": len(slice_ms), "slice_ms": [round(v, 4) for v in slice_ms]},
         "roofline": roofline,
         "multi_gpu": {"render_ms_slowest_rank": round(render_ms_max, 4), "render_ms_fastest_rank": round(render_ms_min, 4),
                       "assembly": assembly, "bands": balance,

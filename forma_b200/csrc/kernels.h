@@ -28,6 +28,7 @@ struct Options {
     int host_slices = 4;     // host frames: tile-row slices rendered as independent upload -> render -> copy-back pipelines on their own streams (1 = off)
     int slice_bands = 2;     //   ... copy bands inside a slice
     int slice_min_points = 65536;  //   ... only for compositions of at least this many points
+    int slice_chain = 1;     //   ... uploads issued slice after slice, each waiting for the one before (0: all at once from the slices' threads)
 };
 Options& options();
 

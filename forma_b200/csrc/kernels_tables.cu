@@ -499,9 +499,13 @@ __global__ void row_cost_kernel(const uint2* __restrict__ tile_range, uint32_t t
         };
         const uint32_t s0 = lower((uint64_t)(row + 1u) << 53), s1 = lower((uint64_t)(row + 2u) << 53);
         out[row] = 32ull * entries + (unsigned long long)(s1 - s0);
-        // Pixel segments of the row; the last row also takes those below the frame (they sort
-        // behind every painted tile), so that the rows of a frame add up to its segment count.
-        if (seg_out) seg_out[row] = (row + 1u == tiles_y ? n : s1) - s0;
+        // Pixel segments and entries of the row. The first row also takes the segments above the
+        // frame (tile_y clamped to -1), the last row those below it (they sort behind every
+        // painted tile), so that the rows of a frame add up to its segment count.
+        if (seg_out) {
+            seg_out[row] = (row + 1u == tiles_y ? n : s1) - (row == 0u ? 0u : s0);
+            seg_out[tiles_y + row] = entries;
+        }
     }
 }
 

@@ -56,7 +56,7 @@ static const OptionName kOptionNames[] = {
     {"paint_wide", &Options::paint_wide, 0, 1},       {"sort_scan_log2", &Options::sort_scan_log2, 10, 31},
     {"sync_free", &Options::sync_free, 0, 1},         {"test_fast_shrink", &Options::test_fast_shrink, 0, 1},
     {"host_slices", &Options::host_slices, 1, 16},    {"slice_bands", &Options::slice_bands, 1, 16},
-    {"slice_min_points", &Options::slice_min_points, 0, 1 << 30},
+    {"slice_min_points", &Options::slice_min_points, 0, 1 << 30}, {"slice_chain", &Options::slice_chain, 0, 1},
 };
 Options& options() {
     static Options o = [] {
@@ -390,10 +390,26 @@ class Renderer {
     PinnedBuffer<unsigned long long> h_row_costs;
     uint32_t row_costs_rows = 0;  // rows of h_row_costs that belong to the last render (0 = none)
     uint32_t last_slices = 0;     // slices of the last host frame (0 = rendered as one piece)
+    // Slice renderers of a host-frame pipeline: the uploads of the slices are issued by one thread,
+    // slice after slice, and chained (a slice's copies wait for the previous slice's), so that slice k
+    // has its geometry - and starts computing - while slices k + 1 ... are still crossing PCIe.
+    cudaEvent_t upload_done_ev = nullptr;  // recorded behind this renderer's last host -> device copy
+    cudaEvent_t upload_after = nullptr;    // this renderer's copies wait for it (the previous slice's upload_done_ev)
+    bool prefetched = false;               // prefetch() ran for the coming render: timer.ev[0] is already recorded
+    int prefetch(Composition& comp, uint64_t width, uint64_t height, const forma_rect* crop);
+    int ensure_timer() {
+        if (!timer.ok) {
+            for (auto& e : timer.ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
+            for (auto& e : timer.sort_ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
+            timer.ok = true;
+        }
+        return FORMA_STATUS_OK;
+    }
 
     ~Renderer() {
         if (pinned_totals) cudaFreeHost(pinned_totals);
         if (count_ev) cudaEventDestroy(count_ev);
+        if (upload_done_ev) cudaEventDestroy(upload_done_ev);
         if (band_streams_ok) {
             for (auto& e : band_ev) cudaEventDestroy(e);
             for (auto& bs : band_stream) cudaStreamDestroy(bs);
@@ -571,6 +587,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
     // The quadratics go first: their expansion kernel runs on a side stream while the copy
     // engine keeps sending the other records.
     bool expanding = false;
+    if (upload_after) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, upload_after, 0));
     if (cd.staged_quads) {
         FORMA_CUDA_TRY(up_quads_raw.reserve(cd.staged_quads + 1));
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_quads_raw.ptr, cd.h_quads.ptr, cd.staged_quads * quad_bytes, cudaMemcpyHostToDevice,
@@ -600,6 +617,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, cd.h_kinds.ptr, cd.staged_recs, cudaMemcpyHostToDevice, stream));
     }
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, cd.h_jobs.ptr, cd.staged_jobs * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
+    if (upload_done_ev) FORMA_CUDA_TRY(cudaEventRecord(upload_done_ev, stream));
     h2d_bytes += cd.staged_splines * sizeof(SplineRec) + cd.staged_recs * (sizeof(PointRec) + 1) +
                  cd.staged_quads * quad_bytes + cd.staged_jobs * sizeof(FlattenJob);
     if (expanding) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, aux_ev[1], 0));
@@ -812,6 +830,28 @@ int Renderer::rasterize(Composition& comp, uint32_t width, uint32_t height, floa
     return FORMA_STATUS_OK;
 }
 
+// The upload half of render() on its own: tables + the geometry that the rows of `crop` need and
+// that is not resident yet. render() then finds everything in place.
+int Renderer::prefetch(Composition& comp, uint64_t width, uint64_t height, const forma_rect* crop) {
+    FORMA_CUDA_TRY(cudaSetDevice(device));
+    const int ts = ensure_timer();
+    if (ts) return ts;
+    const uint32_t tiles_y = (uint32_t)((height + 15u) / 16u);
+    uint32_t ty_lo = 0, ty_hi = tiles_y;
+    if (crop) {  // as in render()
+        ty_lo = (uint32_t)std::min<uint64_t>(crop->vert_start / 16u, tiles_y);
+        ty_hi = (uint32_t)std::min<uint64_t>((crop->vert_end + 15u) / 16u, tiles_y);
+        if (ty_hi < ty_lo) ty_hi = ty_lo;
+    }
+    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
+    prefetched = true;
+    if (upload_after) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, upload_after, 0));
+    const float band_lo = (float)(ty_lo * 16u), band_hi = (float)std::min<uint64_t>((uint64_t)ty_hi * 16u, height);
+    int st = upload_tables(comp, -1);
+    if (st) return st;
+    return flush_geometry(comp, band_lo, band_hi, ty_lo > 0u || ty_hi < tiles_y);
+}
+
 int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, uint64_t width, uint64_t stride,
                      uint64_t height, const uint32_t channels_in[4], const float clear[4], const forma_rect* crop,
                      LayerCache* cache, forma_timings* timings) {
@@ -823,10 +863,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     }
     FORMA_CUDA_TRY(cudaSetDevice(device));
     last_slices = 0;
-    if (!timer.ok) {
-        for (auto& e : timer.ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
-        for (auto& e : timer.sort_ev) FORMA_CUDA_TRY(cudaEventCreate(&e));
-        timer.ok = true;
+    {
+        const int ts = ensure_timer();
+        if (ts) return ts;
     }
 
     PaintScene S{};
@@ -855,7 +894,8 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         if (S.ty_hi < S.ty_lo) S.ty_hi = S.ty_lo;
     }
 
-    FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
+    if (!prefetched) FORMA_CUDA_TRY(cudaEventRecord(timer.ev[0], stream));
+    prefetched = false;
     // Lines entirely above / below the painted tile rows cannot reach a painted tile: they are
     // culled per line (rasterize), and whole inserts are left out of the device's segment
     // buffer when the band is narrower than the frame (flush_geometry).
@@ -1135,11 +1175,11 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     launches += n_entries ? 1 : 0;
     row_costs_rows = 0;
     if (track_row_costs && n > 0) {
-        FORMA_CUDA_TRY(d_row_costs.reserve(2u * S.tiles_y));  // costs, then pixel segments per row
-        FORMA_CUDA_TRY(h_row_costs.reserve(2u * S.tiles_y));
+        FORMA_CUDA_TRY(d_row_costs.reserve(3u * S.tiles_y));  // per row: cost, pixel segments, entries
+        FORMA_CUDA_TRY(h_row_costs.reserve(3u * S.tiles_y));
         launch_row_costs(tile_range.ptr, S.tiles_x, S.tiles_y, segs.ptr, n, d_row_costs.ptr, stream, d_row_costs.ptr + S.tiles_y);
         ++launches;
-        FORMA_CUDA_TRY(cudaMemcpyAsync(h_row_costs.ptr, d_row_costs.ptr, 2u * S.tiles_y * sizeof(unsigned long long),
+        FORMA_CUDA_TRY(cudaMemcpyAsync(h_row_costs.ptr, d_row_costs.ptr, 3u * S.tiles_y * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, stream));
         row_costs_rows = S.tiles_y;
     }
@@ -1835,13 +1875,13 @@ struct forma_renderer_multi {
     bool peer_ok = true;           // every device may store into the first device's memory
     std::vector<double> last_ms;   // device-timeline ms of each band in the last frame
     size_t active = 0;             // bands used by the last frame (a sliced host frame may use fewer than dev.size())
-    uint64_t last_own_segments = 0;  // pixel segments of the last frame, every band counting its own rows only
+    uint64_t last_own_segments = 0, last_own_entries = 0;  // pixel segments / entries of the last frame, every band counting its own rows only
     WorkerPool pool;
 };
 
 static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint8_t* buffer, bool on_device, uint64_t width,
                              uint64_t stride, uint64_t height, const uint32_t channels[4], const float clear[4],
-                             const forma_rect* crop, forma_timings* timings, size_t n_use = 0) {
+                             const forma_rect* crop, forma_timings* timings, size_t n_use = 0, bool chained_uploads = false) {
     const size_t n = n_use ? std::min(n_use, m->dev.size()) : m->dev.size();
     m->active = n;
     if (!n || !width || !height || width > FORMA_MAX_WIDTH || height > FORMA_MAX_HEIGHT) {
@@ -1885,16 +1925,34 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
     std::vector<std::string> errors(n);
     std::vector<forma_timings> tms(n);
     std::vector<std::vector<uint64_t>> costs(n);
-    std::vector<uint64_t> own_segments(n, 0);
+    std::vector<uint64_t> own_segments(n, 0), own_entries(n, 0);
     m->last_ms.assign(n, 0.0);
+    auto band_of = [&](size_t i, forma_rect* band) {
+        const uint32_t r0 = m->bounds[i], r1 = m->bounds[i + 1];
+        if (r1 <= r0) return false;
+        *band = full;
+        band->vert_start = std::max<uint64_t>(full.vert_start, (uint64_t)r0 * 16u);
+        band->vert_end = std::min<uint64_t>(std::min<uint64_t>(full.vert_end, height), (uint64_t)r1 * 16u);
+        return band->vert_end > band->vert_start;
+    };
+    if (chained_uploads) {
+        // Slices of one device share its PCIe link: their uploads are issued here, in slice order,
+        // each waiting for the one before (Renderer::upload_after), instead of all at once.
+        for (size_t i = 0; i < n; ++i) {
+            forma_rect band;
+            if (!band_of(i, &band)) continue;
+            const int st = m->dev[i]->r.prefetch(comp, width, height, &band);
+            if (st) {
+                for (size_t k = 0; k < n; ++k) m->dev[k]->r.prefetched = false;
+                return st;
+            }
+        }
+    }
     auto work = [&](size_t i) {
         const uint32_t r0 = m->bounds[i], r1 = m->bounds[i + 1];
         std::memset(&tms[i], 0, sizeof(forma_timings));
-        if (r1 <= r0) return;
-        forma_rect band = full;
-        band.vert_start = std::max<uint64_t>(full.vert_start, (uint64_t)r0 * 16u);
-        band.vert_end = std::min<uint64_t>(std::min<uint64_t>(full.vert_end, height), (uint64_t)r1 * 16u);
-        if (band.vert_end <= band.vert_start) return;
+        forma_rect band;
+        if (!band_of(i, &band)) return;
         Renderer& R = m->dev[i]->r;
         status[i] = guarded((int)FORMA_ERR_CAPACITY, [&] {
             return R.render(comp, buffer, on_device, width, stride, height, channels, clear, &band, nullptr, &tms[i]);
@@ -1909,11 +1967,16 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
         // A line that crosses a band boundary is rasterized by both neighbours: the frame's
         // segment count is the sum of the segments every band has in its own rows.
         if (R.row_costs_rows == tiles_y) {
-            uint64_t own = 0;
-            for (uint32_t r = r0; r < std::min(r1, tiles_y); ++r) own += R.h_row_costs.ptr[tiles_y + r];
+            uint64_t own = 0, own_e = 0;
+            for (uint32_t r = r0; r < std::min(r1, tiles_y); ++r) {
+                own += R.h_row_costs.ptr[tiles_y + r];
+                own_e += R.h_row_costs.ptr[2u * tiles_y + r];
+            }
             own_segments[i] = own;
+            own_entries[i] = own_e;
         } else {
             own_segments[i] = R.last_segments;
+            own_entries[i] = R.last_entries;
         }
     };
     m->pool.run(n, [&](size_t i) {
@@ -1940,8 +2003,11 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
             timings->n_segments += own_segments[i];
         }
     }
-    m->last_own_segments = 0;
-    for (size_t i = 0; i < n; ++i) m->last_own_segments += own_segments[i];
+    m->last_own_segments = m->last_own_entries = 0;
+    for (size_t i = 0; i < n; ++i) {
+        m->last_own_segments += own_segments[i];
+        m->last_own_entries += own_entries[i];
+    }
     // Next frame's bands: equal shares of this frame's row costs (+ a floor per row: every
     // tile is at least cleared and stored).
     if (n > 1 && row_hi > row_lo) {
@@ -2098,6 +2164,8 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
             q->r.owns_stream = true;
             q->r.res_key = P.device + 4096 * (int)(i + 1);
             q->r.track_row_costs = true;
+            if (cudaEventCreateWithFlags(&q->r.upload_done_ev, cudaEventDisableTiming) != cudaSuccess) q->r.upload_done_ev = nullptr;
+            if (i > 0) q->r.upload_after = m->dev[i - 1]->r.upload_done_ev;
             m->dev.push_back(q);
         }
         r->slicer = m.release();
@@ -2114,7 +2182,8 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
         FORMA_CUDA_TRY(cudaStreamWaitEvent(Q.stream, P.count_ev, 0));
         before[i] = {Q.launches, Q.h2d_bytes, Q.d2h_bytes};
     }
-    const int st = multi_render_impl(m, c, buffer, false, width, stride, height, channels, clear, crop, timings, n);
+    const int st = multi_render_impl(m, c, buffer, false, width, stride, height, channels, clear, crop, timings, n,
+                                     options().slice_chain != 0);
     if (st) return st;
     // What the caller reads from this renderer after a frame: sums over the slices; stage times:
     // the slowest slice (the slices overlap, so their sum means nothing).
@@ -2127,7 +2196,6 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
         P.h2d_bytes += Q.h2d_bytes - before[i].h2d;
         P.d2h_bytes += Q.d2h_bytes - before[i].d2h;
         P.last_cells += Q.last_cells;
-        P.last_entries += Q.last_entries;
         for (int k = 0; k < 8; ++k) P.stage_ms[k] = std::max(P.stage_ms[k], Q.stage_ms[k]);
         redone = redone || Q.last_tables_redone;
         all_fast = all_fast && Q.last_tables_sync_free;
@@ -2142,6 +2210,9 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
     P.last_written_tiles = 0;
     P.last_tiles_x = P.last_tiles_y = 0;
     P.last_segments = (uint32_t)std::min<uint64_t>(m->last_own_segments, 0xFFFFFFFFu);
+    P.last_entries = (uint32_t)std::min<uint64_t>(m->last_own_entries, 0xFFFFFFFFu);
+    // (cells: a slice also forms the cells of segments that boundary-crossing lines leave in its
+    // neighbours' rows, so the sum over the slices is an upper bound of the frame's cell count)
     P.last_slices = (uint32_t)n;
     return FORMA_STATUS_OK;
 }

@@ -271,7 +271,10 @@ void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
  * host_slices): slice k + 1 uploads its band's geometry while slice k computes and slice k - 1
  * copies its rows back. Returns the number of slices of the last host frame (0 = one piece);
  * out_ms (may be null, room for 16) receives each slice's device-timeline ms. After a sliced
- * frame the counters above are sums over the slices and the stage times those of the slowest. */
+ * frame the counters above are sums over the slices (pixel segments and entries: every slice
+ * counts its own rows, so they are the frame's; cells: an upper bound, a slice also sees the
+ * segments boundary-crossing lines leave in its neighbours' rows) and the stage times those of
+ * the slowest slice. */
 int forma_renderer_host_slices(const forma_renderer*, double* out_ms);
 
 /* Cost of every tile row of the last render (32 x its (tile, layer) entries + its pixel
@@ -282,7 +285,7 @@ uint64_t forma_renderer_row_costs(forma_renderer*, uint64_t cap, uint64_t* out);
 
 /* Schedule switches of the library (process-wide; none changes results): "speculate",
  * "band_copy", "copy_bands", "sort_full_key", "sort_big_log2", "sort_scan_log2", "paint_lpt",
- * "paint_wide", "band_filter", "sync_free", "host_slices", "slice_bands", "slice_min_points",
+ * "paint_wide", "band_filter", "sync_free", "host_slices", "slice_bands", "slice_min_points", "slice_chain",
  * "test_gap_cap", "test_fast_shrink".
  * Defaults come from the environment (FORMA_SPECULATE, ...); see DESIGN.md section 6. */
 int forma_set_option(const char* name, int value);

@@ -32,7 +32,7 @@ def expected(oracle_api):
 
 @pytest.fixture()
 def slice_options(cuda_api):
-    names = ("host_slices", "slice_bands", "slice_min_points", "sync_free", "band_filter")
+    names = ("host_slices", "slice_bands", "slice_min_points", "slice_chain", "sync_free", "band_filter")
     saved = {n: cuda_api.get_option(n) for n in names}
     cuda_api.set_option("slice_min_points", 0)
     yield
@@ -70,7 +70,9 @@ def test_sliced_counters_are_those_of_the_whole_frame(cuda_api, slice_options):
     cuda_api.set_option("host_slices", 4)
     r4.render(comp, buf, W, H, RGBA, CLEAR)
     c = r4.counters()
-    assert (c["segments"], c["cells"], c["entries"]) == (whole["segments"], whole["cells"], whole["entries"])
+    assert c["segments"] == whole["segments"]  # every slice counts the segments of its own rows
+    # a slice also forms the cells of the segments that boundary-crossing lines leave in its neighbours' rows
+    assert whole["cells"] <= c["cells"] < 1.2 * whole["cells"] and 0.9 * whole["entries"] < c["entries"] < 1.2 * whole["entries"]
     assert c["d2h_bytes"] == whole["d2h_bytes"] == W * H * 4
     assert c["launches"] > whole["launches"]
     # every slice uploads its band's geometry (shapes crossing a boundary twice), never the whole composition four times
@@ -153,5 +155,11 @@ def test_frames_the_pipeline_leaves_alone(cuda_api, oracle_api, slice_options):
     assert r.host_slices() == [] and np.array_equal(buf2, want)
     cuda_api.set_option("slice_min_points", 0)
     cuda_api.set_option("band_filter", 0)                       # every slice keeps everything resident: still exact
+    r.render(comp, buf2, W, H, RGBA, CLEAR)
+    assert len(r.host_slices()) == 4 and np.array_equal(buf2, want)
+    cuda_api.set_option("band_filter", 1)
+    cuda_api.set_option("slice_chain", 0)                       # uploads issued by the slices' threads, all at once
+    comp.evict()
+    buf2[:] = 0
     r.render(comp, buf2, W, H, RGBA, CLEAR)
     assert len(r.host_slices()) == 4 and np.array_equal(buf2, want)

@@ -86,11 +86,12 @@ def main():
         run("plain", {"host_slices": 1}, True)
         for cb in (4, 16):
             run("plain", {"host_slices": 1, "copy_bands": cb}, True)
-        for hs in (2, 3, 4, 6, 8):
+        for hs in (2, 3, 4, 5, 6, 8):
             for sb in (1, 2, 4):
                 if heavy and sb == 4:
                     continue
                 run("sliced", {"host_slices": hs, "slice_bands": sb}, True)
+        run("sliced_unchained", {"host_slices": 4, "slice_bands": 2, "slice_chain": 0}, True)
         run("sliced_sync", {"host_slices": 4, "slice_bands": 2, "sync_free": 0}, True)
         # frame left in HBM: painter tables with / without count read-backs
         run("device", {"sync_free": 1}, False)

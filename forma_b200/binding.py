@@ -276,7 +276,7 @@ SIGNATURES = {
     "renderer_launch_count": (C.c_uint64, [_vp]),
     "renderer_stage_times": (None, [_vp, C.POINTER(C.c_double)]),
     "renderer_counters": (None, [_vp, _u64p]),
-    "renderer_host_slices": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "renderer_host_slices": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "renderer_kernel_times": (None, [_vp, C.POINTER(C.c_double), _u32p]),
     "renderer_set_stream": (None, [_vp, _vp]),
     "shared_frame_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]),
@@ -705,8 +705,14 @@ class Renderer:
     def host_slices(self) -> list:
         """Device-timeline ms of every slice of the last host frame ([] = rendered as one piece)."""
         ms = (C.c_double * 16)()
-        n = int(self._api.renderer_host_slices(self._h, ms))
+        n = int(self._api.renderer_host_slices(self._h, ms, None))
         return [float(ms[i]) for i in range(n)]
+
+    def host_slice_stages(self) -> list:
+        """Stage times of every slice of the last host frame (dicts keyed like stage_times())."""
+        ms, st = (C.c_double * 16)(), (C.c_double * 128)()
+        n = int(self._api.renderer_host_slices(self._h, ms, st))
+        return [dict(zip(self.STAGES, [float(st[8 * i + k]) for k in range(8)])) for i in range(n)]
 
     def row_costs(self) -> np.ndarray:
         """Per-tile-row cost of the last render (forma_renderer_row_costs)."""

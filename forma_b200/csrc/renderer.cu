@@ -349,7 +349,8 @@ class Renderer {
     cudaStream_t aux_stream = nullptr;  // side stream of the geometry upload (see flush_geometry)
     cudaEvent_t aux_ev[2];
     cudaStream_t band_stream[kMaxCopyBands];
-    bool band_streams_ok = false;
+    uint32_t band_streams_made = 0;  // created as needed: streams beyond the device's hardware queues alias onto them
+    bool band_streams_ok = false;    // the band events exist
     cudaEvent_t band_ev[kMaxCopyBands + 1];
     cudaEvent_t count_ev = nullptr;  // completion of a count read-back (waited on instead of the whole stream)
     cudaError_t ensure_count_event() {
@@ -410,10 +411,9 @@ class Renderer {
         if (pinned_totals) cudaFreeHost(pinned_totals);
         if (count_ev) cudaEventDestroy(count_ev);
         if (upload_done_ev) cudaEventDestroy(upload_done_ev);
-        if (band_streams_ok) {
+        if (band_streams_ok)
             for (auto& e : band_ev) cudaEventDestroy(e);
-            for (auto& bs : band_stream) cudaStreamDestroy(bs);
-        }
+        for (uint32_t k = 0; k < band_streams_made; ++k) cudaStreamDestroy(band_stream[k]);
         if (timer.ok) {
             for (auto& e : timer.ev) cudaEventDestroy(e);
             for (auto& e : timer.sort_ev) cudaEventDestroy(e);
@@ -1194,19 +1194,23 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
     const uint32_t paint_rows = S.ty_hi - S.ty_lo;
     if (!buffer_on_device && !cache && paint_rows >= (copy_bands_override ? 8u : 32u) && S.tx_hi > S.tx_lo && band_copies_enabled()) {
         if (!band_streams_ok) {
-            for (auto& bs : band_stream) FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&bs, cudaStreamNonBlocking));
             for (auto& e : band_ev) FORMA_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             band_streams_ok = true;
         }
         const uint64_t x0 = (uint64_t)S.tx_lo * 16u, x1 = std::min<uint64_t>((uint64_t)S.tx_hi * 16u, width);
         const uint32_t kCopyBands = std::max(1u, std::min(copy_bands(), paint_rows / 8u));
-        FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], stream));  // the tables are ready
+        // One band: paint and copy on the render stream itself.
+        while (kCopyBands > 1u && band_streams_made < kCopyBands) {
+            FORMA_CUDA_TRY(cudaStreamCreateWithFlags(&band_stream[band_streams_made], cudaStreamNonBlocking));
+            ++band_streams_made;
+        }
+        if (kCopyBands > 1u) FORMA_CUDA_TRY(cudaEventRecord(band_ev[kMaxCopyBands], stream));  // the tables are ready
         for (uint32_t k = 0; k < kCopyBands; ++k) {
             PaintScene Sb = S;
             Sb.ty_lo = S.ty_lo + paint_rows * k / kCopyBands;
             Sb.ty_hi = S.ty_lo + paint_rows * (k + 1u) / kCopyBands;
-            cudaStream_t bs = band_stream[k];
-            FORMA_CUDA_TRY(cudaStreamWaitEvent(bs, band_ev[kMaxCopyBands], 0));
+            cudaStream_t bs = kCopyBands > 1u ? band_stream[k] : stream;
+            if (kCopyBands > 1u) FORMA_CUDA_TRY(cudaStreamWaitEvent(bs, band_ev[kMaxCopyBands], 0));
             launch_paint(Sb, segs.ptr, recs.ptr, tile_range.ptr, heavy_lists, heavy_counts, eflags.ptr, fb, totals.ptr + 16 + k, bs);
             ++launches;
             const uint64_t y0 = (uint64_t)Sb.ty_lo * 16u, y1 = std::min<uint64_t>((uint64_t)Sb.ty_hi * 16u, height);
@@ -1218,9 +1222,9 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
                                                      (x1 - x0) * 4, y1 - y0, cudaMemcpyDeviceToHost, bs));
                 d2h_bytes += (x1 - x0) * 4 * (y1 - y0);
             }
-            FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], bs));
+            if (kCopyBands > 1u) FORMA_CUDA_TRY(cudaEventRecord(band_ev[k], bs));
         }
-        for (uint32_t k = 0; k < kCopyBands; ++k) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[k], 0));
+        for (uint32_t k = 0; kCopyBands > 1u && k < kCopyBands; ++k) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, band_ev[k], 0));
         paint_launches = kCopyBands;
         copied_in_bands = true;
     } else {
@@ -2220,10 +2224,15 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
 extern "C" {
 
 /* Slices of this renderer's last host frame (0 = rendered as one piece); out_ms (may be null,
- * room for 16) receives the device-timeline ms of every slice. */
-int forma_renderer_host_slices(const forma_renderer* r, double* out_ms) {
+ * room for 16) receives the device-timeline ms of every slice, out_stage_ms (may be null, room for
+ * 16 x 8) every slice's stage times in the order of forma_renderer_stage_times. */
+int forma_renderer_host_slices(const forma_renderer* r, double* out_ms, double* out_stage_ms) {
     if (!r || !r->r.last_slices || !r->slicer) return 0;
-    for (size_t i = 0; out_ms && i < r->slicer->last_ms.size() && i < 16; ++i) out_ms[i] = r->slicer->last_ms[i];
+    const size_t n = std::min<size_t>(r->r.last_slices, 16);
+    for (size_t i = 0; i < n && i < r->slicer->dev.size(); ++i) {
+        if (out_ms) out_ms[i] = r->slicer->dev[i]->r.stage_ms[7];
+        for (int k = 0; out_stage_ms && k < 8; ++k) out_stage_ms[8 * i + k] = r->slicer->dev[i]->r.stage_ms[k];
+    }
     return (int)r->r.last_slices;
 }
 

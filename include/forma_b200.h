@@ -270,12 +270,14 @@ void forma_renderer_counters(const forma_renderer*, uint64_t out[8]);
  * transform are rendered as a pipeline of tile-row slices on the renderer's device (option
  * host_slices): slice k + 1 uploads its band's geometry while slice k computes and slice k - 1
  * copies its rows back. Returns the number of slices of the last host frame (0 = one piece);
- * out_ms (may be null, room for 16) receives each slice's device-timeline ms. After a sliced
+ * out_ms (may be null, room for 16) receives each slice's device-timeline ms (from the start of the
+ * frame: a slice's upload waits for those of the slices before it), out_stage_ms (may be null,
+ * room for 16 x 8) each slice's stage times as in forma_renderer_stage_times. After a sliced
  * frame the counters above are sums over the slices (pixel segments and entries: every slice
  * counts its own rows, so they are the frame's; cells: an upper bound, a slice also sees the
  * segments boundary-crossing lines leave in its neighbours' rows) and the stage times those of
  * the slowest slice. */
-int forma_renderer_host_slices(const forma_renderer*, double* out_ms);
+int forma_renderer_host_slices(const forma_renderer*, double* out_ms, double* out_stage_ms);
 
 /* Cost of every tile row of the last render (32 x its (tile, layer) entries + its pixel
  * segments; rows outside the rendered crop cost 0): what a caller balances the tile-row

@@ -75,8 +75,9 @@ def test_sliced_counters_are_those_of_the_whole_frame(cuda_api, slice_options):
     assert whole["cells"] <= c["cells"] < 1.2 * whole["cells"] and 0.9 * whole["entries"] < c["entries"] < 1.2 * whole["entries"]
     assert c["d2h_bytes"] == whole["d2h_bytes"] == W * H * 4
     assert c["launches"] > whole["launches"]
-    # every slice uploads its band's geometry (shapes crossing a boundary twice), never the whole composition four times
-    assert whole["h2d_bytes"] <= c["h2d_bytes"] < 2.0 * whole["h2d_bytes"]
+    # every slice uploads the tables (one style record per layer here) and its band's geometry (shapes
+    # crossing a boundary twice), never the whole composition four times
+    assert whole["h2d_bytes"] <= c["h2d_bytes"] < 3.5 * whole["h2d_bytes"]
     assert r4.segments().size == 0  # no single sorted array after a sliced frame
 
 

@@ -15,7 +15,7 @@ namespace forma {
 struct Options {
     int speculate = 1;       // launch kernels ahead of their count read-backs (0: strictly after)
     int band_copy = 1;       // host frames: paint / copy back in bands of tile rows
-    int copy_bands = 8;      //   ... how many (1..16; measured on paris@4K: 1 -> 481, 2 -> 492, 4 -> 484, 8 -> 511 frames/s end to end)
+    int copy_bands = 4;      //   ... how many (1..16; paris@4K end to end, r2 final build: 4 -> 582.7, 8 -> 567.9, 16 -> 553.8 frames/s; cubics100k 303.6 / 298.6 / 291.1; circles8k 102.3 / 101.1 / 97.7)
     int sort_full_key = 0;   // 1: sort the layer digits even when the inserts are in layer order
     int sort_big_log2 = 19;  // key count from which the 4096-key tiles / reduce-then-scan passes are used
     int sort_scan_log2 = 22; // key-only sorts: key count from which the reduce-then-scan passes replace the single-sweep ones (measured on paris@4K bands: 0.7 M keys 0.044 vs 0.055 ms, 3 M equal, 5.9 M 0.130 vs 0.105 ms)
@@ -25,7 +25,9 @@ struct Options {
     int band_filter = 1;     // a render cropped to a band of rows only makes the band's geometry resident
     int sync_free = 1;       // painter tables without count read-backs when the previous frame's counts bound this one's (redone the slow way if they do not)
     int test_fast_shrink = 0;  // test hook: halve the bounds of the sync-free tables (forces the redo)
-    int host_slices = 4;     // host frames: tile-row slices rendered as independent upload -> render -> copy-back pipelines on their own streams (1 = off)
+    int host_slices = 1;     // host frames: > 1 = that many tile-row slices rendered as independent upload -> render -> copy-back pipelines on their own streams.
+                             //   Off by default: measured on paris@4K 578.9 (off) vs 544-587 frames/s (2-4 slices), 509 (6), 422 (8); cubics100k 298.6 vs 280 / 237;
+                             //   the slices' kernel chains do not overlap on the device (latency-bound kernels that fill the SMs), see DESIGN.md section 3
     int slice_bands = 2;     //   ... copy bands inside a slice
     int slice_min_points = 65536;  //   ... only for compositions of at least this many points
     int slice_chain = 1;     //   ... uploads issued slice after slice, each waiting for the one before (0: all at once from the slices' threads)

@@ -30,7 +30,6 @@ struct Options {
                              //   the slices' kernel chains do not overlap on the device (latency-bound kernels that fill the SMs), see DESIGN.md section 3
     int slice_bands = 2;     //   ... copy bands inside a slice
     int slice_min_points = 65536;  //   ... only for compositions of at least this many points
-    int slice_gate = 1;      //   ... the slices' threads queue their work one after the other (IssueGate) instead of all at once
     int slice_chain = 1;     //   ... uploads issued slice after slice, each waiting for the one before (0: all at once from the slices' threads)
 };
 Options& options();

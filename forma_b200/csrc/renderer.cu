@@ -57,7 +57,6 @@ static const OptionName kOptionNames[] = {
     {"sync_free", &Options::sync_free, 0, 1},         {"test_fast_shrink", &Options::test_fast_shrink, 0, 1},
     {"host_slices", &Options::host_slices, 1, 16},    {"slice_bands", &Options::slice_bands, 1, 16},
     {"slice_min_points", &Options::slice_min_points, 0, 1 << 30}, {"slice_chain", &Options::slice_chain, 0, 1},
-    {"slice_gate", &Options::slice_gate, 0, 1},
 };
 Options& options() {
     static Options o = [] {
@@ -312,29 +311,6 @@ struct Timer {
     bool ok = false;
 };
 
-// Turnstile of a host-frame pipeline: the slices' threads issue their work one after the other,
-// in slice order. Threads that launch into one context at the same time contend for the
-// driver's lock and every launch gets slower; a slice's kernel chain is a sequence of ~40 small
-// launches, so a chain issued under contention is issue-bound on the host instead of running
-// back to back on the device. A slice holds the gate from the start of its render to the point
-// where everything is queued and only the final wait is left.
-struct IssueGate {
-    std::mutex mu;
-    std::condition_variable cv;
-    int turn = 0;
-    void acquire(int ticket) {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return turn >= ticket; });
-    }
-    void pass(int ticket) {  // lets ticket + 1 in (idempotent)
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            if (turn < ticket + 1) turn = ticket + 1;
-        }
-        cv.notify_all();
-    }
-};
-
 class Renderer {
    public:
     int device = 0;
@@ -421,9 +397,6 @@ class Renderer {
     cudaEvent_t upload_done_ev = nullptr;  // recorded behind this renderer's last host -> device copy
     cudaEvent_t upload_after = nullptr;    // this renderer's copies wait for it (the previous slice's upload_done_ev)
     bool prefetched = false;               // prefetch() ran for the coming render: timer.ev[0] is already recorded
-    IssueGate* gate = nullptr;             // set for the coming render of a slice renderer (see IssueGate)
-    int gate_ticket = 0;
-    cudaEvent_t done_ev = nullptr;         // blocking-sync event: a slice's thread sleeps until its frame part is done
     int prefetch(Composition& comp, uint64_t width, uint64_t height, const forma_rect* crop);
     int ensure_timer() {
         if (!timer.ok) {
@@ -438,7 +411,6 @@ class Renderer {
         if (pinned_totals) cudaFreeHost(pinned_totals);
         if (count_ev) cudaEventDestroy(count_ev);
         if (upload_done_ev) cudaEventDestroy(upload_done_ev);
-        if (done_ev) cudaEventDestroy(done_ev);
         if (band_streams_ok)
             for (auto& e : band_ev) cudaEventDestroy(e);
         for (uint32_t k = 0; k < band_streams_made; ++k) cudaStreamDestroy(band_stream[k]);
@@ -883,19 +855,6 @@ int Renderer::prefetch(Composition& comp, uint64_t width, uint64_t height, const
 int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, uint64_t width, uint64_t stride,
                      uint64_t height, const uint32_t channels_in[4], const float clear[4], const forma_rect* crop,
                      LayerCache* cache, forma_timings* timings) {
-    // A slice of a host-frame pipeline queues its work when it is its turn; whatever way this call
-    // ends, the next slice is let in.
-    struct GateHold {
-        IssueGate* g;
-        int ticket;
-        ~GateHold() { pass(); }
-        void pass() {
-            if (g) g->pass(ticket);
-            g = nullptr;
-        }
-    } gate_hold{gate, gate_ticket};
-    gate = nullptr;
-    if (gate_hold.g) gate_hold.g->acquire(gate_hold.ticket);
     // LinearLayout::new asserts (layout/mod.rs:188-193) + consts.rs limits.
     if (!buffer || width == 0 || height == 0 || width * 4 > stride || width > FORMA_MAX_WIDTH || height > FORMA_MAX_HEIGHT) {
         set_error("invalid render target %llux%llu stride %llu", (unsigned long long)width, (unsigned long long)height,
@@ -1321,14 +1280,7 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         }
     }
     FORMA_CUDA_TRY(cudaEventRecord(timer.ev[6], stream));
-    if (gate_hold.g && done_ev) {  // everything is queued: next slice; this thread sleeps until its part is done
-        FORMA_CUDA_TRY(cudaEventRecord(done_ev, stream));
-        gate_hold.pass();
-        FORMA_CUDA_TRY(cudaEventSynchronize(done_ev));
-    } else {
-        gate_hold.pass();
-        FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
-    }
+    FORMA_CUDA_TRY(cudaStreamSynchronize(stream));
     if (fast && n > 0) {
         last_cells = pinned_totals[1];
         last_gaps = pinned_totals[2];
@@ -1927,7 +1879,6 @@ struct forma_renderer_multi {
     bool peer_ok = true;           // every device may store into the first device's memory
     std::vector<double> last_ms;   // device-timeline ms of each band in the last frame
     size_t active = 0;             // bands used by the last frame (a sliced host frame may use fewer than dev.size())
-    IssueGate gate;                // host-frame pipeline: the slices queue their work in slice order
     uint64_t last_own_segments = 0, last_own_entries = 0;  // pixel segments / entries of the last frame, every band counting its own rows only
     WorkerPool pool;
 };
@@ -1988,13 +1939,6 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
         band->vert_end = std::min<uint64_t>(std::min<uint64_t>(full.vert_end, height), (uint64_t)r1 * 16u);
         return band->vert_end > band->vert_start;
     };
-    if (chained_uploads && options().slice_gate) {
-        m->gate.turn = 0;
-        for (size_t i = 0; i < n; ++i) {
-            m->dev[i]->r.gate = &m->gate;
-            m->dev[i]->r.gate_ticket = (int)i;
-        }
-    }
     if (chained_uploads) {
         // Slices of one device share its PCIe link: their uploads are issued here, in slice order,
         // each waiting for the one before (Renderer::upload_after), instead of all at once.
@@ -2003,10 +1947,7 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
             if (!band_of(i, &band)) continue;
             const int st = m->dev[i]->r.prefetch(comp, width, height, &band);
             if (st) {
-                for (size_t k = 0; k < n; ++k) {
-                    m->dev[k]->r.prefetched = false;
-                    m->dev[k]->r.gate = nullptr;
-                }
+                for (size_t k = 0; k < n; ++k) m->dev[k]->r.prefetched = false;
                 return st;
             }
         }
@@ -2015,12 +1956,8 @@ static int multi_render_impl(forma_renderer_multi* m, forma_composition* c, uint
         const uint32_t r0 = m->bounds[i], r1 = m->bounds[i + 1];
         std::memset(&tms[i], 0, sizeof(forma_timings));
         forma_rect band;
+        if (!band_of(i, &band)) return;
         Renderer& R = m->dev[i]->r;
-        if (!band_of(i, &band)) {
-            if (R.gate) R.gate->pass(R.gate_ticket);
-            R.gate = nullptr;
-            return;
-        }
         status[i] = guarded((int)FORMA_ERR_CAPACITY, [&] {
             return R.render(comp, buffer, on_device, width, stride, height, channels, clear, &band, nullptr, &tms[i]);
         });
@@ -2233,8 +2170,6 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
             q->r.track_row_costs = true;
             if (cudaEventCreateWithFlags(&q->r.upload_done_ev, cudaEventDisableTiming) != cudaSuccess) q->r.upload_done_ev = nullptr;
             if (i > 0) q->r.upload_after = m->dev[i - 1]->r.upload_done_ev;
-            if (cudaEventCreateWithFlags(&q->r.done_ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
-                q->r.done_ev = nullptr;
             m->dev.push_back(q);
         }
         r->slicer = m.release();

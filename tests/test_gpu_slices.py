@@ -32,7 +32,7 @@ def expected(oracle_api):
 
 @pytest.fixture()
 def slice_options(cuda_api):
-    names = ("host_slices", "slice_bands", "slice_min_points", "slice_chain", "slice_gate", "sync_free", "band_filter")
+    names = ("host_slices", "slice_bands", "slice_min_points", "slice_chain", "sync_free", "band_filter")
     saved = {n: cuda_api.get_option(n) for n in names}
     cuda_api.set_option("slice_min_points", 0)
     yield
@@ -159,11 +159,6 @@ def test_frames_the_pipeline_leaves_alone(cuda_api, oracle_api, slice_options):
     r.render(comp, buf2, W, H, RGBA, CLEAR)
     assert len(r.host_slices()) == 4 and np.array_equal(buf2, want)
     cuda_api.set_option("band_filter", 1)
-    cuda_api.set_option("slice_gate", 0)                        # the slices' threads queue their work all at once
-    comp.evict()
-    buf2[:] = 0
-    r.render(comp, buf2, W, H, RGBA, CLEAR)
-    assert len(r.host_slices()) == 4 and np.array_equal(buf2, want)
     cuda_api.set_option("slice_chain", 0)                       # uploads issued by the slices' threads, all at once
     comp.evict()
     buf2[:] = 0

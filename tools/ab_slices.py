@@ -95,8 +95,6 @@ def main():
                     continue
                 run("sliced", {"host_slices": hs, "slice_bands": sb}, True)
         if quick:
-            for hs in (2, 3, 4):
-                run("sliced_ungated", {"host_slices": hs, "slice_bands": 1, "slice_gate": 0}, True)
             continue
         run("sliced_unchained", {"host_slices": 4, "slice_bands": 2, "slice_chain": 0}, True)
         run("sliced_sync", {"host_slices": 4, "slice_bands": 2, "sync_free": 0}, True)

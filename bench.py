@@ -620,6 +620,7 @@ def run_cuda(args):
            "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32+f64/u64", "data": data_of(args), "config": config_of(args, world)}
     out.update(res)
+    out["library_options"] = {k: env["api"].get_option(k) for k in ("sync_free", "speculate", "copy_bands", "host_slices", "band_filter", "paint_lpt")}
     out["clocks"] = sampler.summary()
     if extras:
         out["extra"] = {}

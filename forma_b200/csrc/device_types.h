@@ -77,16 +77,18 @@ struct FlattenProgram {
 
 // A batch entry of flatten_eval_kernel: points [first, first+count) of the
 // batch belong to this insert job (Layer::insert, composition/layer.rs:90-111).
-struct FlattenJob {
-    uint32_t first_point;   // first output point of the job in the batch
-    uint32_t count;
+struct FlattenJob {          // 24 B per Layer::insert of an uploaded batch
+    uint32_t first_point;   // first output point of the job in the batch = its offset in the destination; the job's
+                            // point count is the next job's first_point (the batch's point count for the last) minus this
     uint32_t quad_base;     // added to SplineRec::first_quad
     uint32_t spline_base;   // the job's splines in the batch's SplineRec array, or its first PointRec
     uint32_t n_splines;     // 0 = point encoding
     uint32_t geom_id;       // id written for non-contour-end points (0 = None)
-    uint32_t has_xf;
-    float xf[6];            // GeomPresTransform: ux, uy, vx, vy, tx, ty
-    uint32_t dst;           // destination offset in the segment buffer
+    uint32_t xf_index;      // 1 + index of the insert's transform in the batch's JobXf array; 0 = none
+};
+// GeomPresTransform of an insert whose path carries one (path.rs:689-706): ux, uy, vx, vy, tx, ty.
+struct JobXf {
+    float xf[6];
 };
 
 // Per-layer record used by line setup (composition/layer.rs:27-31 InnerLayer).

@@ -67,12 +67,13 @@ struct CompDevice {
     PinnedBuffer<uint8_t> h_kinds;
     PinnedBuffer<QuadUp> h_quads;
     PinnedBuffer<FlattenJob> h_jobs;
+    PinnedBuffer<JobXf> h_xfs;        // transforms of the staged jobs that carry one (FlattenJob::xf_index)
     bool staged_valid = false;
     bool staged_rational = true;      // the staged quadratics are QuadUp (else QuadUpPoly)
     bool staged_filtered = false;
     float staged_lo = 0.0f, staged_hi = 0.0f;
     size_t staged_from = 0, staged_to = 0, staged_jobs = 0, staged_splines = 0, staged_recs = 0, staged_quads = 0,
-           staged_points = 0;
+           staged_points = 0, staged_xfs = 0;
     // Tables.
     uint64_t tables_version = 0;      // Composition::tables_version of the device copies (0 = none)
     DeviceBuffer<uint32_t> d_layer_bits;

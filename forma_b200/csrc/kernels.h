@@ -50,8 +50,9 @@ struct RasterArgs {
 
 // ---- kernels_raster.cu ------------------------------------------------------
 void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const uint8_t* kinds, const QuadRec* quads,
-                         const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, uint32_t dst_base /* + job.dst */, float* x,
-                         float* y, uint32_t* gid, cudaStream_t stream);
+                         const FlattenJob* jobs, const JobXf* xfs, uint32_t n_jobs, uint32_t n_points,
+                         uint32_t dst_base /* first point of the batch in the segment buffer */, float* x, float* y, uint32_t* gid,
+                         cudaStream_t stream);
 // Rebuilds the device-resident QuadRecs from the uploaded control points (quad_math.h).
 void launch_quad_expand(const QuadUp* in, QuadRec* out, uint32_t n, cudaStream_t stream);
 void launch_quad_expand_poly(const QuadUpPoly* in, QuadRec* out, uint32_t n, cudaStream_t stream);  // all weights 1

@@ -90,8 +90,8 @@ void launch_quad_expand_poly(const QuadUpPoly* in, QuadRec* out, uint32_t n, cud
 // PCIe instead of 16 B per point).
 __global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const PointRec* __restrict__ points,
                                     const uint8_t* __restrict__ kinds, const QuadRec* __restrict__ quads,
-                                    const FlattenJob* __restrict__ jobs, uint32_t n_jobs, uint32_t n_points,
-                                    uint32_t dst_base /* added to every job's dst */, float* __restrict__ out_x,
+                                    const FlattenJob* __restrict__ jobs, const JobXf* __restrict__ xfs, uint32_t n_jobs,
+                                    uint32_t n_points, uint32_t dst_base /* first point of the batch */, float* __restrict__ out_x,
                                     float* __restrict__ out_y, uint32_t* __restrict__ out_gid) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_points) return;
@@ -103,6 +103,7 @@ __global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const
     }
     const FlattenJob job = jobs[lo];
     const uint32_t local = i - job.first_point;
+    const uint32_t count = (lo + 1u < n_jobs ? jobs[lo + 1u].first_point : n_points) - job.first_point;
     uint32_t kind;  // 0 literal, 1 literal + contour end, 2 evaluated
     float px = 0.0f, py = 0.0f, pi = 0.0f;
     const QuadRec* qp = nullptr;
@@ -161,16 +162,17 @@ __global__ void flatten_eval_kernel(const SplineRec* __restrict__ splines, const
         px = d_mix(t, d_mix(t, q.px[0], q.px[1]), d_mix(t, q.px[1], q.px[2])) * w_recip;
         py = d_mix(t, d_mix(t, q.py[0], q.py[1]), d_mix(t, q.py[1], q.py[2])) * w_recip;
     }
-    if (job.has_xf) {  // path.rs:689-706, GeomPresTransform::transform
-        float tx = fmaf(job.xf[0], px, fmaf(job.xf[2], py, job.xf[4]));
-        float ty = fmaf(job.xf[1], px, fmaf(job.xf[3], py, job.xf[5]));
+    if (job.xf_index) {  // path.rs:689-706, GeomPresTransform::transform
+        const JobXf m = xfs[job.xf_index - 1u];
+        float tx = fmaf(m.xf[0], px, fmaf(m.xf[2], py, m.xf[4]));
+        float ty = fmaf(m.xf[1], px, fmaf(m.xf[3], py, m.xf[5]));
         px = tx;
         py = ty;
     }
-    uint32_t dst = dst_base + job.dst + local;
+    uint32_t dst = dst_base + i;  // the batch's points land in job order
     // ids: None at contour ends; the id of the last point of an insert is
     // replaced by the trailing None (segment.rs:181-198).
-    bool none = kind == 1u || local + 1u == job.count;
+    bool none = kind == 1u || local + 1u == count;
     out_x[dst] = px;
     out_y[dst] = py;
     out_gid[dst] = none ? 0u : job.geom_id;
@@ -466,11 +468,11 @@ void launch_line_records(const RasterArgs& args, uint32_t n, uint32_t* orders, f
 // Host launchers
 // ---------------------------------------------------------------------------
 void launch_flatten_eval(const SplineRec* splines, const PointRec* points, const uint8_t* kinds, const QuadRec* quads,
-                         const FlattenJob* jobs, uint32_t n_jobs, uint32_t n_points, uint32_t dst_base, float* x, float* y,
-                         uint32_t* gid, cudaStream_t stream) {
+                         const FlattenJob* jobs, const JobXf* xfs, uint32_t n_jobs, uint32_t n_points, uint32_t dst_base,
+                         float* x, float* y, uint32_t* gid, cudaStream_t stream) {
     if (!n_points || !n_jobs) return;
-    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, points, kinds, quads, jobs, n_jobs, n_points, dst_base,
-                                                                    x, y, gid);
+    flatten_eval_kernel<<<(n_points + 255) / 256, 256, 0, stream>>>(splines, points, kinds, quads, jobs, xfs, n_jobs, n_points,
+                                                                    dst_base, x, y, gid);
 }
 
 uint32_t raster_num_blocks(uint32_t n_points) { return n_points ? (n_points + kRasterThreads - 1) / kRasterThreads : 0; }

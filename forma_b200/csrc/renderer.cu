@@ -373,6 +373,7 @@ class Renderer {
     DeviceBuffer<uint8_t> up_kinds;
     DeviceBuffer<QuadRec> up_quads;
     DeviceBuffer<FlattenJob> up_jobs;
+    DeviceBuffer<JobXf> up_xfs;
 
     uint32_t last_segments = 0, last_cells = 0, last_entries = 0, last_gaps = 0;
     bool last_tables_sync_free = false, last_tables_redone = false;  // how the last frame's painter tables were built
@@ -495,13 +496,14 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
     if (!cd.staged_valid || cd.staged_from != from || cd.staged_to != to || cd.staged_filtered != cd.filtered ||
         (cd.filtered && (cd.staged_lo != cd.band_lo || cd.staged_hi != cd.band_hi))) {
         // (Re)build the pinned staging copy of the flatten programs of the wanted jobs in [from, to).
-        size_t n_jobs = 0, n_splines = 0, n_quads = 0, n_pts = 0, n_recs = 0;
+        size_t n_jobs = 0, n_splines = 0, n_quads = 0, n_pts = 0, n_recs = 0, n_xfs = 0;
         bool rational = false;  // any weight != 1 in the batch: 48-byte QuadUp, else 36-byte QuadUpPoly
         for (size_t j = from; j < to; ++j) {
             if (!wanted(comp.jobs[j])) continue;
             const FlattenProgram& prog = comp.jobs[j].data->program();
             rational = rational || prog.rational;
             ++n_jobs;
+            n_xfs += comp.jobs[j].has_xf ? 1u : 0u;
             n_splines += prog.splines.size();
             n_recs += prog.points.size();
             n_quads += prog.quads.size();
@@ -517,21 +519,23 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
         FORMA_CUDA_TRY(cd.h_kinds.reserve(n_recs + 1));
         FORMA_CUDA_TRY(cd.h_quads.reserve(n_quads + 1));
         FORMA_CUDA_TRY(cd.h_jobs.reserve(n_jobs + 1));
-        size_t ji = 0, si = 0, qi = 0, pi = 0, ri = 0;
+        FORMA_CUDA_TRY(cd.h_xfs.reserve(n_xfs + 1));
+        size_t ji = 0, si = 0, qi = 0, pi = 0, ri = 0, xi = 0;
         for (size_t j = from; j < to; ++j) {
             const PendingInsert& p = comp.jobs[j];
             if (!wanted(p)) continue;
             const FlattenProgram& prog = p.data->program();
             FlattenJob& job = cd.h_jobs.ptr[ji++];
-            job.first_point = (uint32_t)pi;
-            job.count = p.count;
+            job.first_point = (uint32_t)pi;  // relative to the batch; the batch lands at the device's resident point count
             job.quad_base = (uint32_t)qi;
             job.spline_base = (uint32_t)(prog.splines.empty() ? ri : si);
             job.n_splines = (uint32_t)prog.splines.size();
             job.geom_id = p.geom_id;
-            job.has_xf = p.has_xf ? 1u : 0u;
-            std::memcpy(job.xf, p.xf, sizeof(job.xf));
-            job.dst = (uint32_t)pi;  // relative to the batch; the batch lands at the device's resident point count
+            job.xf_index = 0;
+            if (p.has_xf) {
+                std::memcpy(cd.h_xfs.ptr[xi].xf, p.xf, sizeof(p.xf));
+                job.xf_index = (uint32_t)++xi;
+            }
             if (!prog.splines.empty())
                 std::memcpy(cd.h_splines.ptr + si, prog.splines.data(), prog.splines.size() * sizeof(SplineRec));
             if (!prog.points.empty()) {
@@ -570,6 +574,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
         cd.staged_recs = n_recs;
         cd.staged_quads = n_quads;
         cd.staged_points = n_pts;
+        cd.staged_xfs = n_xfs;
         cd.staged_rational = rational;
     }  // else: the same batch as last time (an evicted composition) is uploaded again from the same staging
     cd.jobs_resident = to;
@@ -584,6 +589,7 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
     FORMA_CUDA_TRY(up_kinds.reserve(cd.staged_recs + 1));
     FORMA_CUDA_TRY(up_quads.reserve(cd.staged_quads + 1));
     FORMA_CUDA_TRY(up_jobs.reserve(cd.staged_jobs));
+    FORMA_CUDA_TRY(up_xfs.reserve(cd.staged_xfs + 1));
     // The quadratics go first: their expansion kernel runs on a side stream while the copy
     // engine keeps sending the other records.
     bool expanding = false;
@@ -617,11 +623,13 @@ int Renderer::flush_geometry(Composition& comp, float band_lo, float band_hi, bo
         FORMA_CUDA_TRY(cudaMemcpyAsync(up_kinds.ptr, cd.h_kinds.ptr, cd.staged_recs, cudaMemcpyHostToDevice, stream));
     }
     FORMA_CUDA_TRY(cudaMemcpyAsync(up_jobs.ptr, cd.h_jobs.ptr, cd.staged_jobs * sizeof(FlattenJob), cudaMemcpyHostToDevice, stream));
+    if (cd.staged_xfs)
+        FORMA_CUDA_TRY(cudaMemcpyAsync(up_xfs.ptr, cd.h_xfs.ptr, cd.staged_xfs * sizeof(JobXf), cudaMemcpyHostToDevice, stream));
     if (upload_done_ev) FORMA_CUDA_TRY(cudaEventRecord(upload_done_ev, stream));
     h2d_bytes += cd.staged_splines * sizeof(SplineRec) + cd.staged_recs * (sizeof(PointRec) + 1) +
-                 cd.staged_quads * quad_bytes + cd.staged_jobs * sizeof(FlattenJob);
+                 cd.staged_quads * quad_bytes + cd.staged_jobs * sizeof(FlattenJob) + cd.staged_xfs * sizeof(JobXf);
     if (expanding) FORMA_CUDA_TRY(cudaStreamWaitEvent(stream, aux_ev[1], 0));
-    launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, (uint32_t)cd.staged_jobs,
+    launch_flatten_eval(up_splines.ptr, up_points.ptr, up_kinds.ptr, up_quads.ptr, up_jobs.ptr, up_xfs.ptr, (uint32_t)cd.staged_jobs,
                         (uint32_t)cd.staged_points, cd.n_resident, cd.d_x.ptr, cd.d_y.ptr, cd.d_gid.ptr, stream);
     ++launches;
     FORMA_CUDA_TRY(cudaGetLastError());
@@ -1477,14 +1485,16 @@ static int path_segments_impl(forma_path* p, const float** x, const float** y, c
     FORMA_CUDA_TRY(dg.reserve(count));
     FlattenJob job{};
     job.first_point = 0;
-    job.count = count;
     job.quad_base = 0;
     job.spline_base = 0;
     job.n_splines = (uint32_t)prog.splines.size();
     job.geom_id = 1;
-    job.has_xf = p->p.has_xf ? 1u : 0u;
-    std::memcpy(job.xf, p->p.xf, sizeof(job.xf));
-    job.dst = 0;
+    job.xf_index = p->p.has_xf ? 1u : 0u;
+    JobXf job_xf{};
+    std::memcpy(job_xf.xf, p->p.xf, sizeof(job_xf.xf));
+    DeviceBuffer<JobXf> dxf;
+    FORMA_CUDA_TRY(dxf.reserve(1));
+    FORMA_CUDA_TRY(cudaMemcpy(dxf.ptr, &job_xf, sizeof(job_xf), cudaMemcpyHostToDevice));
     DeviceBuffer<PointRec> dp;
     DeviceBuffer<uint8_t> dk;
     FORMA_CUDA_TRY(dp.reserve(prog.points.size() + 1));
@@ -1505,7 +1515,7 @@ static int path_segments_impl(forma_path* p, const float** x, const float** y, c
         FORMA_CUDA_TRY(cudaDeviceSynchronize());
     }
     FORMA_CUDA_TRY(cudaMemcpy(dj.ptr, &job, sizeof(job), cudaMemcpyHostToDevice));
-    launch_flatten_eval(dc.ptr, dp.ptr, dk.ptr, dq.ptr, dj.ptr, 1, count, 0, dx.ptr, dy.ptr, dg.ptr, 0);
+    launch_flatten_eval(dc.ptr, dp.ptr, dk.ptr, dq.ptr, dj.ptr, dxf.ptr, 1, count, 0, dx.ptr, dy.ptr, dg.ptr, 0);
     FORMA_CUDA_TRY(cudaGetLastError());
     FORMA_CUDA_TRY(cudaMemcpy(p->x.data(), dx.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));
     FORMA_CUDA_TRY(cudaMemcpy(p->y.data(), dy.ptr, count * sizeof(float), cudaMemcpyDeviceToHost));

@@ -289,6 +289,42 @@ def test_crop_touches_only_cropped_tiles(cuda_api, oracle_api, cuda_renderer, or
     assert_same(a, b, "crop")
 
 
+def test_inserts_with_and_without_path_transforms_in_one_batch(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
+    """Path::transform with a transform that preserves geometry (rotation / translation / shrink:
+    math/transform.rs:161-221) keeps the path's data and applies the transform to the flattened
+    points at insert time (path.rs:689-706). One upload batch mixes such inserts with plain ones
+    and with up-scaled paths (re-flattened): every insert must pick its own transform."""
+    import math
+    w, h = 640, 400
+    outs = []
+    for api, r in ((cuda_api, cuda_renderer), (oracle_api, oracle_renderer)):
+        comp = api.Composition()
+        rng = synth.SplitMix64(23)
+        for i in range(120):
+            cx, cy, e = rng.uniform(60, w - 60), rng.uniform(60, h - 60), rng.uniform(10, 70)
+            pb = api.PathBuilder().move_to(Point(synth.f32(cx - e), synth.f32(cy)))
+            pb.cubic_to(Point(synth.f32(cx), synth.f32(cy - e)), Point(synth.f32(cx + e), synth.f32(cy - 0.3 * e)),
+                        Point(synth.f32(cx + 0.6 * e), synth.f32(cy + e)))
+            pb.quad_to(Point(synth.f32(cx), synth.f32(cy + 1.4 * e)), Point(synth.f32(cx - e), synth.f32(cy + 0.2 * e)))
+            path = pb.build()
+            kind = i % 4
+            if kind == 1:    # rotation about the origin + translation back into the frame
+                a = rng.uniform(-0.4, 0.4)
+                c_, s_ = math.cos(a), math.sin(a)
+                path = path.transform([c_, -s_, synth.f32(rng.uniform(-20, 60)), s_, c_, synth.f32(rng.uniform(-40, 40)), 0.0, 0.0, 1.0])
+            elif kind == 2:  # shrink
+                k = rng.uniform(0.4, 0.95)
+                path = path.transform([k, 0.0, synth.f32(rng.uniform(0, 80)), 0.0, k, synth.f32(rng.uniform(0, 50)), 0.0, 0.0, 1.0])
+            elif kind == 3:  # scale up: control points transformed, path re-flattened
+                path = path.transform([1.3, 0.0, -90.0, 0.0, 1.2, -40.0, 0.0, 0.0, 1.0])
+            col = Color(rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.3, 1.0))
+            comp.get_mut_or_insert_default(i).insert(path).set_props(Props(func=Func.Draw(Style(fill=Fill.Solid(col)))))
+        buf = np.zeros(w * h * 4, np.uint8)
+        r.render(comp, buf, w, h, RGBA, Color(1, 1, 1, 1))
+        outs.append(buf)
+    assert_same(outs[0].reshape(h, -1), outs[1].reshape(h, -1), "inserts with path transforms")
+
+
 def test_layer_ops_disable_transform_clear_remove(cuda_api, oracle_api, cuda_renderer, oracle_renderer):
     """composition/mod.rs:520-1000 style sequence: several renders of one composition."""
     outs = []

@@ -7,6 +7,10 @@ R=${1:-r2}
 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -3 > gpurun_out/${R}_gpu_tests.txt
 python -c "import __graft_entry__ as g; g.smoke()" >> gpurun_out/${R}_gpu_tests.txt 2>&1
 cat gpurun_out/${R}_gpu_tests.txt
+if grep -q "failed\|error" gpurun_out/${R}_gpu_tests.txt; then
+  python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -40
+  echo "GPU tests failed: stopping before the benches"; exit 1
+fi
 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/${R}_bench_reference_paris4k.json 2>/dev/null
 python bench.py > gpurun_out/${R}_bench_paris4k.json 2> gpurun_out/${R}_bench_paris4k.err
 for w in cubics100k circles8k paris4k_grad; do

@@ -33,13 +33,14 @@ vals = {}
 
 def put(prefix, d):
     if not d:
-        for k in ("v", "ms", "seg", "e2e"):
+        for k in ("v", "ms", "seg", "e2e", "io"):
             vals[f"{prefix}_{k}"] = "n/a"
         return
     vals[f"{prefix}_v"] = f1(d["value"])
     vals[f"{prefix}_ms"] = f"{1e3 / d['value']:.3f}"
     vals[f"{prefix}_seg"] = f"{d['mpixel_segments_per_s']:,.0f}".replace(",", " ")
     vals[f"{prefix}_e2e"] = f1(d["e2e"]["value"])
+    vals[f"{prefix}_io"] = f"{d['e2e']['h2d_bytes_per_step'] / 1e6:.1f} MB / {d['e2e']['d2h_bytes_per_step'] / 1e6:.1f} MB"
 
 
 put("paris", main)

@@ -382,7 +382,7 @@ def bench_workload(env, args, name, steps, warmup, headline):
     cache_host = renderer.create_buffer_layer_cache() if animate else None
 
     def frame_device():
-        renderer.render_device(comp, frame_ptr, w, h, RGBA, clear, crop, cache_dev, stride)
+        renderer.render_device(comp, frame_ptr, w, h, RGBA, clear, crop, cache_dev, stride, timings=False)
         if world > 1:
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(stream)
@@ -403,12 +403,14 @@ def bench_workload(env, args, name, steps, warmup, headline):
         # (evict) and the frame (this rank's band) is copied back to (its place in) the host
         # frame, all inside the timed region.
         comp.evict()
-        renderer.render(comp, host_np, w, h, RGBA, clear, crop, cache_host, stride)
+        renderer.render(comp, host_np, w, h, RGBA, clear, crop, cache_host, stride, timings=False)
 
     flush = env["flush"]
 
-    def timed(fn, n):
-        """Per-step CUDA events on the launching stream; the L2 flush runs between steps, untimed."""
+    def timed(fn, n, after=None):
+        """Per-step CUDA events on the launching stream; the L2 flush runs between steps, untimed.
+        `after` (reading the step's stage times: a dozen event queries) runs behind the step's
+        closing synchronisation, outside the timed interval - it is diagnostics, not rendering."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         wall = 0.0
         for a, b in evs:
@@ -426,6 +428,8 @@ def bench_workload(env, args, name, steps, warmup, headline):
             b.record(stream)
             torch.cuda.synchronize()
             wall += time.perf_counter() - t0  # all ranks start together (barrier above); the frame is complete after the slowest one (max over ranks below)
+            if after:
+                after()
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         return dev_ms, wall * 1e3
 
@@ -450,8 +454,7 @@ def bench_workload(env, args, name, steps, warmup, headline):
     stage_acc = {k: 0.0 for k in renderer.STAGES}
     kern_acc, step_trace = {}, []
 
-    def frame_device_acc():
-        frame_device()
+    def device_acc():
         st = renderer.stage_times()
         step_trace.append(round(st["total"], 3))
         for k, v in st.items():
@@ -460,7 +463,7 @@ def bench_workload(env, args, name, steps, warmup, headline):
             a = kern_acc.setdefault(k, {"ms": 0.0, "launches": 0})
             a["ms"] += v["ms"]
             a["launches"] += v["launches"]
-    dev_ms, wall_ms = timed(frame_device_acc, steps)
+    dev_ms, wall_ms = timed(frame_device, steps, device_acc)
     c1 = renderer.counters()
     gather_ms = sum(a.elapsed_time(b) for a, b in gather_events[-steps:]) / steps if gather_events else 0.0
     render_ms = stage_acc["total"] / steps
@@ -470,11 +473,10 @@ def bench_workload(env, args, name, steps, warmup, headline):
     c2 = renderer.counters()
     e2e_stage_acc = {k: 0.0 for k in renderer.STAGES}
 
-    def frame_e2e_acc():
-        frame_e2e()
+    def e2e_acc():
         for k, v in renderer.stage_times().items():
             e2e_stage_acc[k] += v
-    e2e_dev_ms, e2e_wall_ms = timed(frame_e2e_acc, steps)
+    e2e_dev_ms, e2e_wall_ms = timed(frame_e2e, steps, e2e_acc)
     c3 = renderer.counters()
     slice_ms = renderer.host_slices() if hasattr(renderer, "host_slices") else []
 

@@ -653,29 +653,34 @@ class Renderer:
 
     def render(self, composition: Composition, buffer: np.ndarray, width: int, height: int,
                channels=RGBA, clear_color: Color = Color(1.0, 1.0, 1.0, 1.0), crop: Optional[Rect] = None,
-               layer_cache: Optional[LayerCache] = None, stride: Optional[int] = None) -> Timings:
-        """`buffer`: writable contiguous uint8 host array of >= height*stride bytes."""
+               layer_cache: Optional[LayerCache] = None, stride: Optional[int] = None, timings: bool = True) -> Optional[Timings]:
+        """`buffer`: writable contiguous uint8 host array of >= height*stride bytes.
+        timings=False passes a null `forma_timings*`: the call then does not query its stage events
+        (stage_times() still can, afterwards)."""
         stride = width * 4 if stride is None else stride
         assert buffer.dtype == np.uint8 and buffer.flags["C_CONTIGUOUS"] and buffer.size >= height * stride
         ch, cc, rect = self._common(channels, clear_color, crop)
-        t = _CTimings()
+        t = _CTimings() if timings else None
         st = self._api.renderer_render(
             self._h, composition._h, buffer.ctypes.data_as(C.c_void_p), width, stride, height, ch, cc,
-            C.byref(rect) if rect is not None else None, layer_cache._h if layer_cache else None, C.byref(t))
+            C.byref(rect) if rect is not None else None, layer_cache._h if layer_cache else None,
+            C.byref(t) if t is not None else None)
         self._api.check(st, "Renderer::render")
-        return Timings(t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms, t.n_lines, t.n_segments)
+        return Timings(t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms, t.n_lines, t.n_segments) if t is not None else None
 
     def render_device(self, composition: Composition, device_ptr: int, width: int, height: int,
                       channels=RGBA, clear_color: Color = Color(1.0, 1.0, 1.0, 1.0), crop: Optional[Rect] = None,
-                      layer_cache: Optional[LayerCache] = None, stride: Optional[int] = None) -> Timings:
+                      layer_cache: Optional[LayerCache] = None, stride: Optional[int] = None,
+                      timings: bool = True) -> Optional[Timings]:
         stride = width * 4 if stride is None else stride
         ch, cc, rect = self._common(channels, clear_color, crop)
-        t = _CTimings()
+        t = _CTimings() if timings else None
         st = self._api.renderer_render_device(
             self._h, composition._h, C.c_void_p(device_ptr), width, stride, height, ch, cc,
-            C.byref(rect) if rect is not None else None, layer_cache._h if layer_cache else None, C.byref(t))
+            C.byref(rect) if rect is not None else None, layer_cache._h if layer_cache else None,
+            C.byref(t) if t is not None else None)
         self._api.check(st, "Renderer::render_device")
-        return Timings(t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms, t.n_lines, t.n_segments)
+        return Timings(t.line_setup_ms, t.rasterize_ms, t.sort_ms, t.paint_ms, t.n_lines, t.n_segments) if t is not None else None
 
     def launch_count(self) -> int:
         return int(self._api.renderer_launch_count(self._h))

@@ -381,9 +381,41 @@ class Renderer {
     RasterArgs last_raster{};        // line-setup arguments of the last render (device pointers owned by its composition)
     bool last_raster_valid = false;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied over PCIe since creation
-    double stage_ms[8] = {0};               // see forma_renderer_stage_times
+    double stage_ms[8] = {0};               // see forma_renderer_stage_times (valid after resolve_times)
     double kernel_ms[4] = {0};              // see forma_renderer_kernel_times
     uint32_t kernel_launches[4] = {0};
+    bool times_pending = false;             // the last render's events have not been turned into stage_ms / kernel_ms yet
+    int pending_sort_passes = 0;
+    uint32_t pending_paint_launches = 0;
+    void resolve_times() {
+        if (!times_pending || !timer.ok) return;
+        times_pending = false;
+        cudaSetDevice(device);
+        auto el = [&](int a, int b) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, timer.ev[a], timer.ev[b]);
+            return (double)ms;
+        };
+        stage_ms[0] = el(0, 7);  // uploads (geometry programs + flatten eval + tables)
+        stage_ms[1] = el(7, 1);  // line setup: count pass + scan (+ count read-back)
+        stage_ms[2] = el(1, 2);  // pixel-grid intersection (emit)
+        stage_ms[3] = el(2, 3);  // sort (upsweep / tile scan / downsweep per digit), no host sync inside
+        stage_ms[4] = el(3, 4);  // painter tables: cells, carries, entries (2 pair sorts)
+        stage_ms[5] = el(4, 5);  // paint kernel alone (host frames: its band launches)
+        stage_ms[6] = el(5, 6);  // device -> host copy of the framebuffer
+        stage_ms[7] = el(0, 6);  // whole call on the device timeline
+        kernel_ms[0] = kernel_ms[1] = 0;
+        for (int p = 0; p < pending_sort_passes; ++p) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, timer.sort_ev[3 * p], timer.sort_ev[3 * p + 1]);
+            cudaEventElapsedTime(&b, timer.sort_ev[3 * p + 1], timer.sort_ev[3 * p + 2]);
+            kernel_ms[1] += a;  // upsweep + tile scan
+            kernel_ms[0] += b;  // downsweep
+        }
+        kernel_launches[0] = kernel_launches[1] = (uint32_t)pending_sort_passes;
+        kernel_ms[2] = stage_ms[5];
+        kernel_launches[2] = pending_paint_launches;
+    }
     uint32_t* pinned_totals = nullptr;  // 4 x u32 pinned host words for count read-backs
     // Renderers of a multi-device / sliced frame: the per-row costs of the frame (see
     // row_cost_kernel) travel back behind the frame itself, without a synchronisation of their own.
@@ -1307,32 +1339,12 @@ int Renderer::render(Composition& comp, uint8_t* buffer, bool buffer_on_device, 
         if (st) return st;
     }
     last_tables_sync_free = fast && !last_tables_redone;
-    {
-        auto el = [&](int a, int b) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, timer.ev[a], timer.ev[b]);
-            return (double)ms;
-        };
-        stage_ms[0] = el(0, 7);  // uploads (geometry programs + flatten eval + tables)
-        stage_ms[1] = el(7, 1);  // line setup: count pass + scan (+ count read-back)
-        stage_ms[2] = el(1, 2);  // pixel-grid intersection (emit)
-        stage_ms[3] = el(2, 3);  // sort (upsweep / tile scan / downsweep per digit), no host sync inside
-        stage_ms[4] = el(3, 4);  // painter tables: cells, carries, entries (2 pair sorts, 2 read-backs)
-        stage_ms[5] = el(4, 5);  // paint kernel alone (host frames: its band launches)
-        stage_ms[6] = el(5, 6);  // device -> host copy of the framebuffer
-        stage_ms[7] = el(0, 6);  // whole call on the device timeline
-        kernel_ms[0] = kernel_ms[1] = 0;
-        for (int p = 0; p < timed_sort_passes; ++p) {
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, timer.sort_ev[3 * p], timer.sort_ev[3 * p + 1]);
-            cudaEventElapsedTime(&b, timer.sort_ev[3 * p + 1], timer.sort_ev[3 * p + 2]);
-            kernel_ms[1] += a;  // upsweep + tile scan
-            kernel_ms[0] += b;  // downsweep
-        }
-        kernel_launches[0] = kernel_launches[1] = (uint32_t)timed_sort_passes;
-        kernel_ms[2] = stage_ms[5];
-        kernel_launches[2] = paint_launches;
-    }
+    // The stage times are read from the events when somebody asks for them (resolve_times): a dozen
+    // event queries are not part of rendering a frame.
+    times_pending = true;
+    pending_sort_passes = timed_sort_passes;
+    pending_paint_launches = paint_launches;
+    if (timings) resolve_times();
     if (timings) {
         timings->line_setup_ms = stage_ms[1];
         timings->rasterize_ms = stage_ms[2];
@@ -2220,6 +2232,7 @@ static int sliced_host_render(forma_renderer* r, forma_composition* c, uint8_t* 
     }
     P.last_tables_redone = redone;
     P.last_tables_sync_free = all_fast && !redone;
+    P.times_pending = false;      // stage_ms was just set from the slices
     P.last_raster_valid = false;  // forma_renderer_lines describes the last unsliced render only
     P.last_written_tiles = 0;
     P.last_tiles_x = P.last_tiles_y = 0;
@@ -2362,9 +2375,11 @@ int forma_debug_selftest(int device, uint64_t* mismatches) {
 
 uint64_t forma_renderer_launch_count(const forma_renderer* r) { return r->r.launches; }
 void forma_renderer_stage_times(const forma_renderer* r, double out_ms[8]) {
+    const_cast<forma_renderer*>(r)->r.resolve_times();
     for (int i = 0; i < 8; ++i) out_ms[i] = r->r.stage_ms[i];
 }
 void forma_renderer_kernel_times(const forma_renderer* r, double out_ms[4], uint32_t out_launches[4]) {
+    const_cast<forma_renderer*>(r)->r.resolve_times();
     for (int i = 0; i < 4; ++i) {
         out_ms[i] = r->r.kernel_ms[i];
         out_launches[i] = r->r.kernel_launches[i];

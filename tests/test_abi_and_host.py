@@ -171,3 +171,30 @@ def test_bands_partition_the_frame(height, world):
         per = b.rows_per_band if per is None else per
         assert b.rows_per_band == per
     assert np.all(covered == 1)
+
+
+def test_schedule_switches_round_trip_without_device():
+    """forma_set_option / forma_get_option are host-side state: every switch DESIGN.md lists
+    exists, keeps its documented default, takes its alternatives and refuses values outside its
+    range (no device needed)."""
+    from forma_b200.binding import FormaError
+    api = forma_b200.load()
+    defaults = {"speculate": 1, "sync_free": 1, "band_copy": 1, "copy_bands": 4, "host_slices": 1, "slice_bands": 2,
+                "slice_chain": 1, "slice_min_points": 65536, "sort_full_key": 0, "sort_big_log2": 19, "sort_scan_log2": 22,
+                "paint_lpt": 1, "paint_wide": 0, "band_filter": 1, "test_gap_cap": 0, "test_fast_shrink": 0}
+    env_overrides = {k for k in defaults if os.environ.get("FORMA_" + k.upper()) is not None}
+    for name, want in defaults.items():
+        if name not in env_overrides:
+            assert api.get_option(name) == want, name
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    for name in defaults:
+        if not name.startswith("test_"):
+            assert f"`{name}`" in design, f"{name} is not documented in DESIGN.md"
+    for name, alt in (("host_slices", 16), ("slice_bands", 16), ("copy_bands", 1), ("slice_chain", 0), ("sync_free", 0)):
+        saved = api.get_option(name)
+        api.set_option(name, alt)
+        assert api.get_option(name) == alt
+        api.set_option(name, saved)
+    for name, bad in (("host_slices", 0), ("host_slices", 17), ("slice_bands", 0), ("copy_bands", 17), ("sync_free", 2)):
+        with pytest.raises(FormaError):
+            api.set_option(name, bad)

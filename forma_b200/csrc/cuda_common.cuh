@@ -4,6 +4,7 @@
 // reference (`mul_add`) is an explicit fmaf()/fma() here.
 #pragma once
 
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -43,14 +44,16 @@ inline int current_device_index() {
     return d;
 }
 inline int device_sm_count() {
-    static int sms[kMaxDevices] = {0};
+    static std::atomic<int> sms[kMaxDevices];  // zero-initialised; several host threads may ask at once
     const int d = current_device_index();
-    if (!sms[d]) {
-        int v = 148;
+    int v = sms[d].load(std::memory_order_relaxed);
+    if (!v) {
+        v = 148;
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
-        sms[d] = v > 0 ? v : 148;
+        if (v <= 0) v = 148;
+        sms[d].store(v, std::memory_order_relaxed);
     }
-    return sms[d];
+    return v;
 }
 
 // Growable device buffer (never shrinks). 180 GB of HBM3e makes "keep the high

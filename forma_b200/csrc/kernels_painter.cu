@@ -32,6 +32,7 @@
 // (tile_index_kernel sorts them into four classes by entry count): a tile is painted by
 // one warp from its first to its last layer, so the heaviest tile bounds the kernel's
 // tail unless it starts early (longest-processing-time order).
+#include <mutex>
 #include "paint_common.cuh"
 #include "paint_math.cuh"
 
@@ -995,12 +996,18 @@ void launch_paint(const PaintScene& S, const uint64_t* segs, const EntryRec* rec
     // Persistent warps: enough CTAs to fill every SM at the kernel's occupancy (per device).
     // Option paint_wide = 1 selects the build with up to 168 registers (6 CTAs / SM) instead of 128 (8 CTAs / SM).
     static int blocks_per_sm[2][kMaxDevices] = {{0}};
+    static std::mutex config_mu;  // several host threads may render on one device
     const int wide = options().paint_wide ? 1 : 0;
-    int& per_sm = blocks_per_sm[wide][current_device_index()];
-    if (!per_sm) {
-        if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paint_kernel<6>, kPaintWarpsPerBlock * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
-        if (per_sm < 1) per_sm = 1;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(config_mu);
+        int& slot = blocks_per_sm[wide][current_device_index()];
+        if (!slot) {
+            if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, paint_kernel<6>, kPaintWarpsPerBlock * 32, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, paint_kernel<8>, kPaintWarpsPerBlock * 32, 0);
+            if (slot < 1) slot = 1;
+        }
+        per_sm = slot;
     }
     const uint32_t want = (uint32_t)(per_sm * device_sm_count());
     const uint32_t need = (n_tiles + kPaintWarpsPerBlock - 1) / kPaintWarpsPerBlock;

@@ -21,10 +21,14 @@
 //   latency-bound at these sizes). A persistent single-sweep kernel for the large sorts
 //   was measured in round 1 (look-back-bound, 34 % of the HBM peak, profiles/r1_v2_*) and
 //   removed in favour of the reduce-then-scan passes.
+#include <mutex>
 #include "cuda_common.cuh"
 #include "kernels.h"
 
 namespace forma {
+
+static std::mutex g_sort_config_mu;  // guards the per-device kernel attributes set at first use
+
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
@@ -555,9 +559,12 @@ static void launch_passes(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals, ui
                           cudaStream_t stream, const uint32_t* n_dev) {
     static bool configured[kMaxDevices] = {false};
     const int dev = current_device_index();
-    if (!configured[dev]) {  // let several CTAs of 18-43 KB share one SM's shared memory
-        cudaFuncSetAttribute(onesweep_pass_kernel<kPairs, kItems>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured[dev] = true;
+    {
+        std::lock_guard<std::mutex> lk(g_sort_config_mu);  // several host threads may render on one device
+        if (!configured[dev]) {  // let several CTAs of 18-43 KB share one SM's shared memory
+            cudaFuncSetAttribute(onesweep_pass_kernel<kPairs, kItems>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            configured[dev] = true;
+        }
     }
     for (uint32_t p = 0; p < plan.n_passes; ++p) {
         const uint64_t* kin = (p & 1u) ? keys_tmp : keys;
@@ -581,15 +588,21 @@ SortResult launch_radix_sort(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
         static int wide_grids[kMaxDevices];
         static bool ds_configured[kMaxDevices] = {false};
         const int cur_dev = current_device_index();
-        int& wide_grid = wide_grids[cur_dev];
-        if (!ds_configured[cur_dev]) {
-            ds_configured[cur_dev] = true;
-            cudaFuncSetAttribute(radix_downsweep_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(DownsweepWideSmem));
-            int per_sm = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_wide_kernel, kWideThreads,
-                                                          sizeof(DownsweepWideSmem));
-            wide_grid = per_sm > 0 ? per_sm * device_sm_count() : 0;
+        int wide_grid = 0;
+        {
+            // Under a lock: a second host thread rendering on the same device (a slice of a host-frame
+            // pipeline) must not see the flag before the attribute is set and the grid is known.
+            std::lock_guard<std::mutex> lk(g_sort_config_mu);
+            if (!ds_configured[cur_dev]) {
+                cudaFuncSetAttribute(radix_downsweep_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(DownsweepWideSmem));
+                int per_sm = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_downsweep_wide_kernel, kWideThreads,
+                                                              sizeof(DownsweepWideSmem));
+                wide_grids[cur_dev] = per_sm > 0 ? per_sm * device_sm_count() : 0;
+                ds_configured[cur_dev] = true;
+            }
+            wide_grid = wide_grids[cur_dev];
         }
         if (wide_grid > 0) {
             const uint32_t tiles_per_chunk = (tiles + kMaxChunks - 1) / kMaxChunks;

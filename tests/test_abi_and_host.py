@@ -114,6 +114,11 @@ def test_renderer_requires_a_gpu():
     path = api.PathBuilder().move_to(Point(0, 0)).quad_to(Point(5, 9), Point(10, 0)).build()
     with pytest.raises(FormaError):
         path.segments()
+    # the multi-device renderer fails the same way, and refuses empty / oversized device lists before looking for devices
+    with pytest.raises(FormaError, match="no CPU fallback"):
+        api.MultiRenderer([0, 1])
+    with pytest.raises(FormaError, match="1..64"):
+        api.MultiRenderer([])
 
 
 def test_flatten_program_matches_the_oracles_point_count(oracle_api):

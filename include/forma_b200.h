@@ -186,7 +186,9 @@ void forma_layer_cache_clear(forma_layer_cache*);                 /* BufferLayer
 /* Renderer::render (:75-224) into a caller-owned HOST buffer laid out like
  * LinearLayout::new(width, width_stride, height) (cpu/buffer/layout/mod.rs:168).
  * Uploads what changed in the composition, runs all stages on the device and
- * copies the framebuffer (or, with a cache, only written tiles) back. */
+ * copies the framebuffer (or, with a cache, only written tiles) back.
+ * `timings` may be NULL: the call then does not read its stage events (a dozen event
+ * queries); forma_renderer_stage_times still returns them afterwards. */
 int forma_renderer_render(forma_renderer*, forma_composition*, uint8_t* buffer, uint64_t width,
                           uint64_t width_stride, uint64_t height, const uint32_t channels[4],
                           const float clear_color[4], const forma_rect* crop /* nullable */,

@@ -115,6 +115,10 @@ for label, pick in (("`paris4k`", lambda d: d), ("`circles8k_1m` (BASELINE confi
     sp = f"{d8['value'] / one['value']:.2f}×" if d8 and one else "—"
     e = f"{f1(one['e2e']['value'])} → {f1(d8['e2e']['value'])}" if d8 and one else "—"
     rows.append(f"| {label} | " + " | ".join(cells) + f" | {sp} | {e} |")
+closing2 = load(f"{TAG}_mgpu_n2_closing.json")
+if closing2:
+    rows.append(f"| `paris4k`, closing build | {f1(main['value'])} | {f1(closing2['value'])} | — | — | — | "
+                f"{f1(main['e2e']['value'])} → {f1(closing2['e2e']['value'])} (N = 2) |")
 vals["mgpu_table"] = "\n".join(rows)
 modes = main.get("library_options", {})
 vals["sync_free_note"] = ("`sync_free` (default): from a renderer's second frame on the table kernels are sized by the previous frame's counts and read "
